@@ -1,0 +1,299 @@
+"""Dense, device-ready tables of the simulator's read-only inputs.
+
+The reference re-reads three files at every ``reset`` (a 600 KB manifest JSON, a viewport
+pickle and a bandwidth pickle: bitrate_selection/simulators/simulator.py:30-38).  Here the
+same data is packed once into flat arrays that are uploaded to HBM and stay resident
+(they are a few MB and live in L2 at the reference's data scale).
+
+Layouts (row-major):
+  size      int32  [V][C][R][64]    tile sizes in bytes                 (manifest "size")
+  quality   float32[V][C][R][64]    tile qualities (raw, == bitrate)    (manifest "quality")
+  video_time int32 [V]              manifest "Video_Time"
+  vp_gt     uint64 [P][CV]          ground-truth tile mask, bit t = tile t (row*8+col)
+  vp_pred   uint64 [P][CV]          predicted tile mask
+  vp_acc    float64[P][CV]          IoU accuracy of the prediction
+  vp_start  int32  [P]              first chunk id of the pair's viewport list
+  vp_end    int32  [P]              last chunk id of the pair's viewport list
+  trace     float64[T][LMAX]        bytes/s of each 1-s segment (ints in the shipped data,
+                                    floats after NetworkTrace rescaling, network.py:11-17)
+  trace_len int32  [T]
+  qoe_w     float32[Q][3]
+  samples   int32  [S][4]           (video_idx, user_idx, trace_idx, qoe_idx) into the above
+with P = V*U and pair = video_idx*U + user_idx.
+"""
+from __future__ import annotations
+
+import json
+import os
+import pickle
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .config import SimConfig
+
+
+def mask_to_bits(mask) -> int:
+    """uint8[64] (row-major 8x8) -> python int bitmask, bit t = tile t."""
+    m = np.asarray(mask).reshape(-1)
+    out = 0
+    for t in np.nonzero(m == 1)[0]:
+        out |= 1 << int(t)
+    return out
+
+
+def masks_to_u64(masks: np.ndarray) -> np.ndarray:
+    """[..., 64] 0/1 array -> uint64[...] bitmasks."""
+    m = (np.asarray(masks) == 1).astype(np.uint64)
+    weights = (np.uint64(1) << np.arange(64, dtype=np.uint64))
+    return (m * weights).sum(axis=-1, dtype=np.uint64)
+
+
+def u64_to_masks(bits: np.ndarray, dtype=np.uint8) -> np.ndarray:
+    """uint64[...] -> [..., 64] 0/1 array."""
+    b = np.asarray(bits, dtype=np.uint64)[..., None]
+    return ((b >> np.arange(64, dtype=np.uint64)) & np.uint64(1)).astype(dtype)
+
+
+@dataclass
+class SimTables:
+    cfg: SimConfig
+    size: np.ndarray
+    quality: np.ndarray
+    video_time: np.ndarray
+    vp_gt: np.ndarray
+    vp_pred: np.ndarray
+    vp_acc: np.ndarray
+    vp_start: np.ndarray
+    vp_end: np.ndarray
+    trace: np.ndarray
+    trace_len: np.ndarray
+    qoe_w: np.ndarray
+    samples: np.ndarray
+    n_users: int
+    # dataset ids for logging (reference prints the dataset's own ids, mansy_env.py:284)
+    video_ids: np.ndarray = None
+    user_ids: np.ndarray = None
+    trace_ids: np.ndarray = None
+
+    def __post_init__(self):
+        self.size = np.ascontiguousarray(self.size, dtype=np.int32)
+        self.quality = np.ascontiguousarray(self.quality, dtype=np.float32)
+        self.video_time = np.ascontiguousarray(self.video_time, dtype=np.int32)
+        self.vp_gt = np.ascontiguousarray(self.vp_gt, dtype=np.uint64)
+        self.vp_pred = np.ascontiguousarray(self.vp_pred, dtype=np.uint64)
+        self.vp_acc = np.ascontiguousarray(self.vp_acc, dtype=np.float64)
+        self.vp_start = np.ascontiguousarray(self.vp_start, dtype=np.int32)
+        self.vp_end = np.ascontiguousarray(self.vp_end, dtype=np.int32)
+        self.trace = np.ascontiguousarray(self.trace, dtype=np.float64)
+        self.trace_len = np.ascontiguousarray(self.trace_len, dtype=np.int32)
+        self.qoe_w = np.ascontiguousarray(self.qoe_w, dtype=np.float32)
+        self.samples = np.ascontiguousarray(self.samples, dtype=np.int32)
+        V = self.size.shape[0]
+        if self.video_ids is None:
+            self.video_ids = np.arange(V, dtype=np.int32)
+        if self.user_ids is None:
+            self.user_ids = np.arange(self.n_users, dtype=np.int32)
+        if self.trace_ids is None:
+            self.trace_ids = np.arange(self.trace.shape[0], dtype=np.int32)
+        self.video_ids = np.asarray(self.video_ids, dtype=np.int32)
+        self.user_ids = np.asarray(self.user_ids, dtype=np.int32)
+        self.trace_ids = np.asarray(self.trace_ids, dtype=np.int32)
+        self.validate()
+
+    # ---- shape helpers -------------------------------------------------
+    @property
+    def n_videos(self) -> int:
+        return self.size.shape[0]
+
+    @property
+    def n_chunks(self) -> int:
+        return self.size.shape[1]
+
+    @property
+    def n_pairs(self) -> int:
+        return self.vp_gt.shape[0]
+
+    @property
+    def n_vp_chunks(self) -> int:
+        return self.vp_gt.shape[1]
+
+    @property
+    def n_traces(self) -> int:
+        return self.trace.shape[0]
+
+    @property
+    def n_samples(self) -> int:
+        return self.samples.shape[0]
+
+    def validate(self) -> None:
+        c = self.cfg
+        c.validate()
+        V, C, R, TT = self.size.shape
+        if (R, TT) != (len(c.video_rates), c.tile_total_num):
+            raise ValueError(f"size table must be [V][C][{len(c.video_rates)}][{c.tile_total_num}]")
+        if self.quality.shape != self.size.shape:
+            raise ValueError("quality table shape != size table shape")
+        if self.vp_gt.shape != self.vp_pred.shape or self.vp_gt.shape != self.vp_acc.shape:
+            raise ValueError("viewport tables disagree in shape")
+        P = self.vp_gt.shape[0]
+        if P != V * self.n_users:
+            raise ValueError("viewport tables must hold V*U pairs")
+        if self.vp_start.shape != (P,) or self.vp_end.shape != (P,):
+            raise ValueError("vp_start/vp_end must be [P]")
+        if np.any(self.vp_end - self.vp_start + 1 > self.vp_gt.shape[1]):
+            raise ValueError("viewport chunk range exceeds table width")
+        # bitrate_selection/simulators/simulator.py:44 (assert startup_download + 1 >= start_chunk)
+        if np.any(self.vp_start > c.startup_download + 1):
+            raise ValueError("a viewport trace starts after the first simulated chunk")
+        end = np.minimum(self.vp_end.reshape(V, self.n_users), (self.video_time - 1)[:, None])
+        if np.any(end >= C):
+            raise ValueError("end chunk beyond the size table")
+        if np.any(end < c.startup_download + 1):
+            raise ValueError("an episode would have no chunk to simulate")
+        if self.trace.shape[0] != self.trace_len.shape[0]:
+            raise ValueError("trace/trace_len disagree")
+        if np.any(self.trace_len < 1) or np.any(self.trace_len > self.trace.shape[1]):
+            raise ValueError("bad trace_len")
+        for t in range(self.trace.shape[0]):
+            row = self.trace[t, : self.trace_len[t]]
+            if not np.any(row > 0):
+                # the reference would loop forever (network.py:24-33)
+                raise ValueError(f"trace {t} has no positive-throughput second")
+            if np.any(row < 0) or not np.all(np.isfinite(row)):
+                raise ValueError(f"trace {t} has negative/non-finite throughput")
+        if np.any(self.size <= 0):
+            raise ValueError("tile sizes must be positive")
+        s = self.samples
+        if s.ndim != 2 or s.shape[1] != 4 or s.shape[0] < 1:
+            raise ValueError("samples must be [S][4]")
+        hi = np.array([V, self.n_users, self.trace.shape[0], self.qoe_w.shape[0]])
+        if np.any(s < 0) or np.any(s >= hi[None, :]):
+            raise ValueError("sample index out of range")
+
+    # ---- (de)serialisation for fixtures ---------------------------------
+    _ARRAYS = ("size", "quality", "video_time", "vp_gt", "vp_pred", "vp_acc", "vp_start", "vp_end",
+               "trace", "trace_len", "qoe_w", "samples", "video_ids", "user_ids", "trace_ids")
+
+    def to_npz_dict(self, prefix: str = "tab_") -> Dict[str, np.ndarray]:
+        d = {prefix + k: getattr(self, k) for k in self._ARRAYS}
+        d[prefix + "n_users"] = np.int32(self.n_users)
+        d[prefix + "rates"] = np.asarray(self.cfg.video_rates, dtype=np.int32)
+        return d
+
+    @classmethod
+    def from_npz_dict(cls, d, prefix: str = "tab_", cfg: Optional[SimConfig] = None) -> "SimTables":
+        if cfg is None:
+            cfg = SimConfig(video_rates=tuple(int(r) for r in d[prefix + "rates"]))
+        kw = {k: np.asarray(d[prefix + k]) for k in cls._ARRAYS}
+        return cls(cfg=cfg, n_users=int(d[prefix + "n_users"]), **kw)
+
+    def with_samples(self, samples: np.ndarray, qoe_w: Optional[np.ndarray] = None) -> "SimTables":
+        kw = {k: getattr(self, k) for k in self._ARRAYS}
+        kw["samples"] = samples
+        if qoe_w is not None:
+            kw["qoe_w"] = qoe_w
+        return SimTables(cfg=self.cfg, n_users=self.n_users, **kw)
+
+
+# ---------------------------------------------------------------------------
+# Sample lists (bitrate_selection/utils/common.py:60-98)
+# ---------------------------------------------------------------------------
+def environment_samples(n_videos: int, n_users: int, n_traces: int, n_qoe: int) -> np.ndarray:
+    """Train/valid sample list: sample i = (i%V, i%U, i%T, i%Q) (common.py:60-84)."""
+    max_len = max(n_videos, n_users, n_traces, n_qoe)
+    vq = n_videos * n_qoe
+    total = max(max_len, vq * (-(-max_len // vq)))
+    i = np.arange(total, dtype=np.int64)
+    return np.stack([i % n_videos, i % n_users, i % n_traces, i % n_qoe], axis=1).astype(np.int32)
+
+
+def environment_test_samples(n_videos: int, n_users: int, n_traces: int, n_qoe: int) -> np.ndarray:
+    """Test sample list: full product, order video->user->trace->qoe (common.py:87-98)."""
+    g = np.meshgrid(np.arange(n_videos), np.arange(n_users), np.arange(n_traces), np.arange(n_qoe),
+                    indexing="ij")
+    return np.stack([x.reshape(-1) for x in g], axis=1).astype(np.int32)
+
+
+# ---------------------------------------------------------------------------
+# Packer from the reference's on-disk formats
+# ---------------------------------------------------------------------------
+def pack_from_reference_layout(config, dataset: str, network_dataset: str, videos: Sequence[int],
+                               users: Sequence[int], traces: Sequence[int], qoe_weights,
+                               mode: str, sim_cfg: Optional[SimConfig] = None,
+                               trace_scale=None) -> SimTables:
+    """Pack manifests / viewport pickles / bandwidth pickles into :class:`SimTables`.
+
+    ``config`` is the reference's config object (attribute access; bitrate_selection/utils/
+    common.py:13-37).  ``videos``/``users``/``traces`` are the split lists
+    (envs/mansy_env.py:44-46); table index i refers to ``videos[i]`` etc., exactly like
+    the reference's sample tuples (mansy_env.py:103-106).
+    """
+    cfg = sim_cfg or SimConfig.from_reference_config(config)
+    R, TT = len(cfg.video_rates), cfg.tile_total_num
+    manifests = []
+    for v in videos:
+        path = os.path.join(config.video_datasets_dir[dataset], f"video{v}.json")
+        with open(path, "r", encoding="utf-8") as fh:
+            manifests.append(json.load(fh))
+    C = max(max(int(k) for k in m["Chunks"].keys()) + 1 for m in manifests)
+    V, U = len(videos), len(users)
+    size = np.ones((V, C, R, TT), dtype=np.int32)
+    quality = np.zeros((V, C, R, TT), dtype=np.float32)
+    video_time = np.zeros(V, dtype=np.int32)
+    for vi, m in enumerate(manifests):
+        video_time[vi] = int(m["Video_Time"])
+        for k, info in m["Chunks"].items():
+            size[vi, int(k)] = np.asarray(info["size"], dtype=np.int64)
+            quality[vi, int(k)] = np.asarray(info["quality"], dtype=np.float32)
+
+    lists = []
+    for v in videos:
+        for u in users:
+            path = os.path.join(config.viewport_datasets_dir[dataset], "prediction", f"video{v}", f"user{u}.pkl")
+            with open(path, "rb") as fh:
+                lists.append(pickle.load(fh))
+    CV = max(len(l) for l in lists)
+    P = V * U
+    vp_gt = np.zeros((P, CV), dtype=np.uint64)
+    vp_pred = np.zeros((P, CV), dtype=np.uint64)
+    vp_acc = np.zeros((P, CV), dtype=np.float64)
+    vp_start = np.zeros(P, dtype=np.int32)
+    vp_end = np.zeros(P, dtype=np.int32)
+    for p, l in enumerate(lists):
+        vp_start[p] = int(l[0][0])
+        vp_end[p] = int(l[-1][0])       # hmdtrace.py:11 -- taken from the last entry, not a count
+        for j, (chunk, gt, pred, acc) in enumerate(l):
+            vp_gt[p, j] = mask_to_bits(gt)
+            vp_pred[p, j] = mask_to_bits(pred)
+            vp_acc[p, j] = float(acc)
+
+    tr = []
+    for t in traces:
+        path = os.path.join(config.network_datasets_dir[network_dataset], config.network_info[network_dataset][t])
+        with open(path, "rb") as fh:
+            raw = pickle.load(fh)
+        thr = [float(x[1]) for x in raw]
+        if trace_scale is not None:     # network.py:11-17
+            mx, mn = max(thr), min(thr)
+            up, low = trace_scale
+            k = (up - low) / (mx - mn)
+            thr = [low + k * (x - mn) for x in thr]
+        tr.append(np.asarray(thr, dtype=np.float64))
+    L = max(len(x) for x in tr)
+    trace = np.zeros((len(tr), L), dtype=np.float64)
+    trace_len = np.zeros(len(tr), dtype=np.int32)
+    for i, x in enumerate(tr):
+        trace[i, : len(x)] = x
+        trace_len[i] = len(x)
+
+    qoe_w = np.asarray(qoe_weights, dtype=np.float32).reshape(-1, 3)
+    if mode == "test":
+        samples = environment_test_samples(V, U, len(traces), qoe_w.shape[0])
+    else:
+        samples = environment_samples(V, U, len(traces), qoe_w.shape[0])
+    return SimTables(cfg=cfg, size=size, quality=quality, video_time=video_time, vp_gt=vp_gt, vp_pred=vp_pred,
+                     vp_acc=vp_acc, vp_start=vp_start, vp_end=vp_end, trace=trace, trace_len=trace_len,
+                     qoe_w=qoe_w, samples=samples, n_users=U, video_ids=np.asarray(videos),
+                     user_ids=np.asarray(users), trace_ids=np.asarray(traces))
