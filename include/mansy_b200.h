@@ -1,0 +1,256 @@
+/*
+ * mansy_b200.h -- C ABI of the B200-native tile-based streaming simulator.
+ *
+ * This is the drop-in boundary for the reference's data-parallel hot path
+ * (bitrate_selection/simulators + bitrate_selection/envs of
+ * duowuyms/MANSY_ImmersiveVideoStreaming).  The reference is pure Python and has no FFI; each
+ * entry point below cites the reference interface it replaces (file:line relative to the
+ * reference root).  Signatures use plain pointers and sizes only -- no torch types.  A Python
+ * caller binds it with ctypes (mansy_immersivevideostreaming_b200/_capi.py; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative MANSY_E_* code; the message is
+ *     available from mansy_last_error() (thread-local).
+ *   - "dev" pointers are device pointers on the handle's GPU, "host" pointers are host memory
+ *     (pinned for asynchronous copies).  `stream` is a cudaStream_t passed as void*; all device
+ *     work is ordered on it and nothing synchronises unless documented.
+ *   - the caller owns observation / reward / done / action buffers; the library owns its copies
+ *     of the read-only tables and the per-environment state.  No allocation happens after
+ *     mansy_create / mansy_policy_create.
+ *   - a handle is not thread-safe; use one host thread per handle.
+ */
+#ifndef MANSY_B200_H_
+#define MANSY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MANSY_ABI_VERSION 1
+
+/* error codes */
+#define MANSY_OK 0
+#define MANSY_E_INVALID (-1) /* bad argument / unsupported configuration */
+#define MANSY_E_CUDA (-2)    /* CUDA runtime error (message holds cudaGetErrorString) */
+#define MANSY_E_NOMEM (-3)
+#define MANSY_E_STATE (-4)   /* call not valid in the handle's current state */
+
+/* observation layouts (float32 words per environment row, see config.py) */
+#define MANSY_OBS_NONE 0
+#define MANSY_OBS_MANSY 1  /* 13 arrays, 777 floats, row stride 784 (envs/mansy_env.py:136-150) */
+#define MANSY_OBS_SIMPLE 2 /* 5 arrays, 395 floats, row stride 400 (envs/simple_rl_env.py:103-109) */
+#define MANSY_OBS_MANSY_STRIDE 784
+#define MANSY_OBS_SIMPLE_STRIDE 400
+
+/* reward modes: envs/mansy_env.py:168-177, envs/simple_rl_env.py:124-127 */
+#define MANSY_REWARD_QOE 0
+#define MANSY_REWARD_QOE_NORM 1 /* qoe / (w1 + w2 + w3) */
+
+/* doubles per environment in the optional `aux` output of mansy_step */
+#define MANSY_AUX_DOUBLES 16
+enum {
+  MANSY_AUX_CHUNK_SIZE = 0,   /* simulators/simulator.py:100  (exact integer) */
+  MANSY_AUX_DOWNLOAD_TIME = 1,/* simulators/network.py:34 */
+  MANSY_AUX_REBUFFER = 2,     /* simulators/buffer.py:8-15 */
+  MANSY_AUX_BUFFER = 3,       /* buffer level after the push */
+  MANSY_AUX_CUR_IDX = 4,      /* network.py cur_idx after the download (exact integer) */
+  MANSY_AUX_CUR_TIME = 5,     /* network.py cur_time after the download */
+  MANSY_AUX_QOE = 6,          /* utils/qoe.py:33 */
+  MANSY_AUX_QOE1 = 7,
+  MANSY_AUX_QOE2 = 8,
+  MANSY_AUX_QOE3 = 9,
+  MANSY_AUX_NEXT_CHUNK = 10,  /* simulator.next_chunk after the step (exact integer) */
+  MANSY_AUX_EP_STEP = 11,     /* steps taken in the episode, this one included */
+  MANSY_AUX_SAMPLE_ID = 12,   /* sample the stepped episode belongs to */
+  MANSY_AUX_REWARD = 13,      /* reward before rounding to float32 */
+  MANSY_AUX_GT_MASK_LO = 14,  /* ground-truth mask used by the QoE, low / high 32 bits */
+  MANSY_AUX_GT_MASK_HI = 15
+};
+
+/* doubles per environment in mansy_episode_stats */
+#define MANSY_STATS_DOUBLES 16
+enum {
+  /* last finished episode (the row envs/mansy_env.py:271-290 `_log` appends) */
+  MANSY_STAT_LAST_SUM_QOE = 0,
+  MANSY_STAT_LAST_SUM_QOE1 = 1,
+  MANSY_STAT_LAST_SUM_QOE2 = 2,
+  MANSY_STAT_LAST_SUM_QOE3 = 3,
+  MANSY_STAT_LAST_STEPS = 4,
+  MANSY_STAT_LAST_SAMPLE = 5,
+  /* totals over all finished episodes since create / mansy_stats_clear */
+  MANSY_STAT_TOT_SUM_QOE = 6,
+  MANSY_STAT_TOT_SUM_QOE1 = 7,
+  MANSY_STAT_TOT_SUM_QOE2 = 8,
+  MANSY_STAT_TOT_SUM_QOE3 = 9,
+  MANSY_STAT_TOT_STEPS = 10,
+  MANSY_STAT_TOT_EPISODES = 11,
+  MANSY_STAT_TOT_RETURN = 12, /* sum of rewards of finished episodes */
+  MANSY_STAT_LAST_RETURN = 13
+};
+
+typedef struct mansy_sim *mansy_handle_t;
+typedef struct mansy_policy *mansy_policy_t;
+
+/*
+ * Read-only inputs, HOST pointers; mansy_create copies them to the device.
+ * Replaces the three files Simulator.__init__ re-reads at every reset
+ * (simulators/simulator.py:30-38): manifest JSON, viewport pickle, bandwidth pickle.
+ */
+typedef struct {
+  const int32_t *size;       /* [n_videos][n_chunks][5][64] tile bytes      (manifest "size") */
+  const float *quality;      /* [n_videos][n_chunks][5][64] tile quality    (manifest "quality") */
+  const int32_t *video_time; /* [n_videos]                                  (manifest "Video_Time") */
+  const uint64_t *vp_gt;     /* [n_videos*n_users][n_vp_chunks] bit t = tile t (row*8+col) */
+  const uint64_t *vp_pred;   /* same shape: predicted viewport */
+  const double *vp_acc;      /* same shape: IoU accuracy */
+  const int32_t *vp_start;   /* [n_videos*n_users] first chunk id  (simulators/hmdtrace.py:10) */
+  const int32_t *vp_end;     /* [n_videos*n_users] last chunk id   (simulators/hmdtrace.py:11) */
+  const double *trace;       /* [n_traces][trace_stride] bytes/s per 1-s segment (network.py:9) */
+  const int32_t *trace_len;  /* [n_traces] */
+  const float *qoe_w;        /* [n_qoe][3] */
+  const int32_t *samples;    /* [n_samples][4] (video, user, trace, qoe) indices (utils/common.py:60-98) */
+  int32_t n_videos, n_chunks, n_users, n_vp_chunks, n_traces, trace_stride, n_qoe, n_samples;
+} mansy_tables_t;
+
+/* Constants of config.yml:68-75,153-157 plus the vector-env geometry. */
+typedef struct {
+  int32_t n_envs;     /* environments owned by this handle (the local shard) */
+  int32_t env_offset; /* global index of local env 0 (multi-GPU sharding; 0 on one GPU) */
+  int32_t worker_num; /* global sample stride (envs/mansy_env.py:56,100-101) */
+  int32_t seed;       /* env k starts at sample (seed + env_offset + k) % worker_num (mansy_env.py:253-256) */
+  int32_t obs_mode;   /* MANSY_OBS_* */
+  int32_t reward_mode;/* MANSY_REWARD_* */
+  int32_t video_rates[5];
+  int32_t startup_download;
+  int32_t chunk_length;
+  int32_t max_size;
+  int32_t max_throughput;
+} mansy_cfg_t;
+
+/* Outputs of one step, DEVICE pointers, row i belongs to env_ids[i] (or env i when env_ids is NULL). */
+typedef struct {
+  float *obs;            /* [n][obs_stride] or NULL (no observation materialised) */
+  int64_t obs_stride;    /* floats between rows; >= the layout's stride and a multiple of 4 */
+  float *reward;         /* [n] or NULL */
+  uint8_t *done;         /* [n] or NULL */
+  double *aux;           /* [n][MANSY_AUX_DOUBLES] or NULL (parity / debugging) */
+  uint8_t *tile_versions;/* [n][64] chosen bitrate version per tile (utils/common.py:142-193) or NULL */
+} mansy_out_t;
+
+const char *mansy_last_error(void);
+int mansy_abi_version(void);
+/* kernels launched by this library in the calling process (all handles), for bench accounting */
+int64_t mansy_kernel_launches(void);
+
+/* Simulator(...) + MANSYEnv/SimpleRLEnv state for n_envs environments
+ * (simulators/simulator.py:15-46, envs/mansy_env.py:19-97). */
+int mansy_create(const mansy_tables_t *tables, const mansy_cfg_t *cfg, int device, mansy_handle_t *out);
+int mansy_destroy(mansy_handle_t h);
+
+/* env.seed(seed) of a vector env: env k gets worker_id (seed + env_offset + k) % worker_num
+ * (envs/mansy_env.py:253-256). */
+int mansy_seed(mansy_handle_t h, int32_t seed, void *stream);
+
+/* env.reset() for the listed envs (env_ids_dev NULL = all): picks the next sample, rebuilds the
+ * episode state and writes the initial observation (envs/mansy_env.py:99-152,
+ * envs/simple_rl_env.py:76-111).  obs_dev may be NULL. */
+int mansy_reset(mansy_handle_t h, const int32_t *env_ids_dev, int32_t n, float *obs_dev, int64_t obs_stride,
+                void *stream);
+
+/* env.step(action) (envs/mansy_env.py:154-248, envs/simple_rl_env.py:113-160) for the listed
+ * envs.  actions_dev[i] belongs to env_ids_dev[i].  With auto_reset != 0 an env whose episode
+ * ended is reset inside the same launch and its row holds the first observation of the next
+ * episode (done is still 1); otherwise the row holds the terminal observation and the env
+ * stays finished until mansy_reset. */
+int mansy_step(mansy_handle_t h, const int32_t *actions_dev, const int32_t *env_ids_dev, int32_t n,
+               int32_t auto_reset, const mansy_out_t *out, void *stream);
+
+/* Same step with HOST buffers: copies actions host->device, steps every env, copies observation,
+ * reward and done device->host and synchronises the stream.  Host buffers should be pinned. */
+int mansy_step_host(mansy_handle_t h, const int32_t *actions_host, int32_t auto_reset, float *obs_host,
+                    float *reward_host, uint8_t *done_host, void *stream);
+int mansy_reset_host(mansy_handle_t h, float *obs_host, void *stream);
+
+/* n_steps lockstep steps with in-kernel actions: action = hash(seed, global env, step0 + t) % 15
+ * (the simulator-only throughput sweep of run_simple_rl.py-style baselines), auto-reset on.
+ * Buffers are [n_steps][n_envs][...] when `per_step_outputs` != 0, otherwise [n_envs][...]
+ * overwritten every step. */
+int mansy_rollout_random(mansy_handle_t h, int32_t n_steps, uint64_t seed, int64_t step0, int32_t per_step_outputs,
+                         const mansy_out_t *out, void *stream);
+
+/* Per-env episode statistics (what `_log` writes per episode, envs/mansy_env.py:271-290, plus
+ * running totals for the per-rollout all-gather): stats_dev is [n_envs][MANSY_STATS_DOUBLES]. */
+int mansy_episode_stats(mansy_handle_t h, double *stats_dev, void *stream);
+int mansy_stats_clear(mansy_handle_t h, void *stream);
+
+/* Field-of-view -> tile masks with per-chunk OR and IoU
+ * (viewport_prediction/utils/common.py:37-58,83-127; viewport_prediction/predict.py:33-48).
+ * gt_xy_dev / pred_xy_dev: float32 [n_chunks][points][2] normalised centres in [0,1];
+ * outputs gt/pred uint64 [n_chunks] (bit t = tile t), acc float64 [n_chunks].  pred_xy_dev,
+ * pred_mask_dev and acc_dev may be NULL together.  Grid fixed to 8x8 tiles. */
+int mansy_viewport_tiles(const float *gt_xy_dev, const float *pred_xy_dev, int64_t n_chunks, int32_t points,
+                         int32_t video_width, int32_t video_height, int32_t fov_width, int32_t fov_height,
+                         uint64_t *gt_mask_dev, uint64_t *pred_mask_dev, double *acc_dev, void *stream);
+
+/* action -> per-tile bitrate versions for standalone masks (utils/common.py:101-119,142-193);
+ * masks_dev uint64[n], actions_dev int32[n], versions_dev uint8[n][64]. */
+int mansy_allocate_tile_versions(const uint64_t *masks_dev, const int32_t *actions_dev, int64_t n,
+                                 const int32_t video_rates[5], uint8_t *versions_dev, void *stream);
+
+/*
+ * Policy / value forward (bitrate_selection/models/mansy.py:26-51,63-66,77-80 and
+ * models/simple_rl.py:21-35,46-49,60-63).  Weights are HOST float32 arrays in the reference's
+ * state-dict layouts; mansy_policy_create repacks and uploads them.
+ */
+typedef struct {
+  int32_t kind; /* MANSY_OBS_MANSY or MANSY_OBS_SIMPLE */
+  /* MANSY: branch weights [128][K_b] for the 10 branches in FeatureNet order, biases [128] */
+  const float *branch_w[10];
+  const float *branch_b[10];
+  const float *actor_fc_w;  /* [128][feature_dim] */
+  const float *actor_fc_b;  /* [128] */
+  const float *actor_out_w; /* [15][128] */
+  const float *actor_out_b; /* [15] */
+  const float *critic_fc_w; /* [128][feature_dim] */
+  const float *critic_fc_b;
+  const float *critic_out_w;/* [1][128] */
+  const float *critic_out_b;/* [1] */
+} mansy_policy_weights_t;
+
+int mansy_policy_create(const mansy_policy_weights_t *w, int device, mansy_policy_t *out);
+int mansy_policy_destroy(mansy_policy_t p);
+/* logits_dev [n][16] (15 used; MANSY: raw logits, SimpleRL: softmax probabilities as the reference's
+ * Actor returns), value_dev [n]. */
+int mansy_policy_forward(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
+                         float *value_dev, void *stream);
+/* Categorical(logits).sample() with a counter-based generator keyed by (seed, env, step)
+ * (run_mansy.py:228-229); also returns log-probabilities. */
+int mansy_policy_sample(const float *logits_dev, int32_t n, int32_t is_probs, uint64_t seed, int64_t step,
+                        int32_t env_offset, int32_t *actions_dev, float *logp_dev, void *stream);
+
+/* Raw copy of the per-environment state records (128 bytes each, layout: csrc/mansy_sim.cuh
+ * EnvState / _capi.ENV_STATE_DTYPE) into state_dev[n_envs*128]; for host-side bookkeeping
+ * (current_video / current_user / ... attributes of the gym envs) and tests. */
+int mansy_state_snapshot(mansy_handle_t h, void *state_dev, void *stream);
+
+/* Non-zero once a kernel met a data error (a trace that can never finish a download). */
+int mansy_error_flag(mansy_handle_t h, int32_t *flag_host);
+
+/* CPU self-tests of the scalar building blocks the kernels are made of (mansy_core.cuh, the same
+ * __host__ __device__ code), so the non-GPU test-suite can check them against the oracle.  Not a
+ * product path: nothing in the package calls them. */
+int mansy_selftest_allocate(uint64_t mask, int32_t action, const int32_t video_rates[5], uint8_t versions_out[64]);
+int mansy_selftest_fov_mask(int32_t x, int32_t y, int32_t width, int32_t height, int32_t fov_w, int32_t fov_h,
+                            uint64_t *mask_out, int32_t *valid_out);
+int mansy_selftest_centre_to_pixel(float v, int32_t length);
+int mansy_selftest_download(const double *thr, int32_t trace_len, int64_t size, int32_t *cur_idx, double *cur_time,
+                            double *buf, double *download_time, double *rebuffer);
+int mansy_selftest_hashed_action(uint64_t seed, uint64_t env, uint64_t step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANSY_B200_H_ */

@@ -1,0 +1,351 @@
+// mansy_policy.cu -- policy / value forward that consumes the simulator's observation rows.
+//
+// Reference: bitrate_selection/models/mansy.py:26-51 (FeatureNet), :63-66 (Actor), :77-80 (Critic);
+// bitrate_selection/models/simple_rl.py:21-35,46-49,60-63; Categorical sampling
+// bitrate_selection/run_mansy.py:228-229.
+//
+// Every Conv1d in the reference has kernel_size == input length, i.e. it is a Linear over the
+// flattened (channels x length) segment of the observation row, so the whole network is
+//   layer 1: 10 (MANSY) / 5 (SimpleRL) independent Linear(K_b -> 128) + LeakyReLU on row segments,
+//   layer 2: Linear(F -> 128) + LeakyReLU for the actor and for the critic (stacked: F -> 256),
+//            MANSY adds the qoe_weight branch features as a residual,
+//   heads  : Linear(128 -> 15) and Linear(128 -> 1); SimpleRL's actor returns softmax probabilities.
+// The FeatureNet instance is shared by actor and critic (run_mansy.py:207-209), so its output is
+// computed once.
+//
+// This file holds the FP32 CUDA-core implementation (exact fp32 FMA math, used for parity against
+// a torch fp32 reference).  Weights are re-laid out K-major at create time so that consecutive
+// threads read consecutive weights.
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mansy_sim.cuh"
+
+namespace mansy {
+int set_error(int code, const std::string &msg);
+void count_launch();
+
+constexpr int kHidden = 128;
+constexpr int kMaxBranches = 10;
+constexpr int kEnvTile = 16;          // environments per CTA
+constexpr int kPolicyThreads = 256;
+constexpr float kLeaky = 0.01f;       // torch.nn.LeakyReLU default negative_slope
+
+struct PolicyDev {
+  int32_t kind;
+  int32_t n_branches;
+  int32_t feat_dim;                    // 128 * n_branches
+  int32_t residual_branch;             // MANSY: 9 (qoe_weight features), SimpleRL: -1
+  int32_t softmax;                     // SimpleRL actor returns probabilities
+  int32_t obs_off[kMaxBranches];       // offset of the branch's segment in the observation row
+  int32_t k[kMaxBranches];             // segment length
+  int32_t w_off[kMaxBranches];         // offset of the branch's [K][128] block in w1t
+  const float *w1t;                    // layer-1 weights, K-major per branch
+  const float *b1;                     // [n_branches][128]
+  const float *wfct;                   // [feat_dim][256]: columns 0..127 actor.fc, 128..255 critic.fc
+  const float *bfc;                    // [256]
+  const float *wout;                   // [16][128]: rows 0..14 actor.out, row 15 critic.out
+  const float *bout;                   // [16]
+};
+
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeaky * x; }
+
+// One CTA = 16 environments.  Dynamic shared memory:
+//   feat [feat_dim][16]  layer-1 activations
+//   xs   [320][16]       staged observation segment of the current branch
+//   hid  [256][16]       layer-2 activations (actor | critic)
+__global__ void __launch_bounds__(kPolicyThreads)
+policy_forward_kernel(const __grid_constant__ PolicyDev P, const float *__restrict__ obs, int64_t obs_stride, int n,
+                      float *__restrict__ logits, float *__restrict__ value) {
+  extern __shared__ __align__(16) float smem[];
+  float *feat = smem;
+  float *xs = feat + (size_t)P.feat_dim * kEnvTile;
+  float *hid = xs + 320 * kEnvTile;
+  const int t = threadIdx.x;
+  const int env0 = blockIdx.x * kEnvTile;
+  const int n_here = min(kEnvTile, n - env0);
+
+  // ---- layer 1 -------------------------------------------------------------------------
+  const int f = t & (kHidden - 1), half = t >> 7;        // 128 features x 2 halves of 8 envs
+  for (int b = 0; b < P.n_branches; ++b) {
+    const int K = P.k[b];
+    for (int idx = t; idx < K * kEnvTile; idx += kPolicyThreads) {
+      const int e = idx / K, kk = idx - e * K;
+      xs[kk * kEnvTile + e] = e < n_here ? __ldg(obs + (size_t)(env0 + e) * obs_stride + P.obs_off[b] + kk) : 0.f;
+    }
+    __syncthreads();
+    float acc[8];
+    const float bias = __ldg(P.b1 + b * kHidden + f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bias;
+    const float *w = P.w1t + P.w_off[b] + f;
+    for (int kk = 0; kk < K; ++kk) {
+      const float wv = __ldg(w + (size_t)kk * kHidden);
+      const float4 x0 = *reinterpret_cast<const float4 *>(xs + kk * kEnvTile + half * 8);
+      const float4 x1 = *reinterpret_cast<const float4 *>(xs + kk * kEnvTile + half * 8 + 4);
+      acc[0] = fmaf(wv, x0.x, acc[0]); acc[1] = fmaf(wv, x0.y, acc[1]);
+      acc[2] = fmaf(wv, x0.z, acc[2]); acc[3] = fmaf(wv, x0.w, acc[3]);
+      acc[4] = fmaf(wv, x1.x, acc[4]); acc[5] = fmaf(wv, x1.y, acc[5]);
+      acc[6] = fmaf(wv, x1.z, acc[6]); acc[7] = fmaf(wv, x1.w, acc[7]);
+    }
+    float *dst = feat + (size_t)(b * kHidden + f) * kEnvTile + half * 8;
+    *reinterpret_cast<float4 *>(dst) = make_float4(leaky(acc[0]), leaky(acc[1]), leaky(acc[2]), leaky(acc[3]));
+    *reinterpret_cast<float4 *>(dst + 4) = make_float4(leaky(acc[4]), leaky(acc[5]), leaky(acc[6]), leaky(acc[7]));
+    __syncthreads();
+  }
+
+  // ---- layer 2: thread t owns hidden unit t (0..127 actor, 128..255 critic) for 16 envs ------
+  {
+    float acc[kEnvTile];
+    const float bias = __ldg(P.bfc + t);
+#pragma unroll
+    for (int i = 0; i < kEnvTile; ++i) acc[i] = bias;
+    const float *w = P.wfct + t;
+    for (int kk = 0; kk < P.feat_dim; ++kk) {
+      const float wv = __ldg(w + (size_t)kk * 256);
+      const float4 *x = reinterpret_cast<const float4 *>(feat + (size_t)kk * kEnvTile);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 v = x[j];
+        acc[4 * j + 0] = fmaf(wv, v.x, acc[4 * j + 0]);
+        acc[4 * j + 1] = fmaf(wv, v.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(wv, v.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(wv, v.w, acc[4 * j + 3]);
+      }
+    }
+    const float *res = P.residual_branch >= 0
+                           ? feat + (size_t)(P.residual_branch * kHidden + (t & (kHidden - 1))) * kEnvTile
+                           : nullptr;
+#pragma unroll
+    for (int i = 0; i < kEnvTile; ++i) {
+      float hv = leaky(acc[i]);
+      if (res) hv += res[i];                       // mansy.py:65,79: fc(features) + qoe_features
+      hid[t * kEnvTile + i] = hv;
+    }
+  }
+  __syncthreads();
+
+  // ---- heads: thread (e, o): o < 15 actor logit, o == 15 critic value ---------------------
+  {
+    const int e = t & (kEnvTile - 1), o = t >> 4;
+    const float *w = P.wout + o * kHidden;
+    const float *hsrc = hid + (o == 15 ? kHidden * kEnvTile : 0) + e;
+    float acc = __ldg(P.bout + o);
+    for (int j = 0; j < kHidden; ++j) acc = fmaf(__ldg(w + j), hsrc[j * kEnvTile], acc);
+    xs[e * 16 + o] = acc;                          // reuse xs as [16 envs][16 outputs]
+  }
+  __syncthreads();
+  if (t < kEnvTile && t < n_here) {
+    const int e = t;
+    float out[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) out[o] = xs[e * 16 + o];
+    if (P.softmax) {                               // simple_rl.py:48
+      float m = out[0];
+#pragma unroll
+      for (int o = 1; o < kActions; ++o) m = fmaxf(m, out[o]);
+      float s = 0.f;
+#pragma unroll
+      for (int o = 0; o < kActions; ++o) { out[o] = expf(out[o] - m); s += out[o]; }
+#pragma unroll
+      for (int o = 0; o < kActions; ++o) out[o] = out[o] / s;
+    }
+    if (value) value[env0 + e] = out[15];
+    if (logits) {
+      float4 *dst = reinterpret_cast<float4 *>(logits + (size_t)(env0 + e) * 16);
+      dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+      dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+      dst[2] = make_float4(out[8], out[9], out[10], out[11]);
+      dst[3] = make_float4(out[12], out[13], out[14], 0.f);
+    }
+  }
+}
+
+// Categorical(logits).sample(): inverse-CDF on softmax(logits) with a uniform from a counter-based
+// hash keyed by (seed, global env, step).
+__global__ void policy_sample_kernel(const float *__restrict__ logits, int n, int is_probs, uint64_t seed,
+                                     int64_t step, int env_offset, int32_t *__restrict__ actions,
+                                     float *__restrict__ logp) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float p[kActions];
+  const float4 *src = reinterpret_cast<const float4 *>(logits + (size_t)e * 16);
+  const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+  p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
+  p[8] = c.x; p[9] = c.y; p[10] = c.z; p[11] = c.w; p[12] = d.x; p[13] = d.y; p[14] = d.z;
+  float s = 0.f;
+  if (!is_probs) {
+    float m = p[0];
+#pragma unroll
+    for (int o = 1; o < kActions; ++o) m = fmaxf(m, p[o]);
+#pragma unroll
+    for (int o = 0; o < kActions; ++o) { p[o] = expf(p[o] - m); s += p[o]; }
+  } else {
+#pragma unroll
+    for (int o = 0; o < kActions; ++o) s += p[o];
+  }
+  uint64_t z = seed * 0x9E3779B97F4A7C15ULL + (uint64_t)(env_offset + e) * 0xBF58476D1CE4E5B9ULL +
+               (uint64_t)step * 0x94D049BB133111EBULL + 0x2545F4914F6CDD1DULL;
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+  z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f) * s;    // uniform in [0, s)
+  int act = kActions - 1;
+  float cum = 0.f;
+  bool found = false;
+#pragma unroll
+  for (int o = 0; o < kActions; ++o) {
+    cum += p[o];
+    if (!found && u < cum) { act = o; found = true; }
+  }
+  actions[e] = act;
+  if (logp) {
+    float pa = p[0];
+#pragma unroll
+    for (int o = 1; o < kActions; ++o) if (o == act) pa = p[o];
+    logp[e] = logf(pa / s);
+  }
+}
+
+}  // namespace mansy
+
+using namespace mansy;
+
+struct mansy_policy {
+  PolicyDev dev;
+  int device = 0;
+  size_t smem_bytes = 0;
+  std::vector<void *> allocs;
+};
+
+namespace {
+int upload_f(mansy_policy *p, const std::vector<float> &host, const float **out) {
+  void *d = nullptr;
+  if (cudaMalloc(&d, host.size() * sizeof(float) + 16) != cudaSuccess) return set_error(MANSY_E_NOMEM, "cudaMalloc failed (policy)");
+  p->allocs.push_back(d);
+  if (cudaMemcpy(d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+    return set_error(MANSY_E_CUDA, "cudaMemcpy failed (policy)");
+  *out = static_cast<const float *>(d);
+  return MANSY_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mansy_policy_create(const mansy_policy_weights_t *w, int device, mansy_policy_t *out) {
+  if (!out) return set_error(MANSY_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (!w) return set_error(MANSY_E_INVALID, "weights is NULL");
+  if (w->kind != MANSY_OBS_MANSY && w->kind != MANSY_OBS_SIMPLE) return set_error(MANSY_E_INVALID, "bad policy kind");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return set_error(MANSY_E_CUDA, "no CUDA device available: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return set_error(MANSY_E_INVALID, "bad device index");
+  if (cudaSetDevice(device) != cudaSuccess) return set_error(MANSY_E_CUDA, "cudaSetDevice failed");
+
+  // branch -> (observation offset, K) in FeatureNet order (config.py row layouts)
+  static const int mansy_off[10] = {0, 8, 328, 648, 728, 736, 744, 752, 779, 776};
+  static const int mansy_k[10] = {8, 320, 320, 64, 8, 8, 8, 8, 1, 3};
+  static const int simple_off[5] = {0, 8, 394, 392, 328};
+  static const int simple_k[5] = {8, 320, 1, 2, 64};
+  const bool is_mansy = w->kind == MANSY_OBS_MANSY;
+  const int nb = is_mansy ? 10 : 5;
+  const int *off = is_mansy ? mansy_off : simple_off;
+  const int *kk = is_mansy ? mansy_k : simple_k;
+  for (int b = 0; b < nb; ++b)
+    if (!w->branch_w[b] || !w->branch_b[b]) return set_error(MANSY_E_INVALID, "a branch weight pointer is NULL");
+  if (!w->actor_fc_w || !w->actor_fc_b || !w->actor_out_w || !w->actor_out_b || !w->critic_fc_w || !w->critic_fc_b ||
+      !w->critic_out_w || !w->critic_out_b)
+    return set_error(MANSY_E_INVALID, "a head weight pointer is NULL");
+
+  mansy_policy *p = new (std::nothrow) mansy_policy();
+  if (!p) return set_error(MANSY_E_NOMEM, "out of host memory");
+  p->device = device;
+  PolicyDev &d = p->dev;
+  memset(&d, 0, sizeof(d));
+  d.kind = w->kind; d.n_branches = nb; d.feat_dim = nb * kHidden;
+  d.residual_branch = is_mansy ? 9 : -1;
+  d.softmax = is_mansy ? 0 : 1;
+  const int F = d.feat_dim;
+
+  std::vector<float> w1t, b1((size_t)nb * kHidden), wfct((size_t)F * 256), bfc(256), wout(16 * kHidden), bout(16);
+  int woff = 0;
+  for (int b = 0; b < nb; ++b) {
+    d.obs_off[b] = off[b]; d.k[b] = kk[b]; d.w_off[b] = woff;
+    w1t.resize((size_t)woff + (size_t)kk[b] * kHidden);
+    for (int f = 0; f < kHidden; ++f) {
+      for (int k = 0; k < kk[b]; ++k) w1t[(size_t)woff + (size_t)k * kHidden + f] = w->branch_w[b][(size_t)f * kk[b] + k];
+      b1[(size_t)b * kHidden + f] = w->branch_b[b][f];
+    }
+    woff += kk[b] * kHidden;
+  }
+  for (int j = 0; j < kHidden; ++j) {
+    for (int k = 0; k < F; ++k) {
+      wfct[(size_t)k * 256 + j] = w->actor_fc_w[(size_t)j * F + k];
+      wfct[(size_t)k * 256 + kHidden + j] = w->critic_fc_w[(size_t)j * F + k];
+    }
+    bfc[j] = w->actor_fc_b[j];
+    bfc[kHidden + j] = w->critic_fc_b[j];
+  }
+  for (int o = 0; o < kActions; ++o) {
+    for (int j = 0; j < kHidden; ++j) wout[(size_t)o * kHidden + j] = w->actor_out_w[(size_t)o * kHidden + j];
+    bout[o] = w->actor_out_b[o];
+  }
+  for (int j = 0; j < kHidden; ++j) wout[(size_t)15 * kHidden + j] = w->critic_out_w[j];
+  bout[15] = w->critic_out_b[0];
+
+  int rc;
+  if ((rc = upload_f(p, w1t, &d.w1t)) || (rc = upload_f(p, b1, &d.b1)) || (rc = upload_f(p, wfct, &d.wfct)) ||
+      (rc = upload_f(p, bfc, &d.bfc)) || (rc = upload_f(p, wout, &d.wout)) || (rc = upload_f(p, bout, &d.bout))) {
+    mansy_policy_destroy(p);
+    return rc;
+  }
+  p->smem_bytes = ((size_t)F * kEnvTile + 320 * kEnvTile + 256 * kEnvTile) * sizeof(float);
+  if (cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_bytes) !=
+      cudaSuccess) {
+    mansy_policy_destroy(p);
+    return set_error(MANSY_E_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+  }
+  *out = p;
+  return MANSY_OK;
+}
+
+int mansy_policy_destroy(mansy_policy_t p) {
+  if (!p) return MANSY_OK;
+  cudaSetDevice(p->device);
+  for (void *q : p->allocs) cudaFree(q);
+  delete p;
+  return MANSY_OK;
+}
+
+int mansy_policy_forward(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
+                         float *value_dev, void *stream) {
+  if (!p || !obs_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (n < 0) return set_error(MANSY_E_INVALID, "n < 0");
+  const int need = p->dev.kind == MANSY_OBS_MANSY ? MANSY_OBS_MANSY_STRIDE : MANSY_OBS_SIMPLE_STRIDE;
+  if (obs_stride < need - 4) return set_error(MANSY_E_INVALID, "obs_stride smaller than the observation row");
+  if (logits_dev && (reinterpret_cast<uintptr_t>(logits_dev) & 15)) return set_error(MANSY_E_INVALID, "logits must be 16-byte aligned");
+  if (n == 0) return MANSY_OK;
+  const int grid = (n + kEnvTile - 1) / kEnvTile;
+  policy_forward_kernel<<<grid, kPolicyThreads, p->smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+      p->dev, obs_dev, obs_stride, n, logits_dev, value_dev);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return set_error(MANSY_E_CUDA, "policy_forward_kernel launch failed");
+  return MANSY_OK;
+}
+
+int mansy_policy_sample(const float *logits_dev, int32_t n, int32_t is_probs, uint64_t seed, int64_t step,
+                        int32_t env_offset, int32_t *actions_dev, float *logp_dev, void *stream) {
+  if (!logits_dev || !actions_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (n < 0) return set_error(MANSY_E_INVALID, "n < 0");
+  if (n == 0) return MANSY_OK;
+  policy_sample_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits_dev, n, is_probs, seed, step, env_offset, actions_dev, logp_dev);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return set_error(MANSY_E_CUDA, "policy_sample_kernel launch failed");
+  return MANSY_OK;
+}
+
+}  // extern "C"

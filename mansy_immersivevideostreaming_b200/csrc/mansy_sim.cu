@@ -1,0 +1,910 @@
+// mansy_sim.cu -- sm_100a kernels and C ABI of the tile-based streaming simulator.
+//
+// Thread mapping: 8 lanes per environment (one lane per row of the 8x8 tile grid), 4 environments
+// per warp, 16 per 128-thread CTA.  The scalar simulator chain (trace walk, buffer, QoE) is
+// computed redundantly by the 8 lanes of a group -- it is a few hundred instructions against a
+// 3.5 KB observation row -- while every table read and every observation write is cooperative:
+// each warp-level 128-bit load/store touches four fully used 128-byte lines.  The kernel is an
+// HBM-bound gather/scatter; there is nothing GEMM-shaped in it.
+//
+// Reference map (file:line relative to the reference root):
+//   step_env        bitrate_selection/envs/mansy_env.py:154-248, envs/simple_rl_env.py:113-160,
+//                   simulators/simulator.py:88-108, simulators/network.py:22-35,
+//                   simulators/buffer.py:8-15, utils/qoe.py:22-34, utils/common.py:101-193
+//   reset_episode   envs/mansy_env.py:99-152, simulators/simulator.py:15-46
+//   emit_obs        envs/mansy_env.py:136-150,232-246, envs/simple_rl_env.py:103-109,152-158
+//   viewport kernel viewport_prediction/utils/common.py:37-58,83-127, predict.py:33-48
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mansy_sim.cuh"
+
+namespace mansy {
+
+// ------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define MANSY_CUDA(expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return mansy::set_error(MANSY_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+struct StepArgs {
+  const int32_t *actions;   // [n] (action_mode 0)
+  const int32_t *env_ids;   // [n] or NULL
+  int32_t n;
+  int32_t auto_reset;
+  int32_t action_mode;      // 0: actions array, 1: hashed_action(seed, global env, step)
+  int32_t n_steps;          // steps executed inside one launch (state stays in registers)
+  uint64_t seed;
+  int64_t step0;
+  int64_t rows_per_step;    // output rows between consecutive steps (0: overwrite the same rows)
+  mansy_out_t out;
+};
+
+__device__ __forceinline__ unsigned group_mask() { return 0xFFu << ((threadIdx.x & 31) & ~7); }
+
+__device__ __forceinline__ int group_sum(int v, unsigned m) {
+  v += __shfl_xor_sync(m, v, 1);
+  v += __shfl_xor_sync(m, v, 2);
+  v += __shfl_xor_sync(m, v, 4);
+  return v;
+}
+__device__ __forceinline__ double group_sum(double v, unsigned m) {
+  v = dadd(v, __shfl_xor_sync(m, v, 1));
+  v = dadd(v, __shfl_xor_sync(m, v, 2));
+  v = dadd(v, __shfl_xor_sync(m, v, 4));
+  return v;
+}
+
+union StateQuads {
+  EnvState s;
+  uint4 q[8];
+  __device__ StateQuads() {}
+};
+
+__device__ __forceinline__ void load_state(const SimDev &S, int e, EnvState &st) {
+  StateQuads u;
+  const uint4 *p = reinterpret_cast<const uint4 *>(S.state + e);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u.q[i] = p[i];   // same address in all 8 lanes: broadcast
+  st = u.s;
+}
+
+__device__ __forceinline__ void store_state(const SimDev &S, int e, const EnvState &st, int sub) {
+  StateQuads u;
+  u.s = st;
+  uint4 v = u.q[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (sub == i) v = u.q[i];
+  reinterpret_cast<uint4 *>(S.state + e)[sub] = v;   // lane i writes quad i: one 128-byte line per env
+}
+
+__device__ __forceinline__ void load_slot(const SimDev &S, int e, int sub, float (&slot)[8]) {
+  const float4 *p = reinterpret_cast<const float4 *>(S.hist + (size_t)e * kHistFloatsPerEnv + sub * 8);
+  const float4 a = p[0], b = p[1];
+  slot[0] = a.x; slot[1] = a.y; slot[2] = a.z; slot[3] = a.w;
+  slot[4] = b.x; slot[5] = b.y; slot[6] = b.z; slot[7] = b.w;
+}
+
+__device__ __forceinline__ void store_slot(const SimDev &S, int e, int sub, const float (&slot)[8]) {
+  float4 *p = reinterpret_cast<float4 *>(S.hist + (size_t)e * kHistFloatsPerEnv + sub * 8);
+  p[0] = make_float4(slot[0], slot[1], slot[2], slot[3]);
+  p[1] = make_float4(slot[4], slot[5], slot[6], slot[7]);
+}
+
+// envs/mansy_env.py:99-134 + simulators/simulator.py:15-46: pick the next sample and rebuild the
+// episode state.  Executed identically by the 8 lanes of the group.
+__device__ __forceinline__ void reset_episode(const SimDev &S, EnvState &st) {
+  const int sid = st.cursor % S.n_samples;
+  st.sample_id = sid;
+  st.cursor = (st.cursor + S.worker_num) % S.n_samples;          // mansy_env.py:100-101
+  const int4 smp = __ldg(reinterpret_cast<const int4 *>(S.samples) + sid);
+  st.video = smp.x;
+  st.pair = smp.x * S.n_users + smp.y;
+  st.trace = smp.z;
+  st.w0 = __ldg(S.qoe_w + smp.w * 3 + 0);
+  st.w1 = __ldg(S.qoe_w + smp.w * 3 + 1);
+  st.w2 = __ldg(S.qoe_w + smp.w * 3 + 2);
+  st.buf = S.chunk_length * 3.0;                                  // buffer.py:6
+  st.cur_time = 0.0;                                              // network.py:19-20
+  st.cur_idx = 0;
+  st.next_chunk = S.startup_download + 1;                         // simulator.py:45
+  st.start_chunk = __ldg(S.vp_start + st.pair);
+  st.end_chunk = min(__ldg(S.vp_end + st.pair), __ldg(S.video_time + st.video) - 1);  // simulator.py:41-42
+  st.prev_vq = 0.0;
+  st.ep_step = 0;
+  st.flags = kNoAction << 8;
+  st.sum_qoe = st.sum_q1 = st.sum_q2 = st.sum_q3 = 0.0;
+  st.ep_return = 0.0;
+}
+
+// Observation row from the env state (a pure function of state + history ring).
+template <int MODE>
+__device__ __forceinline__ void emit_obs(const SimDev &S, const EnvState &st, const float (&slot)[8], int sub,
+                                         unsigned gmask, float *__restrict__ row) {
+  const int pushes = st.ep_step;
+  const int newest = (pushes - 1) & 7;
+  const int k = (newest - sub) & 7;         // observation index of this lane's slot (0 = newest)
+  const bool valid = k < pushes;            // older entries are still the zeros of reset
+  const int la = (st.flags >> 8) & 0xFF;    // last action: 0..14, 15 = out-of-table action, 255 = none
+  const int obs_chunk = min(st.next_chunk, st.end_chunk);   // terminal obs repeats the last chunk
+  const uint64_t pred = __ldg(S.vp_pred + (size_t)st.pair * S.n_vp_chunks + (obs_chunk - st.start_chunk));
+  const size_t tab = ((size_t)st.video * S.n_chunks + obs_chunk) * kTableRow;
+  const uint32_t pbyte = (uint32_t)(pred >> (8 * sub)) & 0xFFu;
+  const float4 p0 = make_float4((float)(pbyte & 1u), (float)((pbyte >> 1) & 1u), (float)((pbyte >> 2) & 1u),
+                                (float)((pbyte >> 3) & 1u));
+  const float4 p1 = make_float4((float)((pbyte >> 4) & 1u), (float)((pbyte >> 5) & 1u),
+                                (float)((pbyte >> 6) & 1u), (float)((pbyte >> 7) & 1u));
+  const float4 *s4 = reinterpret_cast<const float4 *>(S.size_norm + tab);
+
+  if (MODE == MANSY_OBS_MANSY) {
+    const float4 *q4 = reinterpret_cast<const float4 *>(S.qual_norm + tab);
+    float4 *ds = reinterpret_cast<float4 *>(row + 8);
+    float4 *dq = reinterpret_cast<float4 *>(row + 328);
+    float4 tv[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) tv[i] = __ldg(s4 + sub + 8 * i);
+    row[0 + k] = valid ? slot[0] : 0.f;      // throughput
+    row[712 + k] = valid ? slot[1] : 0.f;    // rates_inside
+    row[720 + k] = valid ? slot[2] : 0.f;    // rates_outside
+    row[728 + k] = valid ? slot[3] : 0.f;    // viewport_acc
+    row[736 + k] = valid ? slot[4] : 0.f;    // past_viewport_qualities
+    row[744 + k] = valid ? slot[5] : 0.f;    // past_quality_variances
+    row[752 + k] = valid ? slot[6] : 0.f;    // past_rebuffering
+#pragma unroll
+    for (int i = 0; i < 10; ++i) ds[sub + 8 * i] = tv[i];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) tv[i] = __ldg(q4 + sub + 8 * i);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) dq[sub + 8 * i] = tv[i];
+    float4 *dp = reinterpret_cast<float4 *>(row + 648);
+    dp[2 * sub] = p0;
+    dp[2 * sub + 1] = p1;
+    if (sub < 4) {            // action_one_hot (15 + 1 pad)
+      const int b = 4 * sub;
+      reinterpret_cast<float4 *>(row + 760)[sub] =
+          make_float4(la == b ? 1.f : 0.f, la == b + 1 ? 1.f : 0.f, la == b + 2 ? 1.f : 0.f,
+                      (la == b + 3 && b + 3 < kActions) ? 1.f : 0.f);
+    } else if (sub == 4) {    // qoe_weight (utils/common.py:55-57) and buffer / startup_download
+      const float ws = (float)dadd(dadd((double)st.w0, (double)st.w1), (double)st.w2);
+      reinterpret_cast<float4 *>(row + 776)[0] =
+          make_float4(fdiv(st.w0, ws), fdiv(st.w1, ws), fdiv(st.w2, ws), fdiv((float)st.buf, S.startup_f));
+    } else if (sub == 5) {
+      reinterpret_cast<float4 *>(row + 780)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {  // MANSY_OBS_SIMPLE
+    float4 *ds = reinterpret_cast<float4 *>(row + 8);
+    float4 sv[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) sv[i] = __ldg(s4 + sub + 8 * i);
+    const float rb_newest = __shfl_sync(gmask, slot[7], ((threadIdx.x & 31) & ~7) + newest);
+    row[0 + k] = valid ? slot[0] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) ds[sub + 8 * i] = sv[i];
+    float4 *dp = reinterpret_cast<float4 *>(row + 328);
+    dp[2 * sub] = p0;
+    dp[2 * sub + 1] = p1;
+    if (sub == 0) {           // last_bitrates (2), rebuffer (1), pad
+      float lb0 = 0.f, lb1 = 0.f;
+      if (la != kNoAction) {
+        int rin, rout;
+        action_to_rates(la, rin, rout);
+        lb0 = S.rate_norm_f32[rin];
+        lb1 = S.rate_norm_f32[rout];
+      }
+      reinterpret_cast<float4 *>(row + 392)[0] = make_float4(lb0, lb1, pushes > 0 ? rb_newest : 0.f, 0.f);
+    } else if (sub == 1) {
+      reinterpret_cast<float4 *>(row + 396)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// One chunk-step of one environment (8 lanes).  Returns the reward; `over` tells whether the
+// episode ended.  aux_row / ver_row may be NULL.
+__device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float (&slot)[8], int sub, unsigned gmask,
+                                           int action, bool &over, double *__restrict__ aux_row,
+                                           uint8_t *__restrict__ ver_row) {
+  const int c = st.next_chunk;
+  const size_t vi = (size_t)st.pair * S.n_vp_chunks + (c - st.start_chunk);   // hmdtrace.py:16-19
+  const uint64_t gt = __ldg(S.vp_gt + vi);
+  const uint64_t pred = __ldg(S.vp_pred + vi);
+  const double acc = __ldg(S.vp_acc + vi);
+
+  int rin, rout;
+  action_to_rates(action, rin, rout);
+  const TileScaleMasks dm = tile_scale_masks(pred);
+  const uint32_t lutw = S.lut[rout];
+  const size_t tab = ((size_t)st.video * S.n_chunks + c) * kTableRow;
+
+  // simulator.py:94-101: gather size / quality of the chosen version of each tile; this lane owns
+  // tiles 8*sub .. 8*sub+7.
+  int sz = 0;
+  double mq = 0.0;
+  float q[8];
+  uint32_t vpack_lo = 0, vpack_hi = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int t = sub * 8 + i;
+    const int ver = tile_version(lutw, rin, tile_scale(dm, t));
+    const int off = ver * kTiles + t;
+    sz += __ldg(S.size + tab + off);
+    q[i] = __ldg(S.quality + tab + off);
+    if ((gt >> t) & 1ULL) mq = dadd(mq, (double)q[i]);
+    if (i < 4) vpack_lo |= (uint32_t)ver << (8 * i); else vpack_hi |= (uint32_t)ver << (8 * (i - 4));
+  }
+  if (ver_row) reinterpret_cast<uint2 *>(ver_row)[sub] = make_uint2(vpack_lo, vpack_hi);
+  sz = group_sum(sz, gmask);
+  mq = group_sum(mq, gmask);
+  const double sm = (double)__popcll(gt);
+
+  // network.py:22-35 / buffer.py:8-15
+  const double *tr = S.trace + (size_t)st.trace * S.trace_stride;
+  const int tlen = __ldg(S.trace_len + st.trace);
+  bool ok = true;
+  const double dl = trace_download((double)sz, TracePtr{tr}, tlen, st.cur_idx, st.cur_time, ok);
+  if (!ok && sub == 0) atomicExch(S.error_flag, 1);
+  const double rebuf = buffer_push(st.buf, S.chunk_length, dl);
+
+  // qoe.py:22-34 (float64 chain; |q - vq| is evaluated in float32 like the reference's array op)
+  const double vq = ddiv(mq, sm);
+  const float vq32 = (float)vq;
+  double dev = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if ((gt >> (sub * 8 + i)) & 1ULL) dev = dadd(dev, (double)fabsf(fsub(q[i], vq32)));
+  dev = group_sum(dev, gmask);
+  const QoE r = qoe_from_sums(vq, dev, sm, rebuf, st.ep_step == 0, st.prev_vq, (double)st.w0, (double)st.w1,
+                              (double)st.w2, S.max_quality);
+  double reward = r.qoe;
+  if (S.reward_mode == MANSY_REWARD_QOE_NORM)
+    reward = ddiv(r.qoe, dadd(dadd((double)st.w0, (double)st.w1), (double)st.w2));
+  st.sum_qoe = dadd(st.sum_qoe, r.qoe);
+  st.sum_q1 = dadd(st.sum_q1, r.q1);
+  st.sum_q2 = dadd(st.sum_q2, r.q2);
+  st.sum_q3 = dadd(st.sum_q3, r.q3);
+  st.ep_return = dadd(st.ep_return, reward);
+
+  // mansy_env.py:192-206: push the newest history values (ring slot = episode step & 7)
+  if (sub == (st.ep_step & 7)) {
+    slot[0] = (float)ddiv(ddiv((double)sz, dl), S.max_throughput);
+    slot[1] = S.rate_norm_hist[rin];
+    slot[2] = S.rate_norm_hist[rout];
+    slot[3] = (float)acc;
+    slot[4] = (float)r.q1;
+    slot[5] = (float)r.q3;
+    slot[6] = (float)ddiv(r.q2, S.startup_d);
+    slot[7] = (float)r.q2;
+  }
+  st.ep_step += 1;
+  st.next_chunk = c + 1;                                   // simulator.py:105-106
+  over = st.next_chunk > st.end_chunk;
+  const int la = (action >= 0 && action < kActions) ? action : kActions;
+  st.flags = (st.flags & 0xFF) | (la << 8);
+
+  if (aux_row) {
+    double a0, a1;
+    switch (sub) {
+      case 0: a0 = (double)sz; a1 = dl; break;
+      case 1: a0 = rebuf; a1 = st.buf; break;
+      case 2: a0 = (double)st.cur_idx; a1 = st.cur_time; break;
+      case 3: a0 = r.qoe; a1 = r.q1; break;
+      case 4: a0 = r.q2; a1 = r.q3; break;
+      case 5: a0 = (double)st.next_chunk; a1 = (double)st.ep_step; break;
+      case 6: a0 = (double)st.sample_id; a1 = reward; break;
+      default: a0 = (double)(uint32_t)(gt & 0xFFFFFFFFULL); a1 = (double)(uint32_t)(gt >> 32); break;
+    }
+    reinterpret_cast<double2 *>(aux_row)[sub] = make_double2(a0, a1);
+  }
+  return reward;
+}
+
+// envs/mansy_env.py:271-290: what `_log` records when an episode ends, plus running totals.
+__device__ __forceinline__ void finish_episode(const SimDev &S, int e, const EnvState &st) {
+  double *row = S.stats + (size_t)e * MANSY_STATS_DOUBLES;
+  row[MANSY_STAT_LAST_SUM_QOE] = st.sum_qoe;
+  row[MANSY_STAT_LAST_SUM_QOE1] = st.sum_q1;
+  row[MANSY_STAT_LAST_SUM_QOE2] = st.sum_q2;
+  row[MANSY_STAT_LAST_SUM_QOE3] = st.sum_q3;
+  row[MANSY_STAT_LAST_STEPS] = (double)st.ep_step;
+  row[MANSY_STAT_LAST_SAMPLE] = (double)st.sample_id;
+  row[MANSY_STAT_LAST_RETURN] = st.ep_return;
+  row[MANSY_STAT_TOT_SUM_QOE] += st.sum_qoe;
+  row[MANSY_STAT_TOT_SUM_QOE1] += st.sum_q1;
+  row[MANSY_STAT_TOT_SUM_QOE2] += st.sum_q2;
+  row[MANSY_STAT_TOT_SUM_QOE3] += st.sum_q3;
+  row[MANSY_STAT_TOT_STEPS] += (double)st.ep_step;
+  row[MANSY_STAT_TOT_EPISODES] += 1.0;
+  row[MANSY_STAT_TOT_RETURN] += st.ep_return;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreadsPerBlock)
+step_kernel(const __grid_constant__ SimDev S, const __grid_constant__ StepArgs A) {
+  const int i = blockIdx.x * kEnvsPerBlock + (threadIdx.x >> 3);   // output row
+  if (i >= A.n) return;                                            // whole 8-lane group leaves together
+  const int sub = threadIdx.x & 7;
+  const unsigned gmask = group_mask();
+  const int e = A.env_ids ? __ldg(A.env_ids + i) : i;
+
+  EnvState st;
+  float slot[8];
+  load_state(S, e, st);
+  load_slot(S, e, sub, slot);
+
+  for (int t = 0; t < A.n_steps; ++t) {
+    const size_t r = (size_t)t * A.rows_per_step + i;
+    float reward_f = 0.f;
+    bool over = true;
+    if (!(st.flags & kFlagFinished)) {
+      const int action = A.action_mode == 0
+                             ? __ldg(A.actions + i)
+                             : hashed_action(A.seed, (uint64_t)(S.env_offset + e), (uint64_t)(A.step0 + t), kActions);
+      const int slot_before = st.ep_step & 7;
+      const double reward = step_env(S, st, slot, sub, gmask, action, over,
+                                     A.out.aux ? A.out.aux + r * MANSY_AUX_DOUBLES : nullptr,
+                                     A.out.tile_versions ? A.out.tile_versions + r * kTiles : nullptr);
+      reward_f = (float)reward;
+      if (A.n_steps == 1 && sub == slot_before) store_slot(S, e, sub, slot);
+      if (over) {
+        if (sub == 0) finish_episode(S, e, st);
+        if (A.auto_reset) reset_episode(S, st);
+        else st.flags |= kFlagFinished;
+      }
+    }
+    if (sub == 0) {
+      if (A.out.reward) A.out.reward[r] = reward_f;
+      if (A.out.done) A.out.done[r] = over ? 1 : 0;
+    }
+    if (MODE != MANSY_OBS_NONE && A.out.obs) emit_obs<MODE>(S, st, slot, sub, gmask, A.out.obs + r * A.out.obs_stride);
+  }
+  if (A.n_steps != 1) store_slot(S, e, sub, slot);
+  store_state(S, e, st, sub);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreadsPerBlock)
+reset_kernel(const __grid_constant__ SimDev S, const int32_t *__restrict__ env_ids, int n, float *__restrict__ obs,
+             int64_t obs_stride) {
+  const int i = blockIdx.x * kEnvsPerBlock + (threadIdx.x >> 3);
+  if (i >= n) return;
+  const int sub = threadIdx.x & 7;
+  const unsigned gmask = group_mask();
+  const int e = env_ids ? __ldg(env_ids + i) : i;
+  EnvState st;
+  load_state(S, e, st);
+  reset_episode(S, st);
+  float slot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (MODE != MANSY_OBS_NONE && obs) emit_obs<MODE>(S, st, slot, sub, gmask, obs + (size_t)i * obs_stride);
+  store_state(S, e, st, sub);
+}
+
+__global__ void seed_kernel(const SimDev S, int32_t seed) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= S.n_envs) return;
+  EnvState st;
+  memset(&st, 0, sizeof(st));
+  // mansy_env.py:253-256 with the vector env handing env k the seed `seed + k`
+  long long wid = ((long long)seed + S.env_offset + e) % S.worker_num;
+  if (wid < 0) wid += S.worker_num;
+  st.cursor = (int32_t)wid;
+  st.flags = kFlagFinished | (kNoAction << 8);     // must be reset before the first step
+  st.end_chunk = S.startup_download + 1;
+  st.next_chunk = S.startup_download + 1;
+  st.start_chunk = 0;
+  S.state[e] = st;
+}
+
+__global__ void stats_clear_kernel(double *stats, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stats[i] = 0.0;
+}
+
+// viewport_prediction/predict.py:33-48: one thread per chunk.
+__global__ void viewport_tiles_kernel(const float *__restrict__ gt_xy, const float *__restrict__ pred_xy, int64_t n,
+                                      int points, int width, int height, int fov_w, int fov_h,
+                                      uint64_t *__restrict__ gt_mask, uint64_t *__restrict__ pred_mask,
+                                      double *__restrict__ acc, int32_t *__restrict__ invalid) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool valid = true;
+  uint64_t g = 0, p = 0;
+  const float2 *gp = reinterpret_cast<const float2 *>(gt_xy) + i * points;
+  for (int j = 0; j < points; ++j) {
+    const float2 v = __ldg(gp + j);
+    g |= fov_tile_mask(centre_to_pixel(v.x, width), centre_to_pixel(v.y, height), width, height, fov_w, fov_h, valid);
+  }
+  gt_mask[i] = g;
+  if (pred_xy) {
+    const float2 *pp = reinterpret_cast<const float2 *>(pred_xy) + i * points;
+    for (int j = 0; j < points; ++j) {
+      const float2 v = __ldg(pp + j);
+      p |= fov_tile_mask(centre_to_pixel(v.x, width), centre_to_pixel(v.y, height), width, height, fov_w, fov_h, valid);
+    }
+    pred_mask[i] = p;
+    acc[i] = ddiv((double)__popcll(g & p), (double)__popcll(g | p));   // IoU, predict.py:46
+  }
+  if (!valid && invalid) atomicExch(invalid, 1);
+}
+
+// utils/common.py:101-119,142-193 for standalone masks: one thread per (mask, action).
+__global__ void allocate_versions_kernel(const uint64_t *__restrict__ masks, const int32_t *__restrict__ actions,
+                                         int64_t n, uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3, uint32_t l4,
+                                         uint8_t *__restrict__ versions) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t lut[5] = {l0, l1, l2, l3, l4};
+  int rin, rout;
+  action_to_rates(__ldg(actions + i), rin, rout);
+  const TileScaleMasks dm = tile_scale_masks(__ldg(masks + i));
+  const uint32_t lutw = lut[rout];
+  uint4 *dst = reinterpret_cast<uint4 *>(versions + i * kTiles);
+#pragma unroll
+  for (int qd = 0; qd < 4; ++qd) {
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      const int t = qd * 16 + b;
+      w[b >> 2] |= (uint32_t)tile_version(lutw, rin, tile_scale(dm, t)) << (8 * (b & 3));
+    }
+    dst[qd] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+}  // namespace mansy
+
+// ------------------------------------------------------------------------------------------
+// host side: handle + C ABI
+// ------------------------------------------------------------------------------------------
+using namespace mansy;
+
+struct mansy_sim {
+  SimDev dev;
+  int device = 0;
+  std::vector<void *> allocs;
+  // lazily allocated device staging for the host-buffer entry points
+  int32_t *stage_actions = nullptr;
+  float *stage_obs = nullptr;
+  float *stage_reward = nullptr;
+  uint8_t *stage_done = nullptr;
+  int64_t obs_stride = 0;
+};
+
+namespace {
+
+template <typename T>
+int upload(mansy_sim *h, const T *host, size_t count, const T **dev_out) {
+  void *d = nullptr;
+  if (cudaMalloc(&d, count * sizeof(T) + 16) != cudaSuccess) return set_error(MANSY_E_NOMEM, "cudaMalloc failed (table)");
+  h->allocs.push_back(d);
+  MANSY_CUDA(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+  *dev_out = static_cast<const T *>(d);
+  return MANSY_OK;
+}
+
+template <typename T>
+int dev_alloc(mansy_sim *h, size_t count, T **out) {
+  void *d = nullptr;
+  if (cudaMalloc(&d, count * sizeof(T) + 16) != cudaSuccess) return set_error(MANSY_E_NOMEM, "cudaMalloc failed (state)");
+  h->allocs.push_back(d);
+  *out = static_cast<T *>(d);
+  return MANSY_OK;
+}
+
+int check_tables(const mansy_tables_t *t) {
+  if (!t) return set_error(MANSY_E_INVALID, "tables is NULL");
+  if (!t->size || !t->quality || !t->video_time || !t->vp_gt || !t->vp_pred || !t->vp_acc || !t->vp_start ||
+      !t->vp_end || !t->trace || !t->trace_len || !t->qoe_w || !t->samples)
+    return set_error(MANSY_E_INVALID, "a table pointer is NULL");
+  if (t->n_videos < 1 || t->n_chunks < 1 || t->n_users < 1 || t->n_vp_chunks < 1 || t->n_traces < 1 ||
+      t->trace_stride < 1 || t->n_qoe < 1 || t->n_samples < 1)
+    return set_error(MANSY_E_INVALID, "a table dimension is < 1");
+  return MANSY_OK;
+}
+
+inline int grid_for(int n) { return (n + kEnvsPerBlock - 1) / kEnvsPerBlock; }
+
+int obs_stride_for(int mode) {
+  return mode == MANSY_OBS_MANSY ? MANSY_OBS_MANSY_STRIDE : (mode == MANSY_OBS_SIMPLE ? MANSY_OBS_SIMPLE_STRIDE : 0);
+}
+
+int check_out(const mansy_sim *h, const mansy_out_t *out) {
+  if (!out) return set_error(MANSY_E_INVALID, "out is NULL");
+  if (out->obs) {
+    if (h->dev.obs_mode == MANSY_OBS_NONE) return set_error(MANSY_E_INVALID, "handle was created with MANSY_OBS_NONE");
+    if (out->obs_stride < obs_stride_for(h->dev.obs_mode) || (out->obs_stride & 3))
+      return set_error(MANSY_E_INVALID, "obs_stride too small or not a multiple of 4 floats");
+    if (reinterpret_cast<uintptr_t>(out->obs) & 15) return set_error(MANSY_E_INVALID, "obs must be 16-byte aligned");
+  }
+  if (out->aux && (reinterpret_cast<uintptr_t>(out->aux) & 15)) return set_error(MANSY_E_INVALID, "aux must be 16-byte aligned");
+  if (out->tile_versions && (reinterpret_cast<uintptr_t>(out->tile_versions) & 7))
+    return set_error(MANSY_E_INVALID, "tile_versions must be 8-byte aligned");
+  return MANSY_OK;
+}
+
+int launch_step(mansy_sim *h, const StepArgs &a, cudaStream_t s) {
+  const int grid = grid_for(a.n);
+  if (grid == 0) return MANSY_OK;
+  switch (h->dev.obs_mode) {
+    case MANSY_OBS_MANSY: step_kernel<MANSY_OBS_MANSY><<<grid, kThreadsPerBlock, 0, s>>>(h->dev, a); break;
+    case MANSY_OBS_SIMPLE: step_kernel<MANSY_OBS_SIMPLE><<<grid, kThreadsPerBlock, 0, s>>>(h->dev, a); break;
+    default: step_kernel<MANSY_OBS_NONE><<<grid, kThreadsPerBlock, 0, s>>>(h->dev, a); break;
+  }
+  count_launch();
+  MANSY_CUDA(cudaGetLastError());
+  return MANSY_OK;
+}
+
+int ensure_staging(mansy_sim *h) {
+  if (h->stage_actions) return MANSY_OK;
+  const size_t n = (size_t)h->dev.n_envs;
+  h->obs_stride = obs_stride_for(h->dev.obs_mode);
+  int rc;
+  if ((rc = dev_alloc(h, n, &h->stage_actions))) return rc;
+  if ((rc = dev_alloc(h, n, &h->stage_reward))) return rc;
+  if ((rc = dev_alloc(h, n, &h->stage_done))) return rc;
+  if (h->obs_stride && (rc = dev_alloc(h, n * (size_t)h->obs_stride, &h->stage_obs))) return rc;
+  return MANSY_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mansy_last_error(void) { return g_last_error.c_str(); }
+int mansy_abi_version(void) { return MANSY_ABI_VERSION; }
+int64_t mansy_kernel_launches(void) { return g_launches.load(); }
+
+int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, mansy_handle_t *out) {
+  if (!out) return set_error(MANSY_E_INVALID, "out is NULL");
+  *out = nullptr;
+  int rc = check_tables(t);
+  if (rc) return rc;
+  if (!cfg) return set_error(MANSY_E_INVALID, "cfg is NULL");
+  if (cfg->n_envs < 1 || cfg->worker_num < 1 || cfg->env_offset < 0)
+    return set_error(MANSY_E_INVALID, "n_envs / worker_num must be >= 1 and env_offset >= 0");
+  if (cfg->obs_mode < MANSY_OBS_NONE || cfg->obs_mode > MANSY_OBS_SIMPLE) return set_error(MANSY_E_INVALID, "bad obs_mode");
+  if (cfg->reward_mode != MANSY_REWARD_QOE && cfg->reward_mode != MANSY_REWARD_QOE_NORM)
+    return set_error(MANSY_E_INVALID, "bad reward_mode");
+  for (int i = 0; i < 5; ++i)
+    if (cfg->video_rates[i] <= 0 || (i && cfg->video_rates[i] < cfg->video_rates[i - 1]))
+      return set_error(MANSY_E_INVALID, "video_rates must be positive and ascending");
+  if (cfg->startup_download < 0 || cfg->chunk_length < 1 || cfg->max_size < 1 || cfg->max_throughput < 1)
+    return set_error(MANSY_E_INVALID, "bad streaming constants");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+    return set_error(MANSY_E_CUDA, "no CUDA device available: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return set_error(MANSY_E_INVALID, "bad device index");
+  MANSY_CUDA(cudaSetDevice(device));
+
+  mansy_sim *h = new (std::nothrow) mansy_sim();
+  if (!h) return set_error(MANSY_E_NOMEM, "out of host memory");
+  h->device = device;
+  SimDev &d = h->dev;
+  memset(&d, 0, sizeof(d));
+  const size_t n_tab = (size_t)t->n_videos * t->n_chunks * kTableRow;
+  const size_t n_vp = (size_t)t->n_videos * t->n_users * t->n_vp_chunks;
+  const size_t n_pairs = (size_t)t->n_videos * t->n_users;
+
+  // host-side validation that the kernels rely on (the reference would raise / loop forever)
+  for (size_t p = 0; p < n_pairs && !rc; ++p) {
+    const int v = (int)(p / t->n_users);
+    const int end = t->vp_end[p] < t->video_time[v] - 1 ? t->vp_end[p] : t->video_time[v] - 1;
+    if (t->vp_start[p] > cfg->startup_download + 1) rc = set_error(MANSY_E_INVALID, "viewport trace starts after the first simulated chunk (simulator.py:44)");
+    else if (end < cfg->startup_download + 1) rc = set_error(MANSY_E_INVALID, "an episode would have no chunk to simulate");
+    else if (end >= t->n_chunks) rc = set_error(MANSY_E_INVALID, "end chunk beyond the size table");
+    else if (t->vp_end[p] - t->vp_start[p] + 1 > t->n_vp_chunks) rc = set_error(MANSY_E_INVALID, "viewport chunk range exceeds n_vp_chunks");
+  }
+  for (int k = 0; k < t->n_traces && !rc; ++k) {
+    if (t->trace_len[k] < 1 || t->trace_len[k] > t->trace_stride) { rc = set_error(MANSY_E_INVALID, "bad trace_len"); break; }
+    bool pos = false;
+    for (int i = 0; i < t->trace_len[k]; ++i) {
+      const double x = t->trace[(size_t)k * t->trace_stride + i];
+      if (!(x >= 0.0) || x > 1e300) { rc = set_error(MANSY_E_INVALID, "negative / non-finite throughput"); break; }
+      pos |= x > 0.0;
+    }
+    if (!rc && !pos) rc = set_error(MANSY_E_INVALID, "a trace has no positive-throughput second (network.py:24 would never return)");
+  }
+  for (int s = 0; s < t->n_samples && !rc; ++s) {
+    const int32_t *q = t->samples + 4 * (size_t)s;
+    if (q[0] < 0 || q[0] >= t->n_videos || q[1] < 0 || q[1] >= t->n_users || q[2] < 0 || q[2] >= t->n_traces ||
+        q[3] < 0 || q[3] >= t->n_qoe)
+      rc = set_error(MANSY_E_INVALID, "sample index out of range");
+  }
+  if (rc) { delete h; return rc; }
+
+  // derived tables: normalised observation rows (utils/common.py:40-47), IEEE float32 division
+  std::vector<float> size_norm(n_tab), qual_norm(n_tab);
+  const float fmax_size = (float)cfg->max_size, fmax_q = (float)cfg->video_rates[4];
+  for (size_t i = 0; i < n_tab; ++i) {
+    if (t->size[i] <= 0) { delete h; return set_error(MANSY_E_INVALID, "tile sizes must be positive"); }
+    size_norm[i] = fdiv((float)t->size[i], fmax_size);
+    qual_norm[i] = fdiv(t->quality[i], fmax_q);
+  }
+
+#define MANSY_TRY(x) do { rc = (x); if (rc) { mansy_destroy(h); return rc; } } while (0)
+  MANSY_TRY(upload(h, t->size, n_tab, &d.size));
+  MANSY_TRY(upload(h, t->quality, n_tab, &d.quality));
+  MANSY_TRY(upload(h, size_norm.data(), n_tab, &d.size_norm));
+  MANSY_TRY(upload(h, qual_norm.data(), n_tab, &d.qual_norm));
+  MANSY_TRY(upload(h, t->video_time, (size_t)t->n_videos, &d.video_time));
+  MANSY_TRY(upload(h, t->vp_gt, n_vp, &d.vp_gt));
+  MANSY_TRY(upload(h, t->vp_pred, n_vp, &d.vp_pred));
+  MANSY_TRY(upload(h, t->vp_acc, n_vp, &d.vp_acc));
+  MANSY_TRY(upload(h, t->vp_start, n_pairs, &d.vp_start));
+  MANSY_TRY(upload(h, t->vp_end, n_pairs, &d.vp_end));
+  MANSY_TRY(upload(h, t->trace, (size_t)t->n_traces * t->trace_stride, &d.trace));
+  MANSY_TRY(upload(h, t->trace_len, (size_t)t->n_traces, &d.trace_len));
+  MANSY_TRY(upload(h, t->qoe_w, (size_t)t->n_qoe * 3, &d.qoe_w));
+  MANSY_TRY(upload(h, t->samples, (size_t)t->n_samples * 4, &d.samples));
+  d.n_videos = t->n_videos; d.n_chunks = t->n_chunks; d.n_users = t->n_users; d.n_vp_chunks = t->n_vp_chunks;
+  d.n_traces = t->n_traces; d.trace_stride = t->trace_stride; d.n_qoe = t->n_qoe; d.n_samples = t->n_samples;
+
+  const size_t n = (size_t)cfg->n_envs;
+  MANSY_TRY(dev_alloc(h, n, &d.state));
+  MANSY_TRY(dev_alloc(h, n * kHistFloatsPerEnv, &d.hist));
+  MANSY_TRY(dev_alloc(h, n * MANSY_STATS_DOUBLES, &d.stats));
+  MANSY_TRY(dev_alloc(h, (size_t)4, &d.error_flag));
+  d.n_envs = cfg->n_envs; d.env_offset = cfg->env_offset; d.worker_num = cfg->worker_num;
+  d.obs_mode = cfg->obs_mode; d.reward_mode = cfg->reward_mode;
+  d.startup_download = cfg->startup_download;
+  d.chunk_length = (double)cfg->chunk_length;
+  d.max_quality = (double)cfg->video_rates[4];
+  d.max_throughput = (double)cfg->max_throughput;
+  d.startup_d = (double)cfg->startup_download;
+  d.startup_f = (float)cfg->startup_download;
+  for (int i = 0; i < kRates; ++i) {
+    d.rate_norm_hist[i] = (float)((double)cfg->video_rates[i] / (double)cfg->video_rates[4]);
+    d.rate_norm_f32[i] = fdiv((float)cfg->video_rates[i], (float)cfg->video_rates[4]);
+  }
+  build_rate_lut(cfg->video_rates, d.lut);
+  {
+    cudaError_t e1 = cudaMemset(d.hist, 0, n * kHistFloatsPerEnv * sizeof(float));
+    cudaError_t e2 = cudaMemset(d.stats, 0, n * MANSY_STATS_DOUBLES * sizeof(double));
+    cudaError_t e3 = cudaMemset(d.error_flag, 0, 16);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { mansy_destroy(h); return set_error(MANSY_E_CUDA, "cudaMemset failed"); }
+  }
+#undef MANSY_TRY
+  rc = mansy_seed(h, cfg->seed, nullptr);
+  if (rc) { mansy_destroy(h); return rc; }
+  cudaError_t e = cudaStreamSynchronize(nullptr);
+  if (e != cudaSuccess) { mansy_destroy(h); return set_error(MANSY_E_CUDA, cudaGetErrorString(e)); }
+  *out = h;
+  return MANSY_OK;
+}
+
+int mansy_destroy(mansy_handle_t h) {
+  if (!h) return MANSY_OK;
+  cudaSetDevice(h->device);
+  for (void *p : h->allocs) cudaFree(p);
+  delete h;
+  return MANSY_OK;
+}
+
+int mansy_seed(mansy_handle_t h, int32_t seed, void *stream) {
+  if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  const int threads = 256, grid = (h->dev.n_envs + threads - 1) / threads;
+  seed_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(h->dev, seed);
+  count_launch();
+  MANSY_CUDA(cudaGetLastError());
+  return MANSY_OK;
+}
+
+int mansy_reset(mansy_handle_t h, const int32_t *env_ids_dev, int32_t n, float *obs_dev, int64_t obs_stride,
+                void *stream) {
+  if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  if (n < 0 || (!env_ids_dev && n != h->dev.n_envs))
+    return set_error(MANSY_E_INVALID, "n must equal n_envs when env_ids is NULL");
+  if (n == 0) return MANSY_OK;
+  if (obs_dev) {
+    mansy_out_t o; memset(&o, 0, sizeof(o)); o.obs = obs_dev; o.obs_stride = obs_stride;
+    int rc = check_out(h, &o);
+    if (rc) return rc;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(n);
+  switch (h->dev.obs_mode) {
+    case MANSY_OBS_MANSY: reset_kernel<MANSY_OBS_MANSY><<<grid, kThreadsPerBlock, 0, s>>>(h->dev, env_ids_dev, n, obs_dev, obs_stride); break;
+    case MANSY_OBS_SIMPLE: reset_kernel<MANSY_OBS_SIMPLE><<<grid, kThreadsPerBlock, 0, s>>>(h->dev, env_ids_dev, n, obs_dev, obs_stride); break;
+    default: reset_kernel<MANSY_OBS_NONE><<<grid, kThreadsPerBlock, 0, s>>>(h->dev, env_ids_dev, n, obs_dev, obs_stride); break;
+  }
+  count_launch();
+  MANSY_CUDA(cudaGetLastError());
+  return MANSY_OK;
+}
+
+int mansy_step(mansy_handle_t h, const int32_t *actions_dev, const int32_t *env_ids_dev, int32_t n, int32_t auto_reset,
+               const mansy_out_t *out, void *stream) {
+  if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  if (!actions_dev) return set_error(MANSY_E_INVALID, "actions is NULL");
+  if (n < 0 || (!env_ids_dev && n != h->dev.n_envs))
+    return set_error(MANSY_E_INVALID, "n must equal n_envs when env_ids is NULL");
+  int rc = check_out(h, out);
+  if (rc) return rc;
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.actions = actions_dev; a.env_ids = env_ids_dev; a.n = n; a.auto_reset = auto_reset; a.action_mode = 0;
+  a.n_steps = 1; a.out = *out;
+  return launch_step(h, a, static_cast<cudaStream_t>(stream));
+}
+
+int mansy_rollout_random(mansy_handle_t h, int32_t n_steps, uint64_t seed, int64_t step0, int32_t per_step_outputs,
+                         const mansy_out_t *out, void *stream) {
+  if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  if (n_steps < 1) return set_error(MANSY_E_INVALID, "n_steps must be >= 1");
+  int rc = check_out(h, out);
+  if (rc) return rc;
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = h->dev.n_envs; a.auto_reset = 1; a.action_mode = 1; a.n_steps = n_steps; a.seed = seed; a.step0 = step0;
+  a.rows_per_step = per_step_outputs ? h->dev.n_envs : 0;
+  a.out = *out;
+  return launch_step(h, a, static_cast<cudaStream_t>(stream));
+}
+
+int mansy_step_host(mansy_handle_t h, const int32_t *actions_host, int32_t auto_reset, float *obs_host,
+                    float *reward_host, uint8_t *done_host, void *stream) {
+  if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  if (!actions_host) return set_error(MANSY_E_INVALID, "actions is NULL");
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)h->dev.n_envs;
+  MANSY_CUDA(cudaMemcpyAsync(h->stage_actions, actions_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.actions = h->stage_actions; a.n = h->dev.n_envs; a.auto_reset = auto_reset; a.n_steps = 1;
+  a.out.obs = obs_host ? h->stage_obs : nullptr; a.out.obs_stride = h->obs_stride;
+  a.out.reward = h->stage_reward; a.out.done = h->stage_done;
+  rc = launch_step(h, a, s);
+  if (rc) return rc;
+  if (obs_host && h->stage_obs)
+    MANSY_CUDA(cudaMemcpyAsync(obs_host, h->stage_obs, n * (size_t)h->obs_stride * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (reward_host) MANSY_CUDA(cudaMemcpyAsync(reward_host, h->stage_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (done_host) MANSY_CUDA(cudaMemcpyAsync(done_host, h->stage_done, n, cudaMemcpyDeviceToHost, s));
+  MANSY_CUDA(cudaStreamSynchronize(s));
+  return MANSY_OK;
+}
+
+int mansy_reset_host(mansy_handle_t h, float *obs_host, void *stream) {
+  if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  rc = mansy_reset(h, nullptr, h->dev.n_envs, obs_host ? h->stage_obs : nullptr, h->obs_stride, stream);
+  if (rc) return rc;
+  if (obs_host && h->stage_obs)
+    MANSY_CUDA(cudaMemcpyAsync(obs_host, h->stage_obs, (size_t)h->dev.n_envs * h->obs_stride * sizeof(float),
+                               cudaMemcpyDeviceToHost, s));
+  MANSY_CUDA(cudaStreamSynchronize(s));
+  return MANSY_OK;
+}
+
+int mansy_episode_stats(mansy_handle_t h, double *stats_dev, void *stream) {
+  if (!h || !stats_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  MANSY_CUDA(cudaMemcpyAsync(stats_dev, h->dev.stats, (size_t)h->dev.n_envs * MANSY_STATS_DOUBLES * sizeof(double),
+                             cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return MANSY_OK;
+}
+
+int mansy_stats_clear(mansy_handle_t h, void *stream) {
+  if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  const size_t n = (size_t)h->dev.n_envs * MANSY_STATS_DOUBLES;
+  stats_clear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(h->dev.stats, n);
+  count_launch();
+  MANSY_CUDA(cudaGetLastError());
+  return MANSY_OK;
+}
+
+int mansy_state_snapshot(mansy_handle_t h, void *state_dev, void *stream) {
+  if (!h || !state_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  MANSY_CUDA(cudaMemcpyAsync(state_dev, h->dev.state, (size_t)h->dev.n_envs * sizeof(EnvState),
+                             cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return MANSY_OK;
+}
+
+int mansy_error_flag(mansy_handle_t h, int32_t *flag_host) {
+  if (!h || !flag_host) return set_error(MANSY_E_INVALID, "NULL argument");
+  MANSY_CUDA(cudaMemcpy(flag_host, h->dev.error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return MANSY_OK;
+}
+
+int mansy_viewport_tiles(const float *gt_xy_dev, const float *pred_xy_dev, int64_t n_chunks, int32_t points,
+                         int32_t video_width, int32_t video_height, int32_t fov_width, int32_t fov_height,
+                         uint64_t *gt_mask_dev, uint64_t *pred_mask_dev, double *acc_dev, void *stream) {
+  if (!gt_xy_dev || !gt_mask_dev) return set_error(MANSY_E_INVALID, "gt pointers are NULL");
+  if ((pred_xy_dev != nullptr) != (pred_mask_dev != nullptr) || (pred_xy_dev != nullptr) != (acc_dev != nullptr))
+    return set_error(MANSY_E_INVALID, "pred_xy, pred_mask and acc must be given together");
+  if (n_chunks < 0 || points < 1) return set_error(MANSY_E_INVALID, "bad n_chunks / points");
+  if (video_width < 8 || video_height < 8 || video_width % 8 || video_height % 8)
+    return set_error(MANSY_E_INVALID, "frame must split into 8x8 tiles");
+  if (fov_width < 0 || fov_height < 0 || fov_width > video_width || fov_height > video_height)
+    return set_error(MANSY_E_INVALID, "FoV larger than the frame is outside the reference's nine cases");
+  if (n_chunks == 0) return MANSY_OK;
+  const int threads = 256;
+  const int64_t grid = (n_chunks + threads - 1) / threads;
+  viewport_tiles_kernel<<<(unsigned)grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      gt_xy_dev, pred_xy_dev, n_chunks, points, video_width, video_height, fov_width, fov_height, gt_mask_dev,
+      pred_mask_dev, acc_dev, nullptr);
+  count_launch();
+  MANSY_CUDA(cudaGetLastError());
+  return MANSY_OK;
+}
+
+int mansy_allocate_tile_versions(const uint64_t *masks_dev, const int32_t *actions_dev, int64_t n,
+                                 const int32_t video_rates[5], uint8_t *versions_dev, void *stream) {
+  if (!masks_dev || !actions_dev || !versions_dev || !video_rates) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (n < 0) return set_error(MANSY_E_INVALID, "n < 0");
+  if (n == 0) return MANSY_OK;
+  uint32_t lut[5];
+  build_rate_lut(video_rates, lut);
+  const int threads = 128;
+  allocate_versions_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      masks_dev, actions_dev, n, lut[0], lut[1], lut[2], lut[3], lut[4], versions_dev);
+  count_launch();
+  MANSY_CUDA(cudaGetLastError());
+  return MANSY_OK;
+}
+
+// ---- CPU self-tests of the shared __host__ __device__ building blocks (no GPU needed) --------
+// These run the same mansy_core.cuh code the kernels run, on the host, so the non-GPU test-suite
+// can compare it with the oracle.  They are not a product path.
+int mansy_selftest_allocate(uint64_t mask, int32_t action, const int32_t video_rates[5], uint8_t versions_out[64]) {
+  uint32_t lut[5];
+  build_rate_lut(video_rates, lut);
+  int rin, rout;
+  action_to_rates(action, rin, rout);
+  const TileScaleMasks dm = tile_scale_masks(mask);
+  for (int t = 0; t < 64; ++t) versions_out[t] = (uint8_t)tile_version(lut[rout], rin, tile_scale(dm, t));
+  return MANSY_OK;
+}
+
+int mansy_selftest_fov_mask(int32_t x, int32_t y, int32_t w, int32_t hgt, int32_t fov_w, int32_t fov_h,
+                            uint64_t *mask_out, int32_t *valid_out) {
+  bool valid = true;
+  *mask_out = fov_tile_mask(x, y, w, hgt, fov_w, fov_h, valid);
+  *valid_out = valid ? 1 : 0;
+  return MANSY_OK;
+}
+
+int mansy_selftest_centre_to_pixel(float v, int32_t length) { return centre_to_pixel(v, length); }
+
+int mansy_selftest_download(const double *thr, int32_t trace_len, int64_t size, int32_t *cur_idx, double *cur_time,
+                            double *buf, double *download_time, double *rebuffer) {
+  bool ok = true;
+  int idx = *cur_idx;
+  double tm = *cur_time;
+  const double dl = trace_download((double)size, TracePtr{thr}, trace_len, idx, tm, ok);
+  *cur_idx = idx; *cur_time = tm;
+  *download_time = dl;
+  *rebuffer = buffer_push(*buf, 1.0, dl);
+  return ok ? MANSY_OK : MANSY_E_STATE;
+}
+
+int mansy_selftest_hashed_action(uint64_t seed, uint64_t env, uint64_t step) { return hashed_action(seed, env, step, kActions); }
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// mansy_sim.cuh -- device-side data layout of the simulator (shared by the .cu files).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#include "mansy_b200.h"
+#include "mansy_core.cuh"
+
+namespace mansy {
+
+constexpr int kTiles = 64;
+constexpr int kRates = 5;
+constexpr int kPastK = 8;
+constexpr int kActions = 15;
+constexpr int kLanesPerEnv = 8;    // one lane per row of the 8x8 tile grid
+constexpr int kThreadsPerBlock = 128;
+constexpr int kEnvsPerBlock = kThreadsPerBlock / kLanesPerEnv;
+constexpr int kTableRow = kRates * kTiles;  // 320 values per (video, chunk)
+constexpr int kNoAction = 255;
+
+// Per-environment state: one 128-byte line, read with 8 broadcast 128-bit loads by the 8 lanes of
+// the env's group and written back one quad per lane.
+struct __align__(16) EnvState {
+  double cur_time;      // q0  network.py cur_time
+  double buf;           //     buffer.py buf_size
+  double prev_vq;       // q1  qoe.py prev_viewport_quality (valid when ep_step > 0)
+  int32_t next_chunk;   //     simulator.py next_chunk
+  int32_t cur_idx;      //     network.py cur_idx
+  int32_t ep_step;      // q2  steps taken in this episode
+  int32_t cursor;       //     mansy_env.py worker_id (next sample to use)
+  int32_t video;        //     table indices of the episode's sample
+  int32_t pair;         //     video * n_users + user
+  int32_t trace;        // q3
+  int32_t end_chunk;    //     min(last viewport chunk, Video_Time - 1)  (simulator.py:41-42)
+  int32_t sample_id;
+  int32_t flags;        //     bit 0: episode finished (awaiting reset); bits 8..15: last action (255 = none)
+  float w0, w1, w2;     // q4  qoe weights of the sample
+  int32_t start_chunk;  //     first chunk of the viewport list (hmdtrace.py:10)
+  double sum_qoe;       // q5  running per-episode sums (mansy_env.py:187-190 log lists)
+  double sum_q1;
+  double sum_q2;        // q6
+  double sum_q3;
+  double ep_return;     // q7  running sum of rewards
+  double reserved;
+};
+static_assert(sizeof(EnvState) == 128, "EnvState must be one 128-byte line");
+
+constexpr int kFlagFinished = 1;
+
+// History ring: hist[env][slot][8]; the value pushed at episode step s lives in slot s & 7.
+// Slot layout (floats): throughput, rate_in, rate_out, accuracy, viewport quality (qoe1),
+// quality variance (qoe3), rebuffer/startup (qoe2/5), raw rebuffer (qoe2; SimpleRL observation).
+constexpr int kHistFloatsPerEnv = 64;
+
+struct SimDev {
+  // read-only tables
+  const int32_t *size;
+  const float *quality;
+  const float *size_norm;   // float(size) / float(max_size)           (utils/common.py:45-47)
+  const float *qual_norm;   // quality / float(video_rates[-1])        (utils/common.py:40-42)
+  const int32_t *video_time;
+  const uint64_t *vp_gt;
+  const uint64_t *vp_pred;
+  const double *vp_acc;
+  const int32_t *vp_start;
+  const int32_t *vp_end;
+  const double *trace;
+  const int32_t *trace_len;
+  const float *qoe_w;
+  const int32_t *samples;
+  int32_t n_videos, n_chunks, n_users, n_vp_chunks, n_traces, trace_stride, n_qoe, n_samples;
+  // per-env state
+  EnvState *state;
+  float *hist;
+  double *stats;            // [n_envs][MANSY_STATS_DOUBLES]
+  int32_t *error_flag;      // set by kernels on data errors (trace that can never finish a download)
+  // configuration
+  int32_t n_envs, env_offset, worker_num, obs_mode, reward_mode;
+  int32_t startup_download;
+  double chunk_length, max_quality, max_throughput, startup_d;
+  float startup_f;
+  float rate_norm_hist[kRates];  // float(rates[r] / rates[-1]) with a float64 division (mansy_env.py:197,199)
+  float rate_norm_f32[kRates];   // float(rates[r]) / float(rates[-1])          (simple_rl_env.py:137-138)
+  uint32_t lut[kRates];
+};
+
+}  // namespace mansy

@@ -296,15 +296,7 @@ def make_real_golden(ref):
     np.savez_compressed(os.path.join(GOLDEN, "mansy_real.npz"), **out)
 
 
-def numpy_state_dict(shapes, seed):
-    """Deterministic weights from numpy (regenerated identically on the GPU box)."""
-    rng = np.random.default_rng(seed)
-    out = {}
-    for name, shape in shapes:
-        fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else int(shape[0])
-        bound = 1.0 / np.sqrt(max(fan_in, 1))
-        out[name] = rng.uniform(-bound, bound, size=shape).astype(np.float32)
-    return out
+from mansy_immersivevideostreaming_b200.policy import seeded_state_dict as numpy_state_dict  # noqa: E402
 
 
 def make_policy(ref):
