@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""Benchmark of the streaming-simulator hot path (BASELINE.json: "simulated chunk-steps/sec").
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm (CPU port, host cores)
+
+Workload at every N (weak scaling): BASELINE.json configs[1] -- 4,096 parallel MANSY envs per GPU,
+PPO rollout = policy forward + Categorical sample + lock-step simulator step, observations written
+straight into the rollout buffer the learner reads.  One "step" = one lock-step chunk-step of all
+envs of the job.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "simulated chunk-steps/sec"
+UNIT = "chunk-steps/s"
+ENVS_PER_GPU = 4096
+# algorithmic HBM bytes per MANSY chunk-step with materialised observation
+BYTES_PER_STEP_MANSY = 3513
+FLOP_PER_STEP_POLICY = 2 * 425_472        # 0.851 MFLOP, shared FeatureNet evaluated once
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=200)
+    p.add_argument("--warmup", type=int, default=20)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    p.add_argument("--sweep", action="store_true", help="also time the simulator-only kernel at larger env counts")
+    p.add_argument("--profile-sim", type=int, default=0,
+                   help="only run a few simulator-only launches at this env count (for ncu captures); prints no bench line")
+    return p.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# shared: synthetic workload
+# ---------------------------------------------------------------------------------------------
+def workload_tables(mask_fn, n_slots):
+    from mansy_immersivevideostreaming_b200 import synth
+    t = synth.make_synthetic_tables(mask_fn, n_videos=24, n_users=60, n_chunks=60, n_traces=40, seed=20260101)
+    return t.with_samples(synth.per_env_samples(t, n_slots))
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (Python, like the reference) on all host cores
+# ---------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seconds, worker, n_workers, tables_path = args
+    import numpy as np
+    from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, REWARD_QOE
+    from mansy_immersivevideostreaming_b200.synth import synthetic_actions
+    from mansy_immersivevideostreaming_b200.tables import SimTables
+    from oracle import sim_oracle as so
+    tables = SimTables.from_npz_dict(np.load(tables_path))
+    env = so.OracleEnv(tables, OBS_MODE_MANSY, REWARD_QOE, "f64", worker_id=worker, worker_num=n_workers)
+    env.reset()
+    actions = [int(a) for a in synthetic_actions(8192, worker, seed=1234)]     # precomputed: not part of the timed work
+    steps = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(50):
+            _, _, done, _ = env.step(actions[steps & 8191])
+            steps += 1
+            if done:
+                env.reset()
+    return steps, time.perf_counter() - t0
+
+
+def cpu_baseline(seconds: float, cores: int):
+    """Chunk-steps/s of the Python oracle port (one env per process, resets included), all cores."""
+    import multiprocessing as mp
+    import numpy as np
+    from oracle import sim_oracle as so
+    from mansy_immersivevideostreaming_b200.config import SimConfig
+    cfg = SimConfig()
+    # a slice of the workload (the oracle needs the masks; its own geometry makes them)
+    from mansy_immersivevideostreaming_b200 import synth
+    t = synth.make_synthetic_tables(lambda g, p: so.chunk_masks(g, p, cfg), n_videos=4, n_users=8, n_chunks=60,
+                                    n_traces=40, seed=20260101)
+    t = t.with_samples(synth.per_env_samples(t, max(cores, 64)))
+    path = os.path.join(tempfile.mkdtemp(prefix="mansy_cpu_"), "tables.npz")
+    np.savez(path, **t.to_npz_dict())
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(seconds, w, cores, path) for w in range(cores)])
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    rate = sum(r[0] / r[1] for r in res)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{total} chunk-steps: {cores} processes x 1 MANSY env (Python float64 oracle port of the "
+                      f"reference's MANSYEnv.step/reset, resets included) for {seconds:.0f} s each on a 4-video x "
+                      f"8-user x 40-trace slice of the workload",
+            "wall_s": wall}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step_seconds = max(2.0, min(10.0, 60.0 / max(args.steps + args.warmup, 1)))
+    # a "step" of this arm = a bounded sample (per_step_seconds of all-core stepping); K steps are averaged
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(per_step_seconds, cores)
+        if i >= args.warmup:
+            rates.append(r)
+        if len(rates) >= 3:          # keep the whole run within a few minutes
+            break
+    value = sum(r["value"] for r in rates) / len(rates)
+    n_env = args.envs_per_gpu * args.gpus
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(rates), "warmup": args.warmup, "ms_per_step": 1e3 * n_env / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"mansy_ppo_rollout_{args.envs_per_gpu}_envs_per_gpu (simulator step only: the reference's "
+                               "policy forward is GPU-side torch and is not part of the CPU arm)",
+                   "envs": n_env},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": rates[0]["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.path = os.path.join(tempfile.mkdtemp(prefix="mansy_clk_"), "clocks.csv")
+        self.proc = None
+        self.idx = device_index
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from mansy_immersivevideostreaming_b200 import _capi
+    from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, OBS_MODE_SIMPLE, REWARD_QOE
+    from mansy_immersivevideostreaming_b200.policy import PolicyNet, mansy_state_dict_shapes, seeded_state_dict
+    from mansy_immersivevideostreaming_b200.rollout import PolicyRollout, gather_episode_stats, summarise_stats
+    from mansy_immersivevideostreaming_b200.simulator import BatchSimulator, ViewportTiler
+    from mansy_immersivevideostreaming_b200.synth import synthetic_actions
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world != 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _capi.load_library()
+
+    n_local = args.envs_per_gpu
+    n_global = n_local * world
+    tiler = ViewportTiler(device=local)
+    tables = workload_tables(tiler.chunk_masks, n_global)        # masks come from the CUDA viewport->tiles kernel
+    sim = BatchSimulator(tables, n_local, OBS_MODE_MANSY, REWARD_QOE, seed=0, worker_num=n_global,
+                         env_offset=rank * n_local, device=local)
+    actor_shapes, critic_shapes = mansy_state_dict_shapes()
+    policy = PolicyNet(seeded_state_dict(actor_shapes, 1), seeded_state_dict(critic_shapes, 2), OBS_MODE_MANSY, device=local)
+    slab_bytes = n_local * sim.obs_stride * 4
+    slabs = max(4, -(-(320 << 20) // slab_bytes))                # rollout buffer > 2.5 x L2 (126 MB)
+    roll = PolicyRollout(sim, policy, slabs, seed=1234)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    roll.run(max(args.warmup, 3))
+    barrier()
+    K = args.steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.mansy_kernel_launches()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    b = roll.buf
+    for k in range(K):
+        s, nxt = roll.t % b.slabs, (roll.t + 1) % b.slabs
+        ev[k][0].record()
+        policy.forward(b.obs[s], b.logits, b.value[s])
+        policy.sample(b.logits, roll.seed, roll.t, sim.env_offset, b.actions[s], b.logp[s])
+        ev[k][1].record()
+        sim.step(b.actions[s], auto_reset=True, obs=b.obs[nxt], reward=b.reward[s], done=b.done[s])
+        ev[k][2].record()
+        roll.t += 1
+    stats = gather_episode_stats(sim)                            # the one collective of the rollout
+    stop.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = lib.mansy_kernel_launches() - launches0
+    if world > 1:
+        tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tmax.item())
+    clk = clocks.stop() if rank == 0 else None
+    policy_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    step_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    summary = summarise_stats(stats)
+
+    # ---- e2e: the reference-facing call with HOST buffers (actions in, observations out) ----------
+    e2e_sim = BatchSimulator(tables, n_local, OBS_MODE_MANSY, REWARD_QOE, seed=0, worker_num=n_global,
+                             env_offset=rank * n_local, device=local)
+    host = e2e_sim.make_host_buffers()
+    e2e_sim.reset_host(host)
+    acts = [torch.from_numpy(synthetic_actions(n_local, t, seed=99, env_offset=rank * n_local)) for t in range(64)]
+    e2e_steps = max(20, min(K, 100))
+    for t in range(5):
+        host["actions"].copy_(acts[t % 64]); e2e_sim.step_host(host)
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(e2e_steps):
+        host["actions"].copy_(acts[t % 64])        # step inputs come from host memory every step
+        e2e_sim.step_host(host)                    # H2D actions, kernel, D2H obs/reward/done, sync
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    h2d = n_local * 4
+    d2h = n_local * (sim.obs_stride * 4 + 4 + 1)
+
+    sweep = None
+    if args.sweep and rank == 0:
+        sweep = simulator_sweep(tables, local)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm_gbs, tflops, peak_src = measured_peaks()
+    value = n_global * K / (elapsed_ms * 1e-3)
+    step_gbs = n_local * BYTES_PER_STEP_MANSY / (step_ms * 1e-3) / 1e9
+    pol_tflops = n_local * FLOP_PER_STEP_POLICY / (policy_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 simulator scalars / f32 observations / fp32 policy", "data": "synthetic",
+        "config": {"workload": f"mansy_ppo_rollout_{n_local}_envs_per_gpu", "envs": n_global, "envs_per_gpu": n_local,
+                   "obs_row_bytes": sim.obs_stride * 4,
+                   "l2": f"observations stream into a {slabs}-slab rollout buffer of {slabs * slab_bytes >> 20} MiB "
+                         "(> L2 126 MB): every step writes a slab last touched >2.5 L2-sizes ago",
+                   "tables": "24 videos x 60 chunks, 1440 viewport pairs, 40 traces (SURVEY.md 8(d))",
+                   "timed": "K x (policy forward + sample + simulator step) + 1 all-gather of episode stats"},
+        "roofline": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": step_gbs / hbm_gbs,
+                     "traffic": None, "kernel": "step_kernel<MANSY>", "bytes_per_launch": n_local * BYTES_PER_STEP_MANSY,
+                     "avg_launch_ms": step_ms, "peak_source": peak_src},
+        "roofline_policy": {"bound": "fp32 cuda cores (round-1 kernel)", "achieved": pol_tflops, "unit": "TFLOP/s",
+                            "kernel": "policy_forward_kernel + policy_sample_kernel", "avg_launch_ms": policy_ms,
+                            "flop_per_launch": n_local * FLOP_PER_STEP_POLICY},
+        "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "path": "mansy_step_host: pinned host actions -> H2D -> step kernel -> D2H obs+reward+done"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "rollout_summary": summary,
+    }
+    if sweep:
+        line["simulator_sweep"] = sweep
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_baseline_seconds, os.cpu_count() or 1)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def simulator_sweep(tables, device_index):
+    """Simulator-only kernel at growing env counts (hashed in-kernel actions, observation
+    materialised, one launch per step, fresh slab per step)."""
+    import torch
+    from mansy_immersivevideostreaming_b200 import synth
+    from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, OBS_MODE_SIMPLE, REWARD_QOE
+    from mansy_immersivevideostreaming_b200.simulator import BatchSimulator
+    hbm_gbs, _, _ = measured_peaks()
+    out = []
+    for mode, name, bytes_per_step in ((OBS_MODE_MANSY, "mansy", 3513), (OBS_MODE_SIMPLE, "simple_rl", 1805)):
+        for n in (4096, 65536, 262144, 1048576):
+            t = tables.with_samples(synth.per_env_samples(tables, n))
+            sim = BatchSimulator(t, n, mode, REWARD_QOE, seed=0, device=device_index)
+            slab = n * sim.obs_stride * 4
+            slabs = max(2, min(8, -(-(320 << 20) // slab)))
+            obs = torch.empty((slabs, n, sim.obs_stride), dtype=torch.float32, device=sim.device)
+            rew = torch.empty(n, dtype=torch.float32, device=sim.device)
+            done = torch.empty(n, dtype=torch.uint8, device=sim.device)
+            sim.reset(None, obs[0])
+            for k in range(5):
+                sim.rollout_random(1, seed=5, step0=k, obs=obs[k % slabs], reward=rew, done=done)
+            torch.cuda.synchronize()
+            reps = 30
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(reps):
+                sim.rollout_random(1, seed=5, step0=5 + k, obs=obs[k % slabs], reward=rew, done=done)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            gbs = n * bytes_per_step / (ms * 1e-3) / 1e9
+            out.append({"env": name, "envs": n, "ms_per_step": ms, "chunk_steps_per_s": n / (ms * 1e-3),
+                        "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_gbs})
+            sim.close()
+            del obs
+    return out
+
+
+def profile_sim(n):
+    """A handful of simulator-only launches at n envs (MANSY obs), for `ncu -k regex:step_kernel`."""
+    import torch
+    from mansy_immersivevideostreaming_b200 import synth
+    from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, REWARD_QOE
+    from mansy_immersivevideostreaming_b200.simulator import BatchSimulator, ViewportTiler
+    tables = workload_tables(ViewportTiler().chunk_masks, n)
+    sim = BatchSimulator(tables, n, OBS_MODE_MANSY, REWARD_QOE, seed=0)
+    slabs = max(2, min(8, -(-(320 << 20) // (n * sim.obs_stride * 4))))
+    obs = torch.empty((slabs, n, sim.obs_stride), dtype=torch.float32, device=sim.device)
+    rew = torch.empty(n, dtype=torch.float32, device=sim.device)
+    done = torch.empty(n, dtype=torch.uint8, device=sim.device)
+    sim.reset(None, obs[0])
+    for k in range(12):
+        sim.rollout_random(1, seed=5, step0=k, obs=obs[k % slabs], reward=rew, done=done)
+    torch.cuda.synchronize()
+
+
+def main():
+    args = parse_args()
+    if args.profile_sim:
+        profile_sim(args.profile_sim)
+        return
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,7 +29,7 @@ MANSY_OBS_SEGMENTS: Tuple[Tuple[str, int, Tuple[int, ...]], ...] = (
     ("qoe_weight", 776, (3,)),
     ("buffer", 779, (1,)),
 )
-MANSY_OBS_FLOATS = 777          # payload (reference: 13 arrays, 777 float32)
+MANSY_OBS_FLOATS = 779          # payload: 13 arrays, 779 float32 (SURVEY.md quotes 777; the shapes sum to 779)
 MANSY_OBS_STRIDE = 784          # padded row: 3136 B = 98 full 32-B sectors
 
 # bitrate_selection/envs/simple_rl_env.py:103-109

@@ -126,10 +126,14 @@ def test_golden_simple_synth():
 # ---------------------------------------------------------------------------------------------
 # many envs in lockstep against the float64 oracle (same chain -> bit-exact or ~1e-16)
 # ---------------------------------------------------------------------------------------------
-def _oracle_tables(n_videos=4, n_users=5, n_traces=6, seed=11, qoe=None):
-    return synth.make_synthetic_tables(lambda g, p: so.chunk_masks(g, p, CFG), n_videos=n_videos, n_users=n_users,
-                                       n_traces=n_traces, seed=seed, trace_len_range=(30, 120), short_tail_frac=0.25,
-                                       qoe_w=qoe)
+def _oracle_tables(n_videos=4, n_users=5, n_traces=6, seed=11, qoe=None, n_samples=256):
+    """Small synthetic dataset (masks from the oracle) with one random sample tuple per env slot: the
+    reference indexes ``samples[worker_id]`` directly (mansy_env.py:100,103), so a vector env of N
+    envs needs at least N samples or the reference -- and the oracle -- raise IndexError."""
+    t = synth.make_synthetic_tables(lambda g, p: so.chunk_masks(g, p, CFG), n_videos=n_videos, n_users=n_users,
+                                    n_traces=n_traces, seed=seed, trace_len_range=(30, 120), short_tail_frac=0.25,
+                                    qoe_w=qoe)
+    return t.with_samples(synth.per_env_samples(t, n_samples, seed=seed + 1))
 
 
 @pytest.mark.parametrize("obs_mode,reward_mode", [(OBS_MODE_MANSY, REWARD_QOE), (OBS_MODE_SIMPLE, REWARD_QOE_NORM)])
