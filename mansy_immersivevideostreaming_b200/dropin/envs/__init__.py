@@ -1,0 +1,2 @@
+from .mansy_env import MANSYEnv            # noqa: F401
+from .simple_rl_env import SimpleRLEnv     # noqa: F401
