@@ -231,6 +231,16 @@ int mansy_policy_forward(mansy_policy_t p, const float *obs_dev, int64_t obs_str
 int mansy_policy_sample(const float *logits_dev, int32_t n, int32_t is_probs, uint64_t seed, int64_t step,
                         int32_t env_offset, int32_t *actions_dev, float *logp_dev, void *stream);
 
+/* Tensor-core (tcgen05, TF32 inputs / fp32 accumulate -- the precision class the reference runs its nets
+ * in, run_mansy.py:253) version of mansy_policy_forward + mansy_policy_sample in ONE launch: 128 environments
+ * per CTA, observation rows are TMA-loaded as the MMA operand.  Any of logits / value / actions / logp may be
+ * NULL.  feat_dbg_dev ([n][n_branches*128], branch PROCESSING order: MANSY conv1d2, conv1d3, conv1d4, conv1d1,
+ * conv1d5..8, fc1, fc2; SimpleRL conv1d_2, fc3, conv1d_1, fc1, fc2) and hid_dbg_dev ([n][256], actor | critic
+ * hidden activations after the residual) are test hooks, normally NULL.  obs_stride must be a multiple of 4. */
+int mansy_policy_forward_tc(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
+                            float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
+                            int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, void *stream);
+
 /* Raw copy of the per-environment state records (128 bytes each, layout: csrc/mansy_sim.cuh
  * EnvState / _capi.ENV_STATE_DTYPE) into state_dev[n_envs*128]; for host-side bookkeeping
  * (current_video / current_user / ... attributes of the gym envs) and tests. */

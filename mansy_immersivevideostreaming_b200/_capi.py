@@ -96,6 +96,8 @@ SIGNATURES = {
     "mansy_policy_destroy": (C.c_int, [_vp]),
     "mansy_policy_forward": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp]),
     "mansy_policy_sample": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, C.c_int32, _vp, _vp, _vp]),
+    "mansy_policy_forward_tc": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int64,
+                                          C.c_int32, _vp, _vp, _vp]),
     "mansy_selftest_allocate": (C.c_int, [C.c_uint64, C.c_int32, C.POINTER(C.c_int32 * 5), C.POINTER(C.c_uint8 * 64)]),
     "mansy_selftest_fov_mask": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),

@@ -21,36 +21,12 @@
 #include <string>
 #include <vector>
 
-#include "mansy_sim.cuh"
+#include "mansy_policy.cuh"
 
 namespace mansy {
-int set_error(int code, const std::string &msg);
-void count_launch();
 
-constexpr int kHidden = 128;
-constexpr int kMaxBranches = 10;
 constexpr int kEnvTile = 16;          // environments per CTA
 constexpr int kPolicyThreads = 256;
-constexpr float kLeaky = 0.01f;       // torch.nn.LeakyReLU default negative_slope
-
-struct PolicyDev {
-  int32_t kind;
-  int32_t n_branches;
-  int32_t feat_dim;                    // 128 * n_branches
-  int32_t residual_branch;             // MANSY: 9 (qoe_weight features), SimpleRL: -1
-  int32_t softmax;                     // SimpleRL actor returns probabilities
-  int32_t obs_off[kMaxBranches];       // offset of the branch's segment in the observation row
-  int32_t k[kMaxBranches];             // segment length
-  int32_t w_off[kMaxBranches];         // offset of the branch's [K][128] block in w1t
-  const float *w1t;                    // layer-1 weights, K-major per branch
-  const float *b1;                     // [n_branches][128]
-  const float *wfct;                   // [feat_dim][256]: columns 0..127 actor.fc, 128..255 critic.fc
-  const float *bfc;                    // [256]
-  const float *wout;                   // [16][128]: rows 0..14 actor.out, row 15 critic.out
-  const float *bout;                   // [16]
-};
-
-__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeaky * x; }
 
 // One CTA = 16 environments.  Dynamic shared memory:
 //   feat [feat_dim][16]  layer-1 activations
@@ -163,8 +139,7 @@ policy_forward_kernel(const __grid_constant__ PolicyDev P, const float *__restri
   }
 }
 
-// Categorical(logits).sample(): inverse-CDF on softmax(logits) with a uniform from a counter-based
-// hash keyed by (seed, global env, step).
+// Categorical(logits).sample(): see categorical_sample (mansy_policy.cuh).
 __global__ void policy_sample_kernel(const float *__restrict__ logits, int n, int is_probs, uint64_t seed,
                                      int64_t step, int env_offset, int32_t *__restrict__ actions,
                                      float *__restrict__ logp) {
@@ -175,50 +150,16 @@ __global__ void policy_sample_kernel(const float *__restrict__ logits, int n, in
   const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
   p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = a.w; p[4] = b.x; p[5] = b.y; p[6] = b.z; p[7] = b.w;
   p[8] = c.x; p[9] = c.y; p[10] = c.z; p[11] = c.w; p[12] = d.x; p[13] = d.y; p[14] = d.z;
-  float s = 0.f;
-  if (!is_probs) {
-    float m = p[0];
-#pragma unroll
-    for (int o = 1; o < kActions; ++o) m = fmaxf(m, p[o]);
-#pragma unroll
-    for (int o = 0; o < kActions; ++o) { p[o] = expf(p[o] - m); s += p[o]; }
-  } else {
-#pragma unroll
-    for (int o = 0; o < kActions; ++o) s += p[o];
-  }
-  uint64_t z = seed * 0x9E3779B97F4A7C15ULL + (uint64_t)(env_offset + e) * 0xBF58476D1CE4E5B9ULL +
-               (uint64_t)step * 0x94D049BB133111EBULL + 0x2545F4914F6CDD1DULL;
-  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
-  z ^= z >> 27; z *= 0x94D049BB133111EBULL;
-  z ^= z >> 31;
-  const float u = (float)(z >> 40) * (1.0f / 16777216.0f) * s;    // uniform in [0, s)
-  int act = kActions - 1;
-  float cum = 0.f;
-  bool found = false;
-#pragma unroll
-  for (int o = 0; o < kActions; ++o) {
-    cum += p[o];
-    if (!found && u < cum) { act = o; found = true; }
-  }
+  int act;
+  float lp;
+  categorical_sample(p, is_probs, seed, (uint64_t)(env_offset + e), (uint64_t)step, act, lp);
   actions[e] = act;
-  if (logp) {
-    float pa = p[0];
-#pragma unroll
-    for (int o = 1; o < kActions; ++o) if (o == act) pa = p[o];
-    logp[e] = logf(pa / s);
-  }
+  if (logp) logp[e] = lp;
 }
 
 }  // namespace mansy
 
 using namespace mansy;
-
-struct mansy_policy {
-  PolicyDev dev;
-  int device = 0;
-  size_t smem_bytes = 0;
-  std::vector<void *> allocs;
-};
 
 namespace {
 int upload_f(mansy_policy *p, const std::vector<float> &host, const float **out) {
@@ -308,6 +249,7 @@ int mansy_policy_create(const mansy_policy_weights_t *w, int device, mansy_polic
     mansy_policy_destroy(p);
     return set_error(MANSY_E_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
   }
+  tc_create(p, w);    // tensor-core images; on failure p->tc stays NULL and mansy_policy_forward_tc reports it
   *out = p;
   return MANSY_OK;
 }
@@ -315,6 +257,7 @@ int mansy_policy_create(const mansy_policy_weights_t *w, int device, mansy_polic
 int mansy_policy_destroy(mansy_policy_t p) {
   if (!p) return MANSY_OK;
   cudaSetDevice(p->device);
+  tc_destroy(p);
   for (void *q : p->allocs) cudaFree(q);
   delete p;
   return MANSY_OK;

@@ -1,0 +1,91 @@
+// mansy_policy.cuh -- shared between the fp32 CUDA-core policy kernel (mansy_policy.cu) and the
+// tcgen05 TF32 kernel (mansy_policy_tc.cu).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "mansy_sim.cuh"
+
+namespace mansy {
+
+int set_error(int code, const std::string &msg);
+void count_launch();
+
+constexpr int kHidden = 128;
+constexpr int kMaxBranches = 10;
+constexpr float kLeaky = 0.01f;       // torch.nn.LeakyReLU default negative_slope
+
+struct PolicyDev {
+  int32_t kind;
+  int32_t n_branches;
+  int32_t feat_dim;                    // 128 * n_branches
+  int32_t residual_branch;             // MANSY: 9 (qoe_weight features), SimpleRL: -1
+  int32_t softmax;                     // SimpleRL actor returns probabilities
+  int32_t obs_off[kMaxBranches];       // offset of the branch's segment in the observation row
+  int32_t k[kMaxBranches];             // segment length
+  int32_t w_off[kMaxBranches];         // offset of the branch's [K][128] block in w1t
+  const float *w1t;                    // layer-1 weights, K-major per branch
+  const float *b1;                     // [n_branches][128]
+  const float *wfct;                   // [feat_dim][256]: columns 0..127 actor.fc, 128..255 critic.fc
+  const float *bfc;                    // [256]
+  const float *wout;                   // [16][128]: rows 0..14 actor.out, row 15 critic.out
+  const float *bout;                   // [16]
+};
+
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeaky * x; }
+
+// Categorical(logits).sample() (bitrate_selection/run_mansy.py:228-229): inverse CDF on the
+// softmax with a uniform from a counter-based hash keyed by (seed, global env, step).
+// `p` holds logits (is_probs == 0) or probabilities; on return it holds unnormalised weights and
+// `s` their sum.
+__device__ __forceinline__ void categorical_sample(float (&p)[kActions], int is_probs, uint64_t seed, uint64_t env,
+                                                   uint64_t step, int &act, float &logp) {
+  float s = 0.f;
+  if (!is_probs) {
+    float m = p[0];
+#pragma unroll
+    for (int o = 1; o < kActions; ++o) m = fmaxf(m, p[o]);
+#pragma unroll
+    for (int o = 0; o < kActions; ++o) { p[o] = expf(p[o] - m); s += p[o]; }
+  } else {
+#pragma unroll
+    for (int o = 0; o < kActions; ++o) s += p[o];
+  }
+  uint64_t z = seed * 0x9E3779B97F4A7C15ULL + env * 0xBF58476D1CE4E5B9ULL + step * 0x94D049BB133111EBULL +
+               0x2545F4914F6CDD1DULL;
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+  z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  const float u = (float)(z >> 40) * (1.0f / 16777216.0f) * s;    // uniform in [0, s)
+  act = kActions - 1;
+  float cum = 0.f;
+  bool found = false;
+#pragma unroll
+  for (int o = 0; o < kActions; ++o) {
+    cum += p[o];
+    if (!found && u < cum) { act = o; found = true; }
+  }
+  float pa = p[0];
+#pragma unroll
+  for (int o = 1; o < kActions; ++o) if (o == act) pa = p[o];
+  logp = logf(pa / s);
+}
+
+struct TcState;   // tensor-core path state (mansy_policy_tc.cu)
+
+}  // namespace mansy
+
+struct mansy_policy {
+  mansy::PolicyDev dev;
+  int device = 0;
+  size_t smem_bytes = 0;
+  std::vector<void *> allocs;
+  mansy::TcState *tc = nullptr;
+};
+
+namespace mansy {
+// Builds the tensor-core weight images / tensor maps for `p`; returns MANSY_OK or an error code
+// (the fp32 path keeps working when this fails; mansy_policy_forward_tc then reports the reason).
+int tc_create(mansy_policy *p, const mansy_policy_weights_t *w);
+void tc_destroy(mansy_policy *p);
+}  // namespace mansy

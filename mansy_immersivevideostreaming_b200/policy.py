@@ -107,6 +107,34 @@ class PolicyNet:
                                             value.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
         return logits, value
 
+    # processing order of the FeatureNet branches inside the tensor-core kernel (csrc/mansy_policy_tc.cu):
+    # position i of ``feat_dbg`` holds branch TC_BRANCH_ORDER[kind][i] of the concat order
+    TC_BRANCH_ORDER = {OBS_MODE_MANSY: (1, 2, 3, 0, 4, 5, 6, 7, 8, 9), OBS_MODE_SIMPLE: (1, 4, 0, 2, 3)}
+
+    def forward_tc(self, obs: torch.Tensor, logits: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None,
+                   actions: Optional[torch.Tensor] = None, logp: Optional[torch.Tensor] = None, seed: int = 0,
+                   step: int = 0, env_offset: int = 0, sample: bool = True, feat_dbg: Optional[torch.Tensor] = None,
+                   hid_dbg: Optional[torch.Tensor] = None):
+        """Tensor-core (tcgen05, TF32) forward + categorical sample in one launch.
+        Returns (logits ``[N, 16]``, value ``[N]``, actions ``[N]`` int32 | None, logp ``[N]`` | None)."""
+        if obs.device != self.device or obs.dtype != torch.float32 or obs.stride(-1) != 1:
+            raise ValueError("obs must be a float32 row-major tensor on the policy's device")
+        n = obs.shape[0]
+        if logits is None:
+            logits = torch.empty((n, 16), dtype=torch.float32, device=self.device)
+        if value is None:
+            value = torch.empty(n, dtype=torch.float32, device=self.device)
+        if sample and actions is None:
+            actions = torch.empty(n, dtype=torch.int32, device=self.device)
+        if sample and logp is None:
+            logp = torch.empty(n, dtype=torch.float32, device=self.device)
+        ptr = lambda t: None if t is None else t.data_ptr()   # noqa: E731
+        check(self.lib.mansy_policy_forward_tc(self._h, obs.data_ptr(), obs.stride(0), n, logits.data_ptr(),
+                                               value.data_ptr(), ptr(actions), ptr(logp), int(seed), int(step),
+                                               int(env_offset), ptr(feat_dbg), ptr(hid_dbg),
+                                               torch.cuda.current_stream(self.device).cuda_stream))
+        return logits, value, actions, logp
+
     def sample(self, logits: torch.Tensor, seed: int, step: int, env_offset: int = 0,
                actions: Optional[torch.Tensor] = None, logp: Optional[torch.Tensor] = None):
         """Categorical(logits).sample() (run_mansy.py:228-229) with a counter-based generator."""
