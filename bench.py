@@ -34,8 +34,8 @@ FLOP_PER_STEP_POLICY = 2 * 425_472        # 0.851 MFLOP, shared 
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=200)
-    p.add_argument("--warmup", type=int, default=20)
+    p.add_argument("--steps", type=int, default=2000)
+    p.add_argument("--warmup", type=int, default=50)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -241,11 +241,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    roll.run(max(args.warmup, 3))
-    barrier()
+    W = max(args.warmup, 3)
     K = args.steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-           torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    roll.reserve_timing(K)
+    roll.run(W)
+    gather_episode_stats(sim)       # warm-up rollouts include their all-gather (first use loads torch's index kernels)
+    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -253,16 +254,7 @@ def run_ours(args):
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
-    b = roll.buf
-    for k in range(K):
-        s, nxt = roll.t % b.slabs, (roll.t + 1) % b.slabs
-        ev[k][0].record()
-        policy.forward(b.obs[s], b.logits, b.value[s])
-        policy.sample(b.logits, roll.seed, roll.t, sim.env_offset, b.actions[s], b.logp[s])
-        ev[k][1].record()
-        sim.step(b.actions[s], auto_reset=True, obs=b.obs[nxt], reward=b.reward[s], done=b.done[s])
-        ev[k][2].record()
-        roll.t += 1
+    roll.run(K, timed=True)                                      # C loop: 2 launches per step, events around each
     stats = gather_episode_stats(sim)                            # the one collective of the rollout
     stop.record()
     barrier()
@@ -273,32 +265,28 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         elapsed_ms = float(tmax.item())
     clk = clocks.stop() if rank == 0 else None
-    policy_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
-    step_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    policy_sum, step_sum, timed_steps = roll.kernel_ms()
+    policy_ms, step_ms = policy_sum / timed_steps, step_sum / timed_steps
     summary = summarise_stats(stats)
 
-    # ---- e2e: the reference-facing call with HOST buffers (actions in, observations out) ----------
+    # ---- e2e: the same rollout with HOST storage (tianshou's replay buffer is numpy): per step D2H actions +
+    # sync, H2D actions, step, D2H next observation / reward / done / logp / value + sync -----------------------
     e2e_sim = BatchSimulator(tables, n_local, OBS_MODE_MANSY, REWARD_QOE, seed=0, worker_num=n_global,
                              env_offset=rank * n_local, device=local)
-    host = e2e_sim.make_host_buffers()
-    e2e_sim.reset_host(host)
-    acts = [torch.from_numpy(synthetic_actions(n_local, t, seed=99, env_offset=rank * n_local)) for t in range(64)]
+    e2e_roll = PolicyRollout(e2e_sim, policy, 4, seed=1234)
+    host = e2e_roll.make_host_buffers(host_slabs=8)              # 8 x 12.9 MB pinned ring
     e2e_steps = max(20, min(K, 100))
-    for t in range(5):
-        host["actions"].copy_(acts[t % 64]); e2e_sim.step_host(host)
+    e2e_roll.run_host(5, host)
     barrier()
     t0 = time.perf_counter()
-    for t in range(e2e_steps):
-        host["actions"].copy_(acts[t % 64])        # step inputs come from host memory every step
-        e2e_sim.step_host(host)                    # H2D actions, kernel, D2H obs/reward/done, sync
+    e2e_roll.run_host(e2e_steps, host)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         tmax = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax.item())
-    h2d = n_local * 4
-    d2h = n_local * (sim.obs_stride * 4 + 4 + 1)
+    h2d, d2h = e2e_roll.host_bytes_per_step()
 
     sweep = None
     if args.sweep and rank == 0:
@@ -312,24 +300,29 @@ def run_ours(args):
     value = n_global * K / (elapsed_ms * 1e-3)
     step_gbs = n_local * BYTES_PER_STEP_MANSY / (step_ms * 1e-3) / 1e9
     pol_tflops = n_local * FLOP_PER_STEP_POLICY / (policy_ms * 1e-3) / 1e12
+    tf32_peak = tflops / 2.0      # TF32 dense rate = 1/2 of bf16 (nominal 1.1 vs 2.25 PFLOP/s); bf16 figure measured
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 simulator scalars / f32 observations / fp32 policy", "data": "synthetic",
+        "dtype": "f64 simulator scalars / f32 observations / tf32 policy (fp32 accumulate)", "data": "synthetic",
         "config": {"workload": f"mansy_ppo_rollout_{n_local}_envs_per_gpu", "envs": n_global, "envs_per_gpu": n_local,
                    "obs_row_bytes": sim.obs_stride * 4,
                    "l2": f"observations stream into a {slabs}-slab rollout buffer of {slabs * slab_bytes >> 20} MiB "
                          "(> L2 126 MB): every step writes a slab last touched >2.5 L2-sizes ago",
                    "tables": "24 videos x 60 chunks, 1440 viewport pairs, 40 traces (SURVEY.md 8(d))",
-                   "timed": "K x (policy forward + sample + simulator step) + 1 all-gather of episode stats"},
+                   "timed": "K x (tcgen05 policy forward+sample launch, simulator step launch) driven from C "
+                            "(mansy_rollout_policy) + 1 all-gather of episode stats"},
         "roofline": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": step_gbs / hbm_gbs,
                      "traffic": None, "kernel": "step_kernel<MANSY>", "bytes_per_launch": n_local * BYTES_PER_STEP_MANSY,
                      "avg_launch_ms": step_ms, "peak_source": peak_src},
-        "roofline_policy": {"bound": "fp32 cuda cores (round-1 kernel)", "achieved": pol_tflops, "unit": "TFLOP/s",
-                            "kernel": "policy_forward_kernel + policy_sample_kernel", "avg_launch_ms": policy_ms,
-                            "flop_per_launch": n_local * FLOP_PER_STEP_POLICY},
+        "roofline_policy": {"bound": "tensor", "achieved": pol_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                            "frac": pol_tflops / tf32_peak, "kernel": "policy_tc_kernel (tcgen05 kind::tf32)",
+                            "avg_launch_ms": policy_ms, "flop_per_launch": n_local * FLOP_PER_STEP_POLICY,
+                            "peak_source": "1/2 x measured bf16 cuBLAS burst (MEASURED_PEAKS.json); TF32 runs at half the bf16 rate"},
         "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "path": "mansy_step_host: pinned host actions -> H2D -> step kernel -> D2H obs+reward+done"},
+                "steps": e2e_steps,
+                "path": "mansy_rollout_policy_host: per step policy launch, D2H actions + sync, H2D actions, step launch, "
+                        "D2H obs+reward+done+logp+value into pinned host slabs + sync"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "rollout_summary": summary,

@@ -241,6 +241,62 @@ int mansy_policy_forward_tc(mansy_policy_t p, const float *obs_dev, int64_t obs_
                             float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
                             int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, void *stream);
 
+/* Same launch with a profiling hook: timeline_dev (int64[512], may be NULL) receives SM-clock stamps of CTA 0:
+ * [0..127] TMA issue per job, [128..255] operand arrival per job, [256..383] MMAs issued per job,
+ * [384 + 2i, 385 + 2i] epilogue begin/end of branch i (then the head epilogue), [511] kernel start. */
+int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
+                                     float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
+                                     int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
+                                     void *stream);
+
+/*
+ * Rollout loop on the device: what tianshou's Collector.collect(n_step) does around policy(batch) and
+ * env.step(act) (test loop bitrate_selection/run_mansy.py:161-175), without a host round trip
+ * per step.  Step t (t = t0 .. t0 + n_steps - 1) reads observation slab t % slabs, writes actions / logp /
+ * value / reward / done of slab t % slabs and the next observation into slab (t + 1) % slabs (auto-reset on).
+ * Slab 0 .. must hold the current observations when the call is made (mansy_reset into slab t0 % slabs).
+ * All pointers are DEVICE memory owned by the caller; two kernel launches per step.
+ */
+typedef struct {
+  float *obs;         /* [slabs][n_envs][obs_stride] */
+  int64_t obs_stride; /* floats between rows */
+  int32_t slabs;
+  int32_t *actions;   /* [slabs][n_envs] */
+  float *logp;        /* [slabs][n_envs] */
+  float *value;       /* [slabs][n_envs] */
+  float *reward;      /* [slabs][n_envs] */
+  uint8_t *done;      /* [slabs][n_envs] */
+  float *logits;      /* [n_envs][16] scratch (overwritten every step) */
+} mansy_rollout_t;
+#define MANSY_ROLLOUT_FP32_POLICY 1 /* use the exact-fp32 CUDA-core policy kernels instead of tcgen05 */
+#define MANSY_ROLLOUT_TIME_KERNELS 2 /* record CUDA events around every policy / step launch */
+int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout_t *buffers, int32_t n_steps, int64_t t0,
+                         uint64_t seed, int32_t flags, void *stream);
+/*
+ * The same loop for callers whose rollout storage is HOST memory (tianshou's replay buffer is numpy): every
+ * step (1) runs the policy on the device-resident observation, (2) copies the sampled actions to the host and
+ * synchronises -- policy(batch) + to_numpy(act), run_mansy.py:169-172 --, (3) copies them back as the input of
+ * env.step(act) (run_mansy.py:173), (4) steps, (5) copies the next observation, reward, done, logp and value
+ * to host slab t % host_slabs and synchronises.  Host buffers should be pinned.
+ */
+typedef struct {
+  int32_t host_slabs;
+  float *obs;       /* [host_slabs][n_envs][obs_stride]: observation AFTER the step */
+  int32_t *actions; /* [host_slabs][n_envs] */
+  float *logp, *value, *reward;
+  uint8_t *done;
+} mansy_rollout_host_t;
+int mansy_rollout_policy_host(mansy_handle_t h, mansy_policy_t p, const mansy_rollout_t *buffers,
+                              const mansy_rollout_host_t *host, int32_t n_steps, int64_t t0, uint64_t seed, int32_t flags,
+                              void *stream);
+
+/* Creates the CUDA events a timed rollout of n_steps needs ahead of time (event creation is slow; keep it out
+ * of a timed region). */
+int mansy_rollout_reserve_timing(mansy_handle_t h, int32_t n_steps);
+/* After the stream has been synchronised: summed event-timed durations (ms) of the policy and step launches
+ * of the last rollout that ran with MANSY_ROLLOUT_TIME_KERNELS, and the number of steps they cover. */
+int mansy_rollout_kernel_ms(mansy_handle_t h, double *policy_ms, double *step_ms, int32_t *n_steps);
+
 /* Raw copy of the per-environment state records (128 bytes each, layout: csrc/mansy_sim.cuh
  * EnvState / _capi.ENV_STATE_DTYPE) into state_dev[n_envs*128]; for host-side bookkeeping
  * (current_video / current_user / ... attributes of the gym envs) and tests. */

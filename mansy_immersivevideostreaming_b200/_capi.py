@@ -61,6 +61,25 @@ class Out(C.Structure):
     ]
 
 
+class Rollout(C.Structure):
+    _fields_ = [
+        ("obs", C.c_void_p), ("obs_stride", C.c_int64), ("slabs", C.c_int32),
+        ("actions", C.c_void_p), ("logp", C.c_void_p), ("value", C.c_void_p), ("reward", C.c_void_p),
+        ("done", C.c_void_p), ("logits", C.c_void_p),
+    ]
+
+
+class RolloutHost(C.Structure):
+    _fields_ = [
+        ("host_slabs", C.c_int32), ("obs", C.c_void_p), ("actions", C.c_void_p), ("logp", C.c_void_p),
+        ("value", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
+    ]
+
+
+ROLLOUT_FP32_POLICY = 1
+ROLLOUT_TIME_KERNELS = 2
+
+
 class PolicyWeights(C.Structure):
     _fields_ = [
         ("kind", C.c_int32),
@@ -98,6 +117,13 @@ SIGNATURES = {
     "mansy_policy_sample": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, C.c_int32, _vp, _vp, _vp]),
     "mansy_policy_forward_tc": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int64,
                                           C.c_int32, _vp, _vp, _vp]),
+    "mansy_policy_forward_tc_timeline": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int64,
+                                                   C.c_int32, _vp, _vp, _vp, _vp]),
+    "mansy_rollout_policy": (C.c_int, [_vp, _vp, C.POINTER(Rollout), C.c_int32, C.c_int64, C.c_uint64, C.c_int32, _vp]),
+    "mansy_rollout_policy_host": (C.c_int, [_vp, _vp, C.POINTER(Rollout), C.POINTER(RolloutHost), C.c_int32, C.c_int64,
+                                            C.c_uint64, C.c_int32, _vp]),
+    "mansy_rollout_reserve_timing": (C.c_int, [_vp, C.c_int32]),
+    "mansy_rollout_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "mansy_selftest_allocate": (C.c_int, [C.c_uint64, C.c_int32, C.POINTER(C.c_int32 * 5), C.POINTER(C.c_uint8 * 64)]),
     "mansy_selftest_fov_mask": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),

@@ -11,18 +11,25 @@
 // branch of the FeatureNet starts on a multiple of 8 floats (= one TF32 K-step of 32 bytes), so
 // layer 1 is, per branch, a run of M128 x N128 x K8 MMAs over the K-steps the branch owns,
 // accumulated in a ping-pong TMEM tile D1.  Four epilogue warps add the bias, apply LeakyReLU and
-// write the 128x128 feature tile back to shared memory in the canonical K-major SWIZZLE_128B
-// layout, where it becomes the A operand of layer 2: D2[128 x 256] += feat_b * Wfc_b^T (actor.fc
-// and critic.fc stacked; the shared FeatureNet is evaluated once).  TMEM: 2 x 128 + 256 = 512
-// columns.  Heads (128 -> 15, 128 -> 1), softmax and the categorical sample run in the final
-// epilogue from registers with the head weights as constant-bank operands.
+// store the 128x128 feature tile back IN PLACE in tensor memory (tcgen05.st), where it is the A
+// operand of layer 2 (A-from-TMEM MMA): D2[128 x 256] += feat_b * Wfc_b^T (actor.fc and critic.fc
+// stacked; the shared FeatureNet is evaluated once).  TMEM: 2 x 128 + 256 = 512 columns; shared
+// memory is TMA staging (5 x 32 KB) plus the resident head weights.  What bounds the kernel is the
+// per-SM TMA ingest (measured ~43 B/clk): a CTA streams 2.4 MB of operands per tile.  The hidden
+// activations (bias, LeakyReLU, residual) are stored back over D2 and the heads (128 -> 15,
+// 128 -> 1) are one more A-from-TMEM MMA chain, D3[128 x 16] = hid[128 x 256] * Wout^T, with the
+// block-structured [16 x 256] head matrix resident in shared memory; softmax and the categorical
+// sample run on its 16 columns.
 //
-// Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (TMEM lane quarter = warp & 3).  Both the producer and the issuer walk
-// the same host-built job list (c_tc[slot].jobs); shared-memory stages are recycled through
-// full/empty mbarriers, accumulators through tcgen05.commit barriers.
+// Warp roles: warps 0..2 = TMA producers (one per stage: a thread's TMA issues serialise at ~370
+// cycles each, measured with tools/ubench/tma_ingest.cu, so one producer cannot feed the tensor
+// core), warp 3 = TMEM allocator + MMA issuer (one elected lane), warps 4..11 = epilogue
+// (TMEM lane quarter = warp & 3, two warps per quarter splitting the columns).  Producers and
+// issuer walk the same host-built job list (c_tc[slot].jobs); shared-memory stages are recycled
+// through full/empty mbarriers, accumulators through tcgen05.commit barriers.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -33,29 +40,32 @@ namespace mansy {
 
 constexpr int kTcSlots = 3;            // policies with live tensor-core state per process
 constexpr int kTcMaxJobs = 96;
-constexpr int kTcThreads = 192;
 constexpr int kTcStages = 3;
-constexpr uint32_t kStageBytes = 32768;   // L1 job: A box 16 KB + W1 box 16 KB;  L2 job: Wfc box 32 KB
+constexpr int kTcProducers = kTcStages;   // warps 0..2: producer w owns stage w (a stage refilled by different
+                                          // producers lets one run two phases ahead, where parity waits alias)
+constexpr int kTcMmaWarp = 3;
+constexpr int kTcEpiWarp0 = 4;            // warps 4..11
+constexpr int kTcThreads = 32 * (kTcEpiWarp0 + 8);
+constexpr uint32_t kStageBytes = 65536;   // L1 job: up to 2 A boxes + 2 W1 boxes of 16 KB;  L2 job: 2 Wfc boxes of 32 KB
 constexpr uint32_t kBoxBytes = 16384;     // 128 rows x 128 B
-constexpr uint32_t kFeatBytes = 65536;    // 128 rows x 128 floats = 4 boxes
-constexpr uint32_t kTcSmemBytes = kTcStages * kStageBytes + 2 * kFeatBytes + 256 /*barriers*/ + 1024 /*alignment*/;
+constexpr uint32_t kWoutBytes = 16384;     // head matrix [16 rows x 256 K] fp32 = 8 boxes of [16 x 32 floats]
+constexpr uint32_t kTcSmemBytes = kTcStages * kStageBytes + kWoutBytes + 256 /*barriers*/ + 1024 /*alignment*/;
 
 enum : uint8_t { kJobL1 = 0, kJobL2 = 1 };
 enum : uint8_t { kFlagFirst = 1, kFlagLast = 2, kFlagTileFirstL2 = 4, kFlagTileLastL2 = 8 };
 
 struct TcJob {
   uint8_t type;     // kJobL1 / kJobL2
-  uint8_t a_box;    // L1: observation box (32 floats)            L2: -
-  uint8_t w_box;    // L1: box of the layer-1 weight image         L2: -
-  uint8_t s_lo;     // L1: first K-step inside the box (0..3)      L2: -
-  uint8_t s_hi;     // L1: one past the last K-step                L2: -
+  uint8_t a_box;    // L1: first observation box (32 floats)       L2: -
+  uint8_t w_box;    // L1: first box of the layer-1 weight image   L2: -
+  uint8_t s_lo;     // L1: first K-step inside the job (0..7)      L2: -
+  uint8_t s_hi;     // L1: one past the last K-step (<= 8)         L2: -
   uint8_t slot;     // branch in processing order (D1 / feature buffer = slot & 1)
   uint8_t flags;
-  uint8_t chunk;    // L2: 32-float chunk of the branch's 128 features (0..3)
+  uint8_t chunk;    // L1: number of boxes (1 or 2)   L2: first of two 32-float chunks of the branch's 128 features (0, 2)
 };
 
 struct TcConst {
-  float wout_t[kHidden][16];   // [j][o]: o < 15 actor.out[o][j], o == 15 critic.out[0][j]
   float bias2[2 * kHidden];    // actor.fc bias | critic.fc bias
   float bias1[kMaxBranches][kHidden];   // processing order
   float bout[16];
@@ -76,11 +86,12 @@ struct TcArgs {
   uint64_t seed;
   int64_t step;
   int32_t env_offset;
+  long long *timeline;  // debug: CTA 0 clock64 stamps [4][128] (producer issue, data arrival, mma committed, epilogue) or NULL
 };
 
 struct TcState {
   int slot = -1;
-  CUtensorMap map_w1, map_wfc;
+  CUtensorMap map_w1, map_wfc, map_wout;
   int obs_floats = 0;          // 784 / 400
   int n_branches = 0;
 };
@@ -89,6 +100,22 @@ struct TcState {
 // PTX wrappers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One lane of a converged warp (the same one every time).  The role loops below run in all 32 lanes with
+// warp-uniform operands and only the TMA / MMA instruction itself is predicated on this, so the
+// descriptors stay in uniform registers (a lane-0-only loop makes the compiler wrap every UTCHMMA /
+// UTMALDG in an R2UR waterfall loop, ~100 cycles per instruction).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -133,6 +160,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand read from tensor memory (lane = row, one 32-bit column per K element).
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once every MMA issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -143,6 +182,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ULL << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46) | (2ULL << 61);
 }
+// The same descriptor as two words, so that a K-step inside the 128-byte swizzle row is one independent add
+// on the low word (+2 per 32 bytes): keeps the issue loop off a long chain of dependent uniform-datapath ops.
+constexpr uint32_t kDescHi = (uint32_t)((1024 >> 4) | (1u << 14) | (2u << 29));     // SBO | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B TF32, both K-major, M = 128.
 __host__ __device__ constexpr uint32_t idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -164,14 +208,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
 }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
 // kernel
@@ -179,40 +244,52 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 template <int SLOT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_constant__ CUtensorMap map_w1,
-                 const __grid_constant__ CUtensorMap map_wfc, const TcArgs A) {
+                 const __grid_constant__ CUtensorMap map_wfc, const __grid_constant__ CUtensorMap map_wout,
+                 const TcArgs A) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const TcConst &K = c_tc[SLOT];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage0 = base;
-  const uint32_t feat0 = base + kTcStages * kStageBytes;
-  const uint32_t bars = feat0 + 2 * kFeatBytes;
+  const uint32_t wout_s = base + kTcStages * kStageBytes;
+  const uint32_t bars = wout_s + kWoutBytes;
   // barrier map (8 bytes each)
-  const uint32_t bar_full = bars;                    // [kTcStages]   TMA -> MMA
-  const uint32_t bar_empty = bars + 8 * kTcStages;   // [kTcStages]   MMA (commit) -> TMA
-  const uint32_t bar_d1_full = bars + 48;            // [2]           MMA (commit) -> epilogue
-  const uint32_t bar_feat_full = bars + 64;          // [2]           epilogue (128 arrivals) -> MMA
-  const uint32_t bar_feat_empty = bars + 80;         // [2]           MMA (commit) -> epilogue
-  const uint32_t bar_d2_full = bars + 96;            //               MMA (commit) -> epilogue
-  const uint32_t bar_d2_empty = bars + 104;          //               epilogue (128 arrivals) -> MMA
-  const uint32_t tmem_slot = bars + 112;             // uint32 written by tcgen05.alloc
+  // A stage has one "full" barrier per 32 KB half: 65536 pending transaction bytes on one mbarrier fault on
+  // sm_100a (compute-sanitizer flags the arrive.expect_tx), and the issuer can start on the first half earlier.
+  const uint32_t bar_full = bars;                    // [kTcStages][2] TMA -> MMA
+  const uint32_t bar_empty = bars + 64;              // [kTcStages]    MMA (commit) -> TMA
+  const uint32_t bar_d1_full = bars + 128;           // [2]           MMA (commit) -> epilogue
+  const uint32_t bar_feat_full = bars + 144;         // [2]           epilogue (128 arrivals) -> MMA
+  const uint32_t bar_d2_full = bars + 160;           //               MMA (commit) -> epilogue
+  const uint32_t bar_d2_empty = bars + 168;          //               epilogue (128 arrivals) -> MMA
+  const uint32_t bar_hid_full = bars + 176;          //               epilogue (128 arrivals) -> MMA: hid stored over D2
+  const uint32_t bar_d3_full = bars + 184;           //               MMA (commit) -> epilogue: head outputs ready
+  const uint32_t bar_wout = bars + 192;              //               TMA -> MMA: head matrix resident (once)
+  const uint32_t tmem_slot = bars + 200;             // uint32 written by tcgen05.alloc
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(bar_full + 16 * s, 1);
+      mbar_init(bar_full + 16 * s + 8, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_d1_full + 8 * b, 1);
-      mbar_init(bar_feat_full + 8 * b, 128);
-      mbar_init(bar_feat_empty + 8 * b, 1);
+      mbar_init(bar_feat_full + 8 * b, 256);
     }
     mbar_init(bar_d2_full, 1);
     mbar_init(bar_d2_empty, 128);
+    mbar_init(bar_hid_full, 256);
+    mbar_init(bar_d3_full, 1);
+    mbar_init(bar_wout, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_obs) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wfc) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wout) : "memory");
   }
-  if (warp == 1) {   // TMEM: all 512 columns (D1[0] 0..127, D1[1] 128..255, D2 256..511)
+  if (warp == kTcMmaWarp) {   // TMEM: all 512 columns (D1[0] 0..127, D1[1] 128..255, D2 256..511)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -223,83 +300,144 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int n_jobs = K.n_jobs;
+  if (A.timeline && blockIdx.x == 0 && threadIdx.x == 0) A.timeline[511] = clock64();
 
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      uint32_t it = 0;
+  if (warp < kTcProducers) {
+    // ===== TMA producers: job `it` uses stage it % kTcStages, which belongs to producer `stage` =====
+    {
+      if (warp == 0 && elect_one()) {
+        mbar_expect_tx(bar_wout, kWoutBytes);          // head matrix: resident for the whole kernel
+        for (int b = 0; b < 8; ++b) tma_load_2d(wout_s + b * 2048, &map_wout, b * 32, 0, bar_wout);
+      }
+      __syncwarp();
+      uint32_t it = 0, s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-        for (int j = 0; j < n_jobs; ++j, ++it) {
+        for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+          if ((int)s != warp) continue;
           const TcJob job = K.jobs[j];
-          const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
           mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-          const uint32_t dst = stage0 + s * kStageBytes, full = bar_full + 8 * s;
-          mbar_expect_tx(full, kStageBytes);
-          if (job.type == kJobL1) {
-            tma_load_2d(dst, &map_obs, job.a_box * 32, tile * 128, full);
-            tma_load_2d(dst + kBoxBytes, &map_w1, job.w_box * 32, 0, full);
-          } else {
-            tma_load_2d(dst, &map_wfc, job.slot * kHidden + job.chunk * 32, 0, full);
+          const uint32_t dst = stage0 + s * kStageBytes, full = bar_full + 16 * s;
+          if (elect_one()) {
+            if (job.type == kJobL1) {     // stage: [A box 0][A box 1][W1 box 0][W1 box 1]
+              mbar_expect_tx(full, 2 * kBoxBytes);
+              tma_load_2d(dst, &map_obs, job.a_box * 32, tile * 128, full);
+              tma_load_2d(dst + 2 * kBoxBytes, &map_w1, job.w_box * 32, 0, full);
+              if (job.chunk > 1) {
+                mbar_expect_tx(full + 8, 2 * kBoxBytes);
+                tma_load_2d(dst + kBoxBytes, &map_obs, job.a_box * 32 + 32, tile * 128, full + 8);
+                tma_load_2d(dst + 3 * kBoxBytes, &map_w1, job.w_box * 32 + 32, 0, full + 8);
+              } else {
+                mbar_arrive(full + 8);    // keep both halves' phases in step
+              }
+            } else {                      // stage: [Wfc chunk c][Wfc chunk c + 1], 256 rows x 128 B each
+              mbar_expect_tx(full, 2 * kBoxBytes);
+              tma_load_2d(dst, &map_wfc, job.slot * kHidden + job.chunk * 32, 0, full);
+              if (job.s_hi > 1) {
+                mbar_expect_tx(full + 8, 2 * kBoxBytes);
+                tma_load_2d(dst + 2 * kBoxBytes, &map_wfc, job.slot * kHidden + job.chunk * 32 + 32, 0, full + 8);
+              } else {
+                mbar_arrive(full + 8);
+              }
+            }
           }
+          __syncwarp();
+          if (A.timeline && blockIdx.x == 0 && it < 128 && lane == 0) A.timeline[it] = clock64();
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kTcMmaWarp) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t kIdesc128 = idesc_tf32(128), kIdesc256 = idesc_tf32(256);
-      uint32_t it = 0, feat_use[2] = {0, 0}, tile_i = 0;
+    {
+      constexpr uint32_t kIdesc128 = idesc_tf32(128), kIdesc256 = idesc_tf32(256), kIdesc16 = idesc_tf32(16);
+      uint32_t it = 0, feat_use[2] = {0, 0}, tile_i = 0, s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_i) {
-        for (int j = 0; j < n_jobs; ++j, ++it) {
-          const TcJob job = K.jobs[j];
-          const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+        // the head epilogue of the previous tile reads D2 (hid), D1[1] (residual) and D3 (= D1[0] columns 0..15)
+        if (tile_i > 0) mbar_wait(bar_d2_empty, (tile_i - 1) & 1u);
+        TcJob job = K.jobs[0];
+        for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+          const TcJob next_job = K.jobs[j + 1 < n_jobs ? j + 1 : 0];      // fetched before the waits below
           const uint32_t buf = job.slot & 1u;
           const uint32_t st_addr = stage0 + s * kStageBytes;
           if (job.type == kJobL1) {
-            // D1[buf] was drained by the epilogue of branch slot-2: its feat_full was awaited before
-            // the layer-2 MMAs of that branch, which precede this job in the list.
-            mbar_wait(bar_full + 8 * s, ph);
-            tc_fence_after();
+            // D1[buf] still holds the features of branch slot-2 until that branch's layer-2 MMAs have
+            // read them; those precede this job in the issue order and the tensor pipe runs in order.
             const uint32_t d1 = tmem_base + buf * 128u;
-            for (int st = job.s_lo; st < job.s_hi; ++st) {
-              const uint64_t ad = smem_desc_sw128(st_addr + st * 32);
-              const uint64_t bd = smem_desc_sw128(st_addr + kBoxBytes + st * 32);
-              umma_tf32(d1, ad, bd, kIdesc128, ((job.flags & kFlagFirst) && st == job.s_lo) ? 0u : 1u);
+            const uint32_t a_lo = smem_desc_lo(st_addr), b_lo = smem_desc_lo(st_addr + 2 * kBoxBytes);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              mbar_wait(bar_full + 16 * s + 8 * h, ph);
+              tc_fence_after();
+              if (h == 0 && A.timeline && blockIdx.x == 0 && it < 128 && lane == 0) A.timeline[128 + it] = clock64();
+              if (elect_one()) {
+#pragma unroll
+                for (int st = 4 * h; st < 4 * h + 4; ++st)
+                  if (st >= job.s_lo && st < job.s_hi)
+                    umma_tf32(d1, make_desc(a_lo + h * (kBoxBytes >> 4) + 2 * (st & 3)),
+                              make_desc(b_lo + h * (kBoxBytes >> 4) + 2 * (st & 3)), kIdesc128,
+                              ((job.flags & kFlagFirst) && st == job.s_lo) ? 0u : 1u);
+              }
+              __syncwarp();
             }
-            umma_commit(bar_empty + 8 * s);
-            if (job.flags & kFlagLast) umma_commit(bar_d1_full + 8 * buf);
+            if (elect_one()) {
+              umma_commit(bar_empty + 8 * s);
+              if (job.flags & kFlagLast) umma_commit(bar_d1_full + 8 * buf);
+            }
+            __syncwarp();
+            if (A.timeline && blockIdx.x == 0 && it < 128 && lane == 0) A.timeline[256 + it] = clock64();
           } else {
             if (job.chunk == 0) {   // feature tile of this branch written by the epilogue warps
               mbar_wait(bar_feat_full + 8 * buf, feat_use[buf] & 1u);
               ++feat_use[buf];
             }
-            if ((job.flags & kFlagTileFirstL2) && tile_i > 0) mbar_wait(bar_d2_empty, (tile_i - 1) & 1u);
-            mbar_wait(bar_full + 8 * s, ph);
-            tc_fence_after();
             const uint32_t d2 = tmem_base + 256u;
-            const uint32_t fa = feat0 + buf * kFeatBytes + job.chunk * kBoxBytes;
+            const uint32_t fa = tmem_base + buf * 128u + job.chunk * 32u;     // features live in D1[buf]
+            const uint32_t b_lo = smem_desc_lo(st_addr);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t ad = smem_desc_sw128(fa + ks * 32);
-              const uint64_t bd = smem_desc_sw128(st_addr + ks * 32);
-              umma_tf32(d2, ad, bd, kIdesc256, ((job.flags & kFlagTileFirstL2) && ks == 0) ? 0u : 1u);
+            for (int h = 0; h < 2; ++h) {
+              mbar_wait(bar_full + 16 * s + 8 * h, ph);
+              tc_fence_after();
+              if (h == 0 && A.timeline && blockIdx.x == 0 && it < 128 && lane == 0) A.timeline[128 + it] = clock64();
+              if (elect_one()) {
+#pragma unroll
+                for (int ks = 4 * h; ks < 4 * h + 4; ++ks)
+                  if (h < job.s_hi)
+                    umma_tf32_ts(d2, fa + ks * 8, make_desc(b_lo + h * (2 * kBoxBytes >> 4) + 2 * (ks & 3)), kIdesc256,
+                                 ((job.flags & kFlagTileFirstL2) && ks == 0) ? 0u : 1u);
+              }
+              __syncwarp();
             }
-            umma_commit(bar_empty + 8 * s);
-            if (job.flags & kFlagLast) umma_commit(bar_feat_empty + 8 * buf);
-            if (job.flags & kFlagTileLastL2) umma_commit(bar_d2_full);
+            if (elect_one()) {
+              umma_commit(bar_empty + 8 * s);
+              if (job.flags & kFlagTileLastL2) umma_commit(bar_d2_full);
+            }
+            __syncwarp();
+            if (A.timeline && blockIdx.x == 0 && it < 128 && lane == 0) A.timeline[256 + it] = clock64();
           }
+          job = next_job;
         }
+        // heads: D3[128 x 16] = hid[128 x 256] (stored over D2 by the epilogue warps) * Wout^T
+        if (tile_i == 0) mbar_wait(bar_wout, 0);
+        mbar_wait(bar_hid_full, tile_i & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t w_lo = smem_desc_lo(wout_s);
+#pragma unroll
+          for (int ks = 0; ks < 32; ++ks)
+            umma_tf32_ts(tmem_base, tmem_base + 256u + ks * 8, make_desc(w_lo + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2),
+                         kIdesc16, ks > 0 ? 1u : 0u);
+          umma_commit(bar_d3_full);
+        }
+        __syncwarp();
       }
     }
   } else {
-    // ===== epilogue warps (2..5) =====
+    // ===== epilogue warps (4..11): two warps per TMEM lane quarter, `half` selects the columns =====
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - kTcEpiWarp0) >> 2;
     const int r = q * 32 + lane;            // row (environment) inside the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-    const uint32_t sw = (uint32_t)(r & 7);
     const int nb = K.n_branches;
-    uint32_t d1_use[2] = {0, 0}, feat_use[2] = {0, 0}, tile_i = 0;
+    uint32_t d1_use[2] = {0, 0}, tile_i = 0;
     for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_i) {
       const int env = tile * 128 + r;
       const bool live = env < A.n;
@@ -308,72 +446,67 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
         mbar_wait(bar_d1_full + 8 * buf, d1_use[buf] & 1u);
         ++d1_use[buf];
         tc_fence_after();
-        if (feat_use[buf] > 0) mbar_wait(bar_feat_empty + 8 * buf, (feat_use[buf] - 1) & 1u);
-        ++feat_use[buf];
-        const uint32_t fb = feat0 + buf * kFeatBytes + row_off;
+        if (A.timeline && blockIdx.x == 0 && threadIdx.x == 32 * kTcEpiWarp0 && tile_i == 0) A.timeline[384 + 2 * i] = clock64();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 2 * half; c < 2 * half + 2; ++c) {
           float v[32];
-          tmem_ld32(tmem_base + lane_addr + buf * 128u + c * 32u, v);
+          const uint32_t ta = tmem_base + lane_addr + buf * 128u + c * 32u;
+          tmem_ld32(ta, v);
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) v[jj] = leaky(v[jj] + K.bias1[i][c * 32 + jj]);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            st_shared_f4(fb + c * kBoxBytes + (((uint32_t)j4 ^ sw) << 4), v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2],
-                         v[4 * j4 + 3]);
+          tmem_st32(ta, v);        // features replace the accumulator in place: A operand of layer 2
           if (A.feat_dbg && live) {
             float *dst = A.feat_dbg + (size_t)env * (nb * kHidden) + i * kHidden + c * 32;
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) dst[jj] = v[jj];
           }
         }
-        fence_async_smem();      // generic-proxy writes -> visible to the tensor core (async proxy)
+        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar_feat_full + 8 * buf);
+        if (A.timeline && blockIdx.x == 0 && threadIdx.x == 32 * kTcEpiWarp0 && tile_i == 0) A.timeline[384 + 2 * i + 1] = clock64();
       }
 
       // ---- final epilogue: hidden layer activation, residual, heads, sample -----------------
       mbar_wait(bar_d2_full, tile_i & 1u);
       tc_fence_after();
-      float acc[16];
-#pragma unroll
-      for (int o = 0; o < 16; ++o) acc[o] = K.bout[o];
+      if (A.timeline && blockIdx.x == 0 && threadIdx.x == 32 * kTcEpiWarp0 && tile_i == 0) A.timeline[384 + 2 * nb] = clock64();
       const int rs = K.residual_slot;
-      const uint32_t rb = feat0 + (uint32_t)(rs & 1) * kFeatBytes + row_off;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        float va[32], vc[32], rr[32];
-        tmem_ld32(tmem_base + lane_addr + 256u + c * 32u, va);
-        tmem_ld32(tmem_base + lane_addr + 384u + c * 32u, vc);
-        if (c == 3) {            // D2 fully read: the next tile's layer 2 may overwrite it
-          tc_fence_before();
-          mbar_arrive(bar_d2_empty);
-        }
-        if (rs >= 0) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 t = ld_shared_f4(rb + c * kBoxBytes + (((uint32_t)j4 ^ sw) << 4));
-            rr[4 * j4] = t.x; rr[4 * j4 + 1] = t.y; rr[4 * j4 + 2] = t.z; rr[4 * j4 + 3] = t.w;
-          }
+        float va[32], rr[32];
+        if (rs >= 0) {           // residual: the features of the last branch are still in D1[rs & 1]
+          tmem_ld32(tmem_base + lane_addr + (uint32_t)(rs & 1) * 128u + c * 32u, rr);
         } else {
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) rr[jj] = 0.f;
         }
+        {                                          // half 0: actor.fc columns, half 1: critic.fc columns
+          const uint32_t ta = tmem_base + lane_addr + 256u + half * 128u + c * 32u;
+          tmem_ld32(ta, va);
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int j = c * 32 + jj;
-          va[jj] = leaky(va[jj] + K.bias2[j]) + rr[jj];                 // mansy.py:65: fc(features) + qoe_features
-          vc[jj] = leaky(vc[jj] + K.bias2[kHidden + j]) + rr[jj];       // mansy.py:79
+          for (int jj = 0; jj < 32; ++jj)          // mansy.py:65,79: fc(features) + qoe_features
+            va[jj] = leaky(va[jj] + K.bias2[half * kHidden + c * 32 + jj]) + rr[jj];
+          tmem_st32(ta, va);
+          if (A.hid_dbg && live) {
+            float *dst = A.hid_dbg + (size_t)env * 256 + half * kHidden + c * 32;
 #pragma unroll
-          for (int o = 0; o < kActions; ++o) acc[o] = fmaf(va[jj], K.wout_t[j][o], acc[o]);
-          acc[15] = fmaf(vc[jj], K.wout_t[j][15], acc[15]);
-        }
-        if (A.hid_dbg && live) {
-          float *dst = A.hid_dbg + (size_t)env * 256 + c * 32;
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) { dst[jj] = va[jj]; dst[kHidden + jj] = vc[jj]; }
+            for (int jj = 0; jj < 32; ++jj) dst[jj] = va[jj];
+          }
         }
       }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_hid_full);
+      if (half != 0) continue;        // the 16 head outputs of a row are handled by one thread
+      mbar_wait(bar_d3_full, tile_i & 1u);
+      tc_fence_after();
+      float acc[16];
+      tmem_ld16(tmem_base + lane_addr, acc);
+      tc_fence_before();
+      mbar_arrive(bar_d2_empty);      // D2, the residual and D3 are consumed: the next tile may start
+#pragma unroll
+      for (int o = 0; o < 16; ++o) acc[o] += K.bout[o];
       if (live) {
         float p[kActions];
 #pragma unroll
@@ -404,12 +537,13 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
           if (A.logp) A.logp[env] = lp;
         }
       }
+      if (A.timeline && blockIdx.x == 0 && threadIdx.x == 32 * kTcEpiWarp0 && tile_i == 0) A.timeline[384 + 2 * nb + 1] = clock64();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kTcMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -517,9 +651,10 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
       }
     }
   }
+  std::vector<float> woutimg((size_t)16 * 256, 0.f);   // rows 0..14: [actor.out | 0], row 15: [0 | critic.out]
   for (int j = 0; j < kHidden; ++j) {
-    for (int o = 0; o < kActions; ++o) hc->wout_t[j][o] = w->actor_out_w[(size_t)o * kHidden + j];
-    hc->wout_t[j][15] = w->critic_out_w[j];
+    for (int o = 0; o < kActions; ++o) woutimg[(size_t)o * 256 + j] = w->actor_out_w[(size_t)o * kHidden + j];
+    woutimg[(size_t)15 * 256 + kHidden + j] = w->critic_out_w[j];
     hc->bias2[j] = w->actor_fc_b[j];
     hc->bias2[kHidden + j] = w->critic_fc_b[j];
   }
@@ -531,24 +666,28 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
 
   // job list: L1(p0), L1(p1), L2(p0), L1(p2), L2(p1), ..., L1(p_last), L2(p_last-1), L2(p_last)
   int nj = 0;
+  const int pair1 = getenv("MANSY_TC_PAIR1") ? atoi(getenv("MANSY_TC_PAIR1")) : 2;   // debugging knobs: boxes / chunks per job
+  const int pair2 = getenv("MANSY_TC_PAIR2") ? atoi(getenv("MANSY_TC_PAIR2")) : 2;
   auto push_l1 = [&](int i) {
     const BranchPlan &b = plan[i];
     const int lo = b.off / 8, hi = (b.off + b.k + 7) / 8;      // K-steps of 8 floats
-    for (int box = lo / 4; box <= (hi - 1) / 4; ++box) {
+    const int box_lo = lo / 4, box_hi = (hi - 1) / 4;          // boxes of 4 K-steps; a job takes up to two
+    for (int box = box_lo; box <= box_hi; box += pair1) {
+      const int nbox = (pair1 == 2 && box + 1 <= box_hi) ? 2 : 1;
       TcJob &j = hc->jobs[nj++];
       j.type = kJobL1; j.a_box = (uint8_t)box; j.w_box = (uint8_t)(b.extra ? main_boxes : box);
       j.s_lo = (uint8_t)((lo > box * 4 ? lo : box * 4) - box * 4);
-      j.s_hi = (uint8_t)((hi < box * 4 + 4 ? hi : box * 4 + 4) - box * 4);
-      j.slot = (uint8_t)i; j.chunk = 0;
-      j.flags = (uint8_t)((box == lo / 4 ? kFlagFirst : 0) | (box == (hi - 1) / 4 ? kFlagLast : 0));
+      j.s_hi = (uint8_t)((hi < (box + nbox) * 4 ? hi : (box + nbox) * 4) - box * 4);
+      j.slot = (uint8_t)i; j.chunk = (uint8_t)nbox;
+      j.flags = (uint8_t)((box == box_lo ? kFlagFirst : 0) | (box + nbox > box_hi ? kFlagLast : 0));
     }
   };
   auto push_l2 = [&](int i) {
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 4; c += pair2) {
       TcJob &j = hc->jobs[nj++];
-      j.type = kJobL2; j.a_box = j.w_box = j.s_lo = j.s_hi = 0; j.slot = (uint8_t)i; j.chunk = (uint8_t)c;
-      j.flags = (uint8_t)((c == 3 ? kFlagLast : 0) | (i == 0 && c == 0 ? kFlagTileFirstL2 : 0) |
-                          (i == nb - 1 && c == 3 ? kFlagTileLastL2 : 0));
+      j.type = kJobL2; j.a_box = j.w_box = j.s_lo = 0; j.s_hi = (uint8_t)pair2; j.slot = (uint8_t)i; j.chunk = (uint8_t)c;
+      j.flags = (uint8_t)((c + pair2 == 4 ? kFlagLast : 0) | (i == 0 && c == 0 ? kFlagTileFirstL2 : 0) |
+                          (i == nb - 1 && c + pair2 == 4 ? kFlagTileLastL2 : 0));
     }
   };
   push_l1(0);
@@ -557,19 +696,23 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
   hc->n_jobs = nj;
 
   int rc = MANSY_OK;
-  float *d_w1 = nullptr, *d_wfc = nullptr;
+  float *d_w1 = nullptr, *d_wfc = nullptr, *d_wout = nullptr;
   if (cudaMalloc(&d_w1, w1img.size() * sizeof(float)) != cudaSuccess ||
-      cudaMalloc(&d_wfc, wfcimg.size() * sizeof(float)) != cudaSuccess)
+      cudaMalloc(&d_wfc, wfcimg.size() * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&d_wout, woutimg.size() * sizeof(float)) != cudaSuccess)
     rc = set_error(MANSY_E_NOMEM, "cudaMalloc failed (tensor-core weight images)");
   if (d_w1) p->allocs.push_back(d_w1);
   if (d_wfc) p->allocs.push_back(d_wfc);
+  if (d_wout) p->allocs.push_back(d_wout);
   if (!rc && (cudaMemcpy(d_w1, w1img.data(), w1img.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
               cudaMemcpy(d_wfc, wfcimg.data(), wfcimg.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+              cudaMemcpy(d_wout, woutimg.data(), woutimg.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
               cudaMemcpyToSymbol(c_tc, hc, sizeof(TcConst), (size_t)st->slot * sizeof(TcConst)) != cudaSuccess))
     rc = set_error(MANSY_E_CUDA, "upload of the tensor-core weight images failed");
   delete hc;
   if (!rc) rc = make_map(&st->map_w1, d_w1, (uint64_t)w1_cols, kHidden, (uint64_t)w1_cols, 128);
   if (!rc) rc = make_map(&st->map_wfc, d_wfc, (uint64_t)F, 256, (uint64_t)F, 256);
+  if (!rc) rc = make_map(&st->map_wout, d_wout, 256, 16, 256, 16);
   if (rc) {
     std::lock_guard<std::mutex> g(g_slot_mutex);
     g_slot_used[st->slot] = false;
@@ -599,6 +742,14 @@ extern "C" {
 int mansy_policy_forward_tc(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
                             float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
                             int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, void *stream) {
+  return mansy_policy_forward_tc_timeline(p, obs_dev, obs_stride, n, logits_dev, value_dev, actions_dev, logp_dev, seed, step,
+                                          env_offset, feat_dbg_dev, hid_dbg_dev, nullptr, stream);
+}
+
+int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
+                                     float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
+                                     int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
+                                     void *stream) {
   if (!p || !obs_dev) return set_error(MANSY_E_INVALID, "NULL argument");
   if (!p->tc) return set_error(MANSY_E_STATE, std::string("tensor-core state unavailable: ") + mansy_last_error());
   if (n < 0) return set_error(MANSY_E_INVALID, "n < 0");
@@ -616,6 +767,7 @@ int mansy_policy_forward_tc(mansy_policy_t p, const float *obs_dev, int64_t obs_
   a.logits = logits_dev; a.value = value_dev; a.actions = actions_dev; a.logp = logp_dev;
   a.feat_dbg = feat_dbg_dev; a.hid_dbg = hid_dbg_dev;
   a.seed = seed; a.step = step; a.env_offset = env_offset;
+  a.timeline = reinterpret_cast<long long *>(timeline_dev);
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
@@ -633,7 +785,7 @@ int mansy_policy_forward_tc(mansy_policy_t p, const float *obs_dev, int64_t obs_
       attr_done = (e == cudaSuccess);                                                                               \
     }                                                                                                               \
     if (e == cudaSuccess)                                                                                           \
-      policy_tc_kernel<SLOT><<<grid, kTcThreads, kTcSmemBytes, s>>>(map_obs, p->tc->map_w1, p->tc->map_wfc, a);      \
+      policy_tc_kernel<SLOT><<<grid, kTcThreads, kTcSmemBytes, s>>>(map_obs, p->tc->map_w1, p->tc->map_wfc, p->tc->map_wout, a);      \
   } while (0)
   switch (p->tc->slot) {
     case 0: MANSY_TC_LAUNCH(0); break;

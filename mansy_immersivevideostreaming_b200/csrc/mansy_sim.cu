@@ -492,6 +492,9 @@ struct mansy_sim {
   float *stage_reward = nullptr;
   uint8_t *stage_done = nullptr;
   int64_t obs_stride = 0;
+  // events of the last instrumented mansy_rollout_policy call: [3 * steps] = before policy, after policy, after step
+  std::vector<cudaEvent_t> events;
+  int timed_steps = 0;
 };
 
 namespace {
@@ -700,6 +703,7 @@ int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, ma
 int mansy_destroy(mansy_handle_t h) {
   if (!h) return MANSY_OK;
   cudaSetDevice(h->device);
+  for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   for (void *p : h->allocs) cudaFree(p);
   delete h;
   return MANSY_OK;
@@ -801,6 +805,121 @@ int mansy_reset_host(mansy_handle_t h, float *obs_host, void *stream) {
     MANSY_CUDA(cudaMemcpyAsync(obs_host, h->stage_obs, (size_t)h->dev.n_envs * h->obs_stride * sizeof(float),
                                cudaMemcpyDeviceToHost, s));
   MANSY_CUDA(cudaStreamSynchronize(s));
+  return MANSY_OK;
+}
+
+int mansy_rollout_reserve_timing(mansy_handle_t h, int32_t n_steps) {
+  if (!h || n_steps < 0) return set_error(MANSY_E_INVALID, "bad argument");
+  while (h->events.size() < (size_t)3 * n_steps) {
+    cudaEvent_t e;
+    MANSY_CUDA(cudaEventCreate(&e));
+    h->events.push_back(e);
+  }
+  return MANSY_OK;
+}
+
+int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout_t *b, int32_t n_steps, int64_t t0,
+                         uint64_t seed, int32_t flags, void *stream) {
+  if (!h || !p || !b) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (n_steps < 0 || t0 < 0) return set_error(MANSY_E_INVALID, "n_steps / t0 must be >= 0");
+  if (b->slabs < 2) return set_error(MANSY_E_INVALID, "a rollout needs at least 2 observation slabs");
+  if (!b->obs || !b->actions || !b->logp || !b->value || !b->reward || !b->done || !b->logits)
+    return set_error(MANSY_E_INVALID, "a rollout buffer pointer is NULL");
+  if (h->dev.obs_mode == MANSY_OBS_NONE) return set_error(MANSY_E_INVALID, "the policy consumes observation rows");
+  const size_t n = (size_t)h->dev.n_envs;
+  const bool timed = (flags & MANSY_ROLLOUT_TIME_KERNELS) != 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (timed) {
+    int rc = mansy_rollout_reserve_timing(h, n_steps);
+    if (rc) return rc;
+    h->timed_steps = n_steps;
+  }
+  const int is_probs = h->dev.obs_mode == MANSY_OBS_SIMPLE ? 1 : 0;
+  for (int32_t k = 0; k < n_steps; ++k) {
+    const int64_t t = t0 + k;
+    const size_t cur = (size_t)(t % b->slabs), nxt = (size_t)((t + 1) % b->slabs);
+    const float *obs = b->obs + cur * n * (size_t)b->obs_stride;
+    int rc;
+    if (timed) MANSY_CUDA(cudaEventRecord(h->events[3 * k], s));
+    if (flags & MANSY_ROLLOUT_FP32_POLICY) {
+      rc = mansy_policy_forward(p, obs, b->obs_stride, h->dev.n_envs, b->logits, b->value + cur * n, stream);
+      if (!rc) rc = mansy_policy_sample(b->logits, h->dev.n_envs, is_probs, seed, t, h->dev.env_offset, b->actions + cur * n,
+                                        b->logp + cur * n, stream);
+    } else {
+      rc = mansy_policy_forward_tc(p, obs, b->obs_stride, h->dev.n_envs, b->logits, b->value + cur * n, b->actions + cur * n,
+                                   b->logp + cur * n, seed, t, h->dev.env_offset, nullptr, nullptr, stream);
+    }
+    if (rc) return rc;
+    if (timed) MANSY_CUDA(cudaEventRecord(h->events[3 * k + 1], s));
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.actions = b->actions + cur * n; a.n = h->dev.n_envs; a.auto_reset = 1; a.n_steps = 1;
+    a.out.obs = b->obs + nxt * n * (size_t)b->obs_stride; a.out.obs_stride = b->obs_stride;
+    a.out.reward = b->reward + cur * n; a.out.done = b->done + cur * n;
+    if (k == 0 && (rc = check_out(h, &a.out))) return rc;
+    if ((rc = launch_step(h, a, s))) return rc;
+    if (timed) MANSY_CUDA(cudaEventRecord(h->events[3 * k + 2], s));
+  }
+  return MANSY_OK;
+}
+
+int mansy_rollout_policy_host(mansy_handle_t h, mansy_policy_t p, const mansy_rollout_t *b, const mansy_rollout_host_t *host,
+                              int32_t n_steps, int64_t t0, uint64_t seed, int32_t flags, void *stream) {
+  if (!h || !p || !b || !host) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (n_steps < 0 || t0 < 0) return set_error(MANSY_E_INVALID, "n_steps / t0 must be >= 0");
+  if (b->slabs < 2 || host->host_slabs < 1) return set_error(MANSY_E_INVALID, "need >= 2 device slabs and >= 1 host slab");
+  if (!b->obs || !b->actions || !b->logp || !b->value || !b->reward || !b->done || !b->logits || !host->obs ||
+      !host->actions || !host->logp || !host->value || !host->reward || !host->done)
+    return set_error(MANSY_E_INVALID, "a rollout buffer pointer is NULL");
+  if (h->dev.obs_mode == MANSY_OBS_NONE) return set_error(MANSY_E_INVALID, "the policy consumes observation rows");
+  const size_t n = (size_t)h->dev.n_envs;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int is_probs = h->dev.obs_mode == MANSY_OBS_SIMPLE ? 1 : 0;
+  const size_t row_bytes = (size_t)b->obs_stride * sizeof(float);
+  for (int32_t k = 0; k < n_steps; ++k) {
+    const int64_t t = t0 + k;
+    const size_t cur = (size_t)(t % b->slabs), nxt = (size_t)((t + 1) % b->slabs), hs = (size_t)(t % host->host_slabs);
+    const float *obs = b->obs + cur * n * (size_t)b->obs_stride;
+    int rc;
+    if (flags & MANSY_ROLLOUT_FP32_POLICY) {
+      rc = mansy_policy_forward(p, obs, b->obs_stride, h->dev.n_envs, b->logits, b->value + cur * n, stream);
+      if (!rc) rc = mansy_policy_sample(b->logits, h->dev.n_envs, is_probs, seed, t, h->dev.env_offset, b->actions + cur * n,
+                                        b->logp + cur * n, stream);
+    } else {
+      rc = mansy_policy_forward_tc(p, obs, b->obs_stride, h->dev.n_envs, b->logits, b->value + cur * n, b->actions + cur * n,
+                                   b->logp + cur * n, seed, t, h->dev.env_offset, nullptr, nullptr, stream);
+    }
+    if (rc) return rc;
+    MANSY_CUDA(cudaMemcpyAsync(host->actions + hs * n, b->actions + cur * n, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    MANSY_CUDA(cudaStreamSynchronize(s));                       // the host now holds act_t
+    MANSY_CUDA(cudaMemcpyAsync(b->actions + cur * n, host->actions + hs * n, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.actions = b->actions + cur * n; a.n = h->dev.n_envs; a.auto_reset = 1; a.n_steps = 1;
+    a.out.obs = b->obs + nxt * n * (size_t)b->obs_stride; a.out.obs_stride = b->obs_stride;
+    a.out.reward = b->reward + cur * n; a.out.done = b->done + cur * n;
+    if (k == 0 && (rc = check_out(h, &a.out))) return rc;
+    if ((rc = launch_step(h, a, s))) return rc;
+    MANSY_CUDA(cudaMemcpyAsync(host->obs + hs * n * (size_t)b->obs_stride, a.out.obs, n * row_bytes, cudaMemcpyDeviceToHost, s));
+    MANSY_CUDA(cudaMemcpyAsync(host->reward + hs * n, a.out.reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    MANSY_CUDA(cudaMemcpyAsync(host->done + hs * n, a.out.done, n, cudaMemcpyDeviceToHost, s));
+    MANSY_CUDA(cudaMemcpyAsync(host->logp + hs * n, b->logp + cur * n, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    MANSY_CUDA(cudaMemcpyAsync(host->value + hs * n, b->value + cur * n, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    MANSY_CUDA(cudaStreamSynchronize(s));
+  }
+  return MANSY_OK;
+}
+
+int mansy_rollout_kernel_ms(mansy_handle_t h, double *policy_ms, double *step_ms, int32_t *n_steps) {
+  if (!h || !policy_ms || !step_ms || !n_steps) return set_error(MANSY_E_INVALID, "NULL argument");
+  double pm = 0.0, sm = 0.0;
+  for (int k = 0; k < h->timed_steps; ++k) {
+    float a = 0.f, c = 0.f;
+    MANSY_CUDA(cudaEventElapsedTime(&a, h->events[3 * k], h->events[3 * k + 1]));
+    MANSY_CUDA(cudaEventElapsedTime(&c, h->events[3 * k + 1], h->events[3 * k + 2]));
+    pm += a; sm += c;
+  }
+  *policy_ms = pm; *step_ms = sm; *n_steps = h->timed_steps;
   return MANSY_OK;
 }
 

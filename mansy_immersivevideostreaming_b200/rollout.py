@@ -11,10 +11,12 @@ Multi-GPU: environments are sharded by contiguous index ranges (no collective on
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+import ctypes as C
+from typing import Dict, Optional, Tuple
 
 import torch
 
+from ._capi import ROLLOUT_FP32_POLICY, ROLLOUT_TIME_KERNELS, Rollout, RolloutHost, check
 from .config import OBS_MODE_NONE
 from .policy import PolicyNet
 from .simulator import BatchSimulator
@@ -42,26 +44,76 @@ class RolloutBuffers:
 
 
 class PolicyRollout:
-    def __init__(self, sim: BatchSimulator, policy: PolicyNet, slabs: int, seed: int = 0):
+    """obs[t] -> logits/value/action (one tcgen05 launch) -> simulator step -> obs[t+1] (one launch).
+
+    ``run`` drives the loop from C (``mansy_rollout_policy``: no Python between launches); ``step`` is the
+    same step from Python; ``run_host`` keeps the rollout storage in pinned host memory
+    (``mansy_rollout_policy_host``), the data flow of tianshou's Collector with numpy buffers."""
+
+    def __init__(self, sim: BatchSimulator, policy: PolicyNet, slabs: int, seed: int = 0, tensor_cores: bool = True):
         if sim.obs_mode == OBS_MODE_NONE:
             raise ValueError("the policy consumes observation rows")
+        if slabs < 2:
+            raise ValueError("a rollout needs at least 2 observation slabs")
         self.sim, self.policy, self.seed = sim, policy, int(seed)
+        self.tensor_cores = bool(tensor_cores)
         self.buf = RolloutBuffers(sim, slabs)
         self.t = 0                                   # global step counter (keys the action sampler)
         sim.reset(None, self.buf.obs[0])
+        b = self.buf
+        self._c = Rollout(b.obs.data_ptr(), b.obs.stride(1), b.slabs, b.actions.data_ptr(), b.logp.data_ptr(),
+                          b.value.data_ptr(), b.reward.data_ptr(), b.done.data_ptr(), b.logits.data_ptr())
+
+    def _flags(self, timed: bool = False) -> int:
+        return (0 if self.tensor_cores else ROLLOUT_FP32_POLICY) | (ROLLOUT_TIME_KERNELS if timed else 0)
 
     def step(self) -> None:
-        """obs[t] -> logits/value -> action -> simulator -> obs[t+1] (3 kernel launches)."""
         b, s = self.buf, self.t % self.buf.slabs
         nxt = (self.t + 1) % b.slabs
-        self.policy.forward(b.obs[s], b.logits, b.value[s])
-        self.policy.sample(b.logits, self.seed, self.t, self.sim.env_offset, b.actions[s], b.logp[s])
+        if self.tensor_cores:
+            self.policy.forward_tc(b.obs[s], b.logits, b.value[s], b.actions[s], b.logp[s], seed=self.seed, step=self.t,
+                                   env_offset=self.sim.env_offset)
+        else:
+            self.policy.forward(b.obs[s], b.logits, b.value[s])
+            self.policy.sample(b.logits, self.seed, self.t, self.sim.env_offset, b.actions[s], b.logp[s])
         self.sim.step(b.actions[s], auto_reset=True, obs=b.obs[nxt], reward=b.reward[s], done=b.done[s])
         self.t += 1
 
-    def run(self, n_steps: int) -> None:
-        for _ in range(n_steps):
-            self.step()
+    def run(self, n_steps: int, timed: bool = False) -> None:
+        """``n_steps`` rollout steps launched from C on the current stream (asynchronous)."""
+        check(self.sim.lib.mansy_rollout_policy(self.sim._h, self.policy._h, C.byref(self._c), int(n_steps), self.t,
+                                                self.seed, self._flags(timed), self.sim._stream()))
+        self.t += int(n_steps)
+
+    def reserve_timing(self, n_steps: int) -> None:
+        """Create the events of a later ``run(n_steps, timed=True)`` now (outside any timed region)."""
+        check(self.sim.lib.mansy_rollout_reserve_timing(self.sim._h, int(n_steps)))
+
+    def kernel_ms(self) -> Tuple[float, float, int]:
+        """(sum policy ms, sum step ms, steps) of the last ``run(..., timed=True)``; call after a synchronize."""
+        pm, sm, n = C.c_double(0), C.c_double(0), C.c_int32(0)
+        check(self.sim.lib.mansy_rollout_kernel_ms(self.sim._h, C.byref(pm), C.byref(sm), C.byref(n)))
+        return pm.value, sm.value, n.value
+
+    def make_host_buffers(self, host_slabs: int = 2) -> Dict[str, torch.Tensor]:
+        n, st = self.sim.n_envs, self.sim.obs_stride
+        pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()   # noqa: E731
+        return {"obs": pin(host_slabs, n, st, dtype=torch.float32), "actions": pin(host_slabs, n, dtype=torch.int32),
+                "logp": pin(host_slabs, n, dtype=torch.float32), "value": pin(host_slabs, n, dtype=torch.float32),
+                "reward": pin(host_slabs, n, dtype=torch.float32), "done": pin(host_slabs, n, dtype=torch.uint8)}
+
+    def run_host(self, n_steps: int, host: Dict[str, torch.Tensor]) -> None:
+        """Rollout with host storage: per step D2H actions + sync, H2D actions, step, D2H results + sync."""
+        hc = RolloutHost(host["obs"].shape[0], host["obs"].data_ptr(), host["actions"].data_ptr(), host["logp"].data_ptr(),
+                         host["value"].data_ptr(), host["reward"].data_ptr(), host["done"].data_ptr())
+        check(self.sim.lib.mansy_rollout_policy_host(self.sim._h, self.policy._h, C.byref(self._c), C.byref(hc), int(n_steps),
+                                                     self.t, self.seed, self._flags(), self.sim._stream()))
+        self.t += int(n_steps)
+
+    def host_bytes_per_step(self) -> Tuple[int, int]:
+        """(H2D, D2H) bytes one ``run_host`` step moves."""
+        n = self.sim.n_envs
+        return 4 * n, n * (self.sim.obs_stride * 4 + 4 + 4 + 4 + 4 + 1)
 
 
 def all_gather_stats(local: torch.Tensor, group=None) -> torch.Tensor:
