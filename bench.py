@@ -154,7 +154,7 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
+                                          "-i", str(self.idx), "-lms", "20"], stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 

@@ -21,9 +21,9 @@
 // block-structured [16 x 256] head matrix resident in shared memory; softmax and the categorical
 // sample run on its 16 columns.
 //
-// Warp roles: warps 0..2 = TMA producers (one per stage: a thread's TMA issues serialise at ~370
-// cycles each, measured with tools/ubench/tma_ingest.cu, so one producer cannot feed the tensor
-// core), warp 3 = TMEM allocator + MMA issuer (one elected lane), warps 4..11 = epilogue
+// Warp roles: warps 0..5 = TMA producers (two per stage, one per 32 KB half: a thread's TMA issues
+// serialise at ~370 cycles each, measured with tools/ubench/tma_ingest.cu, so one producer cannot
+// feed the tensor core), warp 6 = TMEM allocator + MMA issuer (one elected lane), warps 8..15 = epilogue
 // (TMEM lane quarter = warp & 3, two warps per quarter splitting the columns).  Producers and
 // issuer walk the same host-built job list (c_tc[slot].jobs); shared-memory stages are recycled
 // through full/empty mbarriers, accumulators through tcgen05.commit barriers.
@@ -41,10 +41,11 @@ namespace mansy {
 constexpr int kTcSlots = 3;            // policies with live tensor-core state per process
 constexpr int kTcMaxJobs = 96;
 constexpr int kTcStages = 3;
-constexpr int kTcProducers = kTcStages;   // warps 0..2: producer w owns stage w (a stage refilled by different
-                                          // producers lets one run two phases ahead, where parity waits alias)
-constexpr int kTcMmaWarp = 3;
-constexpr int kTcEpiWarp0 = 4;            // warps 4..11
+constexpr int kTcProducers = 2 * kTcStages;   // warps 0..5: producer w owns half (w & 1) of stage w >> 1.  (A stage
+                                              // refilled by different producers lets one run two phases ahead,
+                                              // where parity waits alias -- hence the fixed ownership.)
+constexpr int kTcMmaWarp = 6;                 // warp 7 idles
+constexpr int kTcEpiWarp0 = 8;                // warps 8..15
 constexpr int kTcThreads = 32 * (kTcEpiWarp0 + 8);
 constexpr uint32_t kStageBytes = 65536;   // L1 job: up to 2 A boxes + 2 W1 boxes of 16 KB;  L2 job: 2 Wfc boxes of 32 KB
 constexpr uint32_t kBoxBytes = 16384;     // 128 rows x 128 B
@@ -303,7 +304,8 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
   if (A.timeline && blockIdx.x == 0 && threadIdx.x == 0) A.timeline[511] = clock64();
 
   if (warp < kTcProducers) {
-    // ===== TMA producers: job `it` uses stage it % kTcStages, which belongs to producer `stage` =====
+    // ===== TMA producers: job `it` uses stage it % kTcStages; producers 2s and 2s+1 fill its two halves =====
+    const int half = warp & 1;
     {
       if (warp == 0 && elect_one()) {
         mbar_expect_tx(bar_wout, kWoutBytes);          // head matrix: resident for the whole kernel
@@ -313,35 +315,30 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
       uint32_t it = 0, s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
         for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
-          if ((int)s != warp) continue;
+          if ((int)s != (warp >> 1)) continue;
           const TcJob job = K.jobs[j];
           mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-          const uint32_t dst = stage0 + s * kStageBytes, full = bar_full + 16 * s;
+          const uint32_t dst = stage0 + s * kStageBytes, full = bar_full + 16 * s + 8 * half;
           if (elect_one()) {
             if (job.type == kJobL1) {     // stage: [A box 0][A box 1][W1 box 0][W1 box 1]
-              mbar_expect_tx(full, 2 * kBoxBytes);
-              tma_load_2d(dst, &map_obs, job.a_box * 32, tile * 128, full);
-              tma_load_2d(dst + 2 * kBoxBytes, &map_w1, job.w_box * 32, 0, full);
-              if (job.chunk > 1) {
-                mbar_expect_tx(full + 8, 2 * kBoxBytes);
-                tma_load_2d(dst + kBoxBytes, &map_obs, job.a_box * 32 + 32, tile * 128, full + 8);
-                tma_load_2d(dst + 3 * kBoxBytes, &map_w1, job.w_box * 32 + 32, 0, full + 8);
+              if (half < job.chunk) {
+                mbar_expect_tx(full, 2 * kBoxBytes);
+                tma_load_2d(dst + half * kBoxBytes, &map_obs, (job.a_box + half) * 32, tile * 128, full);
+                tma_load_2d(dst + (2 + half) * kBoxBytes, &map_w1, (job.w_box + half) * 32, 0, full);
               } else {
-                mbar_arrive(full + 8);    // keep both halves' phases in step
+                mbar_arrive(full);        // nothing to load: keep both halves' phases in step
               }
             } else {                      // stage: [Wfc chunk c][Wfc chunk c + 1], 256 rows x 128 B each
-              mbar_expect_tx(full, 2 * kBoxBytes);
-              tma_load_2d(dst, &map_wfc, job.slot * kHidden + job.chunk * 32, 0, full);
-              if (job.s_hi > 1) {
-                mbar_expect_tx(full + 8, 2 * kBoxBytes);
-                tma_load_2d(dst + 2 * kBoxBytes, &map_wfc, job.slot * kHidden + job.chunk * 32 + 32, 0, full + 8);
+              if (half < job.s_hi) {
+                mbar_expect_tx(full, 2 * kBoxBytes);
+                tma_load_2d(dst + half * 2 * kBoxBytes, &map_wfc, job.slot * kHidden + (job.chunk + half) * 32, 0, full);
               } else {
-                mbar_arrive(full + 8);
+                mbar_arrive(full);
               }
             }
           }
           __syncwarp();
-          if (A.timeline && blockIdx.x == 0 && it < 128 && lane == 0) A.timeline[it] = clock64();
+          if (A.timeline && blockIdx.x == 0 && it < 128 && lane == 0 && half == 0) A.timeline[it] = clock64();
         }
       }
     }
@@ -430,8 +427,8 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
         __syncwarp();
       }
     }
-  } else {
-    // ===== epilogue warps (4..11): two warps per TMEM lane quarter, `half` selects the columns =====
+  } else if (warp >= kTcEpiWarp0) {
+    // ===== epilogue warps (8..15): two warps per TMEM lane quarter, `half` selects the columns =====
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - kTcEpiWarp0) >> 2;
     const int r = q * 32 + lane;            // row (environment) inside the tile
