@@ -248,6 +248,15 @@ int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int
                                      float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
                                      int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
                                      void *stream);
+/* How a 128-environment tile is mapped to SMs by the tensor-core forward: 1 = one CTA per tile (persistent
+ * over tiles), 4 = a 4-CTA thread-block cluster per tile, each CTA running layer 1 for a subset of the
+ * FeatureNet branches and the matching K-slice of actor.fc | critic.fc, partial sums reduce-scattered over
+ * distributed shared memory (for batches whose tiles cannot fill the SMs), 0 = chosen from the batch size
+ * (default).  In split mode hid_dbg_dev receives the hidden activations WITHOUT the `+ qoe_features`
+ * residual (models/mansy.py:65,79), which that kernel applies through the output heads; in the timeline
+ * [480..486] are the phase stamps (partial done, cluster sync 1, partials pushed, sync 2, heads issued,
+ * sync 3, rows written) of the CTA selected with the environment variable MANSY_TC_TIMELINE_CTA. */
+int mansy_policy_tc_set_split(mansy_policy_t p, int32_t split);
 
 /*
  * Rollout loop on the device: what tianshou's Collector.collect(n_step) does around policy(batch) and
@@ -270,6 +279,7 @@ typedef struct {
 } mansy_rollout_t;
 #define MANSY_ROLLOUT_FP32_POLICY 1 /* use the exact-fp32 CUDA-core policy kernels instead of tcgen05 */
 #define MANSY_ROLLOUT_TIME_KERNELS 2 /* record CUDA events around every policy / step launch */
+#define MANSY_ROLLOUT_NO_PDL 4       /* launch without programmatic dependent launch (kernels strictly one after another) */
 int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout_t *buffers, int32_t n_steps, int64_t t0,
                          uint64_t seed, int32_t flags, void *stream);
 /*

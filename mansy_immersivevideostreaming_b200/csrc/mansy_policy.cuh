@@ -88,4 +88,9 @@ namespace mansy {
 // (the fp32 path keeps working when this fails; mansy_policy_forward_tc then reports the reason).
 int tc_create(mansy_policy *p, const mansy_policy_weights_t *w);
 void tc_destroy(mansy_policy *p);
+// Tensor-core forward launch shared by the C entry points and the rollout loops (mansy_policy_tc.cu).
+int policy_forward_tc_launch(mansy_policy *p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
+                             float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
+                             int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
+                             int32_t timeline_cta, bool pdl, void *stream);
 }  // namespace mansy

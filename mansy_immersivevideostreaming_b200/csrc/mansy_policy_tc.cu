@@ -66,12 +66,25 @@ struct TcJob {
   uint8_t chunk;    // L1: number of boxes (1 or 2)   L2: first of two 32-float chunks of the branch's 128 features (0, 2)
 };
 
+// Split-K plan of the 4-CTA cluster kernel: CTA `rank` of a cluster owns a subset of the branches (layer 1 of
+// the branch and the rows of actor.fc / critic.fc that multiply its 128 features).
+constexpr int kTcRanks = 4;
+constexpr int kTcRankJobs = 32;
+struct TcRankPlan {
+  TcJob jobs[kTcRankJobs];     // job.slot = LOCAL branch index (D1 buffer = slot & 1)
+  int32_t n_jobs, n_branches;
+  int32_t resid_local;         // local index of the residual branch (always the last one) or -1
+  int32_t pad;
+  uint8_t branch[16];          // local index -> processing-order index (bias1 row, Wfc column block)
+};
+
 struct TcConst {
   float bias2[2 * kHidden];    // actor.fc bias | critic.fc bias
   float bias1[kMaxBranches][kHidden];   // processing order
   float bout[16];
   TcJob jobs[kTcMaxJobs];
   int32_t n_jobs, n_branches, residual_slot, softmax;
+  TcRankPlan rank[kTcRanks];
 };
 
 __constant__ TcConst c_tc[kTcSlots];
@@ -87,14 +100,16 @@ struct TcArgs {
   uint64_t seed;
   int64_t step;
   int32_t env_offset;
-  long long *timeline;  // debug: CTA 0 clock64 stamps [4][128] (producer issue, data arrival, mma committed, epilogue) or NULL
+  long long *timeline;  // debug: clock64 stamps [4][128] (producer issue, data arrival, mma committed, epilogue) of one CTA or NULL
+  int32_t timeline_cta; // blockIdx.x of the CTA that writes the timeline
 };
 
 struct TcState {
   int slot = -1;
-  CUtensorMap map_w1, map_wfc, map_wout;
+  CUtensorMap map_w1, map_wfc, map_wout, map_wres;
   int obs_floats = 0;          // 784 / 400
   int n_branches = 0;
+  int split = 0;               // 0 = by batch size, 1 = one CTA per 128-env tile, 4 = split-K cluster of 4 CTAs per tile
 };
 
 // ------------------------------------------------------------------------------------------
@@ -147,6 +162,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Programmatic dependent launch (no-ops when the kernel was launched without the attribute)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate, issued by one thread.
@@ -302,6 +320,7 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
 
   const int n_jobs = K.n_jobs;
   if (A.timeline && blockIdx.x == 0 && threadIdx.x == 0) A.timeline[511] = clock64();
+  griddep_launch();
 
   if (warp < kTcProducers) {
     // ===== TMA producers: job `it` uses stage it % kTcStages; producers 2s and 2s+1 fill its two halves =====
@@ -312,6 +331,7 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
         for (int b = 0; b < 8; ++b) tma_load_2d(wout_s + b * 2048, &map_wout, b * 32, 0, bar_wout);
       }
       __syncwarp();
+      griddep_wait();                                  // observation rows come from the previous kernel in the stream
       uint32_t it = 0, s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
         for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
@@ -435,6 +455,7 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int nb = K.n_branches;
     uint32_t d1_use[2] = {0, 0}, tile_i = 0;
+    griddep_wait();
     for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_i) {
       const int env = tile * 128 + r;
       const bool live = env < A.n;
@@ -537,6 +558,401 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
       if (A.timeline && blockIdx.x == 0 && threadIdx.x == 32 * kTcEpiWarp0 && tile_i == 0) A.timeline[384 + 2 * nb + 1] = clock64();
     }
   }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kTcMmaWarp) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// split-K cluster kernel (small batches)
+// ------------------------------------------------------------------------------------------
+// With 4 096 environments there are only 32 tiles of 128 rows, and what bounds a tile is the operand
+// stream into ONE SM (2.4 MB of weights + rows at ~50-60 B/clk) -- 32 of 148 SMs busy for ~30 us.  Here a
+// cluster of 4 CTAs shares a tile: CTA `rank` runs layer 1 for its own branches and multiplies their
+// features with the matching rows of actor.fc | critic.fc, so each CTA streams a quarter of the operands and
+// holds a PARTIAL D2[128 x 256] in tensor memory.  The partials are reduce-scattered over distributed shared
+// memory (rank d owns hidden columns 64d .. 64d+63: st.shared::cluster into d's idle TMA stages), the owner
+// adds bias + LeakyReLU, stores its 64 hidden columns back to TMEM and runs ITS K-slice of the heads
+// (D3[128 x 16] partial); the residual `+ qoe_features` (mansy.py:65,79) is linear after the activation, so
+// the rank that owns the qoe branch adds feat_qoe * [actor.out ; critic.out]^T to its D3 partial instead of
+// shipping the feature tile around.  The four D3 partials are summed on rank 0, which applies the head bias,
+// softmax and the categorical sample.  Three barrier.cluster phases: stages idle -> partials delivered ->
+// head partials delivered.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t caddr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+constexpr uint32_t kRecvD2Bytes = 4 * 32768;   // [src rank 4][column half 2][float4 column 8][row 128] x 16 B (stage memory)
+constexpr uint32_t kRecvD3Off = kRecvD2Bytes;  // [src rank 4][float4 column 4][row 128] x 16 B (rank 0 only)
+
+template <int SLOT>
+__global__ void __cluster_dims__(kTcRanks, 1, 1) __launch_bounds__(kTcThreads, 1)
+policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_constant__ CUtensorMap map_w1,
+                  const __grid_constant__ CUtensorMap map_wfc, const __grid_constant__ CUtensorMap map_wout,
+                  const __grid_constant__ CUtensorMap map_wres, const TcArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const TcConst &K = c_tc[SLOT];
+  const uint32_t rank = cluster_ctarank();
+  const TcRankPlan &P = K.rank[rank];
+  const int tile = blockIdx.x / kTcRanks;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stage0 = base;
+  const uint32_t wout_s = base + kTcStages * kStageBytes;   // this rank's K-slice of the head matrix: 2 boxes [16 x 32 floats]
+  const uint32_t wres_s = wout_s + 4096;                    // [actor.out ; critic.out] for the residual: 4 boxes
+  const uint32_t bars = wout_s + kWoutBytes;
+  const uint32_t bar_full = bars;                    // [kTcStages][2] TMA -> MMA
+  const uint32_t bar_empty = bars + 64;              // [kTcStages]    MMA (commit) -> TMA
+  const uint32_t bar_d1_full = bars + 128;           // [2]           MMA (commit) -> epilogue
+  const uint32_t bar_feat_full = bars + 144;         // [2]           epilogue (256 arrivals) -> MMA
+  const uint32_t bar_d2_full = bars + 160;           //               MMA (commit) -> epilogue: partial D2 complete
+  const uint32_t bar_hid_full = bars + 176;          //               epilogue (256 arrivals) -> MMA: hidden slice stored
+  const uint32_t bar_d3_full = bars + 184;           //               MMA (commit) -> epilogue: head partial ready
+  const uint32_t bar_wout = bars + 192;              //               TMA -> MMA: head matrices resident
+  const uint32_t tmem_slot = bars + 200;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tl = A.timeline != nullptr && (int)blockIdx.x == A.timeline_cta;
+  const int n_jobs = P.n_jobs, nloc = P.n_branches, resid = P.resid_local;
+  // D3 (head partial, 16 columns) lives in the D1 buffer the residual features do NOT occupy
+  const uint32_t d3_col = resid >= 0 ? (uint32_t)((resid & 1) ^ 1) * 128u : 0u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(bar_full + 16 * s, 1);
+      mbar_init(bar_full + 16 * s + 8, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_d1_full + 8 * b, 1);
+      mbar_init(bar_feat_full + 8 * b, 256);
+    }
+    mbar_init(bar_d2_full, 1);
+    mbar_init(bar_hid_full, 256);
+    mbar_init(bar_d3_full, 1);
+    mbar_init(bar_wout, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_obs) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wfc) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wout) : "memory");
+  }
+  if (warp == kTcMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (tl && threadIdx.x == 0) A.timeline[511] = clock64();
+  griddep_launch();                // the simulator step after us may be scheduled (it waits for our completion itself)
+
+  // epilogue-warp coordinates (used in several phases below)
+  const int q = warp & 3;
+  const int half = (warp - kTcEpiWarp0) >> 2;
+  const int r = q * 32 + lane;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  const int env = tile * 128 + r;
+  const bool live = env < A.n;
+  float own[32];      // this rank's own partial of the 32 hidden columns the thread finishes
+
+  // ================= phase A: the rank's branches -> partial D2 =================
+  if (warp < kTcProducers) {
+    const int hf = warp & 1;
+    if (warp == 0 && elect_one()) {          // weights do not depend on the previous kernel in the stream
+      mbar_expect_tx(bar_wout, 4096u + (resid >= 0 ? 8192u : 0u));
+      for (int b = 0; b < 2; ++b) tma_load_2d(wout_s + b * 2048, &map_wout, (int)(2 * rank + b) * 32, 0, bar_wout);
+      if (resid >= 0)
+        for (int b = 0; b < 4; ++b) tma_load_2d(wres_s + b * 2048, &map_wres, b * 32, 0, bar_wout);
+    }
+    __syncwarp();
+    griddep_wait();                          // observation rows are written by the simulator step before us
+    uint32_t it = 0, s = 0, ph = 0;
+    for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+      if ((int)s != (warp >> 1)) continue;
+      const TcJob job = P.jobs[j];
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+      const uint32_t dst = stage0 + s * kStageBytes, full = bar_full + 16 * s + 8 * hf;
+      if (elect_one()) {
+        if (job.type == kJobL1) {
+          if (hf < job.chunk) {
+            mbar_expect_tx(full, 2 * kBoxBytes);
+            tma_load_2d(dst + hf * kBoxBytes, &map_obs, (job.a_box + hf) * 32, tile * 128, full);
+            tma_load_2d(dst + (2 + hf) * kBoxBytes, &map_w1, (job.w_box + hf) * 32, 0, full);
+          } else {
+            mbar_arrive(full);
+          }
+        } else {
+          if (hf < job.s_hi) {
+            mbar_expect_tx(full, 2 * kBoxBytes);
+            tma_load_2d(dst + hf * 2 * kBoxBytes, &map_wfc, (int)P.branch[job.slot] * kHidden + (job.chunk + hf) * 32, 0, full);
+          } else {
+            mbar_arrive(full);
+          }
+        }
+      }
+      __syncwarp();
+      if (tl && it < 128 && lane == 0 && hf == 0) A.timeline[it] = clock64();
+    }
+  } else if (warp == kTcMmaWarp) {
+    constexpr uint32_t kIdesc128 = idesc_tf32(128), kIdesc256 = idesc_tf32(256), kIdesc16 = idesc_tf32(16);
+    uint32_t it = 0, feat_use[2] = {0, 0}, s = 0, ph = 0;
+    TcJob job = P.jobs[0];
+    for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+      const TcJob next_job = P.jobs[j + 1 < n_jobs ? j + 1 : 0];
+      const uint32_t buf = job.slot & 1u;
+      const uint32_t st_addr = stage0 + s * kStageBytes;
+      if (job.type == kJobL1) {
+        const uint32_t d1 = tmem_base + buf * 128u;
+        const uint32_t a_lo = smem_desc_lo(st_addr), b_lo = smem_desc_lo(st_addr + 2 * kBoxBytes);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar_full + 16 * s + 8 * h, ph);
+          tc_fence_after();
+          if (h == 0 && tl && it < 128 && lane == 0) A.timeline[128 + it] = clock64();
+          if (elect_one()) {
+#pragma unroll
+            for (int st = 4 * h; st < 4 * h + 4; ++st)
+              if (st >= job.s_lo && st < job.s_hi)
+                umma_tf32(d1, make_desc(a_lo + h * (kBoxBytes >> 4) + 2 * (st & 3)),
+                          make_desc(b_lo + h * (kBoxBytes >> 4) + 2 * (st & 3)), kIdesc128,
+                          ((job.flags & kFlagFirst) && st == job.s_lo) ? 0u : 1u);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          umma_commit(bar_empty + 8 * s);
+          if (job.flags & kFlagLast) umma_commit(bar_d1_full + 8 * buf);
+        }
+        __syncwarp();
+      } else {
+        if (job.chunk == 0) {
+          mbar_wait(bar_feat_full + 8 * buf, feat_use[buf] & 1u);
+          ++feat_use[buf];
+        }
+        const uint32_t d2 = tmem_base + 256u;
+        const uint32_t fa = tmem_base + buf * 128u + job.chunk * 32u;
+        const uint32_t b_lo = smem_desc_lo(st_addr);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar_full + 16 * s + 8 * h, ph);
+          tc_fence_after();
+          if (h == 0 && tl && it < 128 && lane == 0) A.timeline[128 + it] = clock64();
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 4 * h; ks < 4 * h + 4; ++ks)
+              if (h < job.s_hi)
+                umma_tf32_ts(d2, fa + ks * 8, make_desc(b_lo + h * (2 * kBoxBytes >> 4) + 2 * (ks & 3)), kIdesc256,
+                             ((job.flags & kFlagTileFirstL2) && ks == 0) ? 0u : 1u);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          umma_commit(bar_empty + 8 * s);
+          if (job.flags & kFlagTileLastL2) umma_commit(bar_d2_full);
+        }
+        __syncwarp();
+      }
+      if (tl && it < 128 && lane == 0) A.timeline[256 + it] = clock64();
+      job = next_job;
+    }
+    if (resid >= 0) {
+      // residual through the heads: D3 = feat_qoe[128 x 128] * [actor.out ; critic.out]^T.  The qoe features sit in
+      // D1[resid & 1] (their layer-2 MMAs above waited for them); the head MMAs of phase C accumulate on top.
+      mbar_wait(bar_wout, 0);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t w_lo = smem_desc_lo(wres_s);
+        const uint32_t fa = tmem_base + (uint32_t)(resid & 1) * 128u;
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks)
+          umma_tf32_ts(tmem_base + d3_col, fa + ks * 8, make_desc(w_lo + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2), kIdesc16,
+                       ks > 0 ? 1u : 0u);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= kTcEpiWarp0) {
+    uint32_t d1_use[2] = {0, 0};
+    for (int i = 0; i < nloc; ++i) {
+      const uint32_t buf = i & 1u;
+      const int bi = P.branch[i];
+      mbar_wait(bar_d1_full + 8 * buf, d1_use[buf] & 1u);
+      ++d1_use[buf];
+      tc_fence_after();
+      if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[384 + 2 * i] = clock64();
+#pragma unroll 1
+      for (int c = 2 * half; c < 2 * half + 2; ++c) {
+        float v[32];
+        const uint32_t ta = tmem_base + lane_addr + buf * 128u + c * 32u;
+        tmem_ld32(ta, v);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) v[jj] = leaky(v[jj] + K.bias1[bi][c * 32 + jj]);
+        tmem_st32(ta, v);
+        if (A.feat_dbg && live) {
+          float *dst = A.feat_dbg + (size_t)env * (K.n_branches * kHidden) + bi * kHidden + c * 32;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) dst[jj] = v[jj];
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_feat_full + 8 * buf);
+      if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[384 + 2 * i + 1] = clock64();
+    }
+    mbar_wait(bar_d2_full, 0);     // every MMA of this CTA has completed: partial D2 final, TMA stages idle
+    tc_fence_after();
+  }
+  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[480] = clock64();
+  cluster_sync_all();              // (1) all four CTAs' stage memory is idle
+  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[481] = clock64();
+
+  // ================= phase B: reduce-scatter the partials over DSMEM =================
+  if (warp >= kTcEpiWarp0) {
+#pragma unroll 1
+    for (uint32_t d = 0; d < (uint32_t)kTcRanks; ++d) {
+      float v[32];
+      tmem_ld32(tmem_base + lane_addr + 256u + d * 64u + (uint32_t)half * 32u, v);
+      if (d == rank) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) own[jj] = v[jj];
+      } else {
+        const uint32_t dst = map_to_rank(stage0 + ((rank * 2u + (uint32_t)half) * 8u) * 2048u + (uint32_t)r * 16u, d);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) st_cluster_v4(dst + c4 * 2048, v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+      }
+    }
+  }
+  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[482] = clock64();
+  cluster_sync_all();              // (2) partials delivered
+  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[483] = clock64();
+
+  // ================= phase C: hidden slice, this rank's K-slice of the heads =================
+  if (warp >= kTcEpiWarp0) {
+#pragma unroll 1
+    for (uint32_t sr = 0; sr < (uint32_t)kTcRanks; ++sr) {
+      if (sr == rank) continue;
+      const uint32_t src = stage0 + ((sr * 2u + (uint32_t)half) * 8u) * 2048u + (uint32_t)r * 16u;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 t = ld_shared_v4(src + c4 * 2048);
+        own[4 * c4] += t.x; own[4 * c4 + 1] += t.y; own[4 * c4 + 2] += t.z; own[4 * c4 + 3] += t.w;
+      }
+    }
+    const int col0 = (int)rank * 64 + half * 32;      // hidden column (0..127 actor.fc, 128..255 critic.fc)
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) own[jj] = leaky(own[jj] + K.bias2[col0 + jj]);
+    tmem_st32(tmem_base + lane_addr + 256u + (uint32_t)col0, own);
+    if (A.hid_dbg && live) {      // NOTE: without the residual (it enters through the heads in this kernel)
+      float *dst = A.hid_dbg + (size_t)env * 256 + col0;
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) dst[jj] = own[jj];
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(bar_hid_full);
+    if (half == 0) {
+      mbar_wait(bar_d3_full, 0);
+      tc_fence_after();
+      float acc[16];
+      tmem_ld16(tmem_base + lane_addr + d3_col, acc);
+      if (rank != 0) {
+        const uint32_t dst = map_to_rank(stage0 + kRecvD3Off + (rank * 4u) * 2048u + (uint32_t)r * 16u, 0);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) st_cluster_v4(dst + c4 * 2048, acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+      } else {
+#pragma unroll
+        for (int o = 0; o < 16; ++o) own[o] = acc[o];
+      }
+    }
+  } else if (warp == kTcMmaWarp) {
+    constexpr uint32_t kIdesc16 = idesc_tf32(16);
+    if (resid < 0) mbar_wait(bar_wout, 0);
+    mbar_wait(bar_hid_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t w_lo = smem_desc_lo(wout_s);
+      const uint32_t ha = tmem_base + 256u + rank * 64u;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        umma_tf32_ts(tmem_base + d3_col, ha + ks * 8, make_desc(w_lo + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2), kIdesc16,
+                     (ks > 0 || resid >= 0) ? 1u : 0u);
+      umma_commit(bar_d3_full);
+    }
+    __syncwarp();
+  }
+  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[484] = clock64();
+  cluster_sync_all();              // (3) head partials delivered to rank 0
+  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[485] = clock64();
+
+  // ================= phase D: rank 0 finishes the rows =================
+  if (rank == 0 && warp >= kTcEpiWarp0 && half == 0) {
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = own[o] + K.bout[o];
+#pragma unroll 1
+    for (uint32_t sr = 1; sr < (uint32_t)kTcRanks; ++sr) {
+      const uint32_t src = stage0 + kRecvD3Off + (sr * 4u) * 2048u + (uint32_t)r * 16u;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 t = ld_shared_v4(src + c4 * 2048);
+        acc[4 * c4] += t.x; acc[4 * c4 + 1] += t.y; acc[4 * c4 + 2] += t.z; acc[4 * c4 + 3] += t.w;
+      }
+    }
+    if (live) {
+      griddep_wait();
+      float p[kActions];
+#pragma unroll
+      for (int o = 0; o < kActions; ++o) p[o] = acc[o];
+      if (K.softmax) {
+        float m = p[0];
+#pragma unroll
+        for (int o = 1; o < kActions; ++o) m = fmaxf(m, p[o]);
+        float s = 0.f;
+#pragma unroll
+        for (int o = 0; o < kActions; ++o) { p[o] = expf(p[o] - m); s += p[o]; }
+#pragma unroll
+        for (int o = 0; o < kActions; ++o) p[o] = p[o] / s;
+      }
+      if (A.value) A.value[env] = acc[15];
+      if (A.logits) {
+        float4 *dst = reinterpret_cast<float4 *>(A.logits + (size_t)env * 16);
+        dst[0] = make_float4(p[0], p[1], p[2], p[3]);
+        dst[1] = make_float4(p[4], p[5], p[6], p[7]);
+        dst[2] = make_float4(p[8], p[9], p[10], p[11]);
+        dst[3] = make_float4(p[12], p[13], p[14], 0.f);
+      }
+      if (A.actions) {
+        int act;
+        float lp;
+        categorical_sample(p, K.softmax, A.seed, (uint64_t)(A.env_offset + env), (uint64_t)A.step, act, lp);
+        A.actions[env] = act;
+        if (A.logp) A.logp[env] = lp;
+      }
+    }
+  }
+  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[486] = clock64();
 
   tc_fence_before();
   __syncthreads();
@@ -655,6 +1071,11 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
     hc->bias2[j] = w->actor_fc_b[j];
     hc->bias2[kHidden + j] = w->critic_fc_b[j];
   }
+  std::vector<float> wresimg((size_t)16 * kHidden, 0.f);   // residual through the heads: rows 0..14 actor.out, row 15 critic.out
+  for (int j = 0; j < kHidden; ++j) {
+    for (int o = 0; o < kActions; ++o) wresimg[(size_t)o * kHidden + j] = w->actor_out_w[(size_t)o * kHidden + j];
+    wresimg[(size_t)15 * kHidden + j] = w->critic_out_w[j];
+  }
   for (int o = 0; o < kActions; ++o) hc->bout[o] = w->actor_out_b[o];
   hc->bout[15] = w->critic_out_b[0];
   hc->n_branches = nb;
@@ -692,24 +1113,78 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
   push_l2(nb - 1);
   hc->n_jobs = nj;
 
+  // split-K plan: longest-processing-time assignment of the branches to the 4 cluster ranks by operand bytes
+  // (layer-1 boxes of observation rows + W1, 128 KB of Wfc rows); the plan is already sorted by size and the
+  // residual branch comes last, so it ends up last on its rank (its features must stay in tensor memory).
+  {
+    int load[kTcRanks] = {0, 0, 0, 0};
+    for (int r = 0; r < kTcRanks; ++r) { hc->rank[r].n_branches = 0; hc->rank[r].resid_local = -1; }
+    for (int i = 0; i < nb; ++i) {
+      const BranchPlan &b = plan[i];
+      const int lo = b.off / 8, hi = (b.off + b.k + 7) / 8;
+      const int boxes = (hi - 1) / 4 - lo / 4 + 1;
+      int best = 0;
+      for (int r = 1; r < kTcRanks; ++r) if (load[r] < load[best]) best = r;
+      load[best] += boxes * 32 + 128;
+      TcRankPlan &rp = hc->rank[best];
+      if (i == hc->residual_slot) rp.resid_local = rp.n_branches;
+      rp.branch[rp.n_branches++] = (uint8_t)i;
+    }
+    for (int r = 0; r < kTcRanks; ++r) {
+      TcRankPlan &rp = hc->rank[r];
+      const int nl = rp.n_branches;
+      int cnt = 0;             // push_l1 / push_l2 append to hc->jobs: use its tail as scratch and copy out
+      auto emit_l1 = [&](int li) {
+        const int before = nj;
+        push_l1(rp.branch[li]);
+        for (int j = before; j < nj; ++j) { rp.jobs[cnt] = hc->jobs[j]; rp.jobs[cnt].slot = (uint8_t)li; ++cnt; }
+        nj = before;
+      };
+      auto emit_l2 = [&](int li) {
+        const int before = nj;
+        push_l2(rp.branch[li]);
+        for (int j = before; j < nj; ++j) {
+          TcJob t = hc->jobs[j];
+          t.slot = (uint8_t)li;
+          t.flags = (uint8_t)(t.flags & ~(kFlagTileFirstL2 | kFlagTileLastL2));
+          if (li == 0 && t.chunk == 0) t.flags |= kFlagTileFirstL2;
+          if (li == nl - 1 && (t.flags & kFlagLast)) t.flags |= kFlagTileLastL2;
+          rp.jobs[cnt++] = t;
+        }
+        nj = before;
+      };
+      if (nl > 0) {
+        emit_l1(0);
+        for (int li = 1; li < nl; ++li) { emit_l1(li); emit_l2(li - 1); }
+        emit_l2(nl - 1);
+      }
+      rp.n_jobs = cnt;
+    }
+    memset(&hc->jobs[nj], 0, sizeof(TcJob) * (kTcMaxJobs - nj));     // scratch entries used above
+  }
+
   int rc = MANSY_OK;
-  float *d_w1 = nullptr, *d_wfc = nullptr, *d_wout = nullptr;
+  float *d_w1 = nullptr, *d_wfc = nullptr, *d_wout = nullptr, *d_wres = nullptr;
   if (cudaMalloc(&d_w1, w1img.size() * sizeof(float)) != cudaSuccess ||
       cudaMalloc(&d_wfc, wfcimg.size() * sizeof(float)) != cudaSuccess ||
-      cudaMalloc(&d_wout, woutimg.size() * sizeof(float)) != cudaSuccess)
+      cudaMalloc(&d_wout, woutimg.size() * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&d_wres, wresimg.size() * sizeof(float)) != cudaSuccess)
     rc = set_error(MANSY_E_NOMEM, "cudaMalloc failed (tensor-core weight images)");
   if (d_w1) p->allocs.push_back(d_w1);
   if (d_wfc) p->allocs.push_back(d_wfc);
   if (d_wout) p->allocs.push_back(d_wout);
+  if (d_wres) p->allocs.push_back(d_wres);
   if (!rc && (cudaMemcpy(d_w1, w1img.data(), w1img.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
               cudaMemcpy(d_wfc, wfcimg.data(), wfcimg.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
               cudaMemcpy(d_wout, woutimg.data(), woutimg.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+              cudaMemcpy(d_wres, wresimg.data(), wresimg.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
               cudaMemcpyToSymbol(c_tc, hc, sizeof(TcConst), (size_t)st->slot * sizeof(TcConst)) != cudaSuccess))
     rc = set_error(MANSY_E_CUDA, "upload of the tensor-core weight images failed");
   delete hc;
   if (!rc) rc = make_map(&st->map_w1, d_w1, (uint64_t)w1_cols, kHidden, (uint64_t)w1_cols, 128);
   if (!rc) rc = make_map(&st->map_wfc, d_wfc, (uint64_t)F, 256, (uint64_t)F, 256);
   if (!rc) rc = make_map(&st->map_wout, d_wout, 256, 16, 256, 16);
+  if (!rc) rc = make_map(&st->map_wres, d_wres, kHidden, 16, kHidden, 16);
   if (rc) {
     std::lock_guard<std::mutex> g(g_slot_mutex);
     g_slot_used[st->slot] = false;
@@ -734,19 +1209,15 @@ void tc_destroy(mansy_policy *p) {
 
 using namespace mansy;
 
-extern "C" {
+namespace mansy {
 
-int mansy_policy_forward_tc(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
-                            float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
-                            int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, void *stream) {
-  return mansy_policy_forward_tc_timeline(p, obs_dev, obs_stride, n, logits_dev, value_dev, actions_dev, logp_dev, seed, step,
-                                          env_offset, feat_dbg_dev, hid_dbg_dev, nullptr, stream);
-}
-
-int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
-                                     float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
-                                     int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
-                                     void *stream) {
+// Launches the tensor-core forward (one CTA per tile, or the split-K cluster kernel for small batches).  `pdl`
+// adds the programmatic-dependent-launch attribute: the kernel may be scheduled while the previous kernel of
+// the stream is still running and orders itself with griddepcontrol.wait before it touches observation rows.
+int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
+                             float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
+                             int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
+                             int32_t timeline_cta, bool pdl, void *stream) {
   if (!p || !obs_dev) return set_error(MANSY_E_INVALID, "NULL argument");
   if (!p->tc) return set_error(MANSY_E_STATE, std::string("tensor-core state unavailable: ") + mansy_last_error());
   if (n < 0) return set_error(MANSY_E_INVALID, "n < 0");
@@ -765,24 +1236,47 @@ int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int
   a.feat_dbg = feat_dbg_dev; a.hid_dbg = hid_dbg_dev;
   a.seed = seed; a.step = step; a.env_offset = env_offset;
   a.timeline = reinterpret_cast<long long *>(timeline_dev);
+  a.timeline_cta = timeline_cta;
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm < 1) n_sm = 148;
   }
-  const int grid = a.n_tiles < n_sm ? a.n_tiles : n_sm;
+  // split-K clusters pay off while the tiles alone cannot fill the SMs (a cluster finishes a tile ~3-4x sooner
+  // but occupies four SMs); beyond ~3/4 of the SM count the persistent one-CTA-per-tile kernel is as fast.
+  const bool split4 = p->tc->split == 4 || (p->tc->split == 0 && 4 * a.n_tiles <= 3 * n_sm);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = kTcSmemBytes;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
 #define MANSY_TC_LAUNCH(SLOT)                                                                                       \
   do {                                                                                                              \
     static bool attr_done = false;                                                                                  \
     if (!attr_done) {                                                                                               \
       e = cudaFuncSetAttribute(policy_tc_kernel<SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes); \
+      if (e == cudaSuccess)                                                                                         \
+        e = cudaFuncSetAttribute(policy_tc4_kernel<SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes); \
       attr_done = (e == cudaSuccess);                                                                               \
     }                                                                                                               \
-    if (e == cudaSuccess)                                                                                           \
-      policy_tc_kernel<SLOT><<<grid, kTcThreads, kTcSmemBytes, s>>>(map_obs, p->tc->map_w1, p->tc->map_wfc, p->tc->map_wout, a);      \
+    if (e == cudaSuccess) {                                                                                         \
+      if (split4) {                                                                                                 \
+        cfg.gridDim = dim3((unsigned)(kTcRanks * a.n_tiles), 1, 1);                                                 \
+        e = cudaLaunchKernelEx(&cfg, policy_tc4_kernel<SLOT>, map_obs, p->tc->map_w1, p->tc->map_wfc, p->tc->map_wout, \
+                               p->tc->map_wres, a);                                                                 \
+      } else {                                                                                                      \
+        cfg.gridDim = dim3((unsigned)(a.n_tiles < n_sm ? a.n_tiles : n_sm), 1, 1);                                  \
+        e = cudaLaunchKernelEx(&cfg, policy_tc_kernel<SLOT>, map_obs, p->tc->map_w1, p->tc->map_wfc, p->tc->map_wout, a); \
+      }                                                                                                             \
+    }                                                                                                               \
   } while (0)
   switch (p->tc->slot) {
     case 0: MANSY_TC_LAUNCH(0); break;
@@ -790,10 +1284,38 @@ int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int
     default: MANSY_TC_LAUNCH(2); break;
   }
 #undef MANSY_TC_LAUNCH
-  if (e != cudaSuccess) return set_error(MANSY_E_CUDA, std::string("policy_tc_kernel attribute: ") + cudaGetErrorString(e));
+  if (e != cudaSuccess) return set_error(MANSY_E_CUDA, std::string("policy_tc_kernel launch: ") + cudaGetErrorString(e));
   count_launch();
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MANSY_E_CUDA, std::string("policy_tc_kernel launch: ") + cudaGetErrorString(e));
+  return MANSY_OK;
+}
+
+}  // namespace mansy
+
+extern "C" {
+
+int mansy_policy_forward_tc(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
+                            float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
+                            int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, void *stream) {
+  return policy_forward_tc_launch(p, obs_dev, obs_stride, n, logits_dev, value_dev, actions_dev, logp_dev, seed, step,
+                                  env_offset, feat_dbg_dev, hid_dbg_dev, nullptr, 0, false, stream);
+}
+
+int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
+                                     float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
+                                     int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
+                                     void *stream) {
+  const char *cta = getenv("MANSY_TC_TIMELINE_CTA");
+  return policy_forward_tc_launch(p, obs_dev, obs_stride, n, logits_dev, value_dev, actions_dev, logp_dev, seed, step,
+                                  env_offset, feat_dbg_dev, hid_dbg_dev, timeline_dev, cta ? atoi(cta) : 0, false, stream);
+}
+
+int mansy_policy_tc_set_split(mansy_policy_t p, int32_t split) {
+  if (!p) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (!p->tc) return set_error(MANSY_E_STATE, "tensor-core state unavailable");
+  if (split != 0 && split != 1 && split != 4) return set_error(MANSY_E_INVALID, "split must be 0 (auto), 1 or 4");
+  p->tc->split = split;
   return MANSY_OK;
 }
 

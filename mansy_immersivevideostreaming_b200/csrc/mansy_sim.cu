@@ -345,10 +345,15 @@ __device__ __forceinline__ void finish_episode(const SimDev &S, int e, const Env
 template <int MODE>
 __global__ void __launch_bounds__(kThreadsPerBlock)
 step_kernel(const __grid_constant__ SimDev S, const __grid_constant__ StepArgs A) {
+  // Programmatic dependent launch (no-ops without the launch attribute): the next kernel of the stream may be
+  // scheduled right away -- it orders itself behind our completion -- and everything we read below (actions,
+  // state, history) may have been written by the kernels before us.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int i = blockIdx.x * kEnvsPerBlock + (threadIdx.x >> 3);   // output row
   if (i >= A.n) return;                                            // whole 8-lane group leaves together
   const int sub = threadIdx.x & 7;
   const unsigned gmask = group_mask();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int e = A.env_ids ? __ldg(A.env_ids + i) : i;
 
   EnvState st;
@@ -482,6 +487,14 @@ __global__ void allocate_versions_kernel(const uint64_t *__restrict__ masks, con
 // ------------------------------------------------------------------------------------------
 using namespace mansy;
 
+namespace mansy {
+// tensor-core policy launch (mansy_policy_tc.cu); mansy_policy_t is opaque here
+int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
+                             float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
+                             int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
+                             int32_t timeline_cta, bool pdl, void *stream);
+}  // namespace mansy
+
 struct mansy_sim {
   SimDev dev;
   int device = 0;
@@ -549,13 +562,23 @@ int check_out(const mansy_sim *h, const mansy_out_t *out) {
   return MANSY_OK;
 }
 
-int launch_step(mansy_sim *h, const StepArgs &a, cudaStream_t s) {
+int launch_step(mansy_sim *h, const StepArgs &a, cudaStream_t s, bool pdl = false) {
   const int grid = grid_for(a.n);
   if (grid == 0) return MANSY_OK;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kThreadsPerBlock, 1, 1);
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   switch (h->dev.obs_mode) {
-    case MANSY_OBS_MANSY: step_kernel<MANSY_OBS_MANSY><<<grid, kThreadsPerBlock, 0, s>>>(h->dev, a); break;
-    case MANSY_OBS_SIMPLE: step_kernel<MANSY_OBS_SIMPLE><<<grid, kThreadsPerBlock, 0, s>>>(h->dev, a); break;
-    default: step_kernel<MANSY_OBS_NONE><<<grid, kThreadsPerBlock, 0, s>>>(h->dev, a); break;
+    case MANSY_OBS_MANSY: MANSY_CUDA(cudaLaunchKernelEx(&cfg, step_kernel<MANSY_OBS_MANSY>, h->dev, a)); break;
+    case MANSY_OBS_SIMPLE: MANSY_CUDA(cudaLaunchKernelEx(&cfg, step_kernel<MANSY_OBS_SIMPLE>, h->dev, a)); break;
+    default: MANSY_CUDA(cudaLaunchKernelEx(&cfg, step_kernel<MANSY_OBS_NONE>, h->dev, a)); break;
   }
   count_launch();
   MANSY_CUDA(cudaGetLastError());
@@ -828,6 +851,9 @@ int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout
   if (h->dev.obs_mode == MANSY_OBS_NONE) return set_error(MANSY_E_INVALID, "the policy consumes observation rows");
   const size_t n = (size_t)h->dev.n_envs;
   const bool timed = (flags & MANSY_ROLLOUT_TIME_KERNELS) != 0;
+  // back-to-back launches overlap their scheduling / prologues (programmatic dependent launch) unless events
+  // are recorded between them (a timed rollout measures the kernels one by one) or the caller opts out
+  const bool pdl = !timed && !(flags & MANSY_ROLLOUT_NO_PDL) && !(flags & MANSY_ROLLOUT_FP32_POLICY);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (timed) {
     int rc = mansy_rollout_reserve_timing(h, n_steps);
@@ -846,8 +872,8 @@ int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout
       if (!rc) rc = mansy_policy_sample(b->logits, h->dev.n_envs, is_probs, seed, t, h->dev.env_offset, b->actions + cur * n,
                                         b->logp + cur * n, stream);
     } else {
-      rc = mansy_policy_forward_tc(p, obs, b->obs_stride, h->dev.n_envs, b->logits, b->value + cur * n, b->actions + cur * n,
-                                   b->logp + cur * n, seed, t, h->dev.env_offset, nullptr, nullptr, stream);
+      rc = policy_forward_tc_launch(p, obs, b->obs_stride, h->dev.n_envs, b->logits, b->value + cur * n, b->actions + cur * n,
+                                    b->logp + cur * n, seed, t, h->dev.env_offset, nullptr, nullptr, nullptr, 0, pdl, stream);
     }
     if (rc) return rc;
     if (timed) MANSY_CUDA(cudaEventRecord(h->events[3 * k + 1], s));
@@ -857,7 +883,7 @@ int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout
     a.out.obs = b->obs + nxt * n * (size_t)b->obs_stride; a.out.obs_stride = b->obs_stride;
     a.out.reward = b->reward + cur * n; a.out.done = b->done + cur * n;
     if (k == 0 && (rc = check_out(h, &a.out))) return rc;
-    if ((rc = launch_step(h, a, s))) return rc;
+    if ((rc = launch_step(h, a, s, pdl))) return rc;
     if (timed) MANSY_CUDA(cudaEventRecord(h->events[3 * k + 2], s));
   }
   return MANSY_OK;

@@ -111,6 +111,11 @@ class PolicyNet:
     # position i of ``feat_dbg`` holds branch TC_BRANCH_ORDER[kind][i] of the concat order
     TC_BRANCH_ORDER = {OBS_MODE_MANSY: (1, 2, 3, 0, 4, 5, 6, 7, 8, 9), OBS_MODE_SIMPLE: (1, 4, 0, 2, 3)}
 
+    def set_tc_split(self, split: int) -> None:
+        """0 = choose from the batch size (default), 1 = one CTA per 128-env tile, 4 = split-K cluster of 4 CTAs per
+        tile (``mansy_policy_tc_set_split``; in split mode ``hid_dbg`` excludes the residual)."""
+        check(self.lib.mansy_policy_tc_set_split(self._h, int(split)))
+
     def forward_tc(self, obs: torch.Tensor, logits: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None,
                    actions: Optional[torch.Tensor] = None, logp: Optional[torch.Tensor] = None, seed: int = 0,
                    step: int = 0, env_offset: int = 0, sample: bool = True, feat_dbg: Optional[torch.Tensor] = None,

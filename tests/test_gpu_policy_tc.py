@@ -39,9 +39,10 @@ def stages_reference(rows, actor, critic, kind):
     return [t.numpy() for t in feats], torch.cat([ha, hc], dim=1).numpy()
 
 
+@pytest.mark.parametrize("split", [1, 4])
 @pytest.mark.parametrize("kind,n", [(OBS_MODE_MANSY, 128), (OBS_MODE_MANSY, 1), (OBS_MODE_MANSY, 1000), (OBS_MODE_SIMPLE, 333),
                                     (OBS_MODE_MANSY, 4096), (OBS_MODE_MANSY, 148 * 128 * 2 + 77)])
-def test_tc_policy_vs_torch_fp32(kind, n):
+def test_tc_policy_vs_torch_fp32(kind, n, split):
     shapes = mansy_state_dict_shapes() if kind == OBS_MODE_MANSY else simple_state_dict_shapes()
     actor, critic = seeded_state_dict(shapes[0], 7), seeded_state_dict(shapes[1], 8)
     stride = 784 if kind == OBS_MODE_MANSY else 400
@@ -49,6 +50,7 @@ def test_tc_policy_vs_torch_fp32(kind, n):
     rng = np.random.default_rng(n)
     rows = rng.random((n, stride)).astype(np.float32)
     net = PolicyNet(actor, critic, kind)
+    net.set_tc_split(split)
     feat = torch.full((n, nb * 128), float("nan"), device="cuda")
     hid = torch.full((n, 256), float("nan"), device="cuda")
     logits, value, actions, logp = net.forward_tc(torch.from_numpy(rows).cuda(), seed=5, step=9, feat_dbg=feat, hid_dbg=hid)
@@ -58,6 +60,8 @@ def test_tc_policy_vs_torch_fp32(kind, n):
     for i, canon in enumerate(PolicyNet.TC_BRANCH_ORDER[kind]):
         np.testing.assert_allclose(got_feat[:, i * 128:(i + 1) * 128], ref_feats[canon], rtol=RTOL, atol=ATOL,
                                    err_msg=f"layer-1 features of branch {canon} (processing slot {i})")
+    if split == 4 and kind == OBS_MODE_MANSY:     # the cluster kernel applies the residual through the heads
+        ref_hid = ref_hid - np.concatenate([ref_feats[-1], ref_feats[-1]], axis=1)
     np.testing.assert_allclose(hid.cpu().numpy(), ref_hid, rtol=RTOL, atol=ATOL, err_msg="hidden activations")
     ref_logits, ref_value = torch_reference(rows, actor, critic, kind)
     np.testing.assert_allclose(logits.cpu().numpy()[:, :15], ref_logits, rtol=RTOL, atol=ATOL)
@@ -71,12 +75,14 @@ def test_tc_policy_vs_torch_fp32(kind, n):
     np.testing.assert_allclose(logits.cpu().numpy()[:, :15], l32.cpu().numpy()[:, :15], rtol=RTOL, atol=ATOL)
 
 
-def test_tc_policy_vs_reference_golden():
+@pytest.mark.parametrize("split", [0, 1, 4])
+def test_tc_policy_vs_reference_golden(split):
     g = load_golden("policy_kat.npz")
     actor = seeded_state_dict(_shapes(g["actor_names"], g["actor_shapes"]), 101)
     critic = seeded_state_dict([(n, s) for n, s in _shapes(g["critic_names"], g["critic_shapes"])
                                 if not n.startswith("feature_net.")], 102)
     net = PolicyNet(actor, critic, OBS_MODE_MANSY)
+    net.set_tc_split(split)
     rows = np.ascontiguousarray(g["mansy_rows"])
     logits, value, _, _ = net.forward_tc(torch.from_numpy(rows).cuda(), sample=False)
     np.testing.assert_allclose(logits.cpu().numpy()[:, :15], g["actor_logits"], rtol=RTOL, atol=ATOL)

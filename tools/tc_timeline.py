@@ -7,8 +7,10 @@ from mansy_immersivevideostreaming_b200.policy import PolicyNet, mansy_state_dic
 from mansy_immersivevideostreaming_b200._capi import check
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+split = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 shapes = mansy_state_dict_shapes()
 net = PolicyNet(seeded_state_dict(shapes[0], 1), seeded_state_dict(shapes[1], 2), OBS_MODE_MANSY)
+net.set_tc_split(split)
 obs = torch.rand((n, 784), device="cuda")
 logits = torch.empty((n, 16), device="cuda"); value = torch.empty(n, device="cuda")
 act = torch.empty(n, dtype=torch.int32, device="cuda"); logp = torch.empty(n, device="cuda")
@@ -28,6 +30,11 @@ for j in range(128):
 print("epilogue begin/end per branch:")
 for i in range(11):
     print(i, t[384+2*i]-t0, t[385+2*i]-t0)
+names = ["partial D2 done", "cluster sync 1", "partials pushed", "cluster sync 2", "heads issued/D3 pushed", "cluster sync 3", "rows written"]
+if t[480]:
+    print("split-K phases (CTA MANSY_TC_TIMELINE_CTA, cycles since kernel start):")
+    for k, nm in enumerate(names):
+        print(f"  {nm:24s} {t[480+k]-t0:7d}")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for rep in range(50):
