@@ -254,7 +254,7 @@ def run_ours(args):
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
-    roll.run(K)                                                  # C loop: 2 launches per step (programmatic dependent launch)
+    roll.run(K)                                                  # ONE launch of the fused policy+step cluster kernel (all tiles resident)
     stats = gather_episode_stats(sim)                            # the one collective of the rollout
     stop.record()
     barrier()
@@ -302,6 +302,11 @@ def run_ours(args):
         return
     hbm_gbs, tflops, peak_src = measured_peaks()
     value = n_global * K / (elapsed_ms * 1e-3)
+    fused = launches == 1
+    # fused kernel: the step's algorithmic bytes (3 513 B) + the policy's outputs (action, logp, value,
+    # logits row: 76 B); the observation rows the policy re-reads were written one phase earlier and are not counted
+    fused_bytes = n_local * (BYTES_PER_STEP_MANSY + 76)
+    fused_gbs = fused_bytes / (elapsed_ms / K * 1e-3) / 1e9
     step_gbs = n_local * BYTES_PER_STEP_MANSY / (step_ms * 1e-3) / 1e9
     pol_tflops = n_local * FLOP_PER_STEP_POLICY / (policy_ms * 1e-3) / 1e12
     tf32_peak = tflops / 2.0      # TF32 dense rate = 1/2 of bf16 (nominal 1.1 vs 2.25 PFLOP/s); bf16 figure measured
@@ -314,13 +319,24 @@ def run_ours(args):
                    "l2": f"observations stream into a {slabs}-slab rollout buffer of {slabs * slab_bytes >> 20} MiB "
                          "(> L2 126 MB): every step writes a slab last touched >2.5 L2-sizes ago",
                    "tables": "24 videos x 60 chunks, 1440 viewport pairs, 40 traces (SURVEY.md 8(d))",
-                   "timed": "K x (tcgen05 policy forward+sample launch, simulator step launch) driven from C "
-                            "(mansy_rollout_policy, programmatic dependent launch) + 1 all-gather of episode stats",
+                   "timed": ("ONE launch of the fused cluster kernel: K x (tcgen05 split-K policy forward + sample + simulator "
+                             "step per 128-env tile) (mansy_rollout_policy) + 1 all-gather of episode stats") if fused else
+                            ("K x (tcgen05 policy forward+sample launch, simulator step launch) driven from C "
+                             "(mansy_rollout_policy, programmatic dependent launch) + 1 all-gather of episode stats"),
                    "kernel_timing": "roofline launch durations: a second pass of the same K steps with CUDA events "
                                     "around every launch on the launching stream (serialised launches)"},
-        "roofline": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": step_gbs / hbm_gbs,
-                     "traffic": None, "kernel": "step_kernel<MANSY>", "bytes_per_launch": n_local * BYTES_PER_STEP_MANSY,
-                     "avg_launch_ms": step_ms, "peak_source": peak_src},
+        "roofline": ({"bound": "hbm", "achieved": fused_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": fused_gbs / hbm_gbs,
+                      "traffic": None, "kernel": "policy_tc4_kernel<fused> (policy + sample + simulator step, K steps per launch)",
+                      "bytes_per_launch": fused_bytes * K, "avg_launch_ms": elapsed_ms, "peak_source": peak_src,
+                      "note": "4096 envs move 14.7 MB per step (2.2 us of HBM time): the step is latency-bound, see "
+                              "roofline_step_kernel / simulator_sweep for the stand-alone kernel at HBM-filling sizes"}
+                     if fused else
+                     {"bound": "hbm", "achieved": step_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": step_gbs / hbm_gbs,
+                      "traffic": None, "kernel": "step_kernel<MANSY>", "bytes_per_launch": n_local * BYTES_PER_STEP_MANSY,
+                      "avg_launch_ms": step_ms, "peak_source": peak_src}),
+        "roofline_step_kernel": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": step_gbs / hbm_gbs,
+                                 "kernel": "step_kernel<MANSY> (stand-alone, second pass)",
+                                 "bytes_per_launch": n_local * BYTES_PER_STEP_MANSY, "avg_launch_ms": step_ms},
         "roofline_policy": {"bound": "tensor", "achieved": pol_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                             "frac": pol_tflops / tf32_peak, "kernel": "policy_tc4_kernel (tcgen05 kind::tf32, split-K 4-CTA clusters)" if 4 * ((n_local + 127) // 128) <= 3 * 148
                             else "policy_tc_kernel (tcgen05 kind::tf32)",

@@ -257,6 +257,10 @@ int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int
  * [480..486] are the phase stamps (partial done, cluster sync 1, partials pushed, sync 2, heads issued,
  * sync 3, rows written) of the CTA selected with the environment variable MANSY_TC_TIMELINE_CTA. */
 int mansy_policy_tc_set_split(mansy_policy_t p, int32_t split);
+/* Profiling hook of the fused rollout kernel (mansy_rollout_policy's one-launch path): CTA `cta` stamps the SM clock
+ * of its SECOND rollout step into timeline_dev (int64[512], layout as above plus [489] step begin, [487] simulator
+ * phase done, [488] cluster sync 5, [490..492] state loaded / step_env done / observation written); NULL turns it off. */
+int mansy_debug_fused_timeline(int64_t *timeline_dev, int32_t cta);
 
 /*
  * Rollout loop on the device: what tianshou's Collector.collect(n_step) does around policy(batch) and
@@ -280,6 +284,8 @@ typedef struct {
 #define MANSY_ROLLOUT_FP32_POLICY 1 /* use the exact-fp32 CUDA-core policy kernels instead of tcgen05 */
 #define MANSY_ROLLOUT_TIME_KERNELS 2 /* record CUDA events around every policy / step launch */
 #define MANSY_ROLLOUT_NO_PDL 4       /* launch without programmatic dependent launch (kernels strictly one after another) */
+#define MANSY_ROLLOUT_TWO_KERNELS 8  /* never use the fused policy+step cluster kernel (one launch for all n_steps), which
+                                        mansy_rollout_policy picks when every 128-env tile's 4-CTA cluster is resident at once */
 int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout_t *buffers, int32_t n_steps, int64_t t0,
                          uint64_t seed, int32_t flags, void *stream);
 /*

@@ -93,4 +93,7 @@ int policy_forward_tc_launch(mansy_policy *p, const float *obs_dev, int64_t obs_
                              float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
                              int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
                              int32_t timeline_cta, bool pdl, void *stream);
+// n_steps x (policy + sample + simulator step) in one launch of the cluster kernel; *launched = 0 if not applicable.
+int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t *b, int32_t n_steps, int64_t t0,
+                         uint64_t seed, void *stream, int *launched);
 }  // namespace mansy

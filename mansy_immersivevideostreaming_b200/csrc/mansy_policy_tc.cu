@@ -35,6 +35,7 @@
 #include <new>
 
 #include "mansy_policy.cuh"
+#include "mansy_step.cuh"
 
 namespace mansy {
 
@@ -384,7 +385,7 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
             for (int h = 0; h < 2; ++h) {
               mbar_wait(bar_full + 16 * s + 8 * h, ph);
               tc_fence_after();
-              if (h == 0 && A.timeline && blockIdx.x == 0 && it < 128 && lane == 0) A.timeline[128 + it] = clock64();
+              if (h == 0 && A.timeline && blockIdx.x == 0 && lane == 0) A.timeline[128 + j] = clock64();
               if (elect_one()) {
 #pragma unroll
                 for (int st = 4 * h; st < 4 * h + 4; ++st)
@@ -400,7 +401,7 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
               if (job.flags & kFlagLast) umma_commit(bar_d1_full + 8 * buf);
             }
             __syncwarp();
-            if (A.timeline && blockIdx.x == 0 && it < 128 && lane == 0) A.timeline[256 + it] = clock64();
+            if (A.timeline && blockIdx.x == 0 && lane == 0) A.timeline[256 + j] = clock64();
           } else {
             if (job.chunk == 0) {   // feature tile of this branch written by the epilogue warps
               mbar_wait(bar_feat_full + 8 * buf, feat_use[buf] & 1u);
@@ -413,7 +414,7 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
             for (int h = 0; h < 2; ++h) {
               mbar_wait(bar_full + 16 * s + 8 * h, ph);
               tc_fence_after();
-              if (h == 0 && A.timeline && blockIdx.x == 0 && it < 128 && lane == 0) A.timeline[128 + it] = clock64();
+              if (h == 0 && A.timeline && blockIdx.x == 0 && lane == 0) A.timeline[128 + j] = clock64();
               if (elect_one()) {
 #pragma unroll
                 for (int ks = 4 * h; ks < 4 * h + 4; ++ks)
@@ -428,7 +429,7 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
               if (job.flags & kFlagTileLastL2) umma_commit(bar_d2_full);
             }
             __syncwarp();
-            if (A.timeline && blockIdx.x == 0 && it < 128 && lane == 0) A.timeline[256 + it] = clock64();
+            if (A.timeline && blockIdx.x == 0 && lane == 0) A.timeline[256 + j] = clock64();
           }
           job = next_job;
         }
@@ -606,11 +607,28 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t saddr) {
 constexpr uint32_t kRecvD2Bytes = 4 * 32768;   // [src rank 4][column half 2][float4 column 8][row 128] x 16 B (stage memory)
 constexpr uint32_t kRecvD3Off = kRecvD2Bytes;  // [src rank 4][float4 column 4][row 128] x 16 B (rank 0 only)
 
-template <int SLOT>
+// Fused rollout (MODE != MANSY_OBS_NONE): the same cluster also runs the simulator step of its 128 environments
+// (32 per CTA, 8 lanes each, on the eight epilogue warps) with the action it has just sampled, writes the next
+// observation slab and loops over the rollout steps without leaving the kernel: no launch, drain or refill
+// between policy and simulator, and the cluster only synchronises with itself (environments never interact,
+// mansy_env.py holds no cross-env state).
+struct FusedArgs {
+  SimDev S;
+  float *obs;          // [slabs][n][obs_stride]   (the TMA map `map_obs` views it as [slabs * n] rows)
+  int64_t obs_stride;
+  int32_t slabs, n_steps;
+  int64_t t0;
+  int32_t *actions;    // [slabs][n]
+  float *logp, *value, *reward;
+  uint8_t *done;
+};
+
+template <int SLOT, int MODE>
 __global__ void __cluster_dims__(kTcRanks, 1, 1) __launch_bounds__(kTcThreads, 1)
 policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_constant__ CUtensorMap map_w1,
                   const __grid_constant__ CUtensorMap map_wfc, const __grid_constant__ CUtensorMap map_wout,
-                  const __grid_constant__ CUtensorMap map_wres, const TcArgs A) {
+                  const __grid_constant__ CUtensorMap map_wres, const TcArgs A, const __grid_constant__ FusedArgs F) {
+  constexpr bool kFused = MODE != MANSY_OBS_NONE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const TcConst &K = c_tc[SLOT];
   const uint32_t rank = cluster_ctarank();
@@ -620,6 +638,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   const uint32_t stage0 = base;
   const uint32_t wout_s = base + kTcStages * kStageBytes;   // this rank's K-slice of the head matrix: 2 boxes [16 x 32 floats]
   const uint32_t wres_s = wout_s + 4096;                    // [actor.out ; critic.out] for the residual: 4 boxes
+  const uint32_t act_s = wout_s + 12288;                    // fused: sampled actions of this CTA's 32 environments
   const uint32_t bars = wout_s + kWoutBytes;
   const uint32_t bar_full = bars;                    // [kTcStages][2] TMA -> MMA
   const uint32_t bar_empty = bars + 64;              // [kTcStages]    MMA (commit) -> TMA
@@ -633,6 +652,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool tl = A.timeline != nullptr && (int)blockIdx.x == A.timeline_cta;
+  const int tlk = kFused ? 1 : 0;          // the rollout step the timeline records (fused: the second, a steady-state one)
   const int n_jobs = P.n_jobs, nloc = P.n_branches, resid = P.resid_local;
   // D3 (head partial, 16 columns) lives in the D1 buffer the residual features do NOT occupy
   const uint32_t d3_col = resid >= 0 ? (uint32_t)((resid & 1) ^ 1) * 128u : 0u;
@@ -667,7 +687,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (tl && threadIdx.x == 0) A.timeline[511] = clock64();
-  griddep_launch();                // the simulator step after us may be scheduled (it waits for our completion itself)
+  griddep_launch();                // the kernel after us may be scheduled (it waits for our completion itself)
 
   // epilogue-warp coordinates (used in several phases below)
   const int q = warp & 3;
@@ -678,281 +698,349 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   const bool live = env < A.n;
   float own[32];      // this rank's own partial of the 32 hidden columns the thread finishes
 
-  // ================= phase A: the rank's branches -> partial D2 =================
-  if (warp < kTcProducers) {
-    const int hf = warp & 1;
-    if (warp == 0 && elect_one()) {          // weights do not depend on the previous kernel in the stream
-      mbar_expect_tx(bar_wout, 4096u + (resid >= 0 ? 8192u : 0u));
-      for (int b = 0; b < 2; ++b) tma_load_2d(wout_s + b * 2048, &map_wout, (int)(2 * rank + b) * 32, 0, bar_wout);
-      if (resid >= 0)
-        for (int b = 0; b < 4; ++b) tma_load_2d(wres_s + b * 2048, &map_wres, b * 32, 0, bar_wout);
-    }
-    __syncwarp();
-    griddep_wait();                          // observation rows are written by the simulator step before us
-    uint32_t it = 0, s = 0, ph = 0;
-    for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
-      if ((int)s != (warp >> 1)) continue;
-      const TcJob job = P.jobs[j];
-      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-      const uint32_t dst = stage0 + s * kStageBytes, full = bar_full + 16 * s + 8 * hf;
-      if (elect_one()) {
-        if (job.type == kJobL1) {
-          if (hf < job.chunk) {
-            mbar_expect_tx(full, 2 * kBoxBytes);
-            tma_load_2d(dst + hf * kBoxBytes, &map_obs, (job.a_box + hf) * 32, tile * 128, full);
-            tma_load_2d(dst + (2 + hf) * kBoxBytes, &map_w1, (job.w_box + hf) * 32, 0, full);
-          } else {
-            mbar_arrive(full);
-          }
-        } else {
-          if (hf < job.s_hi) {
-            mbar_expect_tx(full, 2 * kBoxBytes);
-            tma_load_2d(dst + hf * 2 * kBoxBytes, &map_wfc, (int)P.branch[job.slot] * kHidden + (job.chunk + hf) * 32, 0, full);
-          } else {
-            mbar_arrive(full);
-          }
-        }
-      }
-      __syncwarp();
-      if (tl && it < 128 && lane == 0 && hf == 0) A.timeline[it] = clock64();
-    }
-  } else if (warp == kTcMmaWarp) {
-    constexpr uint32_t kIdesc128 = idesc_tf32(128), kIdesc256 = idesc_tf32(256), kIdesc16 = idesc_tf32(16);
-    uint32_t it = 0, feat_use[2] = {0, 0}, s = 0, ph = 0;
-    TcJob job = P.jobs[0];
-    for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
-      const TcJob next_job = P.jobs[j + 1 < n_jobs ? j + 1 : 0];
-      const uint32_t buf = job.slot & 1u;
-      const uint32_t st_addr = stage0 + s * kStageBytes;
-      if (job.type == kJobL1) {
-        const uint32_t d1 = tmem_base + buf * 128u;
-        const uint32_t a_lo = smem_desc_lo(st_addr), b_lo = smem_desc_lo(st_addr + 2 * kBoxBytes);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(bar_full + 16 * s + 8 * h, ph);
-          tc_fence_after();
-          if (h == 0 && tl && it < 128 && lane == 0) A.timeline[128 + it] = clock64();
-          if (elect_one()) {
-#pragma unroll
-            for (int st = 4 * h; st < 4 * h + 4; ++st)
-              if (st >= job.s_lo && st < job.s_hi)
-                umma_tf32(d1, make_desc(a_lo + h * (kBoxBytes >> 4) + 2 * (st & 3)),
-                          make_desc(b_lo + h * (kBoxBytes >> 4) + 2 * (st & 3)), kIdesc128,
-                          ((job.flags & kFlagFirst) && st == job.s_lo) ? 0u : 1u);
-          }
-          __syncwarp();
-        }
-        if (elect_one()) {
-          umma_commit(bar_empty + 8 * s);
-          if (job.flags & kFlagLast) umma_commit(bar_d1_full + 8 * buf);
-        }
-        __syncwarp();
-      } else {
-        if (job.chunk == 0) {
-          mbar_wait(bar_feat_full + 8 * buf, feat_use[buf] & 1u);
-          ++feat_use[buf];
-        }
-        const uint32_t d2 = tmem_base + 256u;
-        const uint32_t fa = tmem_base + buf * 128u + job.chunk * 32u;
-        const uint32_t b_lo = smem_desc_lo(st_addr);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(bar_full + 16 * s + 8 * h, ph);
-          tc_fence_after();
-          if (h == 0 && tl && it < 128 && lane == 0) A.timeline[128 + it] = clock64();
-          if (elect_one()) {
-#pragma unroll
-            for (int ks = 4 * h; ks < 4 * h + 4; ++ks)
-              if (h < job.s_hi)
-                umma_tf32_ts(d2, fa + ks * 8, make_desc(b_lo + h * (2 * kBoxBytes >> 4) + 2 * (ks & 3)), kIdesc256,
-                             ((job.flags & kFlagTileFirstL2) && ks == 0) ? 0u : 1u);
-          }
-          __syncwarp();
-        }
-        if (elect_one()) {
-          umma_commit(bar_empty + 8 * s);
-          if (job.flags & kFlagTileLastL2) umma_commit(bar_d2_full);
-        }
-        __syncwarp();
-      }
-      if (tl && it < 128 && lane == 0) A.timeline[256 + it] = clock64();
-      job = next_job;
-    }
-    if (resid >= 0) {
-      // residual through the heads: D3 = feat_qoe[128 x 128] * [actor.out ; critic.out]^T.  The qoe features sit in
-      // D1[resid & 1] (their layer-2 MMAs above waited for them); the head MMAs of phase C accumulate on top.
-      mbar_wait(bar_wout, 0);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t w_lo = smem_desc_lo(wres_s);
-        const uint32_t fa = tmem_base + (uint32_t)(resid & 1) * 128u;
-#pragma unroll
-        for (int ks = 0; ks < 16; ++ks)
-          umma_tf32_ts(tmem_base + d3_col, fa + ks * 8, make_desc(w_lo + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2), kIdesc16,
-                       ks > 0 ? 1u : 0u);
-      }
-      __syncwarp();
-    }
-  } else if (warp >= kTcEpiWarp0) {
-    uint32_t d1_use[2] = {0, 0};
-    for (int i = 0; i < nloc; ++i) {
-      const uint32_t buf = i & 1u;
-      const int bi = P.branch[i];
-      mbar_wait(bar_d1_full + 8 * buf, d1_use[buf] & 1u);
-      ++d1_use[buf];
-      tc_fence_after();
-      if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[384 + 2 * i] = clock64();
+  if (warp == 0 && elect_one()) {            // weights do not depend on the previous kernel in the stream
+    mbar_expect_tx(bar_wout, 4096u + (resid >= 0 ? 8192u : 0u));
+    for (int b = 0; b < 2; ++b) tma_load_2d(wout_s + b * 2048, &map_wout, (int)(2 * rank + b) * 32, 0, bar_wout);
+    if (resid >= 0)
+      for (int b = 0; b < 4; ++b) tma_load_2d(wres_s + b * 2048, &map_wres, b * 32, 0, bar_wout);
+  }
+  __syncwarp();
+  if (warp < kTcProducers || warp >= kTcEpiWarp0) griddep_wait();   // rows come from / results go to stream-ordered memory
+
+  // pipeline state carried across the rollout steps of the fused kernel
+  uint32_t it = 0, s = 0, ph = 0;          // TMA producers and MMA issuer walk the same job sequence
+  uint32_t feat_use[2] = {0, 0}, d1_use[2] = {0, 0};
+  const int n_steps = kFused ? F.n_steps : 1;
+
 #pragma unroll 1
-      for (int c = 2 * half; c < 2 * half + 2; ++c) {
-        float v[32];
-        const uint32_t ta = tmem_base + lane_addr + buf * 128u + c * 32u;
-        tmem_ld32(ta, v);
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) v[jj] = leaky(v[jj] + K.bias1[bi][c * 32 + jj]);
-        tmem_st32(ta, v);
-        if (A.feat_dbg && live) {
-          float *dst = A.feat_dbg + (size_t)env * (K.n_branches * kHidden) + bi * kHidden + c * 32;
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) dst[jj] = v[jj];
+  for (int k = 0; k < n_steps; ++k) {
+    const uint32_t par = (uint32_t)k & 1u;
+    const int64_t t = kFused ? F.t0 + k : A.step;
+    const int cur = kFused ? (int)(t % F.slabs) : 0;
+    const int row0 = cur * A.n + tile * 128;          // first row of the tile in the (slab-stacked) observation tensor
+    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[489] = clock64();
+
+    // ================= phase A: the rank's branches -> partial D2 =================
+    if (warp < kTcProducers) {
+      const int hf = warp & 1;
+      if (kFused && k > 0) fence_async_smem();      // the stages were read / written through the generic proxy (phases B-D)
+      for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+        if ((int)s != (warp >> 1)) continue;
+        const TcJob job = P.jobs[j];
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        const uint32_t dst = stage0 + s * kStageBytes, full = bar_full + 16 * s + 8 * hf;
+        if (elect_one()) {
+          if (job.type == kJobL1) {
+            if (hf < job.chunk) {
+              mbar_expect_tx(full, 2 * kBoxBytes);
+              tma_load_2d(dst + hf * kBoxBytes, &map_obs, (job.a_box + hf) * 32, row0, full);
+              tma_load_2d(dst + (2 + hf) * kBoxBytes, &map_w1, (job.w_box + hf) * 32, 0, full);
+            } else {
+              mbar_arrive(full);
+            }
+          } else {
+            if (hf < job.s_hi) {
+              mbar_expect_tx(full, 2 * kBoxBytes);
+              tma_load_2d(dst + hf * 2 * kBoxBytes, &map_wfc, (int)P.branch[job.slot] * kHidden + (job.chunk + hf) * 32, 0, full);
+            } else {
+              mbar_arrive(full);
+            }
+          }
         }
+        __syncwarp();
+        if (tl && k == tlk && lane == 0 && hf == 0) A.timeline[j] = clock64();
+      }
+    } else if (warp == kTcMmaWarp) {
+      constexpr uint32_t kIdesc128 = idesc_tf32(128), kIdesc256 = idesc_tf32(256), kIdesc16 = idesc_tf32(16);
+      tc_fence_after();
+      TcJob job = P.jobs[0];
+      for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
+        const TcJob next_job = P.jobs[j + 1 < n_jobs ? j + 1 : 0];
+        const uint32_t buf = job.slot & 1u;
+        const uint32_t st_addr = stage0 + s * kStageBytes;
+        if (job.type == kJobL1) {
+          const uint32_t d1 = tmem_base + buf * 128u;
+          const uint32_t a_lo = smem_desc_lo(st_addr), b_lo = smem_desc_lo(st_addr + 2 * kBoxBytes);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar_full + 16 * s + 8 * h, ph);
+            tc_fence_after();
+            if (h == 0 && tl && k == tlk && lane == 0) A.timeline[128 + j] = clock64();
+            if (elect_one()) {
+#pragma unroll
+              for (int st = 4 * h; st < 4 * h + 4; ++st)
+                if (st >= job.s_lo && st < job.s_hi)
+                  umma_tf32(d1, make_desc(a_lo + h * (kBoxBytes >> 4) + 2 * (st & 3)),
+                            make_desc(b_lo + h * (kBoxBytes >> 4) + 2 * (st & 3)), kIdesc128,
+                            ((job.flags & kFlagFirst) && st == job.s_lo) ? 0u : 1u);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) {
+            umma_commit(bar_empty + 8 * s);
+            if (job.flags & kFlagLast) umma_commit(bar_d1_full + 8 * buf);
+          }
+          __syncwarp();
+        } else {
+          if (job.chunk == 0) {
+            mbar_wait(bar_feat_full + 8 * buf, feat_use[buf] & 1u);
+            ++feat_use[buf];
+          }
+          const uint32_t d2 = tmem_base + 256u;
+          const uint32_t fa = tmem_base + buf * 128u + job.chunk * 32u;
+          const uint32_t b_lo = smem_desc_lo(st_addr);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar_full + 16 * s + 8 * h, ph);
+            tc_fence_after();
+            if (h == 0 && tl && k == tlk && lane == 0) A.timeline[128 + j] = clock64();
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 4 * h; ks < 4 * h + 4; ++ks)
+                if (h < job.s_hi)
+                  umma_tf32_ts(d2, fa + ks * 8, make_desc(b_lo + h * (2 * kBoxBytes >> 4) + 2 * (ks & 3)), kIdesc256,
+                               ((job.flags & kFlagTileFirstL2) && ks == 0) ? 0u : 1u);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) {
+            umma_commit(bar_empty + 8 * s);
+            if (job.flags & kFlagTileLastL2) umma_commit(bar_d2_full);
+          }
+          __syncwarp();
+        }
+        if (tl && k == tlk && lane == 0) A.timeline[256 + j] = clock64();
+        job = next_job;
+      }
+      if (resid >= 0) {
+        // residual through the heads: D3 = feat_qoe[128 x 128] * [actor.out ; critic.out]^T.  The qoe features sit in
+        // D1[resid & 1] (their layer-2 MMAs above waited for them); the head MMAs of phase C accumulate on top.
+        if (k == 0) mbar_wait(bar_wout, 0);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t w_lo = smem_desc_lo(wres_s);
+          const uint32_t fa = tmem_base + (uint32_t)(resid & 1) * 128u;
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks)
+            umma_tf32_ts(tmem_base + d3_col, fa + ks * 8, make_desc(w_lo + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2), kIdesc16,
+                         ks > 0 ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+    } else if (warp >= kTcEpiWarp0) {
+      for (int i = 0; i < nloc; ++i) {
+        const uint32_t buf = i & 1u;
+        const int bi = P.branch[i];
+        mbar_wait(bar_d1_full + 8 * buf, d1_use[buf] & 1u);
+        ++d1_use[buf];
+        tc_fence_after();
+        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[384 + 2 * i] = clock64();
+#pragma unroll 1
+        for (int c = 2 * half; c < 2 * half + 2; ++c) {
+          float v[32];
+          const uint32_t ta = tmem_base + lane_addr + buf * 128u + c * 32u;
+          tmem_ld32(ta, v);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) v[jj] = leaky(v[jj] + K.bias1[bi][c * 32 + jj]);
+          tmem_st32(ta, v);
+          if (!kFused && A.feat_dbg && live) {
+            float *dst = A.feat_dbg + (size_t)env * (K.n_branches * kHidden) + bi * kHidden + c * 32;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) dst[jj] = v[jj];
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar_feat_full + 8 * buf);
+        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[384 + 2 * i + 1] = clock64();
+      }
+      mbar_wait(bar_d2_full, par);   // every MMA of this CTA has completed: partial D2 final, TMA stages idle
+      tc_fence_after();
+    }
+    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[480] = clock64();
+    cluster_sync_all();              // (1) all four CTAs' stage memory is idle
+    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[481] = clock64();
+
+    // ================= phase B: reduce-scatter the partials over DSMEM =================
+    if (warp >= kTcEpiWarp0) {
+#pragma unroll 1
+      for (uint32_t d = 0; d < (uint32_t)kTcRanks; ++d) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_addr + 256u + d * 64u + (uint32_t)half * 32u, v);
+        if (d == rank) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) own[jj] = v[jj];
+        } else {
+          const uint32_t dst = map_to_rank(stage0 + ((rank * 2u + (uint32_t)half) * 8u) * 2048u + (uint32_t)r * 16u, d);
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) st_cluster_v4(dst + c4 * 2048, v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        }
+      }
+    }
+    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[482] = clock64();
+    cluster_sync_all();              // (2) partials delivered
+    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[483] = clock64();
+
+    // ================= phase C: hidden slice, this rank's K-slice of the heads =================
+    if (warp >= kTcEpiWarp0) {
+#pragma unroll 1
+      for (uint32_t sr = 0; sr < (uint32_t)kTcRanks; ++sr) {
+        if (sr == rank) continue;
+        const uint32_t src = stage0 + ((sr * 2u + (uint32_t)half) * 8u) * 2048u + (uint32_t)r * 16u;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 tt = ld_shared_v4(src + c4 * 2048);
+          own[4 * c4] += tt.x; own[4 * c4 + 1] += tt.y; own[4 * c4 + 2] += tt.z; own[4 * c4 + 3] += tt.w;
+        }
+      }
+      const int col0 = (int)rank * 64 + half * 32;      // hidden column (0..127 actor.fc, 128..255 critic.fc)
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) own[jj] = leaky(own[jj] + K.bias2[col0 + jj]);
+      tmem_st32(tmem_base + lane_addr + 256u + (uint32_t)col0, own);
+      if (!kFused && A.hid_dbg && live) {      // NOTE: without the residual (it enters through the heads in this kernel)
+        float *dst = A.hid_dbg + (size_t)env * 256 + col0;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) dst[jj] = own[jj];
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_feat_full + 8 * buf);
-      if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[384 + 2 * i + 1] = clock64();
-    }
-    mbar_wait(bar_d2_full, 0);     // every MMA of this CTA has completed: partial D2 final, TMA stages idle
-    tc_fence_after();
-  }
-  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[480] = clock64();
-  cluster_sync_all();              // (1) all four CTAs' stage memory is idle
-  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[481] = clock64();
-
-  // ================= phase B: reduce-scatter the partials over DSMEM =================
-  if (warp >= kTcEpiWarp0) {
-#pragma unroll 1
-    for (uint32_t d = 0; d < (uint32_t)kTcRanks; ++d) {
-      float v[32];
-      tmem_ld32(tmem_base + lane_addr + 256u + d * 64u + (uint32_t)half * 32u, v);
-      if (d == rank) {
+      mbar_arrive(bar_hid_full);
+      if (half == 0) {
+        mbar_wait(bar_d3_full, par);
+        tc_fence_after();
+        float acc[16];
+        tmem_ld16(tmem_base + lane_addr + d3_col, acc);
+        if (rank != 0) {
+          const uint32_t dst = map_to_rank(stage0 + kRecvD3Off + (rank * 4u) * 2048u + (uint32_t)r * 16u, 0);
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) own[jj] = v[jj];
-      } else {
-        const uint32_t dst = map_to_rank(stage0 + ((rank * 2u + (uint32_t)half) * 8u) * 2048u + (uint32_t)r * 16u, d);
+          for (int c4 = 0; c4 < 4; ++c4) st_cluster_v4(dst + c4 * 2048, acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+        } else {
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) st_cluster_v4(dst + c4 * 2048, v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+          for (int o = 0; o < 16; ++o) own[o] = acc[o];
+        }
       }
-    }
-  }
-  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[482] = clock64();
-  cluster_sync_all();              // (2) partials delivered
-  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[483] = clock64();
-
-  // ================= phase C: hidden slice, this rank's K-slice of the heads =================
-  if (warp >= kTcEpiWarp0) {
-#pragma unroll 1
-    for (uint32_t sr = 0; sr < (uint32_t)kTcRanks; ++sr) {
-      if (sr == rank) continue;
-      const uint32_t src = stage0 + ((sr * 2u + (uint32_t)half) * 8u) * 2048u + (uint32_t)r * 16u;
-#pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 t = ld_shared_v4(src + c4 * 2048);
-        own[4 * c4] += t.x; own[4 * c4 + 1] += t.y; own[4 * c4 + 2] += t.z; own[4 * c4 + 3] += t.w;
-      }
-    }
-    const int col0 = (int)rank * 64 + half * 32;      // hidden column (0..127 actor.fc, 128..255 critic.fc)
-#pragma unroll
-    for (int jj = 0; jj < 32; ++jj) own[jj] = leaky(own[jj] + K.bias2[col0 + jj]);
-    tmem_st32(tmem_base + lane_addr + 256u + (uint32_t)col0, own);
-    if (A.hid_dbg && live) {      // NOTE: without the residual (it enters through the heads in this kernel)
-      float *dst = A.hid_dbg + (size_t)env * 256 + col0;
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) dst[jj] = own[jj];
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    mbar_arrive(bar_hid_full);
-    if (half == 0) {
-      mbar_wait(bar_d3_full, 0);
+      tc_fence_before();
+    } else if (warp == kTcMmaWarp) {
+      constexpr uint32_t kIdesc16 = idesc_tf32(16);
+      if (resid < 0 && k == 0) mbar_wait(bar_wout, 0);
+      mbar_wait(bar_hid_full, par);
       tc_fence_after();
-      float acc[16];
-      tmem_ld16(tmem_base + lane_addr + d3_col, acc);
-      if (rank != 0) {
-        const uint32_t dst = map_to_rank(stage0 + kRecvD3Off + (rank * 4u) * 2048u + (uint32_t)r * 16u, 0);
+      if (elect_one()) {
+        const uint32_t w_lo = smem_desc_lo(wout_s);
+        const uint32_t ha = tmem_base + 256u + rank * 64u;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) st_cluster_v4(dst + c4 * 2048, acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
-      } else {
-#pragma unroll
-        for (int o = 0; o < 16; ++o) own[o] = acc[o];
+        for (int ks = 0; ks < 8; ++ks)
+          umma_tf32_ts(tmem_base + d3_col, ha + ks * 8, make_desc(w_lo + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2), kIdesc16,
+                       (ks > 0 || resid >= 0) ? 1u : 0u);
+        umma_commit(bar_d3_full);
       }
+      __syncwarp();
     }
-  } else if (warp == kTcMmaWarp) {
-    constexpr uint32_t kIdesc16 = idesc_tf32(16);
-    if (resid < 0) mbar_wait(bar_wout, 0);
-    mbar_wait(bar_hid_full, 0);
-    tc_fence_after();
-    if (elect_one()) {
-      const uint32_t w_lo = smem_desc_lo(wout_s);
-      const uint32_t ha = tmem_base + 256u + rank * 64u;
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks)
-        umma_tf32_ts(tmem_base + d3_col, ha + ks * 8, make_desc(w_lo + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2), kIdesc16,
-                     (ks > 0 || resid >= 0) ? 1u : 0u);
-      umma_commit(bar_d3_full);
-    }
-    __syncwarp();
-  }
-  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[484] = clock64();
-  cluster_sync_all();              // (3) head partials delivered to rank 0
-  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[485] = clock64();
+    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[484] = clock64();
+    cluster_sync_all();              // (3) head partials delivered to rank 0
+    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[485] = clock64();
 
-  // ================= phase D: rank 0 finishes the rows =================
-  if (rank == 0 && warp >= kTcEpiWarp0 && half == 0) {
-    float acc[16];
+    // ================= phase D: rank 0 finishes the rows =================
+    if (rank == 0 && warp >= kTcEpiWarp0 && half == 0) {
+      float acc[16];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) acc[o] = own[o] + K.bout[o];
+      for (int o = 0; o < 16; ++o) acc[o] = own[o] + K.bout[o];
 #pragma unroll 1
-    for (uint32_t sr = 1; sr < (uint32_t)kTcRanks; ++sr) {
-      const uint32_t src = stage0 + kRecvD3Off + (sr * 4u) * 2048u + (uint32_t)r * 16u;
+      for (uint32_t sr = 1; sr < (uint32_t)kTcRanks; ++sr) {
+        const uint32_t src = stage0 + kRecvD3Off + (sr * 4u) * 2048u + (uint32_t)r * 16u;
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const float4 t = ld_shared_v4(src + c4 * 2048);
-        acc[4 * c4] += t.x; acc[4 * c4 + 1] += t.y; acc[4 * c4 + 2] += t.z; acc[4 * c4 + 3] += t.w;
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 tt = ld_shared_v4(src + c4 * 2048);
+          acc[4 * c4] += tt.x; acc[4 * c4 + 1] += tt.y; acc[4 * c4 + 2] += tt.z; acc[4 * c4 + 3] += tt.w;
+        }
+      }
+      int act = 0;
+      if (live) {
+        const size_t orow = kFused ? (size_t)cur * A.n + env : (size_t)env;   // fused: outputs of step t live in slab t % slabs
+        float p[kActions];
+#pragma unroll
+        for (int o = 0; o < kActions; ++o) p[o] = acc[o];
+        if (K.softmax) {
+          float m = p[0];
+#pragma unroll
+          for (int o = 1; o < kActions; ++o) m = fmaxf(m, p[o]);
+          float sum = 0.f;
+#pragma unroll
+          for (int o = 0; o < kActions; ++o) { p[o] = expf(p[o] - m); sum += p[o]; }
+#pragma unroll
+          for (int o = 0; o < kActions; ++o) p[o] = p[o] / sum;
+        }
+        if (A.value) A.value[orow] = acc[15];
+        if (A.logits) {
+          float4 *dst = reinterpret_cast<float4 *>(A.logits + (size_t)env * 16);
+          dst[0] = make_float4(p[0], p[1], p[2], p[3]);
+          dst[1] = make_float4(p[4], p[5], p[6], p[7]);
+          dst[2] = make_float4(p[8], p[9], p[10], p[11]);
+          dst[3] = make_float4(p[12], p[13], p[14], 0.f);
+        }
+        if (A.actions) {
+          float lp;
+          categorical_sample(p, K.softmax, A.seed, (uint64_t)(A.env_offset + env), (uint64_t)t, act, lp);
+          A.actions[orow] = act;
+          if (A.logp) A.logp[orow] = lp;
+        }
+      }
+      if (kFused) {     // hand the action to the CTA that steps this environment (rows 32d .. 32d+31 -> rank d)
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(map_to_rank(act_s + (uint32_t)(r & 31) * 4u, (uint32_t)(r >> 5))), "r"(act) : "memory");
       }
     }
-    if (live) {
-      griddep_wait();
-      float p[kActions];
-#pragma unroll
-      for (int o = 0; o < kActions; ++o) p[o] = acc[o];
-      if (K.softmax) {
-        float m = p[0];
-#pragma unroll
-        for (int o = 1; o < kActions; ++o) m = fmaxf(m, p[o]);
-        float s = 0.f;
-#pragma unroll
-        for (int o = 0; o < kActions; ++o) { p[o] = expf(p[o] - m); s += p[o]; }
-#pragma unroll
-        for (int o = 0; o < kActions; ++o) p[o] = p[o] / s;
+    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[486] = clock64();
+
+    if (kFused) {
+      cluster_sync_all();            // (4) actions delivered
+      // ================= phase E: simulator chunk-step of this CTA's 32 environments =================
+      if (warp >= kTcEpiWarp0) {
+        const int et = (int)threadIdx.x - 32 * kTcEpiWarp0;
+        const int i = tile * 128 + (int)rank * 32 + (et >> 3);
+        const int sub = et & 7;
+        if (i < A.n) {                 // the 8 lanes of an environment leave together
+          const SimDev &S = F.S;
+          const unsigned gmask = group_mask();
+          const int nxt = (int)((t + 1) % F.slabs);
+          EnvState st;
+          float slot[8];
+          load_state(S, i, st);
+          load_slot(S, i, sub, slot);
+          if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[490] = clock64() + (st.flags & 0);
+          float reward_f = 0.f;
+          bool over = true;
+          if (!(st.flags & kFlagFinished)) {
+            int action;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(action) : "r"(act_s + (uint32_t)(et >> 3) * 4u) : "memory");
+            const int slot_before = st.ep_step & 7;
+            const double reward = step_env(S, st, slot, sub, gmask, action, over, nullptr, nullptr);
+            reward_f = (float)reward;
+            if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[491] = clock64() + (reward_f > 1e30f);
+            if (sub == slot_before) store_slot(S, i, sub, slot);
+            if (over) {
+              if (sub == 0) finish_episode(S, i, st);
+              reset_episode(S, st);
+            }
+          }
+          if (sub == 0) {
+            F.reward[(size_t)cur * A.n + i] = reward_f;
+            F.done[(size_t)cur * A.n + i] = over ? 1 : 0;
+          }
+          emit_obs<MODE>(S, st, slot, sub, gmask, F.obs + ((size_t)nxt * A.n + i) * F.obs_stride);
+          store_state(S, i, st, sub);
+          if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[492] = clock64();
+        }
+        // the next step's TMA (async proxy) reads the rows just written through the generic proxy, and writes the
+        // stage memory read above
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
       }
-      if (A.value) A.value[env] = acc[15];
-      if (A.logits) {
-        float4 *dst = reinterpret_cast<float4 *>(A.logits + (size_t)env * 16);
-        dst[0] = make_float4(p[0], p[1], p[2], p[3]);
-        dst[1] = make_float4(p[4], p[5], p[6], p[7]);
-        dst[2] = make_float4(p[8], p[9], p[10], p[11]);
-        dst[3] = make_float4(p[12], p[13], p[14], 0.f);
-      }
-      if (A.actions) {
-        int act;
-        float lp;
-        categorical_sample(p, K.softmax, A.seed, (uint64_t)(A.env_offset + env), (uint64_t)A.step, act, lp);
-        A.actions[env] = act;
-        if (A.logp) A.logp[env] = lp;
-      }
+      if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[487] = clock64();
+      cluster_sync_all();            // (5) the next observation rows of the tile are complete
+      if (warp < kTcProducers) asm volatile("fence.proxy.async;" ::: "memory");
+      if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[488] = clock64();
     }
   }
-  if (tl && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[486] = clock64();
 
   tc_fence_before();
   __syncthreads();
@@ -1248,6 +1336,7 @@ int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs
   const bool split4 = p->tc->split == 4 || (p->tc->split == 0 && 4 * a.n_tiles <= 3 * n_sm);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
+  static const FusedArgs *fz = new FusedArgs();      // value-initialised: the policy-only instantiation ignores it
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
@@ -1264,14 +1353,15 @@ int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs
     if (!attr_done) {                                                                                               \
       e = cudaFuncSetAttribute(policy_tc_kernel<SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes); \
       if (e == cudaSuccess)                                                                                         \
-        e = cudaFuncSetAttribute(policy_tc4_kernel<SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes); \
+        e = cudaFuncSetAttribute(policy_tc4_kernel<SLOT, MANSY_OBS_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)kTcSmemBytes);                                                                \
       attr_done = (e == cudaSuccess);                                                                               \
     }                                                                                                               \
     if (e == cudaSuccess) {                                                                                         \
       if (split4) {                                                                                                 \
         cfg.gridDim = dim3((unsigned)(kTcRanks * a.n_tiles), 1, 1);                                                 \
-        e = cudaLaunchKernelEx(&cfg, policy_tc4_kernel<SLOT>, map_obs, p->tc->map_w1, p->tc->map_wfc, p->tc->map_wout, \
-                               p->tc->map_wres, a);                                                                 \
+        e = cudaLaunchKernelEx(&cfg, policy_tc4_kernel<SLOT, MANSY_OBS_NONE>, map_obs, p->tc->map_w1, p->tc->map_wfc,   \
+                               p->tc->map_wout, p->tc->map_wres, a, *fz);                                           \
       } else {                                                                                                      \
         cfg.gridDim = dim3((unsigned)(a.n_tiles < n_sm ? a.n_tiles : n_sm), 1, 1);                                  \
         e = cudaLaunchKernelEx(&cfg, policy_tc_kernel<SLOT>, map_obs, p->tc->map_w1, p->tc->map_wfc, p->tc->map_wout, a); \
@@ -1288,6 +1378,84 @@ int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs
   count_launch();
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MANSY_E_CUDA, std::string("policy_tc_kernel launch: ") + cudaGetErrorString(e));
+  return MANSY_OK;
+}
+
+// Fused rollout: n_steps x (policy forward + sample + simulator step) in ONE launch of the split-K cluster kernel.
+// Returns MANSY_OK with *launched = 0 when the configuration does not qualify (the caller then runs the
+// two-kernel loop): every cluster must be resident at once for the launch to make progress on all tiles together.
+static long long *g_fused_timeline = nullptr;    // debug hook: mansy_debug_fused_timeline
+static int g_fused_timeline_cta = 0;
+
+int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t *b, int32_t n_steps, int64_t t0,
+                         uint64_t seed, void *stream, int *launched) {
+  *launched = 0;
+  if (!p || !p->tc || !b) return MANSY_OK;
+  if (S.obs_mode != MANSY_OBS_MANSY && S.obs_mode != MANSY_OBS_SIMPLE) return MANSY_OK;
+  if (p->dev.kind != S.obs_mode || p->tc->split == 1 || n_steps < 1) return MANSY_OK;
+  const int n = S.n_envs, n_tiles = (n + 127) / 128;
+  if (b->obs_stride < p->tc->obs_floats || (b->obs_stride & 3) || (reinterpret_cast<uintptr_t>(b->obs) & 15) ||
+      (reinterpret_cast<uintptr_t>(b->logits) & 15))
+    return MANSY_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(kTcRanks * n_tiles), 1, 1);
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = kTcSmemBytes;
+  cfg.stream = s;
+  // (the cluster shape is compiled into the kernel: __cluster_dims__)
+
+  CUtensorMap map_obs;     // all slabs as one row-major tensor: row = slab * n + env
+  int rc = make_map(&map_obs, b->obs, (uint64_t)p->tc->obs_floats, (uint64_t)n * (uint64_t)b->slabs, (uint64_t)b->obs_stride, 128);
+  if (rc) return rc;
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = n; a.n_tiles = n_tiles;
+  a.logits = b->logits; a.value = b->value; a.actions = b->actions; a.logp = b->logp;
+  a.seed = seed; a.step = t0; a.env_offset = S.env_offset;
+  a.timeline = g_fused_timeline; a.timeline_cta = g_fused_timeline_cta;
+  FusedArgs f;
+  memset(&f, 0, sizeof(f));
+  f.S = S;
+  f.obs = b->obs; f.obs_stride = b->obs_stride; f.slabs = b->slabs; f.n_steps = n_steps; f.t0 = t0;
+  f.actions = b->actions; f.logp = b->logp; f.value = b->value; f.reward = b->reward; f.done = b->done;
+  cudaError_t e = cudaSuccess;
+#define MANSY_FUSED_LAUNCH(SLOT, MODE)                                                                              \
+  do {                                                                                                              \
+    static int max_clusters = -1;                                                                                   \
+    if (max_clusters < 0) {                                                                                         \
+      e = cudaFuncSetAttribute(policy_tc4_kernel<SLOT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes); \
+      int mc = 0;                                                                                                   \
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&mc, policy_tc4_kernel<SLOT, MODE>, &cfg);           \
+      if (e == cudaSuccess) max_clusters = mc;                                                                      \
+    }                                                                                                               \
+    if (e == cudaSuccess && n_tiles <= max_clusters) {                                                              \
+      e = cudaLaunchKernelEx(&cfg, policy_tc4_kernel<SLOT, MODE>, map_obs, p->tc->map_w1, p->tc->map_wfc, p->tc->map_wout, \
+                             p->tc->map_wres, a, f);                                                                \
+      if (e == cudaSuccess) *launched = 1;                                                                          \
+    }                                                                                                               \
+  } while (0)
+  if (S.obs_mode == MANSY_OBS_MANSY) {
+    switch (p->tc->slot) {
+      case 0: MANSY_FUSED_LAUNCH(0, MANSY_OBS_MANSY); break;
+      case 1: MANSY_FUSED_LAUNCH(1, MANSY_OBS_MANSY); break;
+      default: MANSY_FUSED_LAUNCH(2, MANSY_OBS_MANSY); break;
+    }
+  } else {
+    switch (p->tc->slot) {
+      case 0: MANSY_FUSED_LAUNCH(0, MANSY_OBS_SIMPLE); break;
+      case 1: MANSY_FUSED_LAUNCH(1, MANSY_OBS_SIMPLE); break;
+      default: MANSY_FUSED_LAUNCH(2, MANSY_OBS_SIMPLE); break;
+    }
+  }
+#undef MANSY_FUSED_LAUNCH
+  if (e != cudaSuccess) return set_error(MANSY_E_CUDA, std::string("fused rollout kernel: ") + cudaGetErrorString(e));
+  if (*launched) {
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(MANSY_E_CUDA, std::string("fused rollout kernel launch: ") + cudaGetErrorString(e));
+  }
   return MANSY_OK;
 }
 
@@ -1309,6 +1477,12 @@ int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int
   const char *cta = getenv("MANSY_TC_TIMELINE_CTA");
   return policy_forward_tc_launch(p, obs_dev, obs_stride, n, logits_dev, value_dev, actions_dev, logp_dev, seed, step,
                                   env_offset, feat_dbg_dev, hid_dbg_dev, timeline_dev, cta ? atoi(cta) : 0, false, stream);
+}
+
+int mansy_debug_fused_timeline(int64_t *timeline_dev, int32_t cta) {
+  g_fused_timeline = reinterpret_cast<long long *>(timeline_dev);
+  g_fused_timeline_cta = cta;
+  return MANSY_OK;
 }
 
 int mansy_policy_tc_set_split(mansy_policy_t p, int32_t split) {

@@ -8,11 +8,7 @@
 // HBM-bound gather/scatter; there is nothing GEMM-shaped in it.
 //
 // Reference map (file:line relative to the reference root):
-//   step_env        bitrate_selection/envs/mansy_env.py:154-248, envs/simple_rl_env.py:113-160,
-//                   simulators/simulator.py:88-108, simulators/network.py:22-35,
-//                   simulators/buffer.py:8-15, utils/qoe.py:22-34, utils/common.py:101-193
-//   reset_episode   envs/mansy_env.py:99-152, simulators/simulator.py:15-46
-//   emit_obs        envs/mansy_env.py:136-150,232-246, envs/simple_rl_env.py:103-109,152-158
+//   step_env / reset_episode / emit_obs: see mansy_step.cuh
 //   viewport kernel viewport_prediction/utils/common.py:37-58,83-127, predict.py:33-48
 #include <atomic>
 #include <cstdio>
@@ -46,298 +42,11 @@ int set_error(int code, const std::string &msg) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-// ------------------------------------------------------------------------------------------
-// device helpers
-// ------------------------------------------------------------------------------------------
-struct StepArgs {
-  const int32_t *actions;   // [n] (action_mode 0)
-  const int32_t *env_ids;   // [n] or NULL
-  int32_t n;
-  int32_t auto_reset;
-  int32_t action_mode;      // 0: actions array, 1: hashed_action(seed, global env, step)
-  int32_t n_steps;          // steps executed inside one launch (state stays in registers)
-  uint64_t seed;
-  int64_t step0;
-  int64_t rows_per_step;    // output rows between consecutive steps (0: overwrite the same rows)
-  mansy_out_t out;
-};
+}  // namespace mansy
 
-__device__ __forceinline__ unsigned group_mask() { return 0xFFu << ((threadIdx.x & 31) & ~7); }
+#include "mansy_step.cuh"  // StepArgs, step_env, emit_obs, reset_episode, finish_episode (device code)
 
-__device__ __forceinline__ int group_sum(int v, unsigned m) {
-  v += __shfl_xor_sync(m, v, 1);
-  v += __shfl_xor_sync(m, v, 2);
-  v += __shfl_xor_sync(m, v, 4);
-  return v;
-}
-__device__ __forceinline__ double group_sum(double v, unsigned m) {
-  v = dadd(v, __shfl_xor_sync(m, v, 1));
-  v = dadd(v, __shfl_xor_sync(m, v, 2));
-  v = dadd(v, __shfl_xor_sync(m, v, 4));
-  return v;
-}
-
-union StateQuads {
-  EnvState s;
-  uint4 q[8];
-  __device__ StateQuads() {}
-};
-
-__device__ __forceinline__ void load_state(const SimDev &S, int e, EnvState &st) {
-  StateQuads u;
-  const uint4 *p = reinterpret_cast<const uint4 *>(S.state + e);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) u.q[i] = p[i];   // same address in all 8 lanes: broadcast
-  st = u.s;
-}
-
-__device__ __forceinline__ void store_state(const SimDev &S, int e, const EnvState &st, int sub) {
-  StateQuads u;
-  u.s = st;
-  uint4 v = u.q[0];
-#pragma unroll
-  for (int i = 1; i < 8; ++i)
-    if (sub == i) v = u.q[i];
-  reinterpret_cast<uint4 *>(S.state + e)[sub] = v;   // lane i writes quad i: one 128-byte line per env
-}
-
-__device__ __forceinline__ void load_slot(const SimDev &S, int e, int sub, float (&slot)[8]) {
-  const float4 *p = reinterpret_cast<const float4 *>(S.hist + (size_t)e * kHistFloatsPerEnv + sub * 8);
-  const float4 a = p[0], b = p[1];
-  slot[0] = a.x; slot[1] = a.y; slot[2] = a.z; slot[3] = a.w;
-  slot[4] = b.x; slot[5] = b.y; slot[6] = b.z; slot[7] = b.w;
-}
-
-__device__ __forceinline__ void store_slot(const SimDev &S, int e, int sub, const float (&slot)[8]) {
-  float4 *p = reinterpret_cast<float4 *>(S.hist + (size_t)e * kHistFloatsPerEnv + sub * 8);
-  p[0] = make_float4(slot[0], slot[1], slot[2], slot[3]);
-  p[1] = make_float4(slot[4], slot[5], slot[6], slot[7]);
-}
-
-// envs/mansy_env.py:99-134 + simulators/simulator.py:15-46: pick the next sample and rebuild the
-// episode state.  Executed identically by the 8 lanes of the group.
-__device__ __forceinline__ void reset_episode(const SimDev &S, EnvState &st) {
-  const int sid = st.cursor % S.n_samples;
-  st.sample_id = sid;
-  st.cursor = (st.cursor + S.worker_num) % S.n_samples;          // mansy_env.py:100-101
-  const int4 smp = __ldg(reinterpret_cast<const int4 *>(S.samples) + sid);
-  st.video = smp.x;
-  st.pair = smp.x * S.n_users + smp.y;
-  st.trace = smp.z;
-  st.w0 = __ldg(S.qoe_w + smp.w * 3 + 0);
-  st.w1 = __ldg(S.qoe_w + smp.w * 3 + 1);
-  st.w2 = __ldg(S.qoe_w + smp.w * 3 + 2);
-  st.buf = S.chunk_length * 3.0;                                  // buffer.py:6
-  st.cur_time = 0.0;                                              // network.py:19-20
-  st.cur_idx = 0;
-  st.next_chunk = S.startup_download + 1;                         // simulator.py:45
-  st.start_chunk = __ldg(S.vp_start + st.pair);
-  st.end_chunk = min(__ldg(S.vp_end + st.pair), __ldg(S.video_time + st.video) - 1);  // simulator.py:41-42
-  st.prev_vq = 0.0;
-  st.ep_step = 0;
-  st.flags = kNoAction << 8;
-  st.sum_qoe = st.sum_q1 = st.sum_q2 = st.sum_q3 = 0.0;
-  st.ep_return = 0.0;
-}
-
-// Observation row from the env state (a pure function of state + history ring).
-template <int MODE>
-__device__ __forceinline__ void emit_obs(const SimDev &S, const EnvState &st, const float (&slot)[8], int sub,
-                                         unsigned gmask, float *__restrict__ row) {
-  const int pushes = st.ep_step;
-  const int newest = (pushes - 1) & 7;
-  const int k = (newest - sub) & 7;         // observation index of this lane's slot (0 = newest)
-  const bool valid = k < pushes;            // older entries are still the zeros of reset
-  const int la = (st.flags >> 8) & 0xFF;    // last action: 0..14, 15 = out-of-table action, 255 = none
-  const int obs_chunk = min(st.next_chunk, st.end_chunk);   // terminal obs repeats the last chunk
-  const uint64_t pred = __ldg(S.vp_pred + (size_t)st.pair * S.n_vp_chunks + (obs_chunk - st.start_chunk));
-  const size_t tab = ((size_t)st.video * S.n_chunks + obs_chunk) * kTableRow;
-  const uint32_t pbyte = (uint32_t)(pred >> (8 * sub)) & 0xFFu;
-  const float4 p0 = make_float4((float)(pbyte & 1u), (float)((pbyte >> 1) & 1u), (float)((pbyte >> 2) & 1u),
-                                (float)((pbyte >> 3) & 1u));
-  const float4 p1 = make_float4((float)((pbyte >> 4) & 1u), (float)((pbyte >> 5) & 1u),
-                                (float)((pbyte >> 6) & 1u), (float)((pbyte >> 7) & 1u));
-  const float4 *s4 = reinterpret_cast<const float4 *>(S.size_norm + tab);
-
-  if (MODE == MANSY_OBS_MANSY) {
-    const float4 *q4 = reinterpret_cast<const float4 *>(S.qual_norm + tab);
-    float4 *ds = reinterpret_cast<float4 *>(row + 8);
-    float4 *dq = reinterpret_cast<float4 *>(row + 328);
-    float4 tv[10];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) tv[i] = __ldg(s4 + sub + 8 * i);
-    row[0 + k] = valid ? slot[0] : 0.f;      // throughput
-    row[712 + k] = valid ? slot[1] : 0.f;    // rates_inside
-    row[720 + k] = valid ? slot[2] : 0.f;    // rates_outside
-    row[728 + k] = valid ? slot[3] : 0.f;    // viewport_acc
-    row[736 + k] = valid ? slot[4] : 0.f;    // past_viewport_qualities
-    row[744 + k] = valid ? slot[5] : 0.f;    // past_quality_variances
-    row[752 + k] = valid ? slot[6] : 0.f;    // past_rebuffering
-#pragma unroll
-    for (int i = 0; i < 10; ++i) ds[sub + 8 * i] = tv[i];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) tv[i] = __ldg(q4 + sub + 8 * i);
-#pragma unroll
-    for (int i = 0; i < 10; ++i) dq[sub + 8 * i] = tv[i];
-    float4 *dp = reinterpret_cast<float4 *>(row + 648);
-    dp[2 * sub] = p0;
-    dp[2 * sub + 1] = p1;
-    if (sub < 4) {            // action_one_hot (15 + 1 pad)
-      const int b = 4 * sub;
-      reinterpret_cast<float4 *>(row + 760)[sub] =
-          make_float4(la == b ? 1.f : 0.f, la == b + 1 ? 1.f : 0.f, la == b + 2 ? 1.f : 0.f,
-                      (la == b + 3 && b + 3 < kActions) ? 1.f : 0.f);
-    } else if (sub == 4) {    // qoe_weight (utils/common.py:55-57) and buffer / startup_download
-      const float ws = (float)dadd(dadd((double)st.w0, (double)st.w1), (double)st.w2);
-      reinterpret_cast<float4 *>(row + 776)[0] =
-          make_float4(fdiv(st.w0, ws), fdiv(st.w1, ws), fdiv(st.w2, ws), fdiv((float)st.buf, S.startup_f));
-    } else if (sub == 5) {
-      reinterpret_cast<float4 *>(row + 780)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  } else {  // MANSY_OBS_SIMPLE
-    float4 *ds = reinterpret_cast<float4 *>(row + 8);
-    float4 sv[10];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) sv[i] = __ldg(s4 + sub + 8 * i);
-    const float rb_newest = __shfl_sync(gmask, slot[7], ((threadIdx.x & 31) & ~7) + newest);
-    row[0 + k] = valid ? slot[0] : 0.f;
-#pragma unroll
-    for (int i = 0; i < 10; ++i) ds[sub + 8 * i] = sv[i];
-    float4 *dp = reinterpret_cast<float4 *>(row + 328);
-    dp[2 * sub] = p0;
-    dp[2 * sub + 1] = p1;
-    if (sub == 0) {           // last_bitrates (2), rebuffer (1), pad
-      float lb0 = 0.f, lb1 = 0.f;
-      if (la != kNoAction) {
-        int rin, rout;
-        action_to_rates(la, rin, rout);
-        lb0 = S.rate_norm_f32[rin];
-        lb1 = S.rate_norm_f32[rout];
-      }
-      reinterpret_cast<float4 *>(row + 392)[0] = make_float4(lb0, lb1, pushes > 0 ? rb_newest : 0.f, 0.f);
-    } else if (sub == 1) {
-      reinterpret_cast<float4 *>(row + 396)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-}
-
-// One chunk-step of one environment (8 lanes).  Returns the reward; `over` tells whether the
-// episode ended.  aux_row / ver_row may be NULL.
-__device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float (&slot)[8], int sub, unsigned gmask,
-                                           int action, bool &over, double *__restrict__ aux_row,
-                                           uint8_t *__restrict__ ver_row) {
-  const int c = st.next_chunk;
-  const size_t vi = (size_t)st.pair * S.n_vp_chunks + (c - st.start_chunk);   // hmdtrace.py:16-19
-  const uint64_t gt = __ldg(S.vp_gt + vi);
-  const uint64_t pred = __ldg(S.vp_pred + vi);
-  const double acc = __ldg(S.vp_acc + vi);
-
-  int rin, rout;
-  action_to_rates(action, rin, rout);
-  const TileScaleMasks dm = tile_scale_masks(pred);
-  const uint32_t lutw = S.lut[rout];
-  const size_t tab = ((size_t)st.video * S.n_chunks + c) * kTableRow;
-
-  // simulator.py:94-101: gather size / quality of the chosen version of each tile; this lane owns
-  // tiles 8*sub .. 8*sub+7.
-  int sz = 0;
-  double mq = 0.0;
-  float q[8];
-  uint32_t vpack_lo = 0, vpack_hi = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int t = sub * 8 + i;
-    const int ver = tile_version(lutw, rin, tile_scale(dm, t));
-    const int off = ver * kTiles + t;
-    sz += __ldg(S.size + tab + off);
-    q[i] = __ldg(S.quality + tab + off);
-    if ((gt >> t) & 1ULL) mq = dadd(mq, (double)q[i]);
-    if (i < 4) vpack_lo |= (uint32_t)ver << (8 * i); else vpack_hi |= (uint32_t)ver << (8 * (i - 4));
-  }
-  if (ver_row) reinterpret_cast<uint2 *>(ver_row)[sub] = make_uint2(vpack_lo, vpack_hi);
-  sz = group_sum(sz, gmask);
-  mq = group_sum(mq, gmask);
-  const double sm = (double)__popcll(gt);
-
-  // network.py:22-35 / buffer.py:8-15
-  const double *tr = S.trace + (size_t)st.trace * S.trace_stride;
-  const int tlen = __ldg(S.trace_len + st.trace);
-  bool ok = true;
-  const double dl = trace_download((double)sz, TracePtr{tr}, tlen, st.cur_idx, st.cur_time, ok);
-  if (!ok && sub == 0) atomicExch(S.error_flag, 1);
-  const double rebuf = buffer_push(st.buf, S.chunk_length, dl);
-
-  // qoe.py:22-34 (float64 chain; |q - vq| is evaluated in float32 like the reference's array op)
-  const double vq = ddiv(mq, sm);
-  const float vq32 = (float)vq;
-  double dev = 0.0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if ((gt >> (sub * 8 + i)) & 1ULL) dev = dadd(dev, (double)fabsf(fsub(q[i], vq32)));
-  dev = group_sum(dev, gmask);
-  const QoE r = qoe_from_sums(vq, dev, sm, rebuf, st.ep_step == 0, st.prev_vq, (double)st.w0, (double)st.w1,
-                              (double)st.w2, S.max_quality);
-  double reward = r.qoe;
-  if (S.reward_mode == MANSY_REWARD_QOE_NORM)
-    reward = ddiv(r.qoe, dadd(dadd((double)st.w0, (double)st.w1), (double)st.w2));
-  st.sum_qoe = dadd(st.sum_qoe, r.qoe);
-  st.sum_q1 = dadd(st.sum_q1, r.q1);
-  st.sum_q2 = dadd(st.sum_q2, r.q2);
-  st.sum_q3 = dadd(st.sum_q3, r.q3);
-  st.ep_return = dadd(st.ep_return, reward);
-
-  // mansy_env.py:192-206: push the newest history values (ring slot = episode step & 7)
-  if (sub == (st.ep_step & 7)) {
-    slot[0] = (float)ddiv(ddiv((double)sz, dl), S.max_throughput);
-    slot[1] = S.rate_norm_hist[rin];
-    slot[2] = S.rate_norm_hist[rout];
-    slot[3] = (float)acc;
-    slot[4] = (float)r.q1;
-    slot[5] = (float)r.q3;
-    slot[6] = (float)ddiv(r.q2, S.startup_d);
-    slot[7] = (float)r.q2;
-  }
-  st.ep_step += 1;
-  st.next_chunk = c + 1;                                   // simulator.py:105-106
-  over = st.next_chunk > st.end_chunk;
-  const int la = (action >= 0 && action < kActions) ? action : kActions;
-  st.flags = (st.flags & 0xFF) | (la << 8);
-
-  if (aux_row) {
-    double a0, a1;
-    switch (sub) {
-      case 0: a0 = (double)sz; a1 = dl; break;
-      case 1: a0 = rebuf; a1 = st.buf; break;
-      case 2: a0 = (double)st.cur_idx; a1 = st.cur_time; break;
-      case 3: a0 = r.qoe; a1 = r.q1; break;
-      case 4: a0 = r.q2; a1 = r.q3; break;
-      case 5: a0 = (double)st.next_chunk; a1 = (double)st.ep_step; break;
-      case 6: a0 = (double)st.sample_id; a1 = reward; break;
-      default: a0 = (double)(uint32_t)(gt & 0xFFFFFFFFULL); a1 = (double)(uint32_t)(gt >> 32); break;
-    }
-    reinterpret_cast<double2 *>(aux_row)[sub] = make_double2(a0, a1);
-  }
-  return reward;
-}
-
-// envs/mansy_env.py:271-290: what `_log` records when an episode ends, plus running totals.
-__device__ __forceinline__ void finish_episode(const SimDev &S, int e, const EnvState &st) {
-  double *row = S.stats + (size_t)e * MANSY_STATS_DOUBLES;
-  row[MANSY_STAT_LAST_SUM_QOE] = st.sum_qoe;
-  row[MANSY_STAT_LAST_SUM_QOE1] = st.sum_q1;
-  row[MANSY_STAT_LAST_SUM_QOE2] = st.sum_q2;
-  row[MANSY_STAT_LAST_SUM_QOE3] = st.sum_q3;
-  row[MANSY_STAT_LAST_STEPS] = (double)st.ep_step;
-  row[MANSY_STAT_LAST_SAMPLE] = (double)st.sample_id;
-  row[MANSY_STAT_LAST_RETURN] = st.ep_return;
-  row[MANSY_STAT_TOT_SUM_QOE] += st.sum_qoe;
-  row[MANSY_STAT_TOT_SUM_QOE1] += st.sum_q1;
-  row[MANSY_STAT_TOT_SUM_QOE2] += st.sum_q2;
-  row[MANSY_STAT_TOT_SUM_QOE3] += st.sum_q3;
-  row[MANSY_STAT_TOT_STEPS] += (double)st.ep_step;
-  row[MANSY_STAT_TOT_EPISODES] += 1.0;
-  row[MANSY_STAT_TOT_RETURN] += st.ep_return;
-}
+namespace mansy {
 
 // ------------------------------------------------------------------------------------------
 // kernels
@@ -493,6 +202,8 @@ int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs
                              float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
                              int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
                              int32_t timeline_cta, bool pdl, void *stream);
+int rollout_fused_launch(mansy_policy_t p, const SimDev &S, const mansy_rollout_t *b, int32_t n_steps, int64_t t0,
+                         uint64_t seed, void *stream, int *launched);
 }  // namespace mansy
 
 struct mansy_sim {
@@ -861,6 +572,13 @@ int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout
     h->timed_steps = n_steps;
   }
   const int is_probs = h->dev.obs_mode == MANSY_OBS_SIMPLE ? 1 : 0;
+  if (!timed && !(flags & (MANSY_ROLLOUT_FP32_POLICY | MANSY_ROLLOUT_TWO_KERNELS)) && n_steps > 0) {
+    // small batches: the whole loop is one launch of the fused cluster kernel (policy + sample + step per tile)
+    int launched = 0;
+    int rc = rollout_fused_launch(p, h->dev, b, n_steps, t0, seed, stream, &launched);
+    if (rc) return rc;
+    if (launched) return MANSY_OK;
+  }
   for (int32_t k = 0; k < n_steps; ++k) {
     const int64_t t = t0 + k;
     const size_t cur = (size_t)(t % b->slabs), nxt = (size_t)((t + 1) % b->slabs);

@@ -16,7 +16,8 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-from ._capi import ROLLOUT_FP32_POLICY, ROLLOUT_TIME_KERNELS, Rollout, RolloutHost, check
+from ._capi import (ROLLOUT_FP32_POLICY, ROLLOUT_NO_PDL, ROLLOUT_TIME_KERNELS, ROLLOUT_TWO_KERNELS, Rollout, RolloutHost,
+                    check)
 from .config import OBS_MODE_NONE
 from .policy import PolicyNet
 from .simulator import BatchSimulator
@@ -64,8 +65,9 @@ class PolicyRollout:
         self._c = Rollout(b.obs.data_ptr(), b.obs.stride(1), b.slabs, b.actions.data_ptr(), b.logp.data_ptr(),
                           b.value.data_ptr(), b.reward.data_ptr(), b.done.data_ptr(), b.logits.data_ptr())
 
-    def _flags(self, timed: bool = False) -> int:
-        return (0 if self.tensor_cores else ROLLOUT_FP32_POLICY) | (ROLLOUT_TIME_KERNELS if timed else 0)
+    def _flags(self, timed: bool = False, fused: bool = True, pdl: bool = True) -> int:
+        return ((0 if self.tensor_cores else ROLLOUT_FP32_POLICY) | (ROLLOUT_TIME_KERNELS if timed else 0) |
+                (0 if fused else ROLLOUT_TWO_KERNELS) | (0 if pdl else ROLLOUT_NO_PDL))
 
     def step(self) -> None:
         b, s = self.buf, self.t % self.buf.slabs
@@ -79,10 +81,12 @@ class PolicyRollout:
         self.sim.step(b.actions[s], auto_reset=True, obs=b.obs[nxt], reward=b.reward[s], done=b.done[s])
         self.t += 1
 
-    def run(self, n_steps: int, timed: bool = False) -> None:
-        """``n_steps`` rollout steps launched from C on the current stream (asynchronous)."""
+    def run(self, n_steps: int, timed: bool = False, fused: bool = True, pdl: bool = True) -> None:
+        """``n_steps`` rollout steps launched from C on the current stream (asynchronous).  Small batches run as ONE
+        launch of the fused policy+step cluster kernel unless ``fused=False`` / ``timed=True`` (two launches per
+        step, programmatic dependent launch unless ``pdl=False``)."""
         check(self.sim.lib.mansy_rollout_policy(self.sim._h, self.policy._h, C.byref(self._c), int(n_steps), self.t,
-                                                self.seed, self._flags(timed), self.sim._stream()))
+                                                self.seed, self._flags(timed, fused, pdl), self.sim._stream()))
         self.t += int(n_steps)
 
     def reserve_timing(self, n_steps: int) -> None:

@@ -68,3 +68,28 @@ def test_host_rollout_equals_device_rollout():
             assert torch.equal(host[name][t], getattr(b.buf, name)[t].cpu()), name
     h2d, d2h = a.host_bytes_per_step()
     assert h2d == 4 * n and d2h == n * (784 * 4 + 17)
+
+
+@pytest.mark.parametrize("kind,n,steps,slabs", [(OBS_MODE_MANSY, 160, 60, 61), (OBS_MODE_MANSY, 4096, 12, 3),
+                                                (OBS_MODE_SIMPLE, 333, 60, 7), (OBS_MODE_MANSY, 1, 55, 4)])
+def test_fused_rollout_equals_two_kernel_rollout(kind, n, steps, slabs):
+    """ONE launch of the fused policy+step cluster kernel for all steps == two launches per step (with and without
+    programmatic dependent launch), bit for bit, including the ring wrap of the slabs and a continued rollout."""
+    _, _, a = _setup(kind, n, True, slabs=slabs)
+    _, _, b = _setup(kind, n, True, slabs=slabs)
+    _, _, c = _setup(kind, n, True, slabs=slabs)
+    launches0 = a.sim.lib.mansy_kernel_launches()
+    a.run(steps - 5)
+    a.run(5)                               # continues at t = steps - 5
+    torch.cuda.synchronize()
+    assert a.sim.lib.mansy_kernel_launches() - launches0 == 2       # fused: one launch per call
+    b.run(steps, fused=False)
+    c.run(steps, fused=False, pdl=False)
+    torch.cuda.synchronize()
+    w = min(steps, slabs)                  # slabs the per-step rings have written (the buffers start uninitialised)
+    for other in (b, c):
+        assert torch.equal(a.buf.obs[:min(steps + 1, slabs)], other.buf.obs[:min(steps + 1, slabs)])
+        for name in ("actions", "reward", "done", "value", "logp"):
+            assert torch.equal(getattr(a.buf, name)[:w], getattr(other.buf, name)[:w]), name
+        assert torch.equal(a.sim.episode_stats(), other.sim.episode_stats())
+    assert a.sim.error_flag() == 0
