@@ -254,12 +254,12 @@ int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int
  * distributed shared memory (for batches whose tiles cannot fill the SMs), 0 = chosen from the batch size
  * (default).  In split mode hid_dbg_dev receives the hidden activations WITHOUT the `+ qoe_features`
  * residual (models/mansy.py:65,79), which that kernel applies through the output heads; in the timeline
- * [480..486] are the phase stamps (partial done, cluster sync 1, partials pushed, sync 2, heads issued,
- * sync 3, rows written) of the CTA selected with the environment variable MANSY_TC_TIMELINE_CTA. */
+ * [480, 482..486] are the phase stamps (partial done, partials stored, cluster sync 1, heads issued, cluster sync 2,
+ * rows written) of the CTA selected with the environment variable MANSY_TC_TIMELINE_CTA. */
 int mansy_policy_tc_set_split(mansy_policy_t p, int32_t split);
 /* Profiling hook of the fused rollout kernel (mansy_rollout_policy's one-launch path): CTA `cta` stamps the SM clock
  * of its SECOND rollout step into timeline_dev (int64[512], layout as above plus [489] step begin, [487] simulator
- * phase done, [488] cluster sync 5, [490..492] state loaded / step_env done / observation written); NULL turns it off. */
+ * phase done, [488] cluster sync 3, [490..492] state loaded / step_env done / observation written); NULL turns it off. */
 int mansy_debug_fused_timeline(int64_t *timeline_dev, int32_t cta);
 
 /*

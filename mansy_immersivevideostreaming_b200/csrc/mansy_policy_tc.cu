@@ -51,7 +51,8 @@ constexpr int kTcThreads = 32 * (kTcEpiWarp0 + 8);
 constexpr uint32_t kStageBytes = 65536;   // L1 job: up to 2 A boxes + 2 W1 boxes of 16 KB;  L2 job: 2 Wfc boxes of 32 KB
 constexpr uint32_t kBoxBytes = 16384;     // 128 rows x 128 B
 constexpr uint32_t kWoutBytes = 16384;     // head matrix [16 rows x 256 K] fp32 = 8 boxes of [16 x 32 floats]
-constexpr uint32_t kTcSmemBytes = kTcStages * kStageBytes + kWoutBytes + 256 /*barriers*/ + 1024 /*alignment*/;
+constexpr uint32_t kD3RecvBytes = 8192;    // cluster kernel: head partials of this CTA's 32 rows from the 4 ranks
+constexpr uint32_t kTcSmemBytes = kTcStages * kStageBytes + kWoutBytes + 256 /*barriers*/ + kD3RecvBytes + 1024 /*alignment*/;
 
 enum : uint8_t { kJobL1 = 0, kJobL2 = 1 };
 enum : uint8_t { kFlagFirst = 1, kFlagLast = 2, kFlagTileFirstL2 = 4, kFlagTileLastL2 = 8 };
@@ -103,6 +104,7 @@ struct TcArgs {
   int32_t env_offset;
   long long *timeline;  // debug: clock64 stamps [4][128] (producer issue, data arrival, mma committed, epilogue) of one CTA or NULL
   int32_t timeline_cta; // blockIdx.x of the CTA that writes the timeline
+  float4 *scratch;      // cluster kernel: [tile][dst rank 4][src rank 4][column half 2][float4 column 8][row 128] partial exchange (L2)
 };
 
 struct TcState {
@@ -111,6 +113,8 @@ struct TcState {
   int obs_floats = 0;          // 784 / 400
   int n_branches = 0;
   int split = 0;               // 0 = by batch size, 1 = one CTA per 128-env tile, 4 = split-K cluster of 4 CTAs per tile
+  float4 *scratch = nullptr;   // partial-sum exchange of the cluster kernel (128 KB per rank and tile), grown on demand
+  int scratch_tiles = 0;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -604,8 +608,10 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
   return v;
 }
-constexpr uint32_t kRecvD2Bytes = 4 * 32768;   // [src rank 4][column half 2][float4 column 8][row 128] x 16 B (stage memory)
-constexpr uint32_t kRecvD3Off = kRecvD2Bytes;  // [src rank 4][float4 column 4][row 128] x 16 B (rank 0 only)
+// Exchange buffer of the partial D2 tiles in global memory (it stays in L2): distributed shared memory moves
+// only ~20 B/clk per SM (measured: 96 KB of st.shared::cluster took 4 600 - 7 800 cycles), the L2 path several
+// times that.  Index in float4: ((((tile * 4 + dst) * 4 + src) * 2 + half) * 8 + c4) * 128 + row.
+constexpr size_t kScratchF4PerTile = 4 * 4 * 2 * 8 * 128;
 
 // Fused rollout (MODE != MANSY_OBS_NONE): the same cluster also runs the simulator step of its 128 environments
 // (32 per CTA, 8 lanes each, on the eight epilogue warps) with the action it has just sampled, writes the next
@@ -649,6 +655,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   const uint32_t bar_d3_full = bars + 184;           //               MMA (commit) -> epilogue: head partial ready
   const uint32_t bar_wout = bars + 192;              //               TMA -> MMA: head matrices resident
   const uint32_t tmem_slot = bars + 200;
+  const uint32_t d3recv = bars + 256;                // [src rank 4][float4 column 4][lane 32] x 16 B
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool tl = A.timeline != nullptr && (int)blockIdx.x == A.timeline_cta;
@@ -723,7 +730,6 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     // ================= phase A: the rank's branches -> partial D2 =================
     if (warp < kTcProducers) {
       const int hf = warp & 1;
-      if (kFused && k > 0) fence_async_smem();      // the stages were read / written through the generic proxy (phases B-D)
       for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
         if ((int)s != (warp >> 1)) continue;
         const TcJob job = P.jobs[j];
@@ -858,10 +864,9 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       tc_fence_after();
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[480] = clock64();
-    cluster_sync_all();              // (1) all four CTAs' stage memory is idle
-    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[481] = clock64();
 
-    // ================= phase B: reduce-scatter the partials over DSMEM =================
+    // ================= phase B: reduce-scatter the partials through L2 =================
+    float4 *const xch = A.scratch + (size_t)tile * kScratchF4PerTile;
     if (warp >= kTcEpiWarp0) {
 #pragma unroll 1
       for (uint32_t d = 0; d < (uint32_t)kTcRanks; ++d) {
@@ -871,27 +876,35 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) own[jj] = v[jj];
         } else {
-          const uint32_t dst = map_to_rank(stage0 + ((rank * 2u + (uint32_t)half) * 8u) * 2048u + (uint32_t)r * 16u, d);
+          float4 *dst = xch + (((d * 4u + rank) * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) st_cluster_v4(dst + c4 * 2048, v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+          for (int c4 = 0; c4 < 8; ++c4) __stcg(dst + c4 * 128, make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
         }
       }
+      tc_fence_before();
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[482] = clock64();
-    cluster_sync_all();              // (2) partials delivered
+    cluster_sync_all();              // (1) partials of all four ranks are in L2 (release / acquire at cluster scope)
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[483] = clock64();
 
     // ================= phase C: hidden slice, this rank's K-slice of the heads =================
     if (warp >= kTcEpiWarp0) {
-#pragma unroll 1
-      for (uint32_t sr = 0; sr < (uint32_t)kTcRanks; ++sr) {
-        if (sr == rank) continue;
-        const uint32_t src = stage0 + ((sr * 2u + (uint32_t)half) * 8u) * 2048u + (uint32_t)r * 16u;
+      {
+        float4 tt[24];
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 tt = ld_shared_v4(src + c4 * 2048);
-          own[4 * c4] += tt.x; own[4 * c4 + 1] += tt.y; own[4 * c4 + 2] += tt.z; own[4 * c4 + 3] += tt.w;
+        for (uint32_t j3 = 0; j3 < 3; ++j3) {
+          const uint32_t sr = j3 + (j3 >= rank ? 1u : 0u);      // the three other ranks
+          const float4 *src = xch + (((rank * 4u + sr) * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) tt[j3 * 8 + c4] = __ldcg(src + c4 * 128);
         }
+#pragma unroll
+        for (int j3 = 0; j3 < 3; ++j3)      // fixed summation order: own + the other ranks in ascending order
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            own[4 * c4] += tt[j3 * 8 + c4].x; own[4 * c4 + 1] += tt[j3 * 8 + c4].y;
+            own[4 * c4 + 2] += tt[j3 * 8 + c4].z; own[4 * c4 + 3] += tt[j3 * 8 + c4].w;
+          }
       }
       const int col0 = (int)rank * 64 + half * 32;      // hidden column (0..127 actor.fc, 128..255 critic.fc)
 #pragma unroll
@@ -906,14 +919,15 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       tc_fence_before();
       mbar_arrive(bar_hid_full);
       if (half == 0) {
+        // head partials: rows 32q .. 32q+31 are finished by rank q -> this warp's 32 rows all go to the same CTA
         mbar_wait(bar_d3_full, par);
         tc_fence_after();
         float acc[16];
         tmem_ld16(tmem_base + lane_addr + d3_col, acc);
-        if (rank != 0) {
-          const uint32_t dst = map_to_rank(stage0 + kRecvD3Off + (rank * 4u) * 2048u + (uint32_t)r * 16u, 0);
+        if ((uint32_t)q != rank) {
+          const uint32_t dst = map_to_rank(d3recv + (rank * 4u) * 512u + (uint32_t)lane * 16u, (uint32_t)q);
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) st_cluster_v4(dst + c4 * 2048, acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+          for (int c4 = 0; c4 < 4; ++c4) st_cluster_v4(dst + c4 * 512, acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
         } else {
 #pragma unroll
           for (int o = 0; o < 16; ++o) own[o] = acc[o];
@@ -937,23 +951,26 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       __syncwarp();
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[484] = clock64();
-    cluster_sync_all();              // (3) head partials delivered to rank 0
+    cluster_sync_all();              // (2) head partials delivered
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[485] = clock64();
 
-    // ================= phase D: rank 0 finishes the rows =================
-    if (rank == 0 && warp >= kTcEpiWarp0 && half == 0) {
+    // ================= phase D: each rank finishes its 32 rows (warp q == rank) =================
+    if (warp >= kTcEpiWarp0 && half == 0 && (uint32_t)q == rank) {
       float acc[16];
 #pragma unroll
-      for (int o = 0; o < 16; ++o) acc[o] = own[o] + K.bout[o];
-#pragma unroll 1
-      for (uint32_t sr = 1; sr < (uint32_t)kTcRanks; ++sr) {
-        const uint32_t src = stage0 + kRecvD3Off + (sr * 4u) * 2048u + (uint32_t)r * 16u;
+      for (int o = 0; o < 16; ++o) acc[o] = own[o];
+#pragma unroll
+      for (uint32_t j3 = 0; j3 < 3; ++j3) {     // fixed order: own + the other ranks ascending
+        const uint32_t sr = j3 + (j3 >= rank ? 1u : 0u);
+        const uint32_t src = d3recv + (sr * 4u) * 512u + (uint32_t)lane * 16u;
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 tt = ld_shared_v4(src + c4 * 2048);
+          const float4 tt = ld_shared_v4(src + c4 * 512);
           acc[4 * c4] += tt.x; acc[4 * c4 + 1] += tt.y; acc[4 * c4 + 2] += tt.z; acc[4 * c4 + 3] += tt.w;
         }
       }
+#pragma unroll
+      for (int o = 0; o < 16; ++o) acc[o] += K.bout[o];
       int act = 0;
       if (live) {
         const size_t orow = kFused ? (size_t)cur * A.n + env : (size_t)env;   // fused: outputs of step t live in slab t % slabs
@@ -985,16 +1002,14 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           if (A.logp) A.logp[orow] = lp;
         }
       }
-      if (kFused) {     // hand the action to the CTA that steps this environment (rows 32d .. 32d+31 -> rank d)
-        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(map_to_rank(act_s + (uint32_t)(r & 31) * 4u, (uint32_t)(r >> 5))), "r"(act) : "memory");
-      }
+      if (kFused) asm volatile("st.shared.s32 [%0], %1;" ::"r"(act_s + (uint32_t)lane * 4u), "r"(act) : "memory");
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[486] = clock64();
 
     if (kFused) {
-      cluster_sync_all();            // (4) actions delivered
       // ================= phase E: simulator chunk-step of this CTA's 32 environments =================
       if (warp >= kTcEpiWarp0) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps: actions are in act_s
         const int et = (int)threadIdx.x - 32 * kTcEpiWarp0;
         const int i = tile * 128 + (int)rank * 32 + (et >> 3);
         const int sub = et & 7;
@@ -1030,13 +1045,12 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           store_state(S, i, st, sub);
           if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[492] = clock64();
         }
-        // the next step's TMA (async proxy) reads the rows just written through the generic proxy, and writes the
-        // stage memory read above
+        // the next step's TMA (async proxy) reads the rows just written through the generic proxy
         asm volatile("fence.proxy.async;" ::: "memory");
         __threadfence();
       }
       if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[487] = clock64();
-      cluster_sync_all();            // (5) the next observation rows of the tile are complete
+      cluster_sync_all();            // (3) the next observation rows of the tile are complete
       if (warp < kTcProducers) asm volatile("fence.proxy.async;" ::: "memory");
       if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[488] = clock64();
     }
@@ -1283,8 +1297,23 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
   return MANSY_OK;
 }
 
+// Exchange buffer of the cluster kernel: (re)allocated when a larger batch shows up (not stream-ordered: callers
+// that time launches warm up first).
+static int ensure_scratch(mansy_policy *p, int n_tiles) {
+  TcState *st = p->tc;
+  if (st->scratch_tiles >= n_tiles) return MANSY_OK;
+  if (st->scratch) { cudaDeviceSynchronize(); cudaFree(st->scratch); st->scratch = nullptr; st->scratch_tiles = 0; }
+  void *d = nullptr;
+  if (cudaMalloc(&d, (size_t)n_tiles * kScratchF4PerTile * sizeof(float4)) != cudaSuccess)
+    return set_error(MANSY_E_NOMEM, "cudaMalloc failed (split-K exchange buffer)");
+  st->scratch = static_cast<float4 *>(d);
+  st->scratch_tiles = n_tiles;
+  return MANSY_OK;
+}
+
 void tc_destroy(mansy_policy *p) {
   if (!p || !p->tc) return;
+  if (p->tc->scratch) cudaFree(p->tc->scratch);
   {
     std::lock_guard<std::mutex> g(g_slot_mutex);
     g_slot_used[p->tc->slot] = false;
@@ -1334,6 +1363,10 @@ int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs
   // split-K clusters pay off while the tiles alone cannot fill the SMs (a cluster finishes a tile ~3-4x sooner
   // but occupies four SMs); beyond ~3/4 of the SM count the persistent one-CTA-per-tile kernel is as fast.
   const bool split4 = p->tc->split == 4 || (p->tc->split == 0 && 4 * a.n_tiles <= 3 * n_sm);
+  if (split4) {
+    if ((rc = ensure_scratch(p, a.n_tiles))) return rc;
+    a.scratch = p->tc->scratch;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
   static const FusedArgs *fz = new FusedArgs();      // value-initialised: the policy-only instantiation ignores it
@@ -1415,6 +1448,8 @@ int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t
   a.logits = b->logits; a.value = b->value; a.actions = b->actions; a.logp = b->logp;
   a.seed = seed; a.step = t0; a.env_offset = S.env_offset;
   a.timeline = g_fused_timeline; a.timeline_cta = g_fused_timeline_cta;
+  if ((rc = ensure_scratch(p, n_tiles))) return rc;
+  a.scratch = p->tc->scratch;
   FusedArgs f;
   memset(&f, 0, sizeof(f));
   f.S = S;

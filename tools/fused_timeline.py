@@ -23,9 +23,9 @@ roll = PolicyRollout(sim, policy, 27, seed=1234)
 roll.run(20)
 torch.cuda.synchronize()
 tl = torch.zeros(512, dtype=torch.int64, device="cuda")
-names = {489: "step begin", 480: "partial D2 done", 481: "cluster sync 1", 482: "partials pushed", 483: "cluster sync 2",
-         484: "heads issued / D3 pushed", 485: "cluster sync 3", 486: "rows written, actions pushed", 490: "sync 4 + state loaded",
-         491: "step_env done", 492: "observation row + state stored", 487: "simulator phase done (fences)", 488: "cluster sync 5"}
+names = {489: "step begin", 480: "partial D2 done", 482: "partials stored (L2 exchange)", 483: "cluster sync 1",
+         484: "hidden slice + heads, D3 pushed", 485: "cluster sync 2", 486: "own 32 rows finished (sample)", 490: "state loaded",
+         491: "step_env done", 492: "observation row + state stored", 487: "simulator phase done (fences)", 488: "cluster sync 3"}
 for cta in ctas:
     tl.zero_()
     check(sim.lib.mansy_debug_fused_timeline(tl.data_ptr(), cta))
@@ -38,7 +38,7 @@ for cta in ctas:
         if t[j] == 0:
             break
         print(f"  job {j:2d}: TMA issue {t[j]-t0:6d}  operands {t[128+j]-t0:6d}  MMAs issued {t[256+j]-t0:6d}")
-    for key in (480, 481, 482, 483, 484, 485, 486, 490, 491, 492, 487, 488):
+    for key in (480, 482, 483, 484, 485, 486, 490, 491, 492, 487, 488):
         print(f"  {names[key]:34s} {t[key]-t0:7d}")
 check(sim.lib.mansy_debug_fused_timeline(None, 0))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

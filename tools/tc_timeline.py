@@ -30,11 +30,12 @@ for j in range(128):
 print("epilogue begin/end per branch:")
 for i in range(11):
     print(i, t[384+2*i]-t0, t[385+2*i]-t0)
-names = ["partial D2 done", "cluster sync 1", "partials pushed", "cluster sync 2", "heads issued/D3 pushed", "cluster sync 3", "rows written"]
+names = {480: "partial D2 done", 482: "partials stored (L2)", 483: "cluster sync 1", 484: "hidden + heads, D3 pushed",
+         485: "cluster sync 2", 486: "own 32 rows written"}
 if t[480]:
     print("split-K phases (CTA MANSY_TC_TIMELINE_CTA, cycles since kernel start):")
-    for k, nm in enumerate(names):
-        print(f"  {nm:24s} {t[480+k]-t0:7d}")
+    for k, nm in names.items():
+        print(f"  {nm:28s} {t[k]-t0:7d}")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for rep in range(50):
