@@ -954,6 +954,32 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     cluster_sync_all();              // (2) head partials delivered
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[485] = clock64();
 
+    if (kFused && warp < kTcEpiWarp0 && warp != kTcMmaWarp) {
+      // Which chunk the NEXT observation describes does not depend on the action about to be sampled
+      // (simulator.py:105-106: next_chunk += 1; mansy_env.py:100-101: the sample after a finished episode), so
+      // its table rows (next chunk sizes / qualities, predicted viewport: 704 of 784 floats) are written by the
+      // seven warps that have nothing else to do (TMA producers, spare warp) while the epilogue warps sample the
+      // actions and run the simulator phase, which then only adds the dynamic columns.  (After cluster sync 2:
+      // barrier.cluster counts every thread, so work placed earlier would hold the other CTAs up.)
+      const int w7 = warp < kTcMmaWarp ? warp : kTcMmaWarp;     // 0..6
+      const int nxt = (int)((t + 1) % F.slabs);
+#pragma unroll 1
+      for (int el = w7 * 4 + (lane >> 3); el < 32; el += 28) {
+        const int ei = tile * 128 + (int)rank * 32 + el;
+        if (ei < A.n) {
+          EnvState nx;
+          load_state(F.S, ei, nx);
+          if (!(nx.flags & kFlagFinished)) {
+            if (nx.next_chunk + 1 > nx.end_chunk) reset_episode(F.S, nx);
+            else nx.next_chunk += 1;
+          }
+          emit_obs_tables<MODE>(F.S, nx.video, nx.pair, nx.start_chunk, min(nx.next_chunk, nx.end_chunk), lane & 7,
+                                F.obs + ((size_t)nxt * A.n + ei) * F.obs_stride);
+        }
+      }
+      asm volatile("bar.arrive 2, 480;" ::: "memory");     // state(t) has been read: the simulator phase may overwrite it
+      asm volatile("fence.proxy.async;" ::: "memory");      // rows are read by the next step's TMA (async proxy)
+    }
     // ================= phase D: each rank finishes its 32 rows (warp q == rank) =================
     if (warp >= kTcEpiWarp0 && half == 0 && (uint32_t)q == rank) {
       float acc[16];
@@ -1013,11 +1039,11 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         const int et = (int)threadIdx.x - 32 * kTcEpiWarp0;
         const int i = tile * 128 + (int)rank * 32 + (et >> 3);
         const int sub = et & 7;
+        const SimDev &S = F.S;
+        EnvState st;
         if (i < A.n) {                 // the 8 lanes of an environment leave together
-          const SimDev &S = F.S;
           const unsigned gmask = group_mask();
           const int nxt = (int)((t + 1) % F.slabs);
-          EnvState st;
           float slot[8];
           load_state(S, i, st);
           load_slot(S, i, sub, slot);
@@ -1041,13 +1067,13 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
             F.reward[(size_t)cur * A.n + i] = reward_f;
             F.done[(size_t)cur * A.n + i] = over ? 1 : 0;
           }
-          emit_obs<MODE>(S, st, slot, sub, gmask, F.obs + ((size_t)nxt * A.n + i) * F.obs_stride);
-          store_state(S, i, st, sub);
-          if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[492] = clock64();
+          emit_obs_dynamic<MODE>(S, st, slot, sub, gmask, F.obs + ((size_t)nxt * A.n + i) * F.obs_stride);
         }
+        asm volatile("bar.sync 2, 480;" ::: "memory");       // the table-row warps have read state(t)
+        if (i < A.n) store_state(S, i, st, sub);
+        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[492] = clock64();
         // the next step's TMA (async proxy) reads the rows just written through the generic proxy
         asm volatile("fence.proxy.async;" ::: "memory");
-        __threadfence();
       }
       if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[487] = clock64();
       cluster_sync_all();            // (3) the next observation rows of the tile are complete

@@ -52,7 +52,7 @@ namespace mansy {
 // kernels
 // ------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kThreadsPerBlock)
+__global__ void __launch_bounds__(kThreadsPerBlock, 4)
 step_kernel(const __grid_constant__ SimDev S, const __grid_constant__ StepArgs A) {
   // Programmatic dependent launch (no-ops without the launch attribute): the next kernel of the stream may be
   // scheduled right away -- it orders itself behind our completion -- and everything we read below (actions,
@@ -101,7 +101,7 @@ step_kernel(const __grid_constant__ SimDev S, const __grid_constant__ StepArgs A
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreadsPerBlock)
+__global__ void __launch_bounds__(kThreadsPerBlock, 4)
 reset_kernel(const __grid_constant__ SimDev S, const int32_t *__restrict__ env_ids, int n, float *__restrict__ obs,
              int64_t obs_stride) {
   const int i = blockIdx.x * kEnvsPerBlock + (threadIdx.x >> 3);
@@ -391,15 +391,44 @@ int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, ma
   MANSY_TRY(upload(h, t->video_time, (size_t)t->n_videos, &d.video_time));
   MANSY_TRY(upload(h, t->vp_gt, n_vp, &d.vp_gt));
   MANSY_TRY(upload(h, t->vp_pred, n_vp, &d.vp_pred));
+  {
+    // allocate_tile_rates' scale map (utils/common.py:142-168) once per (viewport pair, chunk) instead of once per
+    // environment step: 64 toroidal distances, 4 bits each, one 32-bit word per tile row
+    std::vector<uint32_t> scale(n_vp * 8);
+    for (size_t v = 0; v < n_vp; ++v) {
+      const TileScaleMasks m = tile_scale_masks(t->vp_pred[v]);
+      for (int row = 0; row < 8; ++row) {
+        uint32_t w = 0;
+        for (int i = 0; i < 8; ++i) w |= (uint32_t)tile_scale(m, row * 8 + i) << (4 * i);
+        scale[v * 8 + row] = w;
+      }
+    }
+    MANSY_TRY(upload(h, scale.data(), scale.size(), &d.vp_scale));
+  }
   MANSY_TRY(upload(h, t->vp_acc, n_vp, &d.vp_acc));
   MANSY_TRY(upload(h, t->vp_start, n_pairs, &d.vp_start));
   MANSY_TRY(upload(h, t->vp_end, n_pairs, &d.vp_end));
-  MANSY_TRY(upload(h, t->trace, (size_t)t->n_traces * t->trace_stride, &d.trace));
+  {
+    // device copy of the traces with 8 wrap-around entries appended to every row (entry[len + m] = entry[m % len]),
+    // so that the 8 lanes of an environment can fetch the window cur_idx .. cur_idx + 7 with one load each and no
+    // modulo (network.py:29 wraps the index)
+    const int stride_dev = t->trace_stride + kTraceWindow;
+    std::vector<double> padded((size_t)t->n_traces * stride_dev, 0.0);
+    for (int k = 0; k < t->n_traces; ++k) {
+      const double *src = t->trace + (size_t)k * t->trace_stride;
+      double *dst = padded.data() + (size_t)k * stride_dev;
+      const int len = t->trace_len[k];
+      for (int i = 0; i < len; ++i) dst[i] = src[i];
+      for (int m = 0; m < kTraceWindow; ++m) dst[len + m] = src[m % len];
+    }
+    MANSY_TRY(upload(h, padded.data(), padded.size(), &d.trace));
+    d.trace_stride = stride_dev;
+  }
   MANSY_TRY(upload(h, t->trace_len, (size_t)t->n_traces, &d.trace_len));
   MANSY_TRY(upload(h, t->qoe_w, (size_t)t->n_qoe * 3, &d.qoe_w));
   MANSY_TRY(upload(h, t->samples, (size_t)t->n_samples * 4, &d.samples));
   d.n_videos = t->n_videos; d.n_chunks = t->n_chunks; d.n_users = t->n_users; d.n_vp_chunks = t->n_vp_chunks;
-  d.n_traces = t->n_traces; d.trace_stride = t->trace_stride; d.n_qoe = t->n_qoe; d.n_samples = t->n_samples;
+  d.n_traces = t->n_traces; d.n_qoe = t->n_qoe; d.n_samples = t->n_samples;
 
   const size_t n = (size_t)cfg->n_envs;
   MANSY_TRY(dev_alloc(h, n, &d.state));

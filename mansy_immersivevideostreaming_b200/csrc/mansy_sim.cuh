@@ -17,6 +17,7 @@ constexpr int kThreadsPerBlock = 128;
 constexpr int kEnvsPerBlock = kThreadsPerBlock / kLanesPerEnv;
 constexpr int kTableRow = kRates * kTiles;  // 320 values per (video, chunk)
 constexpr int kNoAction = 255;
+constexpr int kTraceWindow = 8;    // trace entries an environment's 8 lanes prefetch per load (device rows are wrap-padded by this)
 
 // Per-environment state: one 128-byte line, read with 8 broadcast 128-bit loads by the 8 lanes of
 // the env's group and written back one quad per lane.
@@ -61,6 +62,7 @@ struct SimDev {
   const int32_t *video_time;
   const uint64_t *vp_gt;
   const uint64_t *vp_pred;
+  const uint32_t *vp_scale;  // [pairs][n_vp_chunks][8]: per tile row, 8 x 4-bit pyramid scales derived from vp_pred (step_env)
   const double *vp_acc;
   const int32_t *vp_start;
   const int32_t *vp_end;

@@ -106,32 +106,88 @@ __device__ __forceinline__ void reset_episode(const SimDev &S, EnvState &st) {
   st.ep_return = 0.0;
 }
 
-// Observation row from the env state (a pure function of state + history ring).
+// network.py:22-35 with the trace window held by the environment's 8 lanes: lane j of the group owns entry
+// cur_idx + j of the wrap-padded row (one load per lane, issued by the caller before the dependent work), the
+// sequential walk reads entry `pos` with a shuffle and only reloads every 8 seconds of simulated download.
+// Arithmetic and operation order are those of trace_download (mansy_core.cuh): results are bit-identical.
+__device__ __forceinline__ double trace_download_window(double size, double win, const double *__restrict__ tr, int trace_len,
+                                                        int &cur_idx, double &cur_time, int sub, unsigned gmask, bool &ok) {
+  const double start = cur_time;
+  const int base = (threadIdx.x & 31) & ~7;
+  int pos = 0, it = 0;
+  while (size > 0.0) {
+    if (pos == kTraceWindow) {
+      win = __ldg(tr + cur_idx + sub);
+      pos = 0;
+    }
+    const double thr = __shfl_sync(gmask, win, base + pos);
+    const double next_tick = floor(dadd(cur_time, 1.0));
+    const double remain = dmul(dsub(next_tick, cur_time), thr);
+    if (size >= remain) {
+      cur_idx = (cur_idx + 1 == trace_len) ? 0 : cur_idx + 1;
+      cur_time = next_tick;
+      size = dsub(size, remain);
+      ++pos;
+    } else {
+      cur_time = dadd(cur_time, ddiv(size, thr));
+      size = 0.0;
+    }
+    if (++it > (1 << 22)) { ok = false; break; }
+  }
+  return dsub(cur_time, start);
+}
+
+// Observation row from the env state (a pure function of state + history ring), in two parts: the rows copied
+// from the read-only tables (next chunk sizes / qualities, predicted viewport), which depend only on WHICH chunk
+// comes next, and the dynamic part (history columns, last action, buffer, qoe weights).  The fused rollout
+// kernel writes the table part early (the next chunk is known before the action is), everything else calls
+// emit_obs.
 template <int MODE>
-__device__ __forceinline__ void emit_obs(const SimDev &S, const EnvState &st, const float (&slot)[8], int sub,
-                                         unsigned gmask, float *__restrict__ row) {
-  const int pushes = st.ep_step;
-  const int newest = (pushes - 1) & 7;
-  const int k = (newest - sub) & 7;         // observation index of this lane's slot (0 = newest)
-  const bool valid = k < pushes;            // older entries are still the zeros of reset
-  const int la = (st.flags >> 8) & 0xFF;    // last action: 0..14, 15 = out-of-table action, 255 = none
-  const int obs_chunk = min(st.next_chunk, st.end_chunk);   // terminal obs repeats the last chunk
-  const uint64_t pred = __ldg(S.vp_pred + (size_t)st.pair * S.n_vp_chunks + (obs_chunk - st.start_chunk));
-  const size_t tab = ((size_t)st.video * S.n_chunks + obs_chunk) * kTableRow;
+__device__ __forceinline__ void emit_obs_tables(const SimDev &S, int video, int pair, int start_chunk, int obs_chunk, int sub,
+                                                float *__restrict__ row) {
+  const uint64_t pred = __ldg(S.vp_pred + (size_t)pair * S.n_vp_chunks + (obs_chunk - start_chunk));
+  const size_t tab = ((size_t)video * S.n_chunks + obs_chunk) * kTableRow;
   const uint32_t pbyte = (uint32_t)(pred >> (8 * sub)) & 0xFFu;
   const float4 p0 = make_float4((float)(pbyte & 1u), (float)((pbyte >> 1) & 1u), (float)((pbyte >> 2) & 1u),
                                 (float)((pbyte >> 3) & 1u));
   const float4 p1 = make_float4((float)((pbyte >> 4) & 1u), (float)((pbyte >> 5) & 1u),
                                 (float)((pbyte >> 6) & 1u), (float)((pbyte >> 7) & 1u));
   const float4 *s4 = reinterpret_cast<const float4 *>(S.size_norm + tab);
-
+  float4 *ds = reinterpret_cast<float4 *>(row + 8);
+  float4 tv[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) tv[i] = __ldg(s4 + sub + 8 * i);
   if (MODE == MANSY_OBS_MANSY) {
     const float4 *q4 = reinterpret_cast<const float4 *>(S.qual_norm + tab);
-    float4 *ds = reinterpret_cast<float4 *>(row + 8);
     float4 *dq = reinterpret_cast<float4 *>(row + 328);
-    float4 tv[10];
+    float4 tq[10];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) tv[i] = __ldg(s4 + sub + 8 * i);
+    for (int i = 0; i < 10; ++i) tq[i] = __ldg(q4 + sub + 8 * i);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) ds[sub + 8 * i] = tv[i];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) dq[sub + 8 * i] = tq[i];
+    float4 *dp = reinterpret_cast<float4 *>(row + 648);
+    dp[2 * sub] = p0;
+    dp[2 * sub + 1] = p1;
+  } else {  // MANSY_OBS_SIMPLE
+#pragma unroll
+    for (int i = 0; i < 10; ++i) ds[sub + 8 * i] = tv[i];
+    float4 *dp = reinterpret_cast<float4 *>(row + 328);
+    dp[2 * sub] = p0;
+    dp[2 * sub + 1] = p1;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void emit_obs_dynamic(const SimDev &S, const EnvState &st, const float (&slot)[8], int sub,
+                                                 unsigned gmask, float *__restrict__ row) {
+  const int pushes = st.ep_step;
+  const int newest = (pushes - 1) & 7;
+  const int k = (newest - sub) & 7;         // observation index of this lane's slot (0 = newest)
+  const bool valid = k < pushes;            // older entries are still the zeros of reset
+  const int la = (st.flags >> 8) & 0xFF;    // last action: 0..14, 15 = out-of-table action, 255 = none
+  if (MODE == MANSY_OBS_MANSY) {
     row[0 + k] = valid ? slot[0] : 0.f;      // throughput
     row[712 + k] = valid ? slot[1] : 0.f;    // rates_inside
     row[720 + k] = valid ? slot[2] : 0.f;    // rates_outside
@@ -139,15 +195,6 @@ __device__ __forceinline__ void emit_obs(const SimDev &S, const EnvState &st, co
     row[736 + k] = valid ? slot[4] : 0.f;    // past_viewport_qualities
     row[744 + k] = valid ? slot[5] : 0.f;    // past_quality_variances
     row[752 + k] = valid ? slot[6] : 0.f;    // past_rebuffering
-#pragma unroll
-    for (int i = 0; i < 10; ++i) ds[sub + 8 * i] = tv[i];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) tv[i] = __ldg(q4 + sub + 8 * i);
-#pragma unroll
-    for (int i = 0; i < 10; ++i) dq[sub + 8 * i] = tv[i];
-    float4 *dp = reinterpret_cast<float4 *>(row + 648);
-    dp[2 * sub] = p0;
-    dp[2 * sub + 1] = p1;
     if (sub < 4) {            // action_one_hot (15 + 1 pad)
       const int b = 4 * sub;
       reinterpret_cast<float4 *>(row + 760)[sub] =
@@ -161,17 +208,8 @@ __device__ __forceinline__ void emit_obs(const SimDev &S, const EnvState &st, co
       reinterpret_cast<float4 *>(row + 780)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else {  // MANSY_OBS_SIMPLE
-    float4 *ds = reinterpret_cast<float4 *>(row + 8);
-    float4 sv[10];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) sv[i] = __ldg(s4 + sub + 8 * i);
     const float rb_newest = __shfl_sync(gmask, slot[7], ((threadIdx.x & 31) & ~7) + newest);
     row[0 + k] = valid ? slot[0] : 0.f;
-#pragma unroll
-    for (int i = 0; i < 10; ++i) ds[sub + 8 * i] = sv[i];
-    float4 *dp = reinterpret_cast<float4 *>(row + 328);
-    dp[2 * sub] = p0;
-    dp[2 * sub + 1] = p1;
     if (sub == 0) {           // last_bitrates (2), rebuffer (1), pad
       float lb0 = 0.f, lb1 = 0.f;
       if (la != kNoAction) {
@@ -187,6 +225,13 @@ __device__ __forceinline__ void emit_obs(const SimDev &S, const EnvState &st, co
   }
 }
 
+template <int MODE>
+__device__ __forceinline__ void emit_obs(const SimDev &S, const EnvState &st, const float (&slot)[8], int sub,
+                                         unsigned gmask, float *__restrict__ row) {
+  emit_obs_tables<MODE>(S, st.video, st.pair, st.start_chunk, min(st.next_chunk, st.end_chunk), sub, row);  // terminal obs repeats the last chunk
+  emit_obs_dynamic<MODE>(S, st, slot, sub, gmask, row);
+}
+
 // One chunk-step of one environment (8 lanes).  Returns the reward; `over` tells whether the
 // episode ended.  aux_row / ver_row may be NULL.
 __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float (&slot)[8], int sub, unsigned gmask,
@@ -195,13 +240,20 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
   const int c = st.next_chunk;
   const size_t vi = (size_t)st.pair * S.n_vp_chunks + (c - st.start_chunk);   // hmdtrace.py:16-19
   const uint64_t gt = __ldg(S.vp_gt + vi);
-  const uint64_t pred = __ldg(S.vp_pred + vi);
+  // pyramid scales (toroidal Chebyshev distance to the predicted viewport, utils/common.py:142-168) of this lane's
+  // 8 tiles, 4 bits each: a table derived from vp_pred when the handle is created (same tile_scale_masks code)
+  const uint32_t scales = __ldg(S.vp_scale + vi * 8 + sub);
   const double acc = __ldg(S.vp_acc + vi);
+
+  // bandwidth-trace window and length: issued before the dependent gather / reduction work below
+  const double *tr = S.trace + (size_t)st.trace * S.trace_stride;
+  const double win = __ldg(tr + st.cur_idx + sub);
+  const int tlen = __ldg(S.trace_len + st.trace);
 
   int rin, rout;
   action_to_rates(action, rin, rout);
-  const TileScaleMasks dm = tile_scale_masks(pred);
-  const uint32_t lutw = S.lut[rout];
+  const uint32_t vtab = (S.lut[rout] & ~7u) | (uint32_t)rin;   // 3-bit entries: scale 0 -> rate_in, s >= 1 -> lut[rate_out][s]
+  const uint32_t gbyte = (uint32_t)(gt >> (8 * sub)) & 0xFFu;  // actual-viewport bits of this lane's tiles
   const size_t tab = ((size_t)st.video * S.n_chunks + c) * kTableRow;
 
   // simulator.py:94-101: gather size / quality of the chosen version of each tile; this lane owns
@@ -213,11 +265,11 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int t = sub * 8 + i;
-    const int ver = tile_version(lutw, rin, tile_scale(dm, t));
+    const int ver = (int)((vtab >> (3u * ((scales >> (4 * i)) & 7u))) & 7u);
     const int off = ver * kTiles + t;
     sz += __ldg(S.size + tab + off);
     q[i] = __ldg(S.quality + tab + off);
-    if ((gt >> t) & 1ULL) mq = dadd(mq, (double)q[i]);
+    if ((gbyte >> i) & 1u) mq = dadd(mq, (double)q[i]);
     if (i < 4) vpack_lo |= (uint32_t)ver << (8 * i); else vpack_hi |= (uint32_t)ver << (8 * (i - 4));
   }
   if (ver_row) reinterpret_cast<uint2 *>(ver_row)[sub] = make_uint2(vpack_lo, vpack_hi);
@@ -226,10 +278,8 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
   const double sm = (double)__popcll(gt);
 
   // network.py:22-35 / buffer.py:8-15
-  const double *tr = S.trace + (size_t)st.trace * S.trace_stride;
-  const int tlen = __ldg(S.trace_len + st.trace);
   bool ok = true;
-  const double dl = trace_download((double)sz, TracePtr{tr}, tlen, st.cur_idx, st.cur_time, ok);
+  const double dl = trace_download_window((double)sz, win, tr, tlen, st.cur_idx, st.cur_time, sub, gmask, ok);
   if (!ok && sub == 0) atomicExch(S.error_flag, 1);
   const double rebuf = buffer_push(st.buf, S.chunk_length, dl);
 
@@ -239,7 +289,7 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
   double dev = 0.0;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
-    if ((gt >> (sub * 8 + i)) & 1ULL) dev = dadd(dev, (double)fabsf(fsub(q[i], vq32)));
+    if ((gbyte >> i) & 1u) dev = dadd(dev, (double)fabsf(fsub(q[i], vq32)));
   dev = group_sum(dev, gmask);
   const QoE r = qoe_from_sums(vq, dev, sm, rebuf, st.ep_step == 0, st.prev_vq, (double)st.w0, (double)st.w1,
                               (double)st.w2, S.max_quality);
