@@ -44,6 +44,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     cmd: List[str] = [find_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC]
+    cmd += os.environ.get("MANSY_NVCC_EXTRA", "").split()          # tuning experiments, e.g. -DMANSY_STEP_MIN_BLOCKS=6
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]

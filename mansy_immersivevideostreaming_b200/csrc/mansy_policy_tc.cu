@@ -1041,20 +1041,23 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         const int sub = et & 7;
         const SimDev &S = F.S;
         EnvState st;
-        if (i < A.n) {                 // the 8 lanes of an environment leave together
-          const unsigned gmask = group_mask();
-          const int nxt = (int)((t + 1) % F.slabs);
-          float slot[8];
+        float slot[8];
+        const bool live_e = i < A.n;
+        if (live_e) {
           load_state(S, i, st);
           load_slot(S, i, sub, slot);
-          if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[490] = clock64() + (st.flags & 0);
+        }
+        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[490] = clock64() + (st.flags & 0);
+        int action;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(action) : "r"(act_s + (uint32_t)(et >> 3) * 4u) : "memory");
+        const int nxt = (int)((t + 1) % F.slabs);
+        // full-mask collectives when all four environments of the warp step together (always, except in a tail tile)
+        auto sim_step = [&](unsigned mask) {
           float reward_f = 0.f;
           bool over = true;
           if (!(st.flags & kFlagFinished)) {
-            int action;
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(action) : "r"(act_s + (uint32_t)(et >> 3) * 4u) : "memory");
             const int slot_before = st.ep_step & 7;
-            const double reward = step_env(S, st, slot, sub, gmask, action, over, nullptr, nullptr);
+            const double reward = step_env(S, st, slot, sub, mask, action, over, nullptr, nullptr);
             reward_f = (float)reward;
             if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[491] = clock64() + (reward_f > 1e30f);
             if (sub == slot_before) store_slot(S, i, sub, slot);
@@ -1067,8 +1070,10 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
             F.reward[(size_t)cur * A.n + i] = reward_f;
             F.done[(size_t)cur * A.n + i] = over ? 1 : 0;
           }
-          emit_obs_dynamic<MODE>(S, st, slot, sub, gmask, F.obs + ((size_t)nxt * A.n + i) * F.obs_stride);
-        }
+          emit_obs_dynamic<MODE>(S, st, slot, sub, mask, F.obs + ((size_t)nxt * A.n + i) * F.obs_stride);
+        };
+        if (__all_sync(0xFFFFFFFFu, live_e && !(st.flags & kFlagFinished))) sim_step(0xFFFFFFFFu);
+        else if (live_e) sim_step(group_mask());
         asm volatile("bar.sync 2, 480;" ::: "memory");       // the table-row warps have read state(t)
         if (i < A.n) store_state(S, i, st, sub);
         if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[492] = clock64();

@@ -20,6 +20,10 @@
 
 #include "mansy_sim.cuh"
 
+#ifndef MANSY_STEP_MIN_BLOCKS
+#define MANSY_STEP_MIN_BLOCKS 5   // resident CTAs per SM the step kernel is compiled for (register cap 65536 / (128 * this)); 4 / 5 / 6 / 8 measured: 58.7 / 65.2 / 63.7 / 58.4 % of HBM peak at 1 Mi envs
+#endif
+
 namespace mansy {
 
 // ------------------------------------------------------------------------------------------
@@ -51,53 +55,67 @@ namespace mansy {
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
+// One step of one environment group inside step_kernel.  `mask` is the shuffle mask of the group's collectives:
+// the constant 0xFFFFFFFF when the whole warp is known to execute this together (plain SHFL), else the 8-lane
+// group mask (partial-mask collectives cost ~10x the instructions).
 template <int MODE>
-__global__ void __launch_bounds__(kThreadsPerBlock, 4)
+__device__ __forceinline__ void step_once(const SimDev &S, const StepArgs &A, EnvState &st, float (&slot)[8], int e, int i,
+                                          int sub, unsigned mask, int t) {
+  const size_t r = (size_t)t * A.rows_per_step + i;
+  float reward_f = 0.f;
+  bool over = true;
+  if (!(st.flags & kFlagFinished)) {
+    const int action = A.action_mode == 0
+                           ? __ldg(A.actions + i)
+                           : hashed_action(A.seed, (uint64_t)(S.env_offset + e), (uint64_t)(A.step0 + t), kActions);
+    const int slot_before = st.ep_step & 7;
+    const double reward = step_env(S, st, slot, sub, mask, action, over,
+                                   A.out.aux ? A.out.aux + r * MANSY_AUX_DOUBLES : nullptr,
+                                   A.out.tile_versions ? A.out.tile_versions + r * kTiles : nullptr);
+    reward_f = (float)reward;
+    if (A.n_steps == 1 && sub == slot_before) store_slot(S, e, sub, slot);
+    if (over) {
+      if (sub == 0) finish_episode(S, e, st);
+      if (A.auto_reset) reset_episode(S, st);
+      else st.flags |= kFlagFinished;
+    }
+  }
+  if (sub == 0) {
+    if (A.out.reward) A.out.reward[r] = reward_f;
+    if (A.out.done) A.out.done[r] = over ? 1 : 0;
+  }
+  if (MODE != MANSY_OBS_NONE && A.out.obs) emit_obs<MODE>(S, st, slot, sub, mask, A.out.obs + r * A.out.obs_stride);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreadsPerBlock, MANSY_STEP_MIN_BLOCKS)
 step_kernel(const __grid_constant__ SimDev S, const __grid_constant__ StepArgs A) {
   // Programmatic dependent launch (no-ops without the launch attribute): the next kernel of the stream may be
   // scheduled right away -- it orders itself behind our completion -- and everything we read below (actions,
   // state, history) may have been written by the kernels before us.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int i = blockIdx.x * kEnvsPerBlock + (threadIdx.x >> 3);   // output row
-  if (i >= A.n) return;                                            // whole 8-lane group leaves together
+  const bool live = i < A.n;                                       // lanes past the end stay for the warp votes below
   const int sub = threadIdx.x & 7;
   const unsigned gmask = group_mask();
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int e = A.env_ids ? __ldg(A.env_ids + i) : i;
+  const int e = live ? (A.env_ids ? __ldg(A.env_ids + i) : i) : 0;
 
   EnvState st;
   float slot[8];
-  load_state(S, e, st);
-  load_slot(S, e, sub, slot);
-
-  for (int t = 0; t < A.n_steps; ++t) {
-    const size_t r = (size_t)t * A.rows_per_step + i;
-    float reward_f = 0.f;
-    bool over = true;
-    if (!(st.flags & kFlagFinished)) {
-      const int action = A.action_mode == 0
-                             ? __ldg(A.actions + i)
-                             : hashed_action(A.seed, (uint64_t)(S.env_offset + e), (uint64_t)(A.step0 + t), kActions);
-      const int slot_before = st.ep_step & 7;
-      const double reward = step_env(S, st, slot, sub, gmask, action, over,
-                                     A.out.aux ? A.out.aux + r * MANSY_AUX_DOUBLES : nullptr,
-                                     A.out.tile_versions ? A.out.tile_versions + r * kTiles : nullptr);
-      reward_f = (float)reward;
-      if (A.n_steps == 1 && sub == slot_before) store_slot(S, e, sub, slot);
-      if (over) {
-        if (sub == 0) finish_episode(S, e, st);
-        if (A.auto_reset) reset_episode(S, st);
-        else st.flags |= kFlagFinished;
-      }
-    }
-    if (sub == 0) {
-      if (A.out.reward) A.out.reward[r] = reward_f;
-      if (A.out.done) A.out.done[r] = over ? 1 : 0;
-    }
-    if (MODE != MANSY_OBS_NONE && A.out.obs) emit_obs<MODE>(S, st, slot, sub, gmask, A.out.obs + r * A.out.obs_stride);
+  if (live) {
+    load_state(S, e, st);
+    load_slot(S, e, sub, slot);
   }
-  if (A.n_steps != 1) store_slot(S, e, sub, slot);
-  store_state(S, e, st, sub);
+  for (int t = 0; t < A.n_steps; ++t) {
+    const bool run = live && !(st.flags & kFlagFinished);
+    if (__all_sync(0xFFFFFFFFu, run)) step_once<MODE>(S, A, st, slot, e, i, sub, 0xFFFFFFFFu, t);   // the common case
+    else if (live) step_once<MODE>(S, A, st, slot, e, i, sub, gmask, t);
+  }
+  if (live) {
+    if (A.n_steps != 1) store_slot(S, e, sub, slot);
+    store_state(S, e, st, sub);
+  }
 }
 
 template <int MODE>

@@ -115,6 +115,34 @@ __device__ __forceinline__ double trace_download_window(double size, double win,
   const double start = cur_time;
   const int base = (threadIdx.x & 31) & ~7;
   int pos = 0, it = 0;
+  if (gmask == 0xFFFFFFFFu) {
+    // whole warp converged (the mask is a compile-time constant here): one warp-uniform loop over the longest of
+    // the four downloads, plain full-mask shuffles instead of the partial-mask collective sequence
+    while (true) {
+      const bool more = size > 0.0 && ok;
+      if (!__any_sync(0xFFFFFFFFu, more)) break;
+      if (pos == kTraceWindow) {
+        win = __ldg(tr + cur_idx + sub);
+        pos = 0;
+      }
+      const double thr = __shfl_sync(0xFFFFFFFFu, win, base + pos);
+      if (more) {
+        const double next_tick = floor(dadd(cur_time, 1.0));
+        const double remain = dmul(dsub(next_tick, cur_time), thr);
+        if (size >= remain) {
+          cur_idx = (cur_idx + 1 == trace_len) ? 0 : cur_idx + 1;
+          cur_time = next_tick;
+          size = dsub(size, remain);
+          ++pos;
+        } else {
+          cur_time = dadd(cur_time, ddiv(size, thr));
+          size = 0.0;
+        }
+        if (++it > (1 << 22)) ok = false;
+      }
+    }
+    return dsub(cur_time, start);
+  }
   while (size > 0.0) {
     if (pos == kTraceWindow) {
       win = __ldg(tr + cur_idx + sub);
