@@ -293,7 +293,9 @@ int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout
  * step (1) runs the policy on the device-resident observation, (2) copies the sampled actions to the host and
  * synchronises -- policy(batch) + to_numpy(act), run_mansy.py:169-172 --, (3) copies them back as the input of
  * env.step(act) (run_mansy.py:173), (4) steps, (5) copies the next observation, reward, done, logp and value
- * to host slab t % host_slabs and synchronises.  Host buffers should be pinned.
+ * to host slab t % host_slabs on a second stream, overlapped with the following step (a device slab is not
+ * rewritten before its copy has finished).  The call returns when every copy has landed.  Host buffers should
+ * be pinned; host_slabs >= n_steps keeps every step's results.
  */
 typedef struct {
   int32_t host_slabs;

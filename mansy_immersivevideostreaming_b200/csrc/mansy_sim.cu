@@ -237,7 +237,11 @@ struct mansy_sim {
   // events of the last instrumented mansy_rollout_policy call: [3 * steps] = before policy, after policy, after step
   std::vector<cudaEvent_t> events;
   int timed_steps = 0;
+  // host-storage rollout: result copies run on their own stream, overlapped with the next step's kernels
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> step_done, copy_done;     // rings of kCopyRing events
 };
+constexpr int kCopyRing = 64;
 
 namespace {
 
@@ -485,6 +489,9 @@ int mansy_destroy(mansy_handle_t h) {
   if (!h) return MANSY_OK;
   cudaSetDevice(h->device);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->step_done) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->copy_done) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (void *p : h->allocs) cudaFree(p);
   delete h;
   return MANSY_OK;
@@ -667,11 +674,25 @@ int mansy_rollout_policy_host(mansy_handle_t h, mansy_policy_t p, const mansy_ro
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int is_probs = h->dev.obs_mode == MANSY_OBS_SIMPLE ? 1 : 0;
   const size_t row_bytes = (size_t)b->obs_stride * sizeof(float);
+  if (!h->copy_stream) {
+    MANSY_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    h->step_done.resize(kCopyRing);
+    h->copy_done.resize(kCopyRing);
+    for (int i = 0; i < kCopyRing; ++i) {
+      MANSY_CUDA(cudaEventCreateWithFlags(&h->step_done[i], cudaEventDisableTiming));
+      MANSY_CUDA(cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t cs = h->copy_stream;
+  // A device slab is rewritten `slabs` steps (observations: slabs - 1) after it was produced; its copy to the host
+  // must have finished by then.  The host ring is only read by the caller after this function returns.
+  const int lag = b->slabs - 1 < kCopyRing ? b->slabs - 1 : kCopyRing;
   for (int32_t k = 0; k < n_steps; ++k) {
     const int64_t t = t0 + k;
     const size_t cur = (size_t)(t % b->slabs), nxt = (size_t)((t + 1) % b->slabs), hs = (size_t)(t % host->host_slabs);
     const float *obs = b->obs + cur * n * (size_t)b->obs_stride;
     int rc;
+    if (k >= lag) MANSY_CUDA(cudaStreamWaitEvent(s, h->copy_done[(k - lag) % kCopyRing], 0));
     if (flags & MANSY_ROLLOUT_FP32_POLICY) {
       rc = mansy_policy_forward(p, obs, b->obs_stride, h->dev.n_envs, b->logits, b->value + cur * n, stream);
       if (!rc) rc = mansy_policy_sample(b->logits, h->dev.n_envs, is_probs, seed, t, h->dev.env_offset, b->actions + cur * n,
@@ -691,13 +712,17 @@ int mansy_rollout_policy_host(mansy_handle_t h, mansy_policy_t p, const mansy_ro
     a.out.reward = b->reward + cur * n; a.out.done = b->done + cur * n;
     if (k == 0 && (rc = check_out(h, &a.out))) return rc;
     if ((rc = launch_step(h, a, s))) return rc;
-    MANSY_CUDA(cudaMemcpyAsync(host->obs + hs * n * (size_t)b->obs_stride, a.out.obs, n * row_bytes, cudaMemcpyDeviceToHost, s));
-    MANSY_CUDA(cudaMemcpyAsync(host->reward + hs * n, a.out.reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    MANSY_CUDA(cudaMemcpyAsync(host->done + hs * n, a.out.done, n, cudaMemcpyDeviceToHost, s));
-    MANSY_CUDA(cudaMemcpyAsync(host->logp + hs * n, b->logp + cur * n, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    MANSY_CUDA(cudaMemcpyAsync(host->value + hs * n, b->value + cur * n, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    MANSY_CUDA(cudaStreamSynchronize(s));
+    MANSY_CUDA(cudaEventRecord(h->step_done[k % kCopyRing], s));
+    MANSY_CUDA(cudaStreamWaitEvent(cs, h->step_done[k % kCopyRing], 0));
+    MANSY_CUDA(cudaMemcpyAsync(host->obs + hs * n * (size_t)b->obs_stride, a.out.obs, n * row_bytes, cudaMemcpyDeviceToHost, cs));
+    MANSY_CUDA(cudaMemcpyAsync(host->reward + hs * n, a.out.reward, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    MANSY_CUDA(cudaMemcpyAsync(host->done + hs * n, a.out.done, n, cudaMemcpyDeviceToHost, cs));
+    MANSY_CUDA(cudaMemcpyAsync(host->logp + hs * n, b->logp + cur * n, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    MANSY_CUDA(cudaMemcpyAsync(host->value + hs * n, b->value + cur * n, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    MANSY_CUDA(cudaEventRecord(h->copy_done[k % kCopyRing], cs));
   }
+  MANSY_CUDA(cudaStreamSynchronize(cs));                        // every result of the n_steps is in host memory
+  MANSY_CUDA(cudaStreamSynchronize(s));
   return MANSY_OK;
 }
 
