@@ -205,8 +205,14 @@ int mansy_allocate_tile_versions(const uint64_t *masks_dev, const int32_t *actio
  * models/simple_rl.py:21-35,46-49,60-63).  Weights are HOST float32 arrays in the reference's
  * state-dict layouts; mansy_policy_create repacks and uploads them.
  */
+#define MANSY_NET_IDENTIFIER 3 /* mansy_policy_weights_t.kind: the QoE identifier (models/mansy.py:83-143): the MANSY FeatureNet
+                                 layout with fc2 over the 15 action_one_hot floats (row[760..774]) as the 10th / residual
+                                 branch, ONE head Linear(128 -> 3) + sigmoid.  branch_w[9] is [128][15], actor_fc_* is
+                                 identifier.fc, actor_out_w / actor_out_b are [3][128] / [3]; the critic_* pointers are
+                                 ignored (may be NULL).  Forward calls return the 3 sigmoid outputs in logits[:, 0..2]
+                                 (columns 3..15 and value are 0). */
 typedef struct {
-  int32_t kind; /* MANSY_OBS_MANSY or MANSY_OBS_SIMPLE */
+  int32_t kind; /* MANSY_OBS_MANSY, MANSY_OBS_SIMPLE or MANSY_NET_IDENTIFIER */
   /* MANSY: branch weights [128][K_b] for the 10 branches in FeatureNet order, biases [128] */
   const float *branch_w[10];
   const float *branch_b[10];
@@ -230,6 +236,27 @@ int mansy_policy_forward(mansy_policy_t p, const float *obs_dev, int64_t obs_str
  * (run_mansy.py:228-229); also returns log-probabilities. */
 int mansy_policy_sample(const float *logits_dev, int32_t n, int32_t is_probs, uint64_t seed, int64_t step,
                         int32_t env_offset, int32_t *actions_dev, float *logp_dev, void *stream);
+
+/*
+ * Identifier reward (bitrate_selection/utils/mansy_utils.py:42-49, models/mansy_ppo.py:40-49):
+ *   ident[i] = 1 - mean_j (pred[i][j] - qoe_weight[i][j])^2   (float32 like F.mse_loss; qoe_weight = obs row floats 776..778)
+ *   mixed[i] = (1 - lamb) * qoe_reward[i] + lamb * ident[i]   (float64 like the numpy expression in PPOPolicy.update)
+ * pred_dev [n][16] is the identifier forward's output; ident_dev (float32 [n]) and mixed_dev (float64 [n]) may be NULL.
+ */
+int mansy_identifier_reward(const float *pred_dev, const float *obs_dev, int64_t obs_stride, const float *qoe_reward_dev,
+                            double lamb, int32_t n, float *ident_dev, double *mixed_dev, void *stream);
+
+/*
+ * Generalised advantage estimation over a rollout ring, one backward scan per environment: what tianshou 0.4.8's
+ * BasePolicy.compute_episodic_return / _gae_return does on the host (pinned README.md:21, source not vendored --
+ * parity unpinned; oracle/gae_oracle.py restates the published algorithm):
+ *   delta_t = rew_t + gamma * v_next_t * (1 - done_t) - v_t;   gae_t = delta_t + gamma * lam * (1 - done_t) * gae_{t+1}
+ *   adv_t = gae_t,  ret_t = gae_t + v_t          (float64 accumulation, outputs float32)
+ * reward / value / done are [T][n] (row t = rollout step t), last_value [n] is V(s_T) of the observation after the
+ * last step; adv_dev / ret_dev [T][n].
+ */
+int mansy_gae(const float *reward_dev, const float *value_dev, const uint8_t *done_dev, const float *last_value_dev,
+              int32_t n_steps, int32_t n, double gamma, double lam, float *adv_dev, float *ret_dev, void *stream);
 
 /* Tensor-core (tcgen05, TF32 inputs / fp32 accumulate -- the precision class the reference runs its nets
  * in, run_mansy.py:253) version of mansy_policy_forward + mansy_policy_sample in ONE launch: 128 environments

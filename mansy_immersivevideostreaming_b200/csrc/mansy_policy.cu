@@ -118,7 +118,10 @@ policy_forward_kernel(const __grid_constant__ PolicyDev P, const float *__restri
     float out[16];
 #pragma unroll
     for (int o = 0; o < 16; ++o) out[o] = xs[e * 16 + o];
-    if (P.softmax) {                               // simple_rl.py:48
+    if (P.softmax == 2) {                          // QoE identifier: torch.sigmoid on its 3 outputs (mansy.py:141)
+#pragma unroll
+      for (int o = 0; o < 3; ++o) out[o] = 1.0f / (1.0f + expf(-out[o]));
+    } else if (P.softmax) {                        // simple_rl.py:48
       float m = out[0];
 #pragma unroll
       for (int o = 1; o < kActions; ++o) m = fmaxf(m, out[o]);
@@ -173,13 +176,55 @@ int upload_f(mansy_policy *p, const std::vector<float> &host, const float **out)
 }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------
+// PPO learner inputs computed where the rollout lives
+// ------------------------------------------------------------------------------------------
+// utils/mansy_utils.py:42-49 + models/mansy_ppo.py:40-49.  F.mse_loss on 3 float32 values: squared differences
+// summed in order, divided by 3; the blend is the float64 numpy expression of PPOPolicy.update.
+__global__ void identifier_reward_kernel(const float *__restrict__ pred, const float *__restrict__ obs, int64_t obs_stride,
+                                         const float *__restrict__ qoe_reward, double lamb, int n, float *__restrict__ ident,
+                                         double *__restrict__ mixed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *w = obs + (size_t)i * obs_stride + 776;      // qoe_weight segment of the MANSY row (config.py)
+  const float *p = pred + (size_t)i * 16;
+  const float d0 = __fsub_rn(p[0], w[0]), d1 = __fsub_rn(p[1], w[1]), d2 = __fsub_rn(p[2], w[2]);
+  const float mse = __fdiv_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), 3.0f);
+  const float r = __fsub_rn(1.0f, mse);
+  if (ident) ident[i] = r;
+  if (mixed) mixed[i] = __dadd_rn(__dmul_rn(__dsub_rn(1.0, lamb), (double)qoe_reward[i]), __dmul_rn(lamb, (double)r));
+}
+
+// tianshou 0.4.8 BasePolicy.compute_episodic_return / _gae_return (not vendored; restated in oracle/gae_oracle.py):
+// one thread per environment walks its T transitions backwards; rows are [T][n] so every step is a coalesced read.
+__global__ void gae_kernel(const float *__restrict__ reward, const float *__restrict__ value, const uint8_t *__restrict__ done,
+                           const float *__restrict__ last_value, int T, int n, double gamma, double lam,
+                           float *__restrict__ adv, float *__restrict__ ret) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double gae = 0.0;
+  double v_next = (double)last_value[e];
+  const double gl = __dmul_rn(gamma, lam);
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t idx = (size_t)t * n + e;
+    const double v = (double)value[idx];
+    const double live = done[idx] ? 0.0 : 1.0;            // value_mask / end_flag
+    const double delta = __dsub_rn(__dadd_rn((double)reward[idx], __dmul_rn(__dmul_rn(v_next, live), gamma)), v);
+    gae = __dadd_rn(delta, __dmul_rn(__dmul_rn(live, gl), gae));
+    if (adv) adv[idx] = (float)gae;
+    if (ret) ret[idx] = (float)__dadd_rn(gae, v);
+    v_next = v;
+  }
+}
+
 extern "C" {
 
 int mansy_policy_create(const mansy_policy_weights_t *w, int device, mansy_policy_t *out) {
   if (!out) return set_error(MANSY_E_INVALID, "out is NULL");
   *out = nullptr;
   if (!w) return set_error(MANSY_E_INVALID, "weights is NULL");
-  if (w->kind != MANSY_OBS_MANSY && w->kind != MANSY_OBS_SIMPLE) return set_error(MANSY_E_INVALID, "bad policy kind");
+  if (w->kind != MANSY_OBS_MANSY && w->kind != MANSY_OBS_SIMPLE && w->kind != MANSY_NET_IDENTIFIER)
+    return set_error(MANSY_E_INVALID, "bad policy kind");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
     return set_error(MANSY_E_CUDA, "no CUDA device available: this library has no CPU fallback");
@@ -191,14 +236,19 @@ int mansy_policy_create(const mansy_policy_weights_t *w, int device, mansy_polic
   static const int mansy_k[10] = {8, 320, 320, 64, 8, 8, 8, 8, 1, 3};
   static const int simple_off[5] = {0, 8, 394, 392, 328};
   static const int simple_k[5] = {8, 320, 1, 2, 64};
-  const bool is_mansy = w->kind == MANSY_OBS_MANSY;
+  // QoE identifier (models/mansy.py:92-101): the same rows, fc2 reads the 15 action_one_hot floats instead of qoe_weight
+  static const int ident_off[10] = {0, 8, 328, 648, 728, 736, 744, 752, 779, 760};
+  static const int ident_k[10] = {8, 320, 320, 64, 8, 8, 8, 8, 1, 15};
+  const bool is_ident = w->kind == MANSY_NET_IDENTIFIER;
+  const bool is_mansy = w->kind == MANSY_OBS_MANSY || is_ident;      // MANSY observation rows
   const int nb = is_mansy ? 10 : 5;
-  const int *off = is_mansy ? mansy_off : simple_off;
-  const int *kk = is_mansy ? mansy_k : simple_k;
+  const int n_out = is_ident ? 3 : kActions;
+  const int *off = is_ident ? ident_off : (is_mansy ? mansy_off : simple_off);
+  const int *kk = is_ident ? ident_k : (is_mansy ? mansy_k : simple_k);
   for (int b = 0; b < nb; ++b)
     if (!w->branch_w[b] || !w->branch_b[b]) return set_error(MANSY_E_INVALID, "a branch weight pointer is NULL");
-  if (!w->actor_fc_w || !w->actor_fc_b || !w->actor_out_w || !w->actor_out_b || !w->critic_fc_w || !w->critic_fc_b ||
-      !w->critic_out_w || !w->critic_out_b)
+  if (!w->actor_fc_w || !w->actor_fc_b || !w->actor_out_w || !w->actor_out_b ||
+      (!is_ident && (!w->critic_fc_w || !w->critic_fc_b || !w->critic_out_w || !w->critic_out_b)))
     return set_error(MANSY_E_INVALID, "a head weight pointer is NULL");
 
   mansy_policy *p = new (std::nothrow) mansy_policy();
@@ -208,7 +258,7 @@ int mansy_policy_create(const mansy_policy_weights_t *w, int device, mansy_polic
   memset(&d, 0, sizeof(d));
   d.kind = w->kind; d.n_branches = nb; d.feat_dim = nb * kHidden;
   d.residual_branch = is_mansy ? 9 : -1;
-  d.softmax = is_mansy ? 0 : 1;
+  d.softmax = is_ident ? 2 : (is_mansy ? 0 : 1);
   const int F = d.feat_dim;
 
   std::vector<float> w1t, b1((size_t)nb * kHidden), wfct((size_t)F * 256), bfc(256), wout(16 * kHidden), bout(16);
@@ -225,17 +275,19 @@ int mansy_policy_create(const mansy_policy_weights_t *w, int device, mansy_polic
   for (int j = 0; j < kHidden; ++j) {
     for (int k = 0; k < F; ++k) {
       wfct[(size_t)k * 256 + j] = w->actor_fc_w[(size_t)j * F + k];
-      wfct[(size_t)k * 256 + kHidden + j] = w->critic_fc_w[(size_t)j * F + k];
+      wfct[(size_t)k * 256 + kHidden + j] = is_ident ? 0.f : w->critic_fc_w[(size_t)j * F + k];
     }
     bfc[j] = w->actor_fc_b[j];
-    bfc[kHidden + j] = w->critic_fc_b[j];
+    bfc[kHidden + j] = is_ident ? 0.f : w->critic_fc_b[j];
   }
-  for (int o = 0; o < kActions; ++o) {
+  for (int o = 0; o < n_out; ++o) {
     for (int j = 0; j < kHidden; ++j) wout[(size_t)o * kHidden + j] = w->actor_out_w[(size_t)o * kHidden + j];
     bout[o] = w->actor_out_b[o];
   }
-  for (int j = 0; j < kHidden; ++j) wout[(size_t)15 * kHidden + j] = w->critic_out_w[j];
-  bout[15] = w->critic_out_b[0];
+  if (!is_ident) {
+    for (int j = 0; j < kHidden; ++j) wout[(size_t)15 * kHidden + j] = w->critic_out_w[j];
+    bout[15] = w->critic_out_b[0];
+  }
 
   int rc;
   if ((rc = upload_f(p, w1t, &d.w1t)) || (rc = upload_f(p, b1, &d.b1)) || (rc = upload_f(p, wfct, &d.wfct)) ||
@@ -267,7 +319,7 @@ int mansy_policy_forward(mansy_policy_t p, const float *obs_dev, int64_t obs_str
                          float *value_dev, void *stream) {
   if (!p || !obs_dev) return set_error(MANSY_E_INVALID, "NULL argument");
   if (n < 0) return set_error(MANSY_E_INVALID, "n < 0");
-  const int need = p->dev.kind == MANSY_OBS_MANSY ? MANSY_OBS_MANSY_STRIDE : MANSY_OBS_SIMPLE_STRIDE;
+  const int need = p->dev.kind == MANSY_OBS_SIMPLE ? MANSY_OBS_SIMPLE_STRIDE : MANSY_OBS_MANSY_STRIDE;
   if (obs_stride < need - 4) return set_error(MANSY_E_INVALID, "obs_stride smaller than the observation row");
   if (logits_dev && (reinterpret_cast<uintptr_t>(logits_dev) & 15)) return set_error(MANSY_E_INVALID, "logits must be 16-byte aligned");
   if (n == 0) return MANSY_OK;
@@ -288,6 +340,34 @@ int mansy_policy_sample(const float *logits_dev, int32_t n, int32_t is_probs, ui
       logits_dev, n, is_probs, seed, step, env_offset, actions_dev, logp_dev);
   count_launch();
   if (cudaGetLastError() != cudaSuccess) return set_error(MANSY_E_CUDA, "policy_sample_kernel launch failed");
+  return MANSY_OK;
+}
+
+int mansy_identifier_reward(const float *pred_dev, const float *obs_dev, int64_t obs_stride, const float *qoe_reward_dev,
+                            double lamb, int32_t n, float *ident_dev, double *mixed_dev, void *stream) {
+  if (!pred_dev || !obs_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (mixed_dev && !qoe_reward_dev) return set_error(MANSY_E_INVALID, "the blended reward needs qoe_reward");
+  if (n < 0 || obs_stride < MANSY_OBS_MANSY_STRIDE) return set_error(MANSY_E_INVALID, "bad n / obs_stride");
+  if (n == 0) return MANSY_OK;
+  identifier_reward_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred_dev, obs_dev, obs_stride,
+                                                                                          qoe_reward_dev, lamb, n, ident_dev,
+                                                                                          mixed_dev);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MANSY_E_CUDA, std::string("identifier_reward_kernel: ") + cudaGetErrorString(e));
+  return MANSY_OK;
+}
+
+int mansy_gae(const float *reward_dev, const float *value_dev, const uint8_t *done_dev, const float *last_value_dev,
+              int32_t n_steps, int32_t n, double gamma, double lam, float *adv_dev, float *ret_dev, void *stream) {
+  if (!reward_dev || !value_dev || !done_dev || !last_value_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (n_steps < 0 || n < 0) return set_error(MANSY_E_INVALID, "bad n_steps / n");
+  if (n_steps == 0 || n == 0) return MANSY_OK;
+  gae_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(reward_dev, value_dev, done_dev, last_value_dev,
+                                                                            n_steps, n, gamma, lam, adv_dev, ret_dev);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MANSY_E_CUDA, std::string("gae_kernel: ") + cudaGetErrorString(e));
   return MANSY_OK;
 }
 

@@ -534,7 +534,10 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
         float p[kActions];
 #pragma unroll
         for (int o = 0; o < kActions; ++o) p[o] = acc[o];
-        if (K.softmax) {          // simple_rl.py:48: the actor returns probabilities
+        if (K.softmax == 2) {     // QoE identifier: torch.sigmoid on its 3 outputs (mansy.py:141)
+#pragma unroll
+          for (int o = 0; o < 3; ++o) p[o] = 1.0f / (1.0f + expf(-p[o]));
+        } else if (K.softmax) {   // simple_rl.py:48: the actor returns probabilities
           float m = p[0];
 #pragma unroll
           for (int o = 1; o < kActions; ++o) m = fmaxf(m, p[o]);
@@ -555,7 +558,7 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
         if (A.actions) {
           int act;
           float lp;
-          categorical_sample(p, K.softmax, A.seed, (uint64_t)(A.env_offset + env), (uint64_t)A.step, act, lp);
+          categorical_sample(p, K.softmax == 1, A.seed, (uint64_t)(A.env_offset + env), (uint64_t)A.step, act, lp);
           A.actions[env] = act;
           if (A.logp) A.logp[env] = lp;
         }
@@ -980,6 +983,20 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       asm volatile("bar.arrive 2, 480;" ::: "memory");     // state(t) has been read: the simulator phase may overwrite it
       asm volatile("fence.proxy.async;" ::: "memory");      // rows are read by the next step's TMA (async proxy)
     }
+    // fused: the simulator phase's action-independent loads (state, history slot, viewport / trace entries) are
+    // issued now, so they land while warp q == rank samples the actions
+    EnvState sim_st;
+    float sim_slot[8];
+    StepInputs sim_in;
+    const int sim_et = (int)threadIdx.x - 32 * kTcEpiWarp0;
+    const int sim_i = tile * 128 + (int)rank * 32 + (sim_et >> 3);
+    const bool sim_live = kFused && warp >= kTcEpiWarp0 && sim_i < A.n;
+    if (kFused && sim_live) {
+      load_state(F.S, sim_i, sim_st);
+      load_slot(F.S, sim_i, sim_et & 7, sim_slot);
+      sim_in = step_prefetch(F.S, sim_st, sim_et & 7);
+    }
+
     // ================= phase D: each rank finishes its 32 rows (warp q == rank) =================
     if (warp >= kTcEpiWarp0 && half == 0 && (uint32_t)q == rank) {
       float acc[16];
@@ -1003,7 +1020,10 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         float p[kActions];
 #pragma unroll
         for (int o = 0; o < kActions; ++o) p[o] = acc[o];
-        if (K.softmax) {
+        if (K.softmax == 2) {     // QoE identifier: torch.sigmoid on its 3 outputs (mansy.py:141)
+#pragma unroll
+          for (int o = 0; o < 3; ++o) p[o] = 1.0f / (1.0f + expf(-p[o]));
+        } else if (K.softmax) {
           float m = p[0];
 #pragma unroll
           for (int o = 1; o < kActions; ++o) m = fmaxf(m, p[o]);
@@ -1023,7 +1043,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         }
         if (A.actions) {
           float lp;
-          categorical_sample(p, K.softmax, A.seed, (uint64_t)(A.env_offset + env), (uint64_t)t, act, lp);
+          categorical_sample(p, K.softmax == 1, A.seed, (uint64_t)(A.env_offset + env), (uint64_t)t, act, lp);
           A.actions[orow] = act;
           if (A.logp) A.logp[orow] = lp;
         }
@@ -1040,13 +1060,9 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         const int i = tile * 128 + (int)rank * 32 + (et >> 3);
         const int sub = et & 7;
         const SimDev &S = F.S;
-        EnvState st;
-        float slot[8];
-        const bool live_e = i < A.n;
-        if (live_e) {
-          load_state(S, i, st);
-          load_slot(S, i, sub, slot);
-        }
+        EnvState &st = sim_st;
+        float (&slot)[8] = sim_slot;
+        const bool live_e = sim_live;
         if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[490] = clock64() + (st.flags & 0);
         int action;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(action) : "r"(act_s + (uint32_t)(et >> 3) * 4u) : "memory");
@@ -1057,7 +1073,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           bool over = true;
           if (!(st.flags & kFlagFinished)) {
             const int slot_before = st.ep_step & 7;
-            const double reward = step_env(S, st, slot, sub, mask, action, over, nullptr, nullptr);
+            const double reward = step_env(S, st, slot, sub, mask, action, over, nullptr, nullptr, sim_in);
             reward_f = (float)reward;
             if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[491] = clock64() + (reward_f > 1e30f);
             if (sub == slot_before) store_slot(S, i, sub, slot);
@@ -1145,8 +1161,10 @@ struct BranchPlan {
 }  // namespace
 
 int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
-  const bool is_mansy = w->kind == MANSY_OBS_MANSY;
+  const bool is_ident = w->kind == MANSY_NET_IDENTIFIER;
+  const bool is_mansy = w->kind == MANSY_OBS_MANSY || is_ident;       // MANSY observation rows
   const int nb = is_mansy ? 10 : 5;
+  const int n_out = is_ident ? 3 : kActions;
   const int obs_floats = is_mansy ? MANSY_OBS_MANSY_STRIDE : MANSY_OBS_SIMPLE_STRIDE;
   // processing order: big branches first, the residual branch last (its feature tile must still
   // be in shared memory when the heads run); `extra` marks the branch whose K-step is shared.
@@ -1155,7 +1173,11 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
       {5, 736, 8, false},  {6, 744, 8, false},   {7, 752, 8, false},  {8, 779, 1, true},  {9, 776, 3, false}};
   static const BranchPlan simple_plan[5] = {
       {1, 8, 320, false}, {4, 328, 64, false}, {0, 0, 8, false}, {2, 394, 1, true}, {3, 392, 2, false}};
-  const BranchPlan *plan = is_mansy ? mansy_plan : simple_plan;
+  // QoE identifier: fc2 reads the 15 action_one_hot floats 760..774 (K-steps 95 and 96: boxes 23 and 24)
+  static const BranchPlan ident_plan[10] = {
+      {1, 8, 320, false},  {2, 328, 320, false}, {3, 648, 64, false}, {0, 0, 8, false},   {4, 728, 8, false},
+      {5, 736, 8, false},  {6, 744, 8, false},   {7, 752, 8, false},  {8, 779, 1, true},  {9, 760, 15, false}};
+  const BranchPlan *plan = is_ident ? ident_plan : (is_mansy ? mansy_plan : simple_plan);
   const int main_boxes = (obs_floats + 31) / 32;          // 25 / 13
   const int w1_cols = (main_boxes + 1) * 32;
   const int F = nb * kHidden;
@@ -1193,26 +1215,27 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
       hc->bias1[i][f] = w->branch_b[b.canon][f];
       for (int j = 0; j < kHidden; ++j) {
         wfcimg[(size_t)j * F + i * kHidden + f] = w->actor_fc_w[(size_t)j * F + b.canon * kHidden + f];
-        wfcimg[(size_t)(kHidden + j) * F + i * kHidden + f] = w->critic_fc_w[(size_t)j * F + b.canon * kHidden + f];
+        if (!is_ident)
+          wfcimg[(size_t)(kHidden + j) * F + i * kHidden + f] = w->critic_fc_w[(size_t)j * F + b.canon * kHidden + f];
       }
     }
   }
   std::vector<float> woutimg((size_t)16 * 256, 0.f);   // rows 0..14: [actor.out | 0], row 15: [0 | critic.out]
   for (int j = 0; j < kHidden; ++j) {
-    for (int o = 0; o < kActions; ++o) woutimg[(size_t)o * 256 + j] = w->actor_out_w[(size_t)o * kHidden + j];
-    woutimg[(size_t)15 * 256 + kHidden + j] = w->critic_out_w[j];
+    for (int o = 0; o < n_out; ++o) woutimg[(size_t)o * 256 + j] = w->actor_out_w[(size_t)o * kHidden + j];
+    if (!is_ident) woutimg[(size_t)15 * 256 + kHidden + j] = w->critic_out_w[j];
     hc->bias2[j] = w->actor_fc_b[j];
-    hc->bias2[kHidden + j] = w->critic_fc_b[j];
+    hc->bias2[kHidden + j] = is_ident ? 0.f : w->critic_fc_b[j];
   }
   std::vector<float> wresimg((size_t)16 * kHidden, 0.f);   // residual through the heads: rows 0..14 actor.out, row 15 critic.out
   for (int j = 0; j < kHidden; ++j) {
-    for (int o = 0; o < kActions; ++o) wresimg[(size_t)o * kHidden + j] = w->actor_out_w[(size_t)o * kHidden + j];
-    wresimg[(size_t)15 * kHidden + j] = w->critic_out_w[j];
+    for (int o = 0; o < n_out; ++o) wresimg[(size_t)o * kHidden + j] = w->actor_out_w[(size_t)o * kHidden + j];
+    if (!is_ident) wresimg[(size_t)15 * kHidden + j] = w->critic_out_w[j];
   }
-  for (int o = 0; o < kActions; ++o) hc->bout[o] = w->actor_out_b[o];
-  hc->bout[15] = w->critic_out_b[0];
+  for (int o = 0; o < n_out; ++o) hc->bout[o] = w->actor_out_b[o];
+  if (!is_ident) hc->bout[15] = w->critic_out_b[0];
   hc->n_branches = nb;
-  hc->softmax = is_mansy ? 0 : 1;
+  hc->softmax = is_ident ? 2 : (is_mansy ? 0 : 1);     // output activation: none / softmax / sigmoid on 3 outputs
   hc->residual_slot = is_mansy ? nb - 1 : -1;
 
   // job list: L1(p0), L1(p1), L2(p0), L1(p2), L2(p1), ..., L1(p_last), L2(p_last-1), L2(p_last)
@@ -1456,7 +1479,7 @@ int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t
   *launched = 0;
   if (!p || !p->tc || !b) return MANSY_OK;
   if (S.obs_mode != MANSY_OBS_MANSY && S.obs_mode != MANSY_OBS_SIMPLE) return MANSY_OK;
-  if (p->dev.kind != S.obs_mode || p->tc->split == 1 || n_steps < 1) return MANSY_OK;
+  if (p->dev.kind != S.obs_mode || p->tc->split == 1 || n_steps < 1) return MANSY_OK;   // (identifier nets never match)
   const int n = S.n_envs, n_tiles = (n + 127) / 128;
   if (b->obs_stride < p->tc->obs_floats || (b->obs_stride & 3) || (reinterpret_cast<uintptr_t>(b->obs) & 15) ||
       (reinterpret_cast<uintptr_t>(b->logits) & 15))
@@ -1548,6 +1571,10 @@ int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int
 int mansy_debug_fused_timeline(int64_t *timeline_dev, int32_t cta) {
   g_fused_timeline = reinterpret_cast<long long *>(timeline_dev);
   g_fused_timeline_cta = cta;
+#ifdef MANSY_STEP_PROFILE
+  long long *sp = timeline_dev ? reinterpret_cast<long long *>(timeline_dev) + 496 : nullptr;   // stamps [496..501]
+  cudaMemcpyToSymbol(d_step_prof, &sp, sizeof(sp));
+#endif
   return MANSY_OK;
 }
 

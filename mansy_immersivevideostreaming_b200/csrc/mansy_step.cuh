@@ -260,23 +260,52 @@ __device__ __forceinline__ void emit_obs(const SimDev &S, const EnvState &st, co
   emit_obs_dynamic<MODE>(S, st, slot, sub, gmask, row);
 }
 
+// What a step reads before it knows the action: the actual-viewport mask, the pyramid scales of this lane's tile
+// row, the prediction accuracy, this lane's entry of the bandwidth-trace window and the trace length.  The fused
+// rollout kernel issues these loads while the policy is still sampling.
+#ifdef MANSY_STEP_PROFILE   // tuning builds only: SM-clock stamps of one thread inside step_env
+static __device__ long long *d_step_prof = nullptr;
+#define MANSY_STEP_STAMP(k, dep) do { if (d_step_prof && blockIdx.x == 0 && threadIdx.x == 256) d_step_prof[k] = clock64() + ((dep) ? 0 : 0); } while (0)
+#else
+#define MANSY_STEP_STAMP(k, dep) do { } while (0)
+#endif
+
+struct StepInputs {
+  uint64_t gt;
+  uint32_t scales;
+  int tlen;
+  double acc, win;
+  const double *tr;
+};
+
+__device__ __forceinline__ StepInputs step_prefetch(const SimDev &S, const EnvState &st, int sub) {
+  StepInputs in;
+  const size_t vi = (size_t)st.pair * S.n_vp_chunks + (st.next_chunk - st.start_chunk);   // hmdtrace.py:16-19
+  in.gt = __ldg(S.vp_gt + vi);
+  // pyramid scales (toroidal Chebyshev distance to the predicted viewport, utils/common.py:142-168) of this lane's
+  // 8 tiles, 4 bits each: a table derived from vp_pred when the handle is created (same tile_scale_masks code)
+  in.scales = __ldg(S.vp_scale + vi * 8 + sub);
+  in.acc = __ldg(S.vp_acc + vi);
+  // bandwidth-trace window and length: issued before the dependent gather / reduction work
+  in.tr = S.trace + (size_t)st.trace * S.trace_stride;
+  in.win = __ldg(in.tr + st.cur_idx + sub);
+  in.tlen = __ldg(S.trace_len + st.trace);
+  return in;
+}
+
 // One chunk-step of one environment (8 lanes).  Returns the reward; `over` tells whether the
 // episode ended.  aux_row / ver_row may be NULL.
 __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float (&slot)[8], int sub, unsigned gmask,
                                            int action, bool &over, double *__restrict__ aux_row,
-                                           uint8_t *__restrict__ ver_row) {
+                                           uint8_t *__restrict__ ver_row, const StepInputs &in) {
+  MANSY_STEP_STAMP(0, action);
   const int c = st.next_chunk;
-  const size_t vi = (size_t)st.pair * S.n_vp_chunks + (c - st.start_chunk);   // hmdtrace.py:16-19
-  const uint64_t gt = __ldg(S.vp_gt + vi);
-  // pyramid scales (toroidal Chebyshev distance to the predicted viewport, utils/common.py:142-168) of this lane's
-  // 8 tiles, 4 bits each: a table derived from vp_pred when the handle is created (same tile_scale_masks code)
-  const uint32_t scales = __ldg(S.vp_scale + vi * 8 + sub);
-  const double acc = __ldg(S.vp_acc + vi);
-
-  // bandwidth-trace window and length: issued before the dependent gather / reduction work below
-  const double *tr = S.trace + (size_t)st.trace * S.trace_stride;
-  const double win = __ldg(tr + st.cur_idx + sub);
-  const int tlen = __ldg(S.trace_len + st.trace);
+  const uint64_t gt = in.gt;
+  const uint32_t scales = in.scales;
+  const double acc = in.acc;
+  const double *tr = in.tr;
+  const double win = in.win;
+  const int tlen = in.tlen;
 
   int rin, rout;
   action_to_rates(action, rin, rout);
@@ -301,6 +330,7 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
     if (i < 4) vpack_lo |= (uint32_t)ver << (8 * i); else vpack_hi |= (uint32_t)ver << (8 * (i - 4));
   }
   if (ver_row) reinterpret_cast<uint2 *>(ver_row)[sub] = make_uint2(vpack_lo, vpack_hi);
+  MANSY_STEP_STAMP(1, sz);
   sz = group_sum(sz, gmask);
   mq = group_sum(mq, gmask);
   const double sm = (double)__popcll(gt);
@@ -309,6 +339,8 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
   bool ok = true;
   const double dl = trace_download_window((double)sz, win, tr, tlen, st.cur_idx, st.cur_time, sub, gmask, ok);
   if (!ok && sub == 0) atomicExch(S.error_flag, 1);
+  MANSY_STEP_STAMP(2, sz + (int)mq);
+  MANSY_STEP_STAMP(3, dl > 0.0);
   const double rebuf = buffer_push(st.buf, S.chunk_length, dl);
 
   // qoe.py:22-34 (float64 chain; |q - vq| is evaluated in float32 like the reference's array op)
@@ -321,6 +353,7 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
   dev = group_sum(dev, gmask);
   const QoE r = qoe_from_sums(vq, dev, sm, rebuf, st.ep_step == 0, st.prev_vq, (double)st.w0, (double)st.w1,
                               (double)st.w2, S.max_quality);
+  MANSY_STEP_STAMP(4, r.qoe > 0.0);
   double reward = r.qoe;
   if (S.reward_mode == MANSY_REWARD_QOE_NORM)
     reward = ddiv(r.qoe, dadd(dadd((double)st.w0, (double)st.w1), (double)st.w2));
@@ -341,6 +374,7 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
     slot[6] = (float)ddiv(r.q2, S.startup_d);
     slot[7] = (float)r.q2;
   }
+  MANSY_STEP_STAMP(5, slot[0] > 0.f);
   st.ep_step += 1;
   st.next_chunk = c + 1;                                   // simulator.py:105-106
   over = st.next_chunk > st.end_chunk;
@@ -384,4 +418,12 @@ __device__ __forceinline__ void finish_episode(const SimDev &S, int e, const Env
 }
 
 
+}  // namespace mansy
+
+namespace mansy {
+__device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float (&slot)[8], int sub, unsigned gmask,
+                                           int action, bool &over, double *__restrict__ aux_row,
+                                           uint8_t *__restrict__ ver_row) {
+  return step_env(S, st, slot, sub, gmask, action, over, aux_row, ver_row, step_prefetch(S, st, sub));
+}
 }  // namespace mansy

@@ -32,6 +32,10 @@ def _arr(x) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(x, dtype=np.float32))
 
 
+IDENT_BRANCH_K = (8, 320, 320, 64, 8, 8, 8, 8, 1, 15)      # QoEIdentifierFeatureNet: fc2 reads action_one_hot (mansy.py:101)
+NET_IDENTIFIER = 3                                          # MANSY_NET_IDENTIFIER (include/mansy_b200.h)
+
+
 class PolicyNet:
     """Actor + critic sharing one FeatureNet, evaluated in one kernel."""
 
@@ -152,6 +156,95 @@ class PolicyNet:
                                            int(step), int(env_offset), actions.data_ptr(), logp.data_ptr(),
                                            torch.cuda.current_stream(self.device).cuda_stream))
         return actions, logp
+
+
+class IdentifierNet:
+    """The QoE identifier (``QoEIdentifierFeatureNet`` + ``QoEIdentifier``, models/mansy.py:83-143) on packed MANSY
+    observation rows: ``pred = sigmoid(out(fc(features) + fc2(action_one_hot)))`` -- the rows already carry the last
+    action's one-hot (``mansy_env.py:243``), which is what ``PPOPolicy.update`` feeds it (``mansy_ppo.py:44-47``).
+    Runs on the same kernels as the policy (tcgen05 TF32 by default, exact fp32 with ``tensor_cores=False``)."""
+
+    def __init__(self, sd: Mapping[str, object], device: int = 0):
+        _require_cuda(device)
+        self.lib = _capi.load_library()
+        self.device = torch.device("cuda", device)
+        keep = []
+        w = PolicyWeights()
+        w.kind = NET_IDENTIFIER
+        for i, (name, k) in enumerate(zip(MANSY_BRANCHES, IDENT_BRANCH_K)):
+            wt = _arr(sd[f"feature_net.{name}.0.weight"]).reshape(128, -1)
+            if wt.shape[1] != k:
+                raise ValueError(f"feature_net.{name}: expected {k} inputs, got {wt.shape[1]}")
+            bs = _arr(sd[f"feature_net.{name}.0.bias"]).reshape(128)
+            keep += [wt, bs]
+            w.branch_w[i], w.branch_b[i] = wt.ctypes.data, bs.ctypes.data
+        for field, key, shape in (("actor_fc_w", "fc.0.weight", (128, 1280)), ("actor_fc_b", "fc.0.bias", (128,)),
+                                  ("actor_out_w", "out.weight", (3, 128)), ("actor_out_b", "out.bias", (3,))):
+            a = _arr(sd[key]).reshape(shape)
+            keep.append(a)
+            setattr(w, field, a.ctypes.data)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.mansy_policy_create(C.byref(w), device, C.byref(h)))
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.mansy_policy_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def forward(self, obs: torch.Tensor, tensor_cores: bool = True, split: int = 0) -> torch.Tensor:
+        """obs ``[N, stride >= 784]`` float32 rows -> predicted (normalised) QoE weights ``[N, 3]`` (a view of the
+        kernel's ``[N, 16]`` output)."""
+        if obs.device != self.device or obs.dtype != torch.float32 or obs.stride(-1) != 1:
+            raise ValueError("obs must be a float32 row-major tensor on the identifier's device")
+        n = obs.shape[0]
+        out = torch.empty((n, 16), dtype=torch.float32, device=self.device)
+        if tensor_cores:
+            check(self.lib.mansy_policy_tc_set_split(self._h, int(split)))
+            check(self.lib.mansy_policy_forward_tc(self._h, obs.data_ptr(), obs.stride(0), n, out.data_ptr(), None, None, None,
+                                                   0, 0, 0, None, None, self._stream()))
+        else:
+            check(self.lib.mansy_policy_forward(self._h, obs.data_ptr(), obs.stride(0), n, out.data_ptr(), None, self._stream()))
+        return out[:, :3]
+
+    def reward(self, obs: torch.Tensor, qoe_reward: torch.Tensor, lamb: float, tensor_cores: bool = True):
+        """``(identifier_reward float32 [N], (1 - lamb) * qoe_reward + lamb * identifier_reward float64 [N])``:
+        ``calculate_indentifier_reward`` (utils/mansy_utils.py:42-49) and the blend of ``PPOPolicy.update``
+        (models/mansy_ppo.py:40-49) for a whole batch of transitions in two launches."""
+        pred = self.forward(obs, tensor_cores)
+        n = obs.shape[0]
+        ident = torch.empty(n, dtype=torch.float32, device=self.device)
+        mixed = torch.empty(n, dtype=torch.float64, device=self.device)
+        q = qoe_reward.to(device=self.device, dtype=torch.float32).contiguous()
+        check(self.lib.mansy_identifier_reward(pred.data_ptr(), obs.data_ptr(), obs.stride(0), q.data_ptr(), float(lamb), n,
+                                               ident.data_ptr(), mixed.data_ptr(), self._stream()))
+        return ident, mixed
+
+
+def gae_returns(reward: torch.Tensor, value: torch.Tensor, done: torch.Tensor, last_value: torch.Tensor, gamma: float,
+                gae_lambda: float):
+    """Generalised advantage estimation on the device over ``[T, N]`` rollout rings (``mansy_gae``; what tianshou's
+    ``compute_episodic_return`` does on the host).  Returns ``(advantage, returns)`` float32 ``[T, N]``."""
+    lib = _capi.load_library()
+    T, n = reward.shape
+    reward, value = reward.contiguous(), value.contiguous()
+    done = done.to(torch.uint8).contiguous()
+    last_value = last_value.to(torch.float32).contiguous()
+    adv = torch.empty((T, n), dtype=torch.float32, device=reward.device)
+    ret = torch.empty((T, n), dtype=torch.float32, device=reward.device)
+    check(lib.mansy_gae(reward.data_ptr(), value.data_ptr(), done.data_ptr(), last_value.data_ptr(), T, n, float(gamma),
+                        float(gae_lambda), adv.data_ptr(), ret.data_ptr(), torch.cuda.current_stream(reward.device).cuda_stream))
+    return adv, ret
 
 
 def seeded_state_dict(shapes, seed: int) -> Dict[str, np.ndarray]:

@@ -143,3 +143,22 @@ def test_log_rows_match_reference_csv():
         assert [float(x) for x in f[3:6]] == list(e["w"])
         for val, key in zip(f[6:], ("qoe", "qoe1", "qoe2", "qoe3")):
             assert abs(float(val) - e[key]) <= 2e-5      # 5-decimal rounding of float32- vs float64-chain means
+
+
+def test_gae_oracle_known_answers():
+    """The GAE restatement (tianshou 0.4.8 algorithm; parity unpinned) on hand-computed cases."""
+    from oracle import gae_oracle
+    rew = np.array([[1.0], [2.0], [3.0]], dtype=np.float32)
+    val = np.array([[0.5], [0.25], [0.125]], dtype=np.float32)
+    done = np.zeros((3, 1), dtype=np.uint8)
+    adv, ret = gae_oracle.gae(rew, val, done, np.array([1.0], np.float32), 0.5, 1.0)
+    # returns with lambda = 1: 3 + .5*1 = 3.5; 2 + .5*3.5 = 3.75; 1 + .5*3.75 = 2.875
+    np.testing.assert_allclose(ret[:, 0], [2.875, 3.75, 3.5])
+    np.testing.assert_allclose(adv[:, 0], [2.875 - 0.5, 3.75 - 0.25, 3.5 - 0.125])
+    done[1, 0] = 1        # the episode ends after step 1: no bootstrap across it
+    adv, ret = gae_oracle.gae(rew, val, done, np.array([1.0], np.float32), 0.5, 1.0)
+    np.testing.assert_allclose(ret[:, 0], [1 + 0.5 * 2.0, 2.0, 3.5])
+    ident, mixed = gae_oracle.identifier_reward(np.array([[0.5, 0.25, 0.25]], np.float32), np.array([[0.25, 0.25, 0.5]], np.float32),
+                                                np.array([2.0]), 0.25)
+    np.testing.assert_allclose(ident, [1 - (0.0625 + 0 + 0.0625) / 3], rtol=1e-7)
+    np.testing.assert_allclose(mixed, [0.75 * 2.0 + 0.25 * float(ident[0])])

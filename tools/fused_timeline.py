@@ -40,6 +40,9 @@ for cta in ctas:
         print(f"  job {j:2d}: TMA issue {t[j]-t0:6d}  operands {t[128+j]-t0:6d}  MMAs issued {t[256+j]-t0:6d}")
     for key in (480, 482, 483, 484, 485, 486, 490, 491, 492, 487, 488):
         print(f"  {names[key]:34s} {t[key]-t0:7d}")
+    if t[496]:      # -DMANSY_STEP_PROFILE build: inside step_env (thread 256 of CTA 0, last stamped step)
+        for j, nm in enumerate(["entry", "gathers issued+summed (own)", "group sums done", "trace walk done", "qoe done", "history slot done"]):
+            print(f"  step_env {nm:30s} {t[496+j]-t[496]:7d}")
 check(sim.lib.mansy_debug_fused_timeline(None, 0))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
