@@ -27,6 +27,9 @@ METRIC = "simulated chunk-steps/sec"
 UNIT = "chunk-steps/s"
 ENVS_PER_GPU = 4096
 # algorithmic HBM bytes per MANSY chunk-step with materialised observation
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE 2000-step launch of the fused kernel at 4096 envs, per rollout
+# step (ncu --set full, profiles/r01r_fused_kernel_2000steps_ncu.txt: 1.05 GB read + 26.59 GB written / 2000)
+FUSED_DRAM_BYTES_PER_STEP_4096 = 13_819_256
 BYTES_PER_STEP_MANSY = 3513
 FLOP_PER_STEP_POLICY = 2 * 425_472        # 0.851 MFLOP, shared FeatureNet evaluated once
 
@@ -326,7 +329,9 @@ def run_ours(args):
                    "kernel_timing": "roofline launch durations: a second pass of the same K steps with CUDA events "
                                     "around every launch on the launching stream (serialised launches)"},
         "roofline": ({"bound": "hbm", "achieved": fused_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": fused_gbs / hbm_gbs,
-                      "traffic": None, "kernel": "policy_tc4_kernel<fused> (policy + sample + simulator step, K steps per launch)",
+                      "traffic": FUSED_DRAM_BYTES_PER_STEP_4096 * K if n_local == 4096 else None,
+                      "traffic_source": "ncu --set full of one 2000-step launch, scaled by K (profiles/r01r_fused_kernel_2000steps_ncu.txt)",
+                      "kernel": "policy_tc4_kernel<fused> (policy + sample + simulator step, K steps per launch)",
                       "bytes_per_launch": fused_bytes * K, "avg_launch_ms": elapsed_ms, "peak_source": peak_src,
                       "note": "4096 envs move 14.7 MB per step (2.2 us of HBM time): the step is latency-bound, see "
                               "roofline_step_kernel / simulator_sweep for the stand-alone kernel at HBM-filling sizes"}

@@ -962,8 +962,9 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       // (simulator.py:105-106: next_chunk += 1; mansy_env.py:100-101: the sample after a finished episode), so
       // its table rows (next chunk sizes / qualities, predicted viewport: 704 of 784 floats) are written by the
       // seven warps that have nothing else to do (TMA producers, spare warp) while the epilogue warps sample the
-      // actions and run the simulator phase, which then only adds the dynamic columns.  (After cluster sync 2:
-      // barrier.cluster counts every thread, so work placed earlier would hold the other CTAs up.)
+      // actions and run the simulator phase, which then only adds the dynamic columns.  (After cluster barrier 2:
+      // barrier.cluster counts every thread, so work placed earlier holds the other CTAs up; arriving early and
+      // waiting late was tried too -- it moves the table traffic onto the partial exchange and gains nothing.)
       const int w7 = warp < kTcMmaWarp ? warp : kTcMmaWarp;     // 0..6
       const int nxt = (int)((t + 1) % F.slabs);
 #pragma unroll 1

@@ -318,3 +318,45 @@ def test_full_size_properties():
     stats = sim.episode_stats().cpu().numpy()
     assert np.array_equal(stats[:, 4], ep_len) and np.all(stats[:, 11] == 1)
     sim.close()
+
+
+def test_full_size_simple_rl_one_million_envs():
+    """BASELINE config 4 (run_simple_rl.py baseline over 1,048,576 envs, simulator only): size-independent
+    properties over a full episode span with auto-reset -- every env finishes episodes of exactly the
+    table-derived length, step counters stay in lockstep, the reward is the same float64 expression of the
+    emitted QoE terms -- plus a strided sample of envs replayed by the scalar oracle."""
+    cfg = SimConfig()
+    N = 1 << 20
+    base = synth.make_synthetic_tables(ViewportTiler(cfg).chunk_masks, n_videos=24, n_users=60, n_traces=40)
+    tables = base.with_samples(synth.per_env_samples(base, N))
+    sim = BatchSimulator(tables, N, OBS_MODE_SIMPLE, REWARD_QOE_NORM, seed=0)
+    sim.reset()
+    aux = sim.new_aux()
+    check = np.arange(0, N, 65_537)
+    orc = [so.OracleEnv(tables, OBS_MODE_SIMPLE, REWARD_QOE_NORM, "f64", worker_id=int(i), worker_num=N) for i in check]
+    for o in orc:
+        o.reset()
+    pair = tables.samples[:, 0] * tables.n_users + tables.samples[:, 1]
+    ep_len = np.minimum(tables.vp_end[pair], tables.video_time[tables.samples[:, 0]] - 1) - cfg.startup_download
+    step_in_ep = np.zeros(N, dtype=np.int64)
+    w = tables.qoe_w[tables.samples[:, 3]].astype(np.float64)
+    for t in range(12):
+        acts = synth.synthetic_actions(N, t, seed=5)
+        o, r, d = sim.step(torch.from_numpy(acts), auto_reset=True, aux=aux)
+        a = aux.cpu().numpy()
+        step_in_ep += 1
+        assert np.array_equal(a[:, AUX["ep_step"]], step_in_ep)
+        assert np.array_equal(d.cpu().numpy().astype(bool), step_in_ep >= ep_len)
+        qoe = w[:, 0] * a[:, AUX["qoe1"]] - w[:, 1] * a[:, AUX["qoe2"]] - w[:, 2] * a[:, AUX["qoe3"]]
+        assert np.array_equal(qoe, a[:, AUX["qoe"]])
+        assert np.array_equal(qoe / ((w[:, 0] + w[:, 1]) + w[:, 2]), a[:, AUX["reward"]])       # simple_rl_env.py:124-127
+        step_in_ep[step_in_ep >= ep_len] = 0                                                      # auto-reset
+        rows = o[torch.from_numpy(check).cuda()].cpu().numpy()
+        for k, (o_env, i) in enumerate(zip(orc, check)):
+            oo, orr, od, _ = o_env.step(int(acts[i]))
+            if od:
+                oo = o_env.reset()
+            assert_rows_match(rows[k], so.flatten_obs(oo, OBS_MODE_SIMPLE), OBS_MODE_SIMPLE, chain_exact=False)
+            assert rel_err(a[i, AUX["reward"]], orr) <= RTOL
+    assert sim.error_flag() == 0
+    sim.close()
