@@ -361,6 +361,68 @@ int mansy_selftest_download(const double *thr, int32_t trace_len, int64_t size, 
                             double *buf, double *download_time, double *rebuffer);
 int mansy_selftest_hashed_action(uint64_t seed, uint64_t env, uint64_t step);
 
+/*
+ * MTIO viewport-prediction transformer, inference path (BASELINE config 5):
+ * replaces ViewportTransformerMTIO.sample (viewport_prediction/models/mtio.py:106-133) as predict.py:27 calls it.
+ * Architecture as the reference constructs it (mtio.py:48-64, customized_transformer.py:39-51, predict.py:73-74):
+ * d_model = dim_feedforward = 512, nn.Transformer defaults (8 heads, post-norm, ReLU), 1..4 encoder and decoder
+ * layers, DistillLayer between them, 6-wide tokens (in_channel 2 x 3 MTIO heads), sigmoid predictor.
+ * Weights are HOST float32 arrays in the layout of the reference's state dict (torch [out][in] matrices); any
+ * *_b pointer may be NULL = zeros (under torch >= 2.1 the reference's positional constructor arguments switch the
+ * transformer's biases off, customized_transformer.py:47-50).  Everything is copied at create.
+ */
+#define MANSY_MTIO_MAX_LAYERS 4
+typedef struct {
+  const float *in_proj_w; /* [1536][512]  q | k | v */
+  const float *in_proj_b; /* [1536] or NULL */
+  const float *out_w;     /* [512][512] */
+  const float *out_b;     /* [512] or NULL */
+} mansy_mtio_attn_t;
+typedef struct {
+  mansy_mtio_attn_t self_attn;
+  mansy_mtio_attn_t cross_attn; /* decoder layers only (multihead_attn) */
+  const float *lin1_w, *lin1_b; /* [512][512], [512] */
+  const float *lin2_w, *lin2_b;
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b;
+  const float *norm3_w, *norm3_b; /* decoder layers only */
+} mansy_mtio_layer_t;
+typedef struct {
+  int32_t n_enc, n_dec;   /* layers (predict.py --block-num, default 2) */
+  int32_t his_window;     /* source tokens (default 5), <= 16 */
+  int32_t fut_window;     /* autoregressive steps (default 15), <= 31 */
+  int32_t pe_rows;        /* rows of `pe` (>= max(his_window, fut_window)) */
+  int32_t reserved;
+  const float *emb_w, *emb_b; /* embedding.linear [512][6], [512] */
+  const float *pe;            /* positional_embedding.pe [pe_rows][512] */
+  mansy_mtio_layer_t enc[MANSY_MTIO_MAX_LAYERS], dec[MANSY_MTIO_MAX_LAYERS];
+  const float *enc_norm_w, *enc_norm_b, *dec_norm_w, *dec_norm_b;
+  const float *conv_w, *conv_b; /* distill_layer.downConv [512][512][3], [512] */
+  const float *bn_w, *bn_b, *bn_mean, *bn_var; /* distill_layer.norm (eval mode) */
+  const float *pred_w, *pred_b; /* predictor.0 [6][512], [6] */
+} mansy_mtio_weights_t;
+typedef struct mansy_mtio *mansy_mtio_t;
+
+/* max_batch = samples processed per pass (workspace is sized for it; larger calls run in chunks). */
+int mansy_mtio_create(const mansy_mtio_weights_t *weights, int device, int32_t max_batch, mansy_mtio_t *out);
+int mansy_mtio_destroy(mansy_mtio_t m);
+#define MANSY_MTIO_FP32 1         /* exact-fp32 CUDA-core GEMMs (parity anchor) instead of tcgen05 kind::tf32 */
+#define MANSY_MTIO_TIME_KERNELS 2 /* CUDA events around every launch (see mansy_mtio_kernel_ms) */
+/*
+ * history_dev [n][his_window][2], current_dev [n][1][2] (viewport centres in [0,1]^2, predict.py:24-27) ->
+ * pred_dev [n][fut_window][2]: the MTIO-head ensemble, wrapped into the unit square (mtio.py:124-132).
+ * tokens_dev ([n][fut_window + 1][6], may be NULL) receives the decoder input tokens (test hook).
+ * The encoder runs once per sample and the decoder keeps its keys / values between the autoregressive steps:
+ * in eval mode that is the same function as the reference's per-step re-encoding (mtio.py:120-123).
+ */
+int mansy_mtio_sample(mansy_mtio_t m, const float *history_dev, const float *current_dev, int32_t n, int32_t flags,
+                      float *pred_dev, float *tokens_dev, void *stream);
+/* Same with HOST buffers (pinned for overlap): copies in, runs, copies out, synchronises the stream. */
+int mansy_mtio_sample_host(mansy_mtio_t m, const float *history_host, const float *current_host, int32_t n, int32_t flags,
+                           float *pred_host, void *stream);
+/* After a MANSY_MTIO_TIME_KERNELS call and a stream synchronise: summed durations (ms) and launch counts of
+ * [0] the GEMM kernels, [1] the attention kernels, [2] everything else (embedding, norms, distillation, head). */
+int mansy_mtio_kernel_ms(mansy_mtio_t m, double ms[3], int32_t launches[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,37 @@ class PolicyWeights(C.Structure):
     ]
 
 
+MTIO_MAX_LAYERS = 4
+MTIO_FP32 = 1
+MTIO_TIME_KERNELS = 2
+
+
+class MtioAttn(C.Structure):
+    _fields_ = [("in_proj_w", C.c_void_p), ("in_proj_b", C.c_void_p), ("out_w", C.c_void_p), ("out_b", C.c_void_p)]
+
+
+class MtioLayer(C.Structure):
+    _fields_ = [
+        ("self_attn", MtioAttn), ("cross_attn", MtioAttn),
+        ("lin1_w", C.c_void_p), ("lin1_b", C.c_void_p), ("lin2_w", C.c_void_p), ("lin2_b", C.c_void_p),
+        ("norm1_w", C.c_void_p), ("norm1_b", C.c_void_p), ("norm2_w", C.c_void_p), ("norm2_b", C.c_void_p),
+        ("norm3_w", C.c_void_p), ("norm3_b", C.c_void_p),
+    ]
+
+
+class MtioWeights(C.Structure):
+    _fields_ = [
+        ("n_enc", C.c_int32), ("n_dec", C.c_int32), ("his_window", C.c_int32), ("fut_window", C.c_int32),
+        ("pe_rows", C.c_int32), ("reserved", C.c_int32),
+        ("emb_w", C.c_void_p), ("emb_b", C.c_void_p), ("pe", C.c_void_p),
+        ("enc", MtioLayer * MTIO_MAX_LAYERS), ("dec", MtioLayer * MTIO_MAX_LAYERS),
+        ("enc_norm_w", C.c_void_p), ("enc_norm_b", C.c_void_p), ("dec_norm_w", C.c_void_p), ("dec_norm_b", C.c_void_p),
+        ("conv_w", C.c_void_p), ("conv_b", C.c_void_p),
+        ("bn_w", C.c_void_p), ("bn_b", C.c_void_p), ("bn_mean", C.c_void_p), ("bn_var", C.c_void_p),
+        ("pred_w", C.c_void_p), ("pred_b", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/mansy_b200.h
 _vp = C.c_void_p
 SIGNATURES = {
@@ -137,6 +168,11 @@ SIGNATURES = {
     "mansy_selftest_download": (C.c_int, [_vp, C.c_int32, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double),
                                           C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mansy_selftest_hashed_action": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64]),
+    "mansy_mtio_create": (C.c_int, [C.POINTER(MtioWeights), C.c_int, C.c_int32, C.POINTER(_vp)]),
+    "mansy_mtio_destroy": (C.c_int, [_vp]),
+    "mansy_mtio_sample": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp]),
+    "mansy_mtio_sample_host": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp]),
+    "mansy_mtio_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_double * 3), C.POINTER(C.c_int32 * 3)]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB = os.path.join(CSRC, "libmansy_b200.so")
-SOURCES = ["mansy_sim.cu", "mansy_policy.cu", "mansy_policy_tc.cu"]
-HEADERS = ["mansy_core.cuh", "mansy_sim.cuh", "mansy_step.cuh", "mansy_policy.cuh"]
+SOURCES = ["mansy_sim.cu", "mansy_policy.cu", "mansy_policy_tc.cu", "mansy_mtio.cu"]
+HEADERS = ["mansy_core.cuh", "mansy_sim.cuh", "mansy_step.cuh", "mansy_policy.cuh", "mansy_tc.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",   # B200 only; no PTX for other targets

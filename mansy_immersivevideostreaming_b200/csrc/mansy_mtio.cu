@@ -1,0 +1,982 @@
+// mansy_mtio.cu -- MTIO viewport-prediction transformer, inference path, for sm_100a.
+//
+// Reference: ViewportTransformerMTIO.sample viewport_prediction/models/mtio.py:106-133 (called by predict.py:27),
+// _process_src_tgt mtio.py:135-148, ViewportEmbedding / PositionalEncoding mtio.py:11-45, Transformer.forward +
+// DistillLayer viewport_prediction/models/customized_transformer.py:13-36,52-70, torch.nn.Transformer
+// (post-norm, ReLU, 8 heads: the constructor defaults the reference passes), to_position_normalized_cartesian
+// viewport_prediction/utils/common.py:61-70.  The reference runs these layers in TF32
+// (torch.set_float32_matmul_precision('high'), predict.py:100).
+//
+// Structure.  In eval mode the encoder output does not depend on the decoding step, so it is computed once per
+// sample; the decoder is causal, so step t only computes token t and keeps the keys / values of tokens 0..t-1
+// per layer in HBM (the reference re-runs encoder and decoder on the whole prefix every step, mtio.py:120-123:
+// ~10x the FLOPs for the same function).  What is left is a chain of [rows x 512] x [512 x N] products shared
+// by all samples:
+//   * mtio_gemm_kernel<BN, EPI>: tcgen05 kind::tf32, one CTA per [128 rows x BN columns] output tile.  A rows and
+//     torch-layout weight rows ([out][in] = K-major) are TMA-loaded as [128 x 32-float] SWIZZLE_128B boxes into a
+//     2-stage ring (4 producer warps: one per stage half), one elected lane issues M128 x N256 x K8 MMAs into
+//     TMEM, four epilogue warps (one per TMEM lane quarter, thread = output row) apply
+//        EPI_NONE / EPI_RELU / EPI_ELU : + bias (+ activation), rows stored as 128-byte runs
+//        EPI_LN (BN = 512 = d_model: the whole row lives in one CTA's TMEM): + bias + residual row, LayerNorm
+//            over the 512 columns in three TMEM passes (sum, centred squares, normalise) -- the post-norm
+//            "x = norm(x + sublayer(x))" of every transformer sub-block in the producing kernel.
+//     BN = 256 tiles use 256 TMEM columns and 100 KB of shared memory: two CTAs per SM, so one tile's epilogue
+//     overlaps the other's operand stream.  Output columns are routed by 512-column segment (pointer + leading
+//     dimension per segment): the fused QKV projection writes q to a scratch row and k / v straight into step t
+//     of the per-layer cache.
+//   * mtio_attn_kernel: one warp per (sample, head); <= 32 keys (5 source tokens, 3 distilled memory tokens,
+//     <= 31 cached target tokens): lane = key for the scores, lane = 2 of the 64 head dims for the output.
+//   * mtio_head_kernel: final decoder LayerNorm + predictor + sigmoid + MTIO-head ensemble + wrap into the unit
+//     square + embedding / positional encoding of the NEXT token, one warp per sample, one launch per step.
+//   * small CUDA-core kernels for the 6-wide embedding, the final encoder norm, the circular-conv im2col of the
+//     DistillLayer (its BatchNorm is folded into the conv weights at create; the conv is a K = 1536 GEMM with
+//     an ELU epilogue) and its max-pool.
+// MANSY_MTIO_FP32 swaps the GEMMs for an exact-fp32 CUDA-core kernel (parity anchor, like mansy_policy.cu).
+#include <cuda.h>
+
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mansy_b200.h"
+#include "mansy_policy.cuh"
+#include "mansy_tc.cuh"
+
+namespace mansy {
+
+constexpr int kD = 512;        // d_model = dim_feedforward (predict.py:73-74)
+constexpr int kMtioHeads = 8;  // nn.Transformer default nhead (customized_transformer.py:40)
+constexpr int kDh = kD / kMtioHeads;
+constexpr int kTok = 6;        // in_channel 2 x 3 MTIO heads (mtio.py:49,55)
+constexpr float kLnEps = 1e-5f;
+
+enum { EPI_NONE = 0, EPI_RELU = 1, EPI_ELU = 2, EPI_LN = 3 };
+
+struct GemmArgs {
+  int32_t M, N, K;
+  const float *bias;       // [N]
+  float *out[3];           // output segment s covers columns [512 s, 512 s + 512)
+  int64_t out_ld[3];       // floats between rows of the segment
+  const float *res;        // EPI_LN: residual rows [M][res_ld]
+  int64_t res_ld;
+  const float *gamma, *beta;
+};
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 GEMM
+// ------------------------------------------------------------------------------------------
+constexpr int kGemmStages = 2;
+constexpr int kGemmMmaWarp = 4;     // warps 0..3: epilogue (TMEM lane quarter = warp), 4: MMA issuer, 5..8: TMA producers
+constexpr int kGemmProd0 = 5;
+constexpr int kGemmThreads = 32 * (kGemmProd0 + 2 * kGemmStages);
+constexpr uint32_t kABoxBytes = 16384;     // 128 rows x 128 B
+
+template <int BN>
+constexpr uint32_t gemm_smem_bytes() {
+  return 1024u + kGemmStages * (kABoxBytes + BN * 128u) + 64u + 3u * BN * 4u;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, BN == 256 ? 2 : 1)
+mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmArgs g) {
+  static_assert(BN == 256 || BN == 512, "tile width");
+  static_assert(EPI != EPI_LN || BN == 512, "the LayerNorm epilogue needs the whole d_model row in one tile");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t kStage = kABoxBytes + BN * 128u;
+  constexpr int NB = BN / 128;                   // weight boxes of 128 rows per stage
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + kGemmStages * kStage;
+  const uint32_t bar_full = bars;                // [stage][half]
+  const uint32_t bar_empty = bars + 32;          // [stage]
+  const uint32_t bar_d = bars + 48;
+  const uint32_t tmem_slot = bars + 56;
+  float *s_bias = reinterpret_cast<float *>(smem_raw + (bars + 64 - raw));
+  float *s_gamma = s_bias + BN, *s_beta = s_gamma + BN;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  const int nk = g.K >> 5;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGemmStages; ++s) {
+      mbar_init(bar_full + 16 * s, 1);
+      mbar_init(bar_full + 16 * s + 8, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_d, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == kGemmMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp < 4) {
+    for (int i = threadIdx.x; i < BN; i += 128) {
+      s_bias[i] = g.bias[n0 + i];
+      if (EPI == EPI_LN) { s_gamma[i] = g.gamma[i]; s_beta[i] = g.beta[i]; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp >= kGemmProd0) {
+    // ===== TMA producers: warp p fills half (p & 1) of stage (p >> 1): half 0 = A box + first NB/2 weight boxes =====
+    const int p = warp - kGemmProd0, s = p >> 1, h = p & 1;
+    const uint32_t dst = base + s * kStage, full = bar_full + 16 * s + 8 * h;
+    for (int it = s; it < nk; it += kGemmStages) {
+      mbar_wait(bar_empty + 8 * s, ((uint32_t)(it / kGemmStages) & 1u) ^ 1u);
+      if (elect_one()) {
+        if (h == 0) {
+          mbar_expect_tx(full, kABoxBytes * (1 + NB / 2));
+          tma_load_2d(dst, &map_a, it * 32, m0, full);
+#pragma unroll
+          for (int b = 0; b < NB / 2; ++b) tma_load_2d(dst + kABoxBytes * (1 + b), &map_w, it * 32, n0 + b * 128, full);
+        } else {
+          mbar_expect_tx(full, kABoxBytes * (NB / 2));
+#pragma unroll
+          for (int b = NB / 2; b < NB; ++b) tma_load_2d(dst + kABoxBytes * (1 + b), &map_w, it * 32, n0 + b * 128, full);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == kGemmMmaWarp) {
+    // ===== MMA issuer: D[128 x BN] (+)= A[128 x 32] * W[BN x 32]^T per stage, four K8 steps =====
+    constexpr uint32_t kIdesc = idesc_tf32(256);
+    for (int it = 0; it < nk; ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+      const uint32_t a_lo = smem_desc_lo(base + s * kStage), b_lo = smem_desc_lo(base + s * kStage + kABoxBytes);
+      if (BN == 256) {
+        mbar_wait(bar_full + 16 * s, ph);
+        mbar_wait(bar_full + 16 * s + 8, ph);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_tf32(tmem_base, make_desc(a_lo + 2 * ks), make_desc(b_lo + 2 * ks), kIdesc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {     // columns 0..255 need half 0 only; 256..511 need the second weight half
+          mbar_wait(bar_full + 16 * s + 8 * h, ph);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32(tmem_base + 256u * h, make_desc(a_lo + 2 * ks), make_desc(b_lo + h * ((2 * kABoxBytes) >> 4) + 2 * ks),
+                        kIdesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) {
+        umma_commit(bar_empty + 8 * s);
+        if (it == nk - 1) umma_commit(bar_d);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue warps 0..3: thread = output row =====
+    const int r = warp * 32 + lane;
+    const int m = m0 + r;
+    const bool live = m < g.M;
+    const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int seg = n0 >> 9, col0 = n0 & 511;
+    float *orow = g.out[seg] + (size_t)(live ? m : 0) * (size_t)g.out_ld[seg] + col0;
+    mbar_wait(bar_d, 0);
+    tc_fence_after();
+    if (EPI != EPI_LN) {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(ta + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = v[j] + s_bias[c * 32 + j];
+          if (EPI == EPI_RELU) x = fmaxf(x, 0.f);
+          if (EPI == EPI_ELU) x = x > 0.f ? x : expm1f(x);
+          v[j] = x;
+        }
+        if (live) {
+          float4 *dst = reinterpret_cast<float4 *>(orow + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    } else {
+      const float *rrow = g.res + (size_t)(live ? m : 0) * (size_t)g.res_ld;
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {     // pass 1: x = acc + bias + residual, kept in TMEM
+        float v[32];
+        tmem_ld32(ta + c * 32, v);
+        const float4 *rs = reinterpret_cast<const float4 *>(rrow + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 q = live ? rs[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * j] += s_bias[c * 32 + 4 * j] + q.x;
+          v[4 * j + 1] += s_bias[c * 32 + 4 * j + 1] + q.y;
+          v[4 * j + 2] += s_bias[c * 32 + 4 * j + 2] + q.z;
+          v[4 * j + 3] += s_bias[c * 32 + 4 * j + 3] + q.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += v[j];
+        tmem_st32(ta + c * 32, v);
+      }
+      tmem_st_wait();
+      const float mean = sum * (1.0f / BN);
+      float ss = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {     // pass 2: centred sum of squares
+        float v[32];
+        tmem_ld32(ta + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; ss += d * d; }
+      }
+      const float rstd = 1.0f / sqrtf(ss * (1.0f / BN) + kLnEps);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {     // pass 3: normalise, affine, store
+        float v[32];
+        tmem_ld32(ta + c * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * s_gamma[c * 32 + j] + s_beta[c * 32 + j];
+        if (live) {
+          float4 *dst = reinterpret_cast<float4 *>(orow + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kGemmMmaWarp) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact-fp32 CUDA-core GEMM (parity anchor): C = epi(A W^T + bias [+ residual]); LayerNorm follows in mtio_ln_kernel
+// ------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(256) mtio_sgemm_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ W,
+                                                         const GemmArgs g) {
+  __shared__ float sa[16][64 + 4], sw[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < g.K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, k = i & 15;
+      sa[k][r] = (m0 + r < g.M) ? A[(size_t)(m0 + r) * (size_t)lda + k0 + k] : 0.f;
+      sw[k][r] = W[(size_t)(n0 + r) * (size_t)g.K + k0 + k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sa[k][ty * 4 + i]; b[i] = sw[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      float x = acc[i][j] + g.bias[n];
+      if (EPI == EPI_RELU) x = fmaxf(x, 0.f);
+      if (EPI == EPI_ELU) x = x > 0.f ? x : expm1f(x);
+      if (EPI == EPI_LN) x += g.res[(size_t)m * (size_t)g.res_ld + n];
+      g.out[n >> 9][(size_t)m * (size_t)g.out_ld[n >> 9] + (n & 511)] = x;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// LayerNorm of one 512-float row held as 4 float4 per lane (columns i * 128 + lane * 4 .. + 3).
+__device__ __forceinline__ void warp_layer_norm(float4 (&x)[4], const float *__restrict__ w, const float *__restrict__ b, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = x[i].x - mean, c = x[i].y - mean, d = x[i].z - mean, e = x[i].w - mean;
+    ss += (a * a + c * c) + (d * d + e * e);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(ss) * (1.0f / kD) + kLnEps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 ww = *reinterpret_cast<const float4 *>(w + i * 128 + lane * 4);
+    const float4 bb = *reinterpret_cast<const float4 *>(b + i * 128 + lane * 4);
+    x[i].x = (x[i].x - mean) * rstd * ww.x + bb.x;
+    x[i].y = (x[i].y - mean) * rstd * ww.y + bb.y;
+    x[i].z = (x[i].z - mean) * rstd * ww.z + bb.z;
+    x[i].w = (x[i].w - mean) * rstd * ww.w + bb.w;
+  }
+}
+
+// rows of `in` -> LayerNorm -> rows of `out` (may alias), one warp per row
+__global__ void __launch_bounds__(256) mtio_ln_kernel(const float *in, float *out, const float *__restrict__ w,
+                                                      const float *__restrict__ b, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const float4 *>(in + row * kD + i * 128 + lane * 4);
+  warp_layer_norm(x, w, b, lane);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4 *>(out + row * kD + i * 128 + lane * 4) = x[i];
+}
+
+// ViewportEmbedding + PositionalEncoding (mtio.py:29-45, 11-27): out[row] = W tok + b + pe[pos_base + row % pos_mod].
+// in_dim 2: the viewport centre repeated for the 3 MTIO heads (mtio.py:113-116); in_dim 6: a predicted token.
+__global__ void __launch_bounds__(256) mtio_embed_kernel(const float *__restrict__ tok, int64_t tok_stride, int in_dim, int64_t rows,
+                                                         int pos_mod, int pos_base, const float *__restrict__ emb_w,
+                                                         const float *__restrict__ emb_b, const float *__restrict__ pe,
+                                                         float *__restrict__ out, float *__restrict__ tok_out, int64_t tok_out_stride) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = idx >> 7;
+  const int c4 = (int)(idx & 127);
+  if (row >= rows) return;
+  float t[kTok];
+  const float *tr = tok + row * tok_stride;
+  if (in_dim == 2) {
+    const float x = tr[0], y = tr[1];
+    t[0] = x; t[1] = y; t[2] = x; t[3] = y; t[4] = x; t[5] = y;
+  } else {
+#pragma unroll
+    for (int o = 0; o < kTok; ++o) t[o] = tr[o];
+  }
+  if (tok_out && c4 == 0) {
+#pragma unroll
+    for (int o = 0; o < kTok; ++o) tok_out[row * tok_out_stride + o] = t[o];
+  }
+  const int pos = pos_base + (int)(row % pos_mod);
+  float r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c4 * 4 + k;
+    float acc = 0.f;
+#pragma unroll
+    for (int o = 0; o < kTok; ++o) acc = fmaf(emb_w[c * kTok + o], t[o], acc);
+    r[k] = (acc + emb_b[c]) + pe[(size_t)pos * kD + c];
+  }
+  *reinterpret_cast<float4 *>(out + row * kD + c4 * 4) = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+// DistillLayer conv input (customized_transformer.py:21-25,32): row (b, t) -> [x[t-1] | x[t] | x[t+1]] with circular wrap
+__global__ void __launch_bounds__(256) mtio_im2col_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t rows, int T) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = idx / 384;
+  const int rem = (int)(idx % 384), k = rem >> 7, c4 = rem & 127;
+  if (row >= rows) return;
+  const int64_t b = row / T;
+  const int t = (int)(row % T);
+  const int src_t = (t + k - 1 + T) % T;
+  *reinterpret_cast<float4 *>(out + row * (3 * kD) + k * kD + c4 * 4) =
+      *reinterpret_cast<const float4 *>(in + (b * T + src_t) * kD + c4 * 4);
+}
+
+// MaxPool1d(kernel 3, stride 2, padding 1) over the T tokens of a sample (customized_transformer.py:28,35)
+__global__ void __launch_bounds__(256) mtio_maxpool_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t n, int T, int To) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t orow = idx >> 7;
+  const int c4 = (int)(idx & 127);
+  if (orow >= n * To) return;
+  const int64_t b = orow / To;
+  const int o = (int)(orow % To);
+  const int lo = max(2 * o - 1, 0), hi = min(2 * o + 1, T - 1);
+  float4 m = *reinterpret_cast<const float4 *>(in + (b * T + lo) * kD + c4 * 4);
+  for (int t = lo + 1; t <= hi; ++t) {
+    const float4 v = *reinterpret_cast<const float4 *>(in + (b * T + t) * kD + c4 * 4);
+    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+  }
+  *reinterpret_cast<float4 *>(out + orow * kD + c4 * 4) = m;
+}
+
+// nn.MultiheadAttention core for short sequences: one block per sample, one warp per head.
+struct AttnArgs {
+  const float *q; int64_t q_ld; int32_t Tq;          // query rows b * Tq + i
+  const float *k, *v; int64_t kv_ld; int32_t kv_rows, Tk;   // key rows b * kv_rows + j, j < Tk <= 32
+  float *out; int64_t out_ld;
+};
+__global__ void __launch_bounds__(32 * kMtioHeads) mtio_attn_kernel(const AttnArgs a) {
+  const int head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = blockIdx.x;
+  const float *kr = a.k + (b * a.kv_rows + (lane < a.Tk ? lane : 0)) * a.kv_ld + head * kDh;
+  for (int qi = 0; qi < a.Tq; ++qi) {
+    const float4 *qr = reinterpret_cast<const float4 *>(a.q + (b * a.Tq + qi) * a.q_ld + head * kDh);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kDh / 4; ++i) {
+      const float4 qq = qr[i];
+      const float4 kk = reinterpret_cast<const float4 *>(kr)[i];
+      dot = fmaf(qq.x, kk.x, dot); dot = fmaf(qq.y, kk.y, dot); dot = fmaf(qq.z, kk.z, dot); dot = fmaf(qq.w, kk.w, dot);
+    }
+    const float s = lane < a.Tk ? dot * 0.125f : -INFINITY;      // 1 / sqrt(head_dim 64)
+    const float mx = warp_max(s);
+    const float e = lane < a.Tk ? expf(s - mx) : 0.f;
+    const float p = e / warp_sum(e);
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < a.Tk; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      const float *vr = a.v + (b * a.kv_rows + j) * a.kv_ld + head * kDh;
+      o0 = fmaf(pj, vr[lane], o0);
+      o1 = fmaf(pj, vr[lane + 32], o1);
+    }
+    float *orow = a.out + (b * a.Tq + qi) * a.out_ld + head * kDh;
+    orow[lane] = o0;
+    orow[lane + 32] = o1;
+  }
+}
+
+// One decoding step's tail (mtio.py:121-131): final decoder norm -> predictor -> sigmoid -> token t + 1, ensemble over
+// the MTIO heads -> wrap -> pred[b][t]; then the embedding + positional encoding of token t + 1 overwrite x[b].
+struct HeadArgs {
+  float *x;                       // [n][512]: decoder output of step t in, embedding of token t + 1 out
+  const float *norm_w, *norm_b, *pred_w, *pred_b, *emb_w, *emb_b, *pe;
+  float *tokens;                  // [n][F + 1][6]
+  float *pred;                    // [n][F][2]
+  int32_t n, t, F;
+};
+__global__ void __launch_bounds__(256) mtio_head_kernel(const HeadArgs h) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= h.n) return;
+  float4 x[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const float4 *>(h.x + b * kD + i * 128 + lane * 4);
+  warp_layer_norm(x, h.norm_w, h.norm_b, lane);
+  float p[kTok];
+#pragma unroll
+  for (int o = 0; o < kTok; ++o) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 w = *reinterpret_cast<const float4 *>(h.pred_w + o * kD + i * 128 + lane * 4);
+      acc = fmaf(x[i].x, w.x, acc); acc = fmaf(x[i].y, w.y, acc); acc = fmaf(x[i].z, w.z, acc); acc = fmaf(x[i].w, w.w, acc);
+    }
+    const float z = warp_sum(acc) + h.pred_b[o];
+    p[o] = 1.0f / (1.0f + expf(-z));
+  }
+  if (lane == 0) {
+    float *tk = h.tokens + (b * (h.F + 1) + h.t + 1) * kTok;
+#pragma unroll
+    for (int o = 0; o < kTok; ++o) tk[o] = p[o];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float v = ((p[c] + p[c + 2]) + p[c + 4]) / 3.0f;            // mtio.py:125-129
+      if (v < 0.f) v = v - truncf(v) + 1.0f;                      // utils/common.py:61-70
+      else if (v > 1.f) v = v - truncf(v);
+      h.pred[(b * h.F + h.t) * 2 + c] = v;
+    }
+  }
+  if (h.t + 1 >= h.F) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = i * 128 + lane * 4 + k;
+      float acc = 0.f;
+#pragma unroll
+      for (int o = 0; o < kTok; ++o) acc = fmaf(h.emb_w[c * kTok + o], p[o], acc);
+      r[k] = (acc + h.emb_b[c]) + h.pe[(size_t)(h.t + 1) * kD + c];
+    }
+    *reinterpret_cast<float4 *>(h.x + b * kD + i * 128 + lane * 4) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+}  // namespace mansy
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+using namespace mansy;
+
+#define MTIO_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return mansy::set_error(MANSY_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+namespace {
+struct AttnDev {
+  float *w = nullptr, *b = nullptr, *ow = nullptr, *ob = nullptr;
+  CUtensorMap map_qkv, map_q, map_kv, map_o;
+};
+struct LayerDev {
+  AttnDev sa, ca;
+  float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+  float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr, *n3w = nullptr, *n3b = nullptr;
+  CUtensorMap map_w1, map_w2;
+};
+}  // namespace
+
+struct mansy_mtio {
+  int device = 0;
+  int n_enc = 0, n_dec = 0, T = 0, F = 0, Tm = 0, max_batch = 0;
+  bool tc_ok = false;
+  std::vector<void *> allocs;
+  LayerDev enc[MANSY_MTIO_MAX_LAYERS], dec[MANSY_MTIO_MAX_LAYERS];
+  float *emb_w = nullptr, *emb_b = nullptr, *pe = nullptr;
+  float *encn_w = nullptr, *encn_b = nullptr, *decn_w = nullptr, *decn_b = nullptr;
+  float *conv_w = nullptr, *conv_b = nullptr;        // [512][3 * 512] (tap-major K), BatchNorm folded in
+  float *pred_w = nullptr, *pred_b = nullptr;
+  CUtensorMap map_conv;
+  // workspace (sized for max_batch samples)
+  float *xs = nullptr, *att_e = nullptr, *x1_e = nullptr, *ff_e = nullptr, *wide_e = nullptr;   // encoder rows; wide_e = qkv / im2col [rows][1536]
+  float *mem = nullptr, *memkv[MANSY_MTIO_MAX_LAYERS] = {};
+  float *x = nullptr, *q = nullptr, *att = nullptr, *x1 = nullptr, *x2 = nullptr, *ffh = nullptr;
+  float *kc[MANSY_MTIO_MAX_LAYERS] = {}, *vc[MANSY_MTIO_MAX_LAYERS] = {};
+  float *tokens = nullptr;
+  float *io_hist = nullptr, *io_cur = nullptr, *io_pred = nullptr;       // staging of the *_host call
+  // timing
+  bool timed = false;
+  std::vector<cudaEvent_t> events;
+  std::vector<int> ev_class;
+  size_t ev_used = 0;
+};
+
+namespace {
+
+int dev_alloc(mansy_mtio *m, float **p, size_t floats) {
+  void *d = nullptr;
+  cudaError_t e = cudaMalloc(&d, floats * sizeof(float));
+  if (e != cudaSuccess) return set_error(MANSY_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  m->allocs.push_back(d);
+  *p = static_cast<float *>(d);
+  return MANSY_OK;
+}
+
+int upload(mansy_mtio *m, float **p, const float *host, size_t floats) {   // NULL host = zeros
+  int rc = dev_alloc(m, p, floats);
+  if (rc) return rc;
+  if (host) MTIO_CUDA(cudaMemcpy(*p, host, floats * sizeof(float), cudaMemcpyHostToDevice));
+  else MTIO_CUDA(cudaMemset(*p, 0, floats * sizeof(float)));
+  return MANSY_OK;
+}
+
+int upload_attn(mansy_mtio *m, AttnDev *d, const mansy_mtio_attn_t *a, const char *what) {
+  if (!a->in_proj_w || !a->out_w) return set_error(MANSY_E_INVALID, std::string(what) + ": NULL attention weight");
+  int rc = upload(m, &d->w, a->in_proj_w, (size_t)3 * kD * kD);
+  if (!rc) rc = upload(m, &d->b, a->in_proj_b, (size_t)3 * kD);
+  if (!rc) rc = upload(m, &d->ow, a->out_w, (size_t)kD * kD);
+  if (!rc) rc = upload(m, &d->ob, a->out_b, kD);
+  return rc;
+}
+
+int make_attn_maps(AttnDev *d) {
+  int rc = tc_make_map(&d->map_qkv, d->w, kD, 3 * kD, kD, 128);
+  if (!rc) rc = tc_make_map(&d->map_q, d->w, kD, kD, kD, 128);
+  if (!rc) rc = tc_make_map(&d->map_kv, d->w + (size_t)kD * kD, kD, 2 * kD, kD, 128);
+  if (!rc) rc = tc_make_map(&d->map_o, d->ow, kD, kD, kD, 128);
+  return rc;
+}
+
+// ---- launches ----
+struct Launcher {
+  mansy_mtio *m;
+  cudaStream_t s;
+  bool fp32;
+  int rc = MANSY_OK;
+
+  bool begin(int cls) {
+    if (rc) return false;
+    if (m->timed) {
+      if (m->ev_used + 2 > m->events.size()) {
+        for (int i = 0; i < 64; ++i) {
+          cudaEvent_t e;
+          if (cudaEventCreate(&e) != cudaSuccess) { rc = set_error(MANSY_E_CUDA, "cudaEventCreate failed"); return false; }
+          m->events.push_back(e);
+        }
+      }
+      m->ev_class.push_back(cls);
+      cudaEventRecord(m->events[m->ev_used++], s);
+    }
+    return true;
+  }
+  void end(const char *what) {
+    if (m->timed) cudaEventRecord(m->events[m->ev_used++], s);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess && !rc) rc = set_error(MANSY_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  }
+
+  template <int BN, int EPI>
+  void tc_gemm(const CUtensorMap &ma, const CUtensorMap &mw, const GemmArgs &g) {
+    static bool attr_done = false;
+    constexpr uint32_t smem = gemm_smem_bytes<BN>();
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(mtio_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { rc = set_error(MANSY_E_CUDA, std::string("mtio_gemm_kernel attribute: ") + cudaGetErrorString(e)); return; }
+      attr_done = true;
+    }
+    dim3 grid((unsigned)((g.M + 127) / 128), (unsigned)(g.N / BN), 1);
+    mtio_gemm_kernel<BN, EPI><<<grid, kGemmThreads, smem, s>>>(ma, mw, g);
+  }
+
+  // C[M][N] = epi(A[M][K] W[N][K]^T + bias): `wmap` / `W` describe the same torch-layout weight rows
+  void gemm(int epi, const float *A, int64_t lda, const CUtensorMap &wmap, const float *W, GemmArgs g) {
+    if (!begin(0)) return;
+    if (fp32) {
+      dim3 grid((unsigned)((g.M + 63) / 64), (unsigned)(g.N / 64), 1);
+      switch (epi) {
+        case EPI_NONE: mtio_sgemm_kernel<EPI_NONE><<<grid, 256, 0, s>>>(A, lda, W, g); break;
+        case EPI_RELU: mtio_sgemm_kernel<EPI_RELU><<<grid, 256, 0, s>>>(A, lda, W, g); break;
+        case EPI_ELU: mtio_sgemm_kernel<EPI_ELU><<<grid, 256, 0, s>>>(A, lda, W, g); break;
+        default: mtio_sgemm_kernel<EPI_LN><<<grid, 256, 0, s>>>(A, lda, W, g); break;
+      }
+      end("mtio_sgemm_kernel");
+      if (epi == EPI_LN && begin(2)) {
+        mtio_ln_kernel<<<(unsigned)((g.M + 7) / 8), 256, 0, s>>>(g.out[0], g.out[0], g.gamma, g.beta, g.M);
+        end("mtio_ln_kernel");
+      }
+      return;
+    }
+    CUtensorMap ma;
+    if (int e = tc_make_map(&ma, A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda, 128)) { rc = e; return; }
+    switch (epi) {
+      case EPI_NONE: tc_gemm<256, EPI_NONE>(ma, wmap, g); break;
+      case EPI_RELU: tc_gemm<256, EPI_RELU>(ma, wmap, g); break;
+      case EPI_ELU: tc_gemm<256, EPI_ELU>(ma, wmap, g); break;
+      default: tc_gemm<512, EPI_LN>(ma, wmap, g); break;
+    }
+    end("mtio_gemm_kernel");
+  }
+
+  void attn(const AttnArgs &a, int64_t n) {
+    if (!begin(1)) return;
+    mtio_attn_kernel<<<(unsigned)n, 32 * kMtioHeads, 0, s>>>(a);
+    end("mtio_attn_kernel");
+  }
+};
+
+GemmArgs gemm_args(int M, int N, int K, const float *bias) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.bias = bias;
+  return g;
+}
+
+// one pass over n <= max_batch samples
+int run_chunk(mansy_mtio *m, const float *hist, const float *cur, int n, int flags, float *pred, float *tokens_out, cudaStream_t s) {
+  Launcher L{m, s, (flags & MANSY_MTIO_FP32) != 0};
+  if (!L.fp32 && !m->tc_ok) return set_error(MANSY_E_STATE, "tensor maps unavailable (cuTensorMapEncodeTiled missing); use MANSY_MTIO_FP32");
+  const int T = m->T, F = m->F, Tm = m->Tm;
+  const int rows = n * T;
+  const unsigned g128 = 256;     // threads per block of the element-wise kernels
+
+  // ---- encoder (once per sample) ----
+  if (L.begin(2)) {
+    mtio_embed_kernel<<<(unsigned)(((int64_t)rows * 128 + g128 - 1) / g128), g128, 0, s>>>(hist, 2, 2, rows, T, 0, m->emb_w, m->emb_b, m->pe,
+                                                                                          m->xs, nullptr, 0);
+    L.end("mtio_embed_kernel");
+  }
+  for (int l = 0; l < m->n_enc; ++l) {
+    LayerDev &E = m->enc[l];
+    GemmArgs g = gemm_args(rows, 3 * kD, kD, E.sa.b);
+    for (int sgm = 0; sgm < 3; ++sgm) { g.out[sgm] = m->wide_e + sgm * kD; g.out_ld[sgm] = 3 * kD; }
+    L.gemm(EPI_NONE, m->xs, kD, E.sa.map_qkv, E.sa.w, g);
+    AttnArgs a{m->wide_e, 3 * kD, T, m->wide_e + kD, m->wide_e + 2 * kD, 3 * kD, T, T, m->att_e, kD};
+    L.attn(a, n);
+    g = gemm_args(rows, kD, kD, E.sa.ob);
+    g.out[0] = m->x1_e; g.out_ld[0] = kD; g.res = m->xs; g.res_ld = kD; g.gamma = E.n1w; g.beta = E.n1b;
+    L.gemm(EPI_LN, m->att_e, kD, E.sa.map_o, E.sa.ow, g);
+    g = gemm_args(rows, kD, kD, E.b1);
+    g.out[0] = m->ff_e; g.out_ld[0] = kD;
+    L.gemm(EPI_RELU, m->x1_e, kD, E.map_w1, E.w1, g);
+    g = gemm_args(rows, kD, kD, E.b2);
+    g.out[0] = m->xs; g.out_ld[0] = kD; g.res = m->x1_e; g.res_ld = kD; g.gamma = E.n2w; g.beta = E.n2b;
+    L.gemm(EPI_LN, m->ff_e, kD, E.map_w2, E.w2, g);
+  }
+  if (L.begin(2)) {   // encoder.norm, then the DistillLayer: im2col -> conv GEMM (+ folded BatchNorm, ELU) -> max-pool
+    mtio_ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(m->xs, m->att_e, m->encn_w, m->encn_b, rows);
+    L.end("mtio_ln_kernel");
+  }
+  if (L.begin(2)) {
+    mtio_im2col_kernel<<<(unsigned)(((int64_t)rows * 384 + g128 - 1) / g128), g128, 0, s>>>(m->att_e, m->wide_e, rows, T);
+    L.end("mtio_im2col_kernel");
+  }
+  {
+    GemmArgs g = gemm_args(rows, kD, 3 * kD, m->conv_b);
+    g.out[0] = m->x1_e; g.out_ld[0] = kD;
+    L.gemm(EPI_ELU, m->wide_e, 3 * kD, m->map_conv, m->conv_w, g);
+  }
+  if (L.begin(2)) {
+    mtio_maxpool_kernel<<<(unsigned)(((int64_t)n * Tm * 128 + g128 - 1) / g128), g128, 0, s>>>(m->x1_e, m->mem, n, T, Tm);
+    L.end("mtio_maxpool_kernel");
+  }
+  for (int l = 0; l < m->n_dec; ++l) {   // cross-attention keys / values of the memory, once per layer
+    AttnDev &C = m->dec[l].ca;
+    GemmArgs g = gemm_args(n * Tm, 2 * kD, kD, C.b + kD);
+    g.out[0] = m->memkv[l]; g.out_ld[0] = 2 * kD;
+    g.out[1] = m->memkv[l] + kD; g.out_ld[1] = 2 * kD;
+    L.gemm(EPI_NONE, m->mem, kD, C.map_kv, C.w + (size_t)kD * kD, g);
+  }
+
+  // ---- decoder: F autoregressive steps, one new token per step ----
+  if (L.begin(2)) {
+    mtio_embed_kernel<<<(unsigned)(((int64_t)n * 128 + g128 - 1) / g128), g128, 0, s>>>(cur, 2, 2, n, 1, 0, m->emb_w, m->emb_b, m->pe, m->x,
+                                                                                       m->tokens, (int64_t)(F + 1) * kTok);
+    L.end("mtio_embed_kernel");
+  }
+  for (int t = 0; t < F; ++t) {
+    for (int l = 0; l < m->n_dec; ++l) {
+      LayerDev &D = m->dec[l];
+      GemmArgs g = gemm_args(n, 3 * kD, kD, D.sa.b);
+      g.out[0] = m->q; g.out_ld[0] = kD;
+      g.out[1] = m->kc[l] + (size_t)t * kD; g.out_ld[1] = (int64_t)F * kD;
+      g.out[2] = m->vc[l] + (size_t)t * kD; g.out_ld[2] = (int64_t)F * kD;
+      L.gemm(EPI_NONE, m->x, kD, D.sa.map_qkv, D.sa.w, g);
+      AttnArgs a{m->q, kD, 1, m->kc[l], m->vc[l], kD, F, t + 1, m->att, kD};
+      L.attn(a, n);
+      g = gemm_args(n, kD, kD, D.sa.ob);
+      g.out[0] = m->x1; g.out_ld[0] = kD; g.res = m->x; g.res_ld = kD; g.gamma = D.n1w; g.beta = D.n1b;
+      L.gemm(EPI_LN, m->att, kD, D.sa.map_o, D.sa.ow, g);
+      g = gemm_args(n, kD, kD, D.ca.b);
+      g.out[0] = m->q; g.out_ld[0] = kD;
+      L.gemm(EPI_NONE, m->x1, kD, D.ca.map_q, D.ca.w, g);
+      AttnArgs c{m->q, kD, 1, m->memkv[l], m->memkv[l] + kD, 2 * kD, Tm, Tm, m->att, kD};
+      L.attn(c, n);
+      g = gemm_args(n, kD, kD, D.ca.ob);
+      g.out[0] = m->x2; g.out_ld[0] = kD; g.res = m->x1; g.res_ld = kD; g.gamma = D.n2w; g.beta = D.n2b;
+      L.gemm(EPI_LN, m->att, kD, D.ca.map_o, D.ca.ow, g);
+      g = gemm_args(n, kD, kD, D.b1);
+      g.out[0] = m->ffh; g.out_ld[0] = kD;
+      L.gemm(EPI_RELU, m->x2, kD, D.map_w1, D.w1, g);
+      g = gemm_args(n, kD, kD, D.b2);
+      g.out[0] = m->x; g.out_ld[0] = kD; g.res = m->x2; g.res_ld = kD; g.gamma = D.n3w; g.beta = D.n3b;
+      L.gemm(EPI_LN, m->ffh, kD, D.map_w2, D.w2, g);
+    }
+    if (L.begin(2)) {
+      HeadArgs h{m->x, m->decn_w, m->decn_b, m->pred_w, m->pred_b, m->emb_w, m->emb_b, m->pe, m->tokens, pred, n, t, F};
+      mtio_head_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(h);
+      L.end("mtio_head_kernel");
+    }
+  }
+  if (L.rc) return L.rc;
+  if (tokens_out)
+    MTIO_CUDA(cudaMemcpyAsync(tokens_out, m->tokens, (size_t)n * (F + 1) * kTok * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return MANSY_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mansy_mtio_destroy(mansy_mtio_t m) {
+  if (!m) return MANSY_OK;
+  cudaSetDevice(m->device);
+  for (void *p : m->allocs) cudaFree(p);
+  for (cudaEvent_t e : m->events) cudaEventDestroy(e);
+  delete m;
+  return MANSY_OK;
+}
+
+int mansy_mtio_create(const mansy_mtio_weights_t *w, int device, int32_t max_batch, mansy_mtio_t *out) {
+  if (!w || !out) return set_error(MANSY_E_INVALID, "NULL argument");
+  *out = nullptr;
+  if (w->n_enc < 1 || w->n_enc > MANSY_MTIO_MAX_LAYERS || w->n_dec < 1 || w->n_dec > MANSY_MTIO_MAX_LAYERS)
+    return set_error(MANSY_E_INVALID, "n_enc / n_dec must be 1..4");
+  if (w->his_window < 1 || w->his_window > 16 || w->fut_window < 1 || w->fut_window > 31)
+    return set_error(MANSY_E_INVALID, "his_window must be 1..16 and fut_window 1..31");
+  if (w->pe_rows < w->his_window || w->pe_rows < w->fut_window) return set_error(MANSY_E_INVALID, "pe_rows too small");
+  if (max_batch < 1) return set_error(MANSY_E_INVALID, "max_batch must be >= 1");
+  if (!w->emb_w || !w->emb_b || !w->pe || !w->enc_norm_w || !w->dec_norm_w || !w->conv_w || !w->conv_b || !w->bn_w || !w->bn_b ||
+      !w->bn_mean || !w->bn_var || !w->pred_w || !w->pred_b)
+    return set_error(MANSY_E_INVALID, "a required weight pointer is NULL");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+    cudaGetLastError();
+    return set_error(MANSY_E_CUDA, "no such CUDA device (this library has no CPU fallback)");
+  }
+  MTIO_CUDA(cudaSetDevice(device));
+  mansy_mtio *m = new (std::nothrow) mansy_mtio();
+  if (!m) return set_error(MANSY_E_NOMEM, "out of host memory");
+  m->device = device;
+  m->n_enc = w->n_enc; m->n_dec = w->n_dec; m->T = w->his_window; m->F = w->fut_window;
+  m->Tm = (m->T + 2 - 3) / 2 + 1;
+  m->max_batch = max_batch;
+  int rc = MANSY_OK;
+#define MTIO_TRY(expr) do { if (!rc) rc = (expr); } while (0)
+  MTIO_TRY(upload(m, &m->emb_w, w->emb_w, (size_t)kD * kTok));
+  MTIO_TRY(upload(m, &m->emb_b, w->emb_b, kD));
+  MTIO_TRY(upload(m, &m->pe, w->pe, (size_t)w->pe_rows * kD));
+  MTIO_TRY(upload(m, &m->encn_w, w->enc_norm_w, kD));
+  MTIO_TRY(upload(m, &m->encn_b, w->enc_norm_b, kD));
+  MTIO_TRY(upload(m, &m->decn_w, w->dec_norm_w, kD));
+  MTIO_TRY(upload(m, &m->decn_b, w->dec_norm_b, kD));
+  MTIO_TRY(upload(m, &m->pred_w, w->pred_w, (size_t)kTok * kD));
+  MTIO_TRY(upload(m, &m->pred_b, w->pred_b, kTok));
+  for (int l = 0; l < m->n_enc + m->n_dec && !rc; ++l) {
+    const bool is_dec = l >= m->n_enc;
+    const mansy_mtio_layer_t *h = is_dec ? &w->dec[l - m->n_enc] : &w->enc[l];
+    LayerDev *d = is_dec ? &m->dec[l - m->n_enc] : &m->enc[l];
+    if (!h->lin1_w || !h->lin2_w || !h->norm1_w || !h->norm2_w || (is_dec && !h->norm3_w)) {
+      rc = set_error(MANSY_E_INVALID, "a required layer weight pointer is NULL");
+      break;
+    }
+    MTIO_TRY(upload_attn(m, &d->sa, &h->self_attn, "self_attn"));
+    if (is_dec) MTIO_TRY(upload_attn(m, &d->ca, &h->cross_attn, "multihead_attn"));
+    MTIO_TRY(upload(m, &d->w1, h->lin1_w, (size_t)kD * kD));
+    MTIO_TRY(upload(m, &d->b1, h->lin1_b, kD));
+    MTIO_TRY(upload(m, &d->w2, h->lin2_w, (size_t)kD * kD));
+    MTIO_TRY(upload(m, &d->b2, h->lin2_b, kD));
+    MTIO_TRY(upload(m, &d->n1w, h->norm1_w, kD));
+    MTIO_TRY(upload(m, &d->n1b, h->norm1_b, kD));
+    MTIO_TRY(upload(m, &d->n2w, h->norm2_w, kD));
+    MTIO_TRY(upload(m, &d->n2b, h->norm2_b, kD));
+    if (is_dec) {
+      MTIO_TRY(upload(m, &d->n3w, h->norm3_w, kD));
+      MTIO_TRY(upload(m, &d->n3b, h->norm3_b, kD));
+    }
+  }
+  if (!rc) {
+    // DistillLayer: y = ELU(BN(conv(x))) with BN in eval mode = per-channel affine, folded into the conv:
+    // W'[o][k * 512 + i] = W[o][i][k] * g[o] / sqrt(var[o] + eps),  b'[o] = (b[o] - mean[o]) * g[o] / sqrt(var[o] + eps) + beta[o]
+    std::vector<float> cw((size_t)kD * 3 * kD), cb(kD);
+    for (int o = 0; o < kD; ++o) {
+      const float sc = w->bn_w[o] / std::sqrt(w->bn_var[o] + 1e-5f);
+      for (int i = 0; i < kD; ++i)
+        for (int k = 0; k < 3; ++k) cw[(size_t)o * 3 * kD + (size_t)k * kD + i] = w->conv_w[((size_t)o * kD + i) * 3 + k] * sc;
+      cb[o] = (w->conv_b[o] - w->bn_mean[o]) * sc + w->bn_b[o];
+    }
+    MTIO_TRY(upload(m, &m->conv_w, cw.data(), cw.size()));
+    MTIO_TRY(upload(m, &m->conv_b, cb.data(), cb.size()));
+  }
+  const size_t B = (size_t)max_batch, rowsE = B * m->T;
+  MTIO_TRY(dev_alloc(m, &m->xs, rowsE * kD));
+  MTIO_TRY(dev_alloc(m, &m->att_e, rowsE * kD));
+  MTIO_TRY(dev_alloc(m, &m->x1_e, rowsE * kD));
+  MTIO_TRY(dev_alloc(m, &m->ff_e, rowsE * kD));
+  MTIO_TRY(dev_alloc(m, &m->wide_e, rowsE * 3 * kD));
+  MTIO_TRY(dev_alloc(m, &m->mem, B * m->Tm * kD));
+  for (int l = 0; l < m->n_dec; ++l) {
+    MTIO_TRY(dev_alloc(m, &m->memkv[l], B * m->Tm * 2 * kD));
+    MTIO_TRY(dev_alloc(m, &m->kc[l], B * m->F * kD));
+    MTIO_TRY(dev_alloc(m, &m->vc[l], B * m->F * kD));
+  }
+  MTIO_TRY(dev_alloc(m, &m->x, B * kD));
+  MTIO_TRY(dev_alloc(m, &m->q, B * kD));
+  MTIO_TRY(dev_alloc(m, &m->att, B * kD));
+  MTIO_TRY(dev_alloc(m, &m->x1, B * kD));
+  MTIO_TRY(dev_alloc(m, &m->x2, B * kD));
+  MTIO_TRY(dev_alloc(m, &m->ffh, B * kD));
+  MTIO_TRY(dev_alloc(m, &m->tokens, B * (m->F + 1) * kTok));
+#undef MTIO_TRY
+  if (rc) { mansy_mtio_destroy(m); return rc; }
+  // tensor maps of the weights (the fp32 path works without them)
+  int mrc = MANSY_OK;
+  for (int l = 0; l < m->n_enc && !mrc; ++l) {
+    mrc = make_attn_maps(&m->enc[l].sa);
+    if (!mrc) mrc = tc_make_map(&m->enc[l].map_w1, m->enc[l].w1, kD, kD, kD, 128);
+    if (!mrc) mrc = tc_make_map(&m->enc[l].map_w2, m->enc[l].w2, kD, kD, kD, 128);
+  }
+  for (int l = 0; l < m->n_dec && !mrc; ++l) {
+    mrc = make_attn_maps(&m->dec[l].sa);
+    if (!mrc) mrc = make_attn_maps(&m->dec[l].ca);
+    if (!mrc) mrc = tc_make_map(&m->dec[l].map_w1, m->dec[l].w1, kD, kD, kD, 128);
+    if (!mrc) mrc = tc_make_map(&m->dec[l].map_w2, m->dec[l].w2, kD, kD, kD, 128);
+  }
+  if (!mrc) mrc = tc_make_map(&m->map_conv, m->conv_w, 3 * kD, kD, 3 * kD, 128);
+  m->tc_ok = (mrc == MANSY_OK);
+  *out = m;
+  return MANSY_OK;
+}
+
+int mansy_mtio_sample(mansy_mtio_t m, const float *history_dev, const float *current_dev, int32_t n, int32_t flags,
+                      float *pred_dev, float *tokens_dev, void *stream) {
+  if (!m || !history_dev || !current_dev || !pred_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (n < 0) return set_error(MANSY_E_INVALID, "n must be >= 0");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  m->timed = (flags & MANSY_MTIO_TIME_KERNELS) != 0;
+  m->ev_used = 0;
+  m->ev_class.clear();
+  for (int64_t off = 0; off < n; off += m->max_batch) {
+    const int c = (int)((n - off) < m->max_batch ? (n - off) : m->max_batch);
+    int rc = run_chunk(m, history_dev + off * m->T * 2, current_dev + off * 2, c, flags, pred_dev + off * m->F * 2,
+                       tokens_dev ? tokens_dev + off * (m->F + 1) * kTok : nullptr, s);
+    if (rc) return rc;
+  }
+  return MANSY_OK;
+}
+
+int mansy_mtio_sample_host(mansy_mtio_t m, const float *history_host, const float *current_host, int32_t n, int32_t flags,
+                           float *pred_host, void *stream) {
+  if (!m || !history_host || !current_host || !pred_host) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (n < 0) return set_error(MANSY_E_INVALID, "n must be >= 0");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!m->io_hist) {
+    const size_t B = (size_t)m->max_batch;
+    int rc = dev_alloc(m, &m->io_hist, B * m->T * 2);
+    if (!rc) rc = dev_alloc(m, &m->io_cur, B * 2);
+    if (!rc) rc = dev_alloc(m, &m->io_pred, B * m->F * 2);
+    if (rc) return rc;
+  }
+  m->timed = false;
+  for (int64_t off = 0; off < n; off += m->max_batch) {
+    const int c = (int)((n - off) < m->max_batch ? (n - off) : m->max_batch);
+    MTIO_CUDA(cudaMemcpyAsync(m->io_hist, history_host + off * m->T * 2, (size_t)c * m->T * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    MTIO_CUDA(cudaMemcpyAsync(m->io_cur, current_host + off * 2, (size_t)c * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = run_chunk(m, m->io_hist, m->io_cur, c, flags & ~MANSY_MTIO_TIME_KERNELS, m->io_pred, nullptr, s);
+    if (rc) return rc;
+    MTIO_CUDA(cudaMemcpyAsync(pred_host + off * m->F * 2, m->io_pred, (size_t)c * m->F * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  MTIO_CUDA(cudaStreamSynchronize(s));
+  return MANSY_OK;
+}
+
+int mansy_mtio_kernel_ms(mansy_mtio_t m, double ms[3], int32_t launches[3]) {
+  if (!m || !ms || !launches) return set_error(MANSY_E_INVALID, "NULL argument");
+  for (int i = 0; i < 3; ++i) { ms[i] = 0.0; launches[i] = 0; }
+  for (size_t i = 0; i < m->ev_class.size() && 2 * i + 1 < m->ev_used; ++i) {
+    float t = 0.f;
+    MTIO_CUDA(cudaEventElapsedTime(&t, m->events[2 * i], m->events[2 * i + 1]));
+    ms[m->ev_class[i]] += t;
+    launches[m->ev_class[i]] += 1;
+  }
+  return MANSY_OK;
+}
+
+}  // extern "C"

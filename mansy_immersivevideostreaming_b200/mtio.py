@@ -1,0 +1,208 @@
+"""MTIO viewport-prediction transformer, inference on the GPU through the C ABI.
+
+Host-side mirror of the reference's ``ViewportTransformerMTIO`` (viewport_prediction/models/mtio.py:48-133) for
+the calls ``predict.py`` makes on it: construct (predict.py:68-75), ``load_state_dict`` (predict.py:17),
+``eval`` / ``to`` (predict.py:22,92) and ``sample(history, current)`` (predict.py:27).  A checkpoint written by
+``run_models.py`` (the model's own state dict) loads unchanged; keys that a modern torch omits
+(``*.bias`` of the transformer, see oracle/mtio_oracle.py) are taken as zeros.  Training (``forward``,
+``loss_function``) is out of scope.
+
+``predict_chunk_masks`` is the rest of ``predict.predict`` (predict.py:33-48): the first ``dataset_frequency``
+predicted points of every sample -> tile masks + IoU, on the device (``mansy_viewport_tiles``), i.e. the
+``vp_pred`` column of the simulator's tables (BASELINE config 5).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Mapping, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import MansyError, MtioWeights, check
+from .simulator import ViewportTiler, _require_cuda
+
+D_MODEL = 512
+TOKEN = 6          # in_channel 2 x 3 MTIO heads
+
+
+def _arr(x) -> np.ndarray:
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+
+
+def positional_encoding(n: int, d: int = D_MODEL) -> np.ndarray:
+    """The registered buffer of ``PositionalEncoding`` (mtio.py:18-26) when the state dict does not carry it."""
+    pe = np.zeros((n, d), dtype=np.float32)
+    position = np.arange(0, n, dtype=np.float32)[:, None]
+    div_term = np.exp(np.arange(0, d, 2, dtype=np.float32) * np.float32(-(math.log(10000.0) / d))).astype(np.float32)
+    pe[:, 0::2] = np.sin(position * div_term)
+    pe[:, 1::2] = np.cos(position * div_term)
+    return pe
+
+
+class ViewportTransformerMTIO:
+    """Same constructor arguments as the reference class (mtio.py:48-50); only the configuration the reference's
+    own scripts build is supported: ``in_channel=2``, ``num_head=3``, ``d_model = dim_feedforward = 512``."""
+
+    def __init__(self, in_channel: int = 2, fut_window: int = 15, d_model: int = D_MODEL, dim_feedforward: int = D_MODEL,
+                 num_head: int = 3, num_encoder_layers: int = 2, num_decoder_layers: int = 2, batch_first: bool = True,
+                 dropout: float = 0.2, device="cuda", repeat_prob: float = 0.5, seed: int = 1, his_window: int = 5,
+                 max_batch: int = 16384):
+        if in_channel != 2 or num_head != 3 or d_model != D_MODEL or dim_feedforward != D_MODEL or not batch_first:
+            raise MansyError("supported MTIO configuration: in_channel=2, num_head=3, d_model=dim_feedforward=512, batch_first")
+        dev = torch.device(device)
+        index = 0 if dev.index is None else dev.index
+        if dev.type != "cuda":
+            raise MansyError("the B200 MTIO path has no CPU fallback (device must be cuda)")
+        _require_cuda(index)
+        self.lib = _capi.load_library()
+        self.device = torch.device("cuda", index)
+        self.fut_window, self.his_window = int(fut_window), int(his_window)
+        self.n_enc, self.n_dec = int(num_encoder_layers), int(num_decoder_layers)
+        self.max_batch = int(max_batch)
+        self.fp32 = False                   # True: exact-fp32 CUDA-core GEMMs instead of tcgen05 TF32
+        self._h: Optional[C.c_void_p] = None
+
+    # -- nn.Module surface predict.py touches --
+    def to(self, device):
+        if torch.device(device).type != "cuda":
+            raise MansyError("the B200 MTIO path has no CPU fallback")
+        return self
+
+    def eval(self):
+        return self
+
+    def load_state_dict(self, sd: Mapping[str, object], strict: bool = True):
+        keep = []
+        w = MtioWeights()
+        w.n_enc, w.n_dec, w.his_window, w.fut_window = self.n_enc, self.n_dec, self.his_window, self.fut_window
+
+        def ptr(key: str, shape, required: bool = True):
+            if key not in sd:
+                if required:
+                    raise KeyError(key)
+                return None
+            a = _arr(sd[key])
+            if a.size != int(np.prod(shape)):
+                raise ValueError(f"{key}: expected shape {tuple(shape)}, got {a.shape}")
+            keep.append(a)
+            return a.ctypes.data
+
+        d = D_MODEL
+        w.emb_w, w.emb_b = ptr("embedding.linear.weight", (d, TOKEN)), ptr("embedding.linear.bias", (d,))
+        rows = max(self.his_window, self.fut_window) + 1
+        if "positional_embedding.pe" in sd:
+            pe = _arr(sd["positional_embedding.pe"]).reshape(-1, d)[:rows].copy()
+        else:
+            pe = positional_encoding(rows)
+        keep.append(pe)
+        w.pe, w.pe_rows = pe.ctypes.data, pe.shape[0]
+
+        def attn(dst, p):
+            dst.in_proj_w = ptr(p + "in_proj_weight", (3 * d, d))
+            dst.in_proj_b = ptr(p + "in_proj_bias", (3 * d,), False)
+            dst.out_w = ptr(p + "out_proj.weight", (d, d))
+            dst.out_b = ptr(p + "out_proj.bias", (d,), False)
+
+        for side, n in (("encoder", self.n_enc), ("decoder", self.n_dec)):
+            for l in range(n):
+                p = f"transformer.{side}.layers.{l}."
+                lay = (w.enc if side == "encoder" else w.dec)[l]
+                attn(lay.self_attn, p + "self_attn.")
+                if side == "decoder":
+                    attn(lay.cross_attn, p + "multihead_attn.")
+                    lay.norm3_w, lay.norm3_b = ptr(p + "norm3.weight", (d,)), ptr(p + "norm3.bias", (d,), False)
+                lay.lin1_w, lay.lin1_b = ptr(p + "linear1.weight", (d, d)), ptr(p + "linear1.bias", (d,), False)
+                lay.lin2_w, lay.lin2_b = ptr(p + "linear2.weight", (d, d)), ptr(p + "linear2.bias", (d,), False)
+                lay.norm1_w, lay.norm1_b = ptr(p + "norm1.weight", (d,)), ptr(p + "norm1.bias", (d,), False)
+                lay.norm2_w, lay.norm2_b = ptr(p + "norm2.weight", (d,)), ptr(p + "norm2.bias", (d,), False)
+            if strict and f"transformer.{side}.layers.{n}.linear1.weight" in sd:
+                raise ValueError(f"state dict has more than {n} {side} layers")
+        w.enc_norm_w, w.enc_norm_b = ptr("transformer.encoder.norm.weight", (d,)), ptr("transformer.encoder.norm.bias", (d,), False)
+        w.dec_norm_w, w.dec_norm_b = ptr("transformer.decoder.norm.weight", (d,)), ptr("transformer.decoder.norm.bias", (d,), False)
+        p = "transformer.distill_layer."
+        w.conv_w, w.conv_b = ptr(p + "downConv.weight", (d, d, 3)), ptr(p + "downConv.bias", (d,))
+        w.bn_w, w.bn_b = ptr(p + "norm.weight", (d,)), ptr(p + "norm.bias", (d,))
+        w.bn_mean, w.bn_var = ptr(p + "norm.running_mean", (d,)), ptr(p + "norm.running_var", (d,))
+        w.pred_w, w.pred_b = ptr("predictor.0.weight", (TOKEN, d)), ptr("predictor.0.bias", (TOKEN,))
+        self.close()
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self.lib.mansy_mtio_create(C.byref(w), self.device.index, self.max_batch, C.byref(h)))
+        self._h = h
+        return self
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.mansy_mtio_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _handle(self):
+        if self._h is None:
+            raise MansyError("load_state_dict() first: the model has no weights")
+        return self._h
+
+    def sample(self, history, current, return_tokens: bool = False, timed: bool = False):
+        """history ``[B, his_window, 2]``, current ``[B, 1, 2]`` -> ensembled, wrapped viewports ``[B, fut_window, 2]``
+        (mtio.py:106-133).  CUDA tensors run in place on the current stream; numpy / CPU tensors go through the
+        host-buffer entry point (copies + synchronise) and come back as the input's kind."""
+        h = self._handle()
+        flags = (_capi.MTIO_FP32 if self.fp32 else 0) | (_capi.MTIO_TIME_KERNELS if timed else 0)
+        on_device = isinstance(history, torch.Tensor) and history.is_cuda
+        if on_device:
+            hist = history.to(device=self.device, dtype=torch.float32).contiguous()
+            cur = current.to(device=self.device, dtype=torch.float32).contiguous()
+            n = hist.shape[0]
+            if hist.shape[1:] != (self.his_window, 2) or cur.shape != (n, 1, 2):
+                raise ValueError("history must be [B, his_window, 2] and current [B, 1, 2]")
+            pred = torch.empty((n, self.fut_window, 2), dtype=torch.float32, device=self.device)
+            tokens = torch.empty((n, self.fut_window + 1, TOKEN), dtype=torch.float32, device=self.device) if return_tokens else None
+            check(self.lib.mansy_mtio_sample(h, hist.data_ptr(), cur.data_ptr(), n, flags, pred.data_ptr(),
+                                             None if tokens is None else tokens.data_ptr(), self._stream()))
+            return (pred, tokens) if return_tokens else pred
+        as_numpy = not isinstance(history, torch.Tensor)
+        hist, cur = _arr(history), _arr(current)
+        n = hist.shape[0]
+        if hist.shape[1:] != (self.his_window, 2) or cur.shape != (n, 1, 2):
+            raise ValueError("history must be [B, his_window, 2] and current [B, 1, 2]")
+        pred = np.empty((n, self.fut_window, 2), dtype=np.float32)
+        check(self.lib.mansy_mtio_sample_host(h, hist.ctypes.data, cur.ctypes.data, n, flags & ~_capi.MTIO_TIME_KERNELS,
+                                              pred.ctypes.data, self._stream()))
+        return pred if as_numpy else torch.from_numpy(pred)
+
+    def sample_host(self, history: torch.Tensor, current: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """Pinned host tensors in / out (the end-to-end path of bench.py)."""
+        n = history.shape[0]
+        flags = _capi.MTIO_FP32 if self.fp32 else 0
+        check(self.lib.mansy_mtio_sample_host(self._handle(), history.data_ptr(), current.data_ptr(), n, flags, out.data_ptr(),
+                                              self._stream()))
+        return out
+
+    def kernel_ms(self) -> Tuple[np.ndarray, np.ndarray]:
+        """After a ``sample(..., timed=True)`` and a synchronise: (ms, launches) of [GEMM, attention, other] kernels."""
+        ms, cnt = (C.c_double * 3)(), (C.c_int32 * 3)()
+        check(self.lib.mansy_mtio_kernel_ms(self._handle(), C.byref(ms), C.byref(cnt)))
+        return np.array(ms[:]), np.array(cnt[:])
+
+    def predict_chunk_masks(self, history, current, gt_future, tiler: Optional[ViewportTiler] = None, frequency: int = 5):
+        """predict.py:27-48 on the device: sample, then OR the tile masks of the first ``frequency`` ground-truth and
+        predicted points and take their IoU.  ``gt_future [B, >= frequency, 2]`` -> (gt masks int64 [B], predicted
+        masks int64 [B], IoU float64 [B], predictions [B, fut_window, 2])."""
+        tiler = tiler or ViewportTiler(device=self.device.index)
+        pred = self.sample(history.to(self.device), current.to(self.device))
+        gt = gt_future.to(device=self.device, dtype=torch.float32)[:, :frequency].contiguous()
+        gt_m, pred_m, acc = tiler.chunk_masks_device(gt, pred[:, :frequency].contiguous())
+        return gt_m, pred_m, acc, pred

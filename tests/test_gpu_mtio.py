@@ -1,0 +1,119 @@
+"""MTIO inference on the GPU (csrc/mansy_mtio.cu through the C ABI) against the oracle and the reference golden.
+
+Tolerances: the exact-fp32 CUDA-core path 3e-5 absolute on viewport coordinates in [0,1] (fp32 summation order);
+the tcgen05 path 5e-3 absolute -- kind::tf32 keeps 10 mantissa bits of every operand, the precision class the
+reference itself runs in (torch.set_float32_matmul_precision('high'), predict.py:100)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden
+from oracle import mtio_oracle as mo
+from oracle import sim_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+TF32_ATOL = 5e-3
+FP32_ATOL = 3e-5
+
+
+def make_model(sd, max_batch=4096, fut=15, **kw):
+    from mansy_immersivevideostreaming_b200.mtio import ViewportTransformerMTIO
+    net = ViewportTransformerMTIO(in_channel=2, fut_window=fut, d_model=512, dim_feedforward=512, device="cuda:0",
+                                  max_batch=max_batch, **kw)
+    return net.load_state_dict(sd).eval()
+
+
+@pytest.mark.parametrize("case,bias", [("nobias", False), ("bias", True)])
+def test_reference_golden(case, bias):
+    g = load_golden("mtio_kat.npz")
+    sd = mo.seeded_mtio_state_dict(int(g[f"{case}_seed"]), bias=bias)
+    net = make_model(sd)
+    hist, cur = torch.from_numpy(g[f"{case}_history"]).cuda(), torch.from_numpy(g[f"{case}_current"]).cuda()
+    net.fp32 = True
+    pred, tokens = net.sample(hist, cur, return_tokens=True)
+    np.testing.assert_allclose(pred.cpu().numpy(), g[f"{case}_pred"], rtol=0, atol=FP32_ATOL)
+    np.testing.assert_allclose(tokens.cpu().numpy(), g[f"{case}_tokens"], rtol=0, atol=FP32_ATOL)
+    net.fp32 = False
+    pred, tokens = net.sample(hist, cur, return_tokens=True)
+    err = np.abs(pred.cpu().numpy() - g[f"{case}_pred"]).max()
+    print(f"{case}: tcgen05 TF32 vs reference fp32 max abs err {err:.2e}")
+    np.testing.assert_allclose(pred.cpu().numpy(), g[f"{case}_pred"], rtol=0, atol=TF32_ATOL)
+    np.testing.assert_allclose(tokens.cpu().numpy(), g[f"{case}_tokens"], rtol=0, atol=TF32_ATOL)
+
+
+@pytest.mark.parametrize("n", [1, 127, 300])
+def test_ragged_batches_vs_oracle(n):
+    """Batches that are not a multiple of the 128-row tile (TMA zero-fill + guarded stores), several tiles."""
+    sd = mo.seeded_mtio_state_dict(21, bias=True)
+    hist, cur = mo.synthetic_history(n, 33)
+    want = mo.sample(sd, hist, cur, 15)
+    net = make_model(sd)
+    for fp32, atol in ((True, FP32_ATOL), (False, TF32_ATOL)):
+        net.fp32 = fp32
+        got = net.sample(torch.from_numpy(hist).cuda(), torch.from_numpy(cur).cuda()).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=0, atol=atol)
+
+
+def test_chunked_and_host_paths_equal_device_path():
+    sd = mo.seeded_mtio_state_dict(22, bias=False)
+    hist, cur = mo.synthetic_history(300, 34)
+    big = make_model(sd, max_batch=512)
+    ref = big.sample(torch.from_numpy(hist).cuda(), torch.from_numpy(cur).cuda()).cpu().numpy()
+    small = make_model(sd, max_batch=128)          # 300 samples = 3 passes (128 + 128 + 44)
+    got = small.sample(torch.from_numpy(hist).cuda(), torch.from_numpy(cur).cuda()).cpu().numpy()
+    assert np.array_equal(got, ref)                # rows are independent: the tiling must not change a bit
+    host = small.sample(hist, cur)                 # numpy in -> host-buffer entry point -> numpy out
+    assert isinstance(host, np.ndarray) and np.array_equal(host, ref)
+    again = big.sample(torch.from_numpy(hist).cuda(), torch.from_numpy(cur).cuda()).cpu().numpy()
+    assert np.array_equal(again, ref)              # deterministic
+
+
+def test_other_windows_and_depths():
+    """his_window 8 (distilled to 4 memory tokens), 10 prediction steps, 1 encoder / 3 decoder layers."""
+    sd = mo.seeded_mtio_state_dict(23, bias=True, n_enc=1, n_dec=3)
+    hist, cur = mo.synthetic_history(40, 35, his_window=8)
+    want = mo.sample(sd, hist, cur, 10)
+    net = make_model(sd, fut=10, num_encoder_layers=1, num_decoder_layers=3, his_window=8)
+    net.fp32 = True
+    np.testing.assert_allclose(net.sample(torch.from_numpy(hist).cuda(), torch.from_numpy(cur).cuda()).cpu().numpy(), want,
+                               rtol=0, atol=FP32_ATOL)
+    net.fp32 = False
+    np.testing.assert_allclose(net.sample(torch.from_numpy(hist).cuda(), torch.from_numpy(cur).cuda()).cpu().numpy(), want,
+                               rtol=0, atol=TF32_ATOL)
+
+
+def test_predicted_masks_feed_the_simulator_tables():
+    """predict.py:33-48 on the device: masks / IoU of the first 5 predicted points are bit-exact functions of the
+    positions the kernels produced (a13-a16), and close positions give the oracle's masks."""
+    from mansy_immersivevideostreaming_b200.config import SimConfig
+    sd = mo.seeded_mtio_state_dict(24, bias=True)
+    n = 200
+    hist, cur = mo.synthetic_history(n, 36)
+    rng = np.random.default_rng(1)
+    gt_future = np.mod(cur + np.cumsum(rng.normal(0, 0.03, size=(n, 15, 2)), axis=1), 1.0).astype(np.float32)
+    net = make_model(sd)
+    gt_m, pred_m, acc, pred = net.predict_chunk_masks(torch.from_numpy(hist), torch.from_numpy(cur), torch.from_numpy(gt_future))
+    p = pred.cpu().numpy()
+    ogt, opred, oacc = so.chunk_masks(gt_future[:, :5], p[:, :5], SimConfig())
+    assert np.array_equal(gt_m.cpu().numpy().view(np.uint64), ogt)
+    assert np.array_equal(pred_m.cpu().numpy().view(np.uint64), opred)
+    assert np.array_equal(acc.cpu().numpy(), oacc)
+    # against the oracle's own predictions: identical masks wherever no point sits within tolerance of a tile edge
+    want = mo.sample(sd, hist, cur, 15)
+    _, opred2, _ = so.chunk_masks(gt_future[:, :5], want[:, :5], SimConfig())
+    same = (opred2 == opred).mean()
+    print(f"predicted masks equal to the fp32 oracle's for {same * 100:.1f}% of samples")
+    assert same >= 0.9
+
+
+def test_kernel_timing_hook():
+    sd = mo.seeded_mtio_state_dict(25, bias=False)
+    hist, cur = mo.synthetic_history(256, 37)
+    net = make_model(sd)
+    net.sample(torch.from_numpy(hist).cuda(), torch.from_numpy(cur).cuda(), timed=True)
+    torch.cuda.synchronize()
+    ms, cnt = net.kernel_ms()
+    # 2 enc layers x 4 + conv + 2 memory kv + 15 steps x 2 layers x 6 GEMMs; attention 2 + 15 x 2 x 2
+    assert cnt[0] == 2 * 4 + 1 + 2 + 15 * 2 * 6 and cnt[1] == 2 + 15 * 2 * 2 and cnt[2] == 5 + 15
+    assert (ms > 0).all()

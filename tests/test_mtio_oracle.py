@@ -1,0 +1,68 @@
+"""MTIO inference oracle (oracle/mtio_oracle.py) against the golden vectors written from the UNMODIFIED reference
+model (oracle/make_golden_mtio.py), plus properties of the restatement the CUDA path relies on.  CPU only."""
+import numpy as np
+import pytest
+
+from helpers import load_golden
+from oracle import mtio_oracle as mo
+
+
+@pytest.mark.parametrize("case,bias", [("nobias", False), ("bias", True)])
+def test_oracle_matches_reference_golden(case, bias):
+    g = load_golden("mtio_kat.npz")
+    sd = mo.seeded_mtio_state_dict(int(g[f"{case}_seed"]), bias=bias)
+    pred, tokens = mo.sample(sd, g[f"{case}_history"], g[f"{case}_current"], 15, return_tokens=True)
+    np.testing.assert_allclose(pred, g[f"{case}_pred"], rtol=0, atol=2e-5)      # reference: torch fp32 on CPU
+    np.testing.assert_allclose(tokens, g[f"{case}_tokens"], rtol=0, atol=2e-5)
+    assert pred.shape == (g[f"{case}_history"].shape[0], 15, 2) and pred.min() >= 0 and pred.max() <= 1
+
+
+def test_decoder_is_causal_and_encoder_step_independent():
+    """What the key/value cache of the CUDA path relies on: with a causal mask, the decoder output of token j does
+    not change when later tokens are appended (mtio.py:120-123 re-runs the whole prefix every step)."""
+    sd = mo.seeded_mtio_state_dict(5, bias=True)
+    hist, cur = mo.synthetic_history(3, 9)
+    pe = mo.positional_encoding(64)
+    memory = mo.encode(sd, mo.embed(sd, np.concatenate([hist] * 3, axis=-1), pe))
+    assert memory.shape == (3, 3, 512)                      # DistillLayer: 5 source tokens -> 3
+    _, tokens = mo.sample(sd, hist, cur, 6, return_tokens=True)
+    full = mo.decode(sd, mo.embed(sd, tokens, pe), memory)
+    for j in (1, 3, 6):
+        part = mo.decode(sd, mo.embed(sd, tokens[:, :j], pe), memory)
+        np.testing.assert_allclose(part, full[:, :j], rtol=0, atol=5e-6)
+
+
+def test_distill_pooling_windows():
+    """MaxPool1d(3, 2, 1) over 5 tokens: windows {0,1}, {1,2,3}, {3,4} (customized_transformer.py:28)."""
+    sd = mo.seeded_mtio_state_dict(6, bias=True)
+    x = np.random.default_rng(0).normal(size=(2, 5, 512)).astype(np.float32)
+    out = mo.distill(sd, x)
+    w = sd["transformer.distill_layer.downConv.weight"]
+    y = sum(np.roll(x, 1 - k, axis=1) @ w[:, :, k].T for k in range(3)) + sd["transformer.distill_layer.downConv.bias"]
+    y = (y - sd["transformer.distill_layer.norm.running_mean"]) / np.sqrt(sd["transformer.distill_layer.norm.running_var"] + 1e-5) \
+        * sd["transformer.distill_layer.norm.weight"] + sd["transformer.distill_layer.norm.bias"]
+    y = np.where(y > 0, y, np.expm1(np.minimum(y, 0)))
+    np.testing.assert_allclose(out[:, 0], np.maximum(y[:, 0], y[:, 1]), atol=1e-5)
+    np.testing.assert_allclose(out[:, 1], y[:, 1:4].max(axis=1), atol=1e-5)
+    np.testing.assert_allclose(out[:, 2], np.maximum(y[:, 3], y[:, 4]), atol=1e-5)
+
+
+def test_wrap_unit():
+    v = np.array([-0.25, 0.0, 0.5, 1.0, 1.25, -1.5, 2.75], dtype=np.float32)
+    np.testing.assert_allclose(mo.wrap_unit(v), [0.75, 0.0, 0.5, 1.0, 0.25, 0.5, 0.75])
+
+
+def test_host_module_positional_encoding_matches_oracle():
+    from mansy_immersivevideostreaming_b200 import mtio
+    assert np.array_equal(mtio.positional_encoding(20), mo.positional_encoding(20))
+
+
+def test_mtio_refuses_without_gpu(built_library):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mansy_immersivevideostreaming_b200 import _capi, mtio
+    with pytest.raises(_capi.MansyError):
+        mtio.ViewportTransformerMTIO(device="cuda")
+    with pytest.raises(_capi.MansyError):
+        mtio.ViewportTransformerMTIO(device="cpu")
