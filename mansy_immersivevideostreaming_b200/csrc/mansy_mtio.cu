@@ -70,17 +70,40 @@ struct GemmArgs {
 constexpr int kGemmStages = 2;
 constexpr int kGemmMmaWarp = 4;     // warps 0..3: epilogue (TMEM lane quarter = warp), 4: MMA issuer, 5..8: TMA producers
 constexpr int kGemmProd0 = 5;
-constexpr int kGemmThreads = 32 * (kGemmProd0 + 2 * kGemmStages);
+constexpr int kGemmResWarp = kGemmProd0 + 2 * kGemmStages;     // warp 9: residual-tile producer of the LayerNorm epilogue
+constexpr int kGemmThreads = 32 * (kGemmResWarp + 1);
 constexpr uint32_t kABoxBytes = 16384;     // 128 rows x 128 B
+constexpr int kResRing = 3;                // residual boxes prefetched while the main loop runs (BN = 512 only)
+constexpr uint32_t kGemmBarBytes = 256;
 
 template <int BN>
 constexpr uint32_t gemm_smem_bytes() {
-  return 1024u + kGemmStages * (kABoxBytes + BN * 128u) + 64u + 3u * BN * 4u;
+  return 1024u + kGemmStages * (kABoxBytes + BN * 128u) + (BN == 512 ? kResRing * kABoxBytes : 0u) + kGemmBarBytes + 3u * BN * 4u;
+}
+
+// TMA store of a [128 x 32-float] SWIZZLE_128B box from shared memory (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, BN == 256 ? 2 : 1)
-mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmArgs g) {
+mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out, const GemmArgs g) {
   static_assert(BN == 256 || BN == 512, "tile width");
   static_assert(EPI != EPI_LN || BN == 512, "the LayerNorm epilogue needs the whole d_model row in one tile");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -88,12 +111,15 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   constexpr int NB = BN / 128;                   // weight boxes of 128 rows per stage
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bars = base + kGemmStages * kStage;
+  const uint32_t ring = base + kGemmStages * kStage;              // LayerNorm epilogue: residual boxes 0..2 (and 13..15)
+  const uint32_t bars = ring + (BN == 512 ? kResRing * kABoxBytes : 0u);
   const uint32_t bar_full = bars;                // [stage][half]
   const uint32_t bar_empty = bars + 32;          // [stage]
   const uint32_t bar_d = bars + 48;
   const uint32_t tmem_slot = bars + 56;
-  float *s_bias = reinterpret_cast<float *>(smem_raw + (bars + 64 - raw));
+  const uint32_t bar_res_full = bars + 64;       // [16] residual box c landed (single use)
+  const uint32_t bar_ring_free = bars + 192;     // [kResRing] ring box consumed by the 128 epilogue threads
+  float *s_bias = reinterpret_cast<float *>(smem_raw + (bars + kGemmBarBytes - raw));
   float *s_gamma = s_bias + BN, *s_beta = s_gamma + BN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,6 +133,12 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_d, 1);
+    if (EPI == EPI_LN) {
+      for (int c = 0; c < 16; ++c) mbar_init(bar_res_full + 8 * c, 1);
+      for (int c = 0; c < kResRing; ++c) mbar_init(bar_ring_free + 8 * c, 128);
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_res) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
@@ -127,7 +159,36 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp >= kGemmProd0) {
+  if (warp == kGemmResWarp) {
+    // ===== residual producer (LayerNorm epilogue): the [128 x 512] residual tile as 16 boxes of 32 columns.  Boxes 0..2
+    // land in the ring while the main loop runs, 3..12 in the operand stages once the last MMA has retired, 13..15 in
+    // the ring again as the epilogue frees it. =====
+    if (EPI == EPI_LN) {
+      if (elect_one()) {
+        for (int c = 0; c < kResRing; ++c) {
+          mbar_expect_tx(bar_res_full + 8 * c, kABoxBytes);
+          tma_load_2d(ring + c * kABoxBytes, &map_res, c * 32, m0, bar_res_full + 8 * c);
+        }
+      }
+      __syncwarp();
+      mbar_wait(bar_d, 0);
+      if (elect_one()) {
+        for (int c = kResRing; c < 16 - kResRing; ++c) {
+          mbar_expect_tx(bar_res_full + 8 * c, kABoxBytes);
+          tma_load_2d(base + (c - kResRing) * kABoxBytes, &map_res, c * 32, m0, bar_res_full + 8 * c);
+        }
+      }
+      __syncwarp();
+      for (int c = 16 - kResRing; c < 16; ++c) {
+        mbar_wait(bar_ring_free + 8 * (c - (16 - kResRing)), 0);
+        if (elect_one()) {
+          mbar_expect_tx(bar_res_full + 8 * c, kABoxBytes);
+          tma_load_2d(ring + (c - (16 - kResRing)) * kABoxBytes, &map_res, c * 32, m0, bar_res_full + 8 * c);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= kGemmProd0) {
     // ===== TMA producers: warp p fills half (p & 1) of stage (p >> 1): half 0 = A box + first NB/2 weight boxes =====
     const int p = warp - kGemmProd0, s = p >> 1, h = p & 1;
     const uint32_t dst = base + s * kStage, full = bar_full + 16 * s + 8 * h;
@@ -213,21 +274,27 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     } else {
-      const float *rrow = g.res + (size_t)(live ? m : 0) * (size_t)g.res_ld;
+      // Residual boxes and output boxes are [128 rows x 128 B] SWIZZLE_128B tiles: row r keeps its 16-byte piece j at
+      // r * 128 + ((j ^ (r & 7)) << 4), so the 8 lanes of a shared-memory phase touch 8 different bank groups.
+      const uint32_t row_off = (uint32_t)r * 128u, sw = (uint32_t)(r & 7);
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {     // pass 1: x = acc + bias + residual, kept in TMEM
+      for (int c = 0; c < 16; ++c) {     // pass 1: x = acc + bias + residual, kept in TMEM
+        const uint32_t buf = (c < kResRing) ? ring + c * kABoxBytes
+                           : (c < 16 - kResRing) ? base + (c - kResRing) * kABoxBytes
+                                                 : ring + (c - (16 - kResRing)) * kABoxBytes;
         float v[32];
         tmem_ld32(ta + c * 32, v);
-        const float4 *rs = reinterpret_cast<const float4 *>(rrow + c * 32);
+        mbar_wait(bar_res_full + 8 * c, 0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 q = live ? rs[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 q = lds128(buf + row_off + ((((uint32_t)j) ^ sw) << 4));
           v[4 * j] += s_bias[c * 32 + 4 * j] + q.x;
           v[4 * j + 1] += s_bias[c * 32 + 4 * j + 1] + q.y;
           v[4 * j + 2] += s_bias[c * 32 + 4 * j + 2] + q.z;
           v[4 * j + 3] += s_bias[c * 32 + 4 * j + 3] + q.w;
         }
+        if (c < kResRing) mbar_arrive(bar_ring_free + 8 * c);
 #pragma unroll
         for (int j = 0; j < 32; ++j) sum += v[j];
         tmem_st32(ta + c * 32, v);
@@ -236,25 +303,36 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const float mean = sum * (1.0f / BN);
       float ss = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {     // pass 2: centred sum of squares
+      for (int c = 0; c < 16; ++c) {     // pass 2: centred sum of squares
         float v[32];
         tmem_ld32(ta + c * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; ss += d * d; }
       }
       const float rstd = 1.0f / sqrtf(ss * (1.0f / BN) + kLnEps);
+      epi_bar_sync();                    // every warp is done reading residual boxes: the stages become output staging
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {     // pass 3: normalise, affine, store
+      for (int c = 0; c < 16; ++c) {     // pass 3: normalise, affine, stage the box, TMA store (rows >= M are clipped)
+        const uint32_t slot = base + (uint32_t)(c & 7) * kABoxBytes;
+        if (c >= 8) {
+          if (threadIdx.x == 0) tma_store_wait_read<7>();     // the store issued 8 boxes ago has read its slot
+          epi_bar_sync();
+        }
         float v[32];
         tmem_ld32(ta + c * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * s_gamma[c * 32 + j] + s_beta[c * 32 + j];
-        if (live) {
-          float4 *dst = reinterpret_cast<float4 *>(orow + c * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 8; ++j)
+          sts128(slot + row_off + ((((uint32_t)j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_async_smem();
+        epi_bar_sync();
+        if (threadIdx.x == 0) {
+          tma_store_2d(&map_out, slot, c * 32, m0);
+          tma_store_commit();
         }
       }
+      if (threadIdx.x == 0) tma_store_wait_all();
     }
   }
 
@@ -397,7 +475,7 @@ __global__ void __launch_bounds__(256) mtio_embed_kernel(const float *__restrict
     const int c = c4 * 4 + k;
     float acc = 0.f;
 #pragma unroll
-    for (int o = 0; o < kTok; ++o) acc = fmaf(emb_w[c * kTok + o], t[o], acc);
+    for (int o = 0; o < kTok; ++o) acc = fmaf(emb_w[o * kD + c], t[o], acc);      // emb_w: transposed [6][512] copy
     r[k] = (acc + emb_b[c]) + pe[(size_t)pos * kD + c];
   }
   *reinterpret_cast<float4 *>(out + row * kD + c4 * 4) = make_float4(r[0], r[1], r[2], r[3]);
@@ -439,33 +517,57 @@ struct AttnArgs {
   const float *k, *v; int64_t kv_ld; int32_t kv_rows, Tk;   // key rows b * kv_rows + j, j < Tk <= 32
   float *out; int64_t out_ld;
 };
+// Lane = (key parity g = lane >> 4, 16-byte part of the 64-float head slice): a half-warp reads one key / value row
+// slice as one 256-byte run, so every sector fetched is fully used; key 2 * it + g is handled in iteration `it`.
+template <int NIT>
 __global__ void __launch_bounds__(32 * kMtioHeads) mtio_attn_kernel(const AttnArgs a) {
   const int head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 4, part = lane & 15;
   const int64_t b = blockIdx.x;
-  const float *kr = a.k + (b * a.kv_rows + (lane < a.Tk ? lane : 0)) * a.kv_ld + head * kDh;
+  const float *kbase = a.k + b * a.kv_rows * a.kv_ld + head * kDh + part * 4;
+  const float *vbase = a.v + b * a.kv_rows * a.kv_ld + head * kDh + part * 4;
   for (int qi = 0; qi < a.Tq; ++qi) {
-    const float4 *qr = reinterpret_cast<const float4 *>(a.q + (b * a.Tq + qi) * a.q_ld + head * kDh);
-    float dot = 0.f;
+    const float4 q4 = *reinterpret_cast<const float4 *>(a.q + (b * a.Tq + qi) * a.q_ld + head * kDh + part * 4);
+    float4 k4[NIT];
 #pragma unroll
-    for (int i = 0; i < kDh / 4; ++i) {
-      const float4 qq = qr[i];
-      const float4 kk = reinterpret_cast<const float4 *>(kr)[i];
-      dot = fmaf(qq.x, kk.x, dot); dot = fmaf(qq.y, kk.y, dot); dot = fmaf(qq.z, kk.z, dot); dot = fmaf(qq.w, kk.w, dot);
+    for (int it = 0; it < NIT; ++it) {
+      const int key = 2 * it + g;
+      k4[it] = key < a.Tk ? *reinterpret_cast<const float4 *>(kbase + (int64_t)key * a.kv_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float s = lane < a.Tk ? dot * 0.125f : -INFINITY;      // 1 / sqrt(head_dim 64)
-    const float mx = warp_max(s);
-    const float e = lane < a.Tk ? expf(s - mx) : 0.f;
-    const float p = e / warp_sum(e);
-    float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < a.Tk; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, p, j);
-      const float *vr = a.v + (b * a.kv_rows + j) * a.kv_ld + head * kDh;
-      o0 = fmaf(pj, vr[lane], o0);
-      o1 = fmaf(pj, vr[lane + 32], o1);
+    float s[NIT];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      float d = fmaf(q4.x, k4[it].x, fmaf(q4.y, k4[it].y, fmaf(q4.z, k4[it].z, q4.w * k4[it].w)));
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      s[it] = (2 * it + g) < a.Tk ? d * 0.125f : -INFINITY;      // 1 / sqrt(head_dim 64)
+      mx = fmaxf(mx, s[it]);
     }
-    float *orow = a.out + (b * a.Tq + qi) * a.out_ld + head * kDh;
-    orow[lane] = o0;
-    orow[lane + 32] = o1;
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    float sum = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      s[it] = (2 * it + g) < a.Tk ? expf(s[it] - mx) : 0.f;
+      sum += s[it];
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+    const float inv = 1.0f / sum;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int key = 2 * it + g;
+      if (key < a.Tk) {
+        const float4 v4 = *reinterpret_cast<const float4 *>(vbase + (int64_t)key * a.kv_ld);
+        const float p = s[it] * inv;
+        acc.x = fmaf(p, v4.x, acc.x); acc.y = fmaf(p, v4.y, acc.y); acc.z = fmaf(p, v4.z, acc.z); acc.w = fmaf(p, v4.w, acc.w);
+      }
+    }
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+    if (g == 0) *reinterpret_cast<float4 *>(a.out + (b * a.Tq + qi) * a.out_ld + head * kDh + part * 4) = acc;
   }
 }
 
@@ -519,7 +621,7 @@ __global__ void __launch_bounds__(256) mtio_head_kernel(const HeadArgs h) {
       const int c = i * 128 + lane * 4 + k;
       float acc = 0.f;
 #pragma unroll
-      for (int o = 0; o < kTok; ++o) acc = fmaf(h.emb_w[c * kTok + o], p[o], acc);
+      for (int o = 0; o < kTok; ++o) acc = fmaf(h.emb_w[o * kD + c], p[o], acc);      // transposed [6][512] copy
       r[k] = (acc + h.emb_b[c]) + h.pe[(size_t)(h.t + 1) * kD + c];
     }
     *reinterpret_cast<float4 *>(h.x + b * kD + i * 128 + lane * 4) = make_float4(r[0], r[1], r[2], r[3]);
@@ -644,7 +746,7 @@ struct Launcher {
   }
 
   template <int BN, int EPI>
-  void tc_gemm(const CUtensorMap &ma, const CUtensorMap &mw, const GemmArgs &g) {
+  void tc_gemm(const CUtensorMap &ma, const CUtensorMap &mw, const CUtensorMap &mres, const CUtensorMap &mout, const GemmArgs &g) {
     static bool attr_done = false;
     constexpr uint32_t smem = gemm_smem_bytes<BN>();
     if (!attr_done) {
@@ -653,7 +755,7 @@ struct Launcher {
       attr_done = true;
     }
     dim3 grid((unsigned)((g.M + 127) / 128), (unsigned)(g.N / BN), 1);
-    mtio_gemm_kernel<BN, EPI><<<grid, kGemmThreads, smem, s>>>(ma, mw, g);
+    mtio_gemm_kernel<BN, EPI><<<grid, kGemmThreads, smem, s>>>(ma, mw, mres, mout, g);
   }
 
   // C[M][N] = epi(A[M][K] W[N][K]^T + bias): `wmap` / `W` describe the same torch-layout weight rows
@@ -676,18 +778,27 @@ struct Launcher {
     }
     CUtensorMap ma;
     if (int e = tc_make_map(&ma, A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda, 128)) { rc = e; return; }
+    CUtensorMap mres = ma, mout = ma;      // only the LayerNorm epilogue reads them
+    if (epi == EPI_LN) {
+      if (int e = tc_make_map(&mres, g.res, kD, (uint64_t)g.M, (uint64_t)g.res_ld, 128)) { rc = e; return; }
+      if (int e = tc_make_map(&mout, g.out[0], kD, (uint64_t)g.M, (uint64_t)g.out_ld[0], 128)) { rc = e; return; }
+    }
     switch (epi) {
-      case EPI_NONE: tc_gemm<256, EPI_NONE>(ma, wmap, g); break;
-      case EPI_RELU: tc_gemm<256, EPI_RELU>(ma, wmap, g); break;
-      case EPI_ELU: tc_gemm<256, EPI_ELU>(ma, wmap, g); break;
-      default: tc_gemm<512, EPI_LN>(ma, wmap, g); break;
+      case EPI_NONE: tc_gemm<256, EPI_NONE>(ma, wmap, mres, mout, g); break;
+      case EPI_RELU: tc_gemm<256, EPI_RELU>(ma, wmap, mres, mout, g); break;
+      case EPI_ELU: tc_gemm<256, EPI_ELU>(ma, wmap, mres, mout, g); break;
+      default: tc_gemm<512, EPI_LN>(ma, wmap, mres, mout, g); break;
     }
     end("mtio_gemm_kernel");
   }
 
   void attn(const AttnArgs &a, int64_t n) {
     if (!begin(1)) return;
-    mtio_attn_kernel<<<(unsigned)n, 32 * kMtioHeads, 0, s>>>(a);
+    const int nit = (a.Tk + 1) / 2;
+    if (nit <= 2) mtio_attn_kernel<2><<<(unsigned)n, 32 * kMtioHeads, 0, s>>>(a);
+    else if (nit <= 4) mtio_attn_kernel<4><<<(unsigned)n, 32 * kMtioHeads, 0, s>>>(a);
+    else if (nit <= 8) mtio_attn_kernel<8><<<(unsigned)n, 32 * kMtioHeads, 0, s>>>(a);
+    else mtio_attn_kernel<16><<<(unsigned)n, 32 * kMtioHeads, 0, s>>>(a);
     end("mtio_attn_kernel");
   }
 };
@@ -840,7 +951,12 @@ int mansy_mtio_create(const mansy_mtio_weights_t *w, int device, int32_t max_bat
   m->max_batch = max_batch;
   int rc = MANSY_OK;
 #define MTIO_TRY(expr) do { if (!rc) rc = (expr); } while (0)
-  MTIO_TRY(upload(m, &m->emb_w, w->emb_w, (size_t)kD * kTok));
+  {   // embedding.linear.weight [512][6] -> [6][512]: a warp reads 32 consecutive outputs of one input column
+    std::vector<float> wt((size_t)kTok * kD);
+    for (int c = 0; c < kD; ++c)
+      for (int o = 0; o < kTok; ++o) wt[(size_t)o * kD + c] = w->emb_w[(size_t)c * kTok + o];
+    MTIO_TRY(upload(m, &m->emb_w, wt.data(), wt.size()));
+  }
   MTIO_TRY(upload(m, &m->emb_b, w->emb_b, kD));
   MTIO_TRY(upload(m, &m->pe, w->pe, (size_t)w->pe_rows * kD));
   MTIO_TRY(upload(m, &m->encn_w, w->enc_norm_w, kD));
