@@ -413,12 +413,15 @@ int mansy_mtio_destroy(mansy_mtio_t m);
  * tokens_dev ([n][fut_window + 1][6], may be NULL) receives the decoder input tokens (test hook).
  * The encoder runs once per sample and the decoder keeps its keys / values between the autoregressive steps:
  * in eval mode that is the same function as the reference's per-step re-encoding (mtio.py:120-123).
+ * n_steps (0 = fut_window) stops the autoregression early: rows [n_steps, fut_window) of pred_dev / tokens_dev are
+ * left untouched.  predict.py:39-44 builds its tile masks from the first `dataset_frequency` (5) predicted points
+ * only, and a prediction never depends on later steps, so the mask pipeline needs 5 of the 15 steps.
  */
-int mansy_mtio_sample(mansy_mtio_t m, const float *history_dev, const float *current_dev, int32_t n, int32_t flags,
+int mansy_mtio_sample(mansy_mtio_t m, const float *history_dev, const float *current_dev, int32_t n, int32_t n_steps, int32_t flags,
                       float *pred_dev, float *tokens_dev, void *stream);
 /* Same with HOST buffers (pinned for overlap): copies in, runs, copies out, synchronises the stream. */
-int mansy_mtio_sample_host(mansy_mtio_t m, const float *history_host, const float *current_host, int32_t n, int32_t flags,
-                           float *pred_host, void *stream);
+int mansy_mtio_sample_host(mansy_mtio_t m, const float *history_host, const float *current_host, int32_t n, int32_t n_steps,
+                           int32_t flags, float *pred_host, void *stream);
 /* After a MANSY_MTIO_TIME_KERNELS call and a stream synchronise: summed durations (ms) and launch counts of
  * [0] the GEMM kernels, [1] the attention kernels, [2] everything else (embedding, norms, distillation, head). */
 int mansy_mtio_kernel_ms(mansy_mtio_t m, double ms[3], int32_t launches[3]);

@@ -170,8 +170,8 @@ SIGNATURES = {
     "mansy_selftest_hashed_action": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64]),
     "mansy_mtio_create": (C.c_int, [C.POINTER(MtioWeights), C.c_int, C.c_int32, C.POINTER(_vp)]),
     "mansy_mtio_destroy": (C.c_int, [_vp]),
-    "mansy_mtio_sample": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp]),
-    "mansy_mtio_sample_host": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp]),
+    "mansy_mtio_sample": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp]),
+    "mansy_mtio_sample_host": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "mansy_mtio_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_double * 3), C.POINTER(C.c_int32 * 3)]),
 }
 

@@ -67,19 +67,31 @@ struct GemmArgs {
 // ------------------------------------------------------------------------------------------
 // tcgen05 GEMM
 // ------------------------------------------------------------------------------------------
-constexpr int kGemmStages = 2;
-constexpr int kGemmMmaWarp = 4;     // warps 0..3: epilogue (TMEM lane quarter = warp), 4: MMA issuer, 5..8: TMA producers
+constexpr int kGemmMmaWarp = 4;     // warps 0..3: epilogue (TMEM lane quarter = warp), 4: MMA issuer, 5..: TMA producers, last: residual producer
 constexpr int kGemmProd0 = 5;
-constexpr int kGemmResWarp = kGemmProd0 + 2 * kGemmStages;     // warp 9: residual-tile producer of the LayerNorm epilogue
-constexpr int kGemmThreads = 32 * (kGemmResWarp + 1);
 constexpr uint32_t kABoxBytes = 16384;     // 128 rows x 128 B
 constexpr int kResRing = 3;                // residual boxes prefetched while the main loop runs (BN = 512 only)
 constexpr uint32_t kGemmBarBytes = 256;
 
-template <int BN>
-constexpr uint32_t gemm_smem_bytes() {
-  return 1024u + kGemmStages * (kABoxBytes + BN * 128u) + (BN == 512 ? kResRing * kABoxBytes : 0u) + kGemmBarBytes + 3u * BN * 4u;
-}
+// Tile shapes.  What bounds these products is the operand stream out of L2 (ncu: tensor pipe ~32 % busy with
+// [128 x 256] tiles while L2 -> SM traffic sits at ~7.6 TB/s), so the tile is made as large as tensor memory allows:
+//   <256, 2>: [256 rows x 256 columns] = two M128 accumulators sharing every weight box (64 KB per K-chunk of 32
+//             for 4.2 MFLOP = 65 FLOP/B), 3 stages, one CTA per SM -- every GEMM without LayerNorm;
+//   <256, 1>: [128 x 256], 2 stages, two CTAs per SM -- batches of <= 128 rows;
+//   <512, 1>: [128 x 512], the LayerNorm epilogue's full-row tile (52 FLOP/B).
+template <int BN, int MT>
+struct GemmCfg {
+  static constexpr int kStages = MT == 2 ? 3 : 2;
+  static constexpr uint32_t kStage = MT * kABoxBytes + BN * 128u;
+  static constexpr int kResWarp = kGemmProd0 + 2 * kStages;
+  static constexpr int kThreads = 32 * (kResWarp + 1);
+  static constexpr uint32_t kRing = BN == 512 ? kResRing * kABoxBytes : 0u;
+  static constexpr uint32_t kSmem = 1024u + kStages * kStage + kRing + kGemmBarBytes + 3u * BN * 4u;
+  static constexpr int kCtasPerSm = (BN == 256 && MT == 1) ? 2 : 1;
+  static constexpr int kOutSlots = BN == 512 ? 8 : 4;       // output staging boxes carved out of the operand stages
+};
+
+struct OutMaps { CUtensorMap m[3]; };      // one tensor map per 512-column output segment
 
 // TMA store of a [128 x 32-float] SWIZZLE_128B box from shared memory (bulk async-group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
@@ -100,34 +112,38 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, BN == 256 ? 2 : 1)
+template <int BN, int MT, int EPI>
+__global__ void __launch_bounds__(GemmCfg<BN, MT>::kThreads, GemmCfg<BN, MT>::kCtasPerSm)
 mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out, const GemmArgs g) {
-  static_assert(BN == 256 || BN == 512, "tile width");
+                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ OutMaps maps_out, const GemmArgs g) {
+  using Cfg = GemmCfg<BN, MT>;
+  static_assert((BN == 256 && (MT == 1 || MT == 2)) || (BN == 512 && MT == 1), "tile shape");
   static_assert(EPI != EPI_LN || BN == 512, "the LayerNorm epilogue needs the whole d_model row in one tile");
+  static_assert(BN * MT <= 512, "tensor memory columns");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  constexpr uint32_t kStage = kABoxBytes + BN * 128u;
+  constexpr uint32_t kStage = Cfg::kStage;
+  constexpr int kStages = Cfg::kStages;
   constexpr int NB = BN / 128;                   // weight boxes of 128 rows per stage
+  constexpr uint32_t kWOff = MT * kABoxBytes;    // weight boxes follow the A boxes inside a stage
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t ring = base + kGemmStages * kStage;              // LayerNorm epilogue: residual boxes 0..2 (and 13..15)
-  const uint32_t bars = ring + (BN == 512 ? kResRing * kABoxBytes : 0u);
-  const uint32_t bar_full = bars;                // [stage][half]
-  const uint32_t bar_empty = bars + 32;          // [stage]
-  const uint32_t bar_d = bars + 48;
-  const uint32_t tmem_slot = bars + 56;
-  const uint32_t bar_res_full = bars + 64;       // [16] residual box c landed (single use)
-  const uint32_t bar_ring_free = bars + 192;     // [kResRing] ring box consumed by the 128 epilogue threads
+  const uint32_t ring = base + kStages * kStage;                  // LayerNorm epilogue: residual boxes 0..2 (and 13..15)
+  const uint32_t bars = ring + Cfg::kRing;
+  const uint32_t bar_full = bars;                // [stage][half], <= 3 stages
+  const uint32_t bar_empty = bars + 48;          // [stage]
+  const uint32_t bar_d = bars + 72;
+  const uint32_t tmem_slot = bars + 80;
+  const uint32_t bar_res_full = bars + 88;       // [16] residual box c landed (single use)
+  const uint32_t bar_ring_free = bars + 216;     // [kResRing] ring box consumed by the 128 epilogue threads
   float *s_bias = reinterpret_cast<float *>(smem_raw + (bars + kGemmBarBytes - raw));
   float *s_gamma = s_bias + BN, *s_beta = s_gamma + BN;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.x * (128 * MT), n0 = blockIdx.y * BN;
   const int nk = g.K >> 5;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGemmStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 16 * s, 1);
       mbar_init(bar_full + 16 * s + 8, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -137,14 +153,14 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int c = 0; c < 16; ++c) mbar_init(bar_res_full + 8 * c, 1);
       for (int c = 0; c < kResRing; ++c) mbar_init(bar_ring_free + 8 * c, 128);
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_res) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps_out.m[n0 >> 9]) : "memory");
   }
   if (warp == kGemmMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BN * MT) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp < 4) {
@@ -159,7 +175,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == kGemmResWarp) {
+  if (warp == Cfg::kResWarp) {
     // ===== residual producer (LayerNorm epilogue): the [128 x 512] residual tile as 16 boxes of 32 columns.  Boxes 0..2
     // land in the ring while the main loop runs, 3..12 in the operand stages once the last MMA has retired, 13..15 in
     // the ring again as the epilogue frees it. =====
@@ -189,40 +205,54 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   } else if (warp >= kGemmProd0) {
-    // ===== TMA producers: warp p fills half (p & 1) of stage (p >> 1): half 0 = A box + first NB/2 weight boxes =====
+    // ===== TMA producers: warp p fills half (p & 1) of stage (p >> 1).
+    // MT = 1: half 0 = A box + first NB/2 weight boxes, half 1 = the other weight boxes;  MT = 2: half 0 = both A boxes,
+    // half 1 = both weight boxes (32 KB each). =====
     const int p = warp - kGemmProd0, s = p >> 1, h = p & 1;
     const uint32_t dst = base + s * kStage, full = bar_full + 16 * s + 8 * h;
-    for (int it = s; it < nk; it += kGemmStages) {
-      mbar_wait(bar_empty + 8 * s, ((uint32_t)(it / kGemmStages) & 1u) ^ 1u);
+    for (int it = s; it < nk; it += kStages) {
+      mbar_wait(bar_empty + 8 * s, ((uint32_t)(it / kStages) & 1u) ^ 1u);
       if (elect_one()) {
-        if (h == 0) {
+        if (MT == 2) {
+          mbar_expect_tx(full, 2 * kABoxBytes);
+          if (h == 0) {
+            tma_load_2d(dst, &map_a, it * 32, m0, full);
+            tma_load_2d(dst + kABoxBytes, &map_a, it * 32, m0 + 128, full);
+          } else {
+            tma_load_2d(dst + kWOff, &map_w, it * 32, n0, full);
+            tma_load_2d(dst + kWOff + kABoxBytes, &map_w, it * 32, n0 + 128, full);
+          }
+        } else if (h == 0) {
           mbar_expect_tx(full, kABoxBytes * (1 + NB / 2));
           tma_load_2d(dst, &map_a, it * 32, m0, full);
 #pragma unroll
-          for (int b = 0; b < NB / 2; ++b) tma_load_2d(dst + kABoxBytes * (1 + b), &map_w, it * 32, n0 + b * 128, full);
+          for (int b = 0; b < NB / 2; ++b) tma_load_2d(dst + kWOff + kABoxBytes * b, &map_w, it * 32, n0 + b * 128, full);
         } else {
           mbar_expect_tx(full, kABoxBytes * (NB / 2));
 #pragma unroll
-          for (int b = NB / 2; b < NB; ++b) tma_load_2d(dst + kABoxBytes * (1 + b), &map_w, it * 32, n0 + b * 128, full);
+          for (int b = NB / 2; b < NB; ++b) tma_load_2d(dst + kWOff + kABoxBytes * b, &map_w, it * 32, n0 + b * 128, full);
         }
       }
       __syncwarp();
     }
   } else if (warp == kGemmMmaWarp) {
-    // ===== MMA issuer: D[128 x BN] (+)= A[128 x 32] * W[BN x 32]^T per stage, four K8 steps =====
+    // ===== MMA issuer: per stage four K8 steps of M128 x N256 MMAs =====
     constexpr uint32_t kIdesc = idesc_tf32(256);
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < nk; ++it) {
-      const int s = it & 1;
-      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-      const uint32_t a_lo = smem_desc_lo(base + s * kStage), b_lo = smem_desc_lo(base + s * kStage + kABoxBytes);
+      const uint32_t a_lo = smem_desc_lo(base + s * kStage), b_lo = smem_desc_lo(base + s * kStage + kWOff);
       if (BN == 256) {
         mbar_wait(bar_full + 16 * s, ph);
         mbar_wait(bar_full + 16 * s + 8, ph);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_tf32(tmem_base, make_desc(a_lo + 2 * ks), make_desc(b_lo + 2 * ks), kIdesc, (it > 0 || ks > 0) ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32(tmem_base + 256u * mt, make_desc(a_lo + mt * (kABoxBytes >> 4) + 2 * ks), make_desc(b_lo + 2 * ks), kIdesc,
+                        (it > 0 || ks > 0) ? 1u : 0u);
         }
         __syncwarp();
       } else {
@@ -244,22 +274,31 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (it == nk - 1) umma_commit(bar_d);
       }
       __syncwarp();
+      if (++s == kStages) { s = 0; ph ^= 1u; }
     }
   } else {
-    // ===== epilogue warps 0..3: thread = output row =====
-    const int r = warp * 32 + lane;
-    const int m = m0 + r;
-    const bool live = m < g.M;
+    // ===== epilogue warps 0..3: thread = output row.  Output (and residual) boxes are [128 rows x 128 B] SWIZZLE_128B
+    // tiles: row r keeps its 16-byte piece j at r * 128 + ((j ^ (r & 7)) << 4), so the 8 lanes of a shared-memory phase
+    // touch 8 different bank groups.  Boxes leave through TMA stores (rows >= M are clipped by the tensor map). =====
+    const int r = warp * 32 + (threadIdx.x & 31);
     const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int seg = n0 >> 9, col0 = n0 & 511;
-    float *orow = g.out[seg] + (size_t)(live ? m : 0) * (size_t)g.out_ld[seg] + col0;
+    const uint32_t row_off = (uint32_t)r * 128u, sw = (uint32_t)(r & 7);
+    const CUtensorMap *omap = &maps_out.m[n0 >> 9];
+    const int col0 = n0 & 511;
+    constexpr int NS = Cfg::kOutSlots;
     mbar_wait(bar_d, 0);
     tc_fence_after();
     if (EPI != EPI_LN) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int ci = 0; ci < MT * (BN / 32); ++ci) {
+        const int mt = ci / (BN / 32), c = ci % (BN / 32);
+        const uint32_t slot = base + (uint32_t)(ci % NS) * kABoxBytes;
+        if (ci >= NS) {
+          if (threadIdx.x == 0) tma_store_wait_read<NS - 1>();      // the store issued NS boxes ago has read its slot
+          epi_bar_sync();
+        }
         float v[32];
-        tmem_ld32(ta + c * 32, v);
+        tmem_ld32(ta + mt * 256 + c * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = v[j] + s_bias[c * 32 + j];
@@ -267,16 +306,18 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (EPI == EPI_ELU) x = x > 0.f ? x : expm1f(x);
           v[j] = x;
         }
-        if (live) {
-          float4 *dst = reinterpret_cast<float4 *>(orow + c * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 8; ++j)
+          sts128(slot + row_off + ((((uint32_t)j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_async_smem();
+        epi_bar_sync();
+        if (threadIdx.x == 0) {
+          tma_store_2d(omap, slot, col0 + c * 32, m0 + mt * 128);
+          tma_store_commit();
         }
       }
+      if (threadIdx.x == 0) tma_store_wait_all();
     } else {
-      // Residual boxes and output boxes are [128 rows x 128 B] SWIZZLE_128B tiles: row r keeps its 16-byte piece j at
-      // r * 128 + ((j ^ (r & 7)) << 4), so the 8 lanes of a shared-memory phase touch 8 different bank groups.
-      const uint32_t row_off = (uint32_t)r * 128u, sw = (uint32_t)(r & 7);
       float sum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 16; ++c) {     // pass 1: x = acc + bias + residual, kept in TMEM
@@ -312,10 +353,10 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const float rstd = 1.0f / sqrtf(ss * (1.0f / BN) + kLnEps);
       epi_bar_sync();                    // every warp is done reading residual boxes: the stages become output staging
 #pragma unroll 1
-      for (int c = 0; c < 16; ++c) {     // pass 3: normalise, affine, stage the box, TMA store (rows >= M are clipped)
-        const uint32_t slot = base + (uint32_t)(c & 7) * kABoxBytes;
-        if (c >= 8) {
-          if (threadIdx.x == 0) tma_store_wait_read<7>();     // the store issued 8 boxes ago has read its slot
+      for (int c = 0; c < 16; ++c) {     // pass 3: normalise, affine, stage the box, TMA store
+        const uint32_t slot = base + (uint32_t)(c % NS) * kABoxBytes;
+        if (c >= NS) {
+          if (threadIdx.x == 0) tma_store_wait_read<NS - 1>();
           epi_bar_sync();
         }
         float v[32];
@@ -328,7 +369,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         fence_async_smem();
         epi_bar_sync();
         if (threadIdx.x == 0) {
-          tma_store_2d(&map_out, slot, c * 32, m0);
+          tma_store_2d(omap, slot, c * 32, m0);
           tma_store_commit();
         }
       }
@@ -340,7 +381,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   if (warp == kGemmMmaWarp) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN * MT) : "memory");
   }
 }
 
@@ -745,17 +786,17 @@ struct Launcher {
     if (e != cudaSuccess && !rc) rc = set_error(MANSY_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
   }
 
-  template <int BN, int EPI>
-  void tc_gemm(const CUtensorMap &ma, const CUtensorMap &mw, const CUtensorMap &mres, const CUtensorMap &mout, const GemmArgs &g) {
+  template <int BN, int MT, int EPI>
+  void tc_gemm(const CUtensorMap &ma, const CUtensorMap &mw, const CUtensorMap &mres, const OutMaps &mout, const GemmArgs &g) {
+    using Cfg = GemmCfg<BN, MT>;
     static bool attr_done = false;
-    constexpr uint32_t smem = gemm_smem_bytes<BN>();
     if (!attr_done) {
-      cudaError_t e = cudaFuncSetAttribute(mtio_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(mtio_gemm_kernel<BN, MT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
       if (e != cudaSuccess) { rc = set_error(MANSY_E_CUDA, std::string("mtio_gemm_kernel attribute: ") + cudaGetErrorString(e)); return; }
       attr_done = true;
     }
-    dim3 grid((unsigned)((g.M + 127) / 128), (unsigned)(g.N / BN), 1);
-    mtio_gemm_kernel<BN, EPI><<<grid, kGemmThreads, smem, s>>>(ma, mw, mres, mout, g);
+    dim3 grid((unsigned)((g.M + 128 * MT - 1) / (128 * MT)), (unsigned)(g.N / BN), 1);
+    mtio_gemm_kernel<BN, MT, EPI><<<grid, Cfg::kThreads, Cfg::kSmem, s>>>(ma, mw, mres, mout, g);
   }
 
   // C[M][N] = epi(A[M][K] W[N][K]^T + bias): `wmap` / `W` describe the same torch-layout weight rows
@@ -778,16 +819,21 @@ struct Launcher {
     }
     CUtensorMap ma;
     if (int e = tc_make_map(&ma, A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda, 128)) { rc = e; return; }
-    CUtensorMap mres = ma, mout = ma;      // only the LayerNorm epilogue reads them
-    if (epi == EPI_LN) {
-      if (int e = tc_make_map(&mres, g.res, kD, (uint64_t)g.M, (uint64_t)g.res_ld, 128)) { rc = e; return; }
-      if (int e = tc_make_map(&mout, g.out[0], kD, (uint64_t)g.M, (uint64_t)g.out_ld[0], 128)) { rc = e; return; }
+    CUtensorMap mres = ma;                 // only the LayerNorm epilogue reads it
+    OutMaps mout;
+    for (int sgm = 0; sgm < 3; ++sgm) {
+      mout.m[sgm] = ma;
+      if (sgm * kD < g.N)
+        if (int e = tc_make_map(&mout.m[sgm], g.out[sgm], kD, (uint64_t)g.M, (uint64_t)g.out_ld[sgm], 128)) { rc = e; return; }
     }
+    if (epi == EPI_LN)
+      if (int e = tc_make_map(&mres, g.res, kD, (uint64_t)g.M, (uint64_t)g.res_ld, 128)) { rc = e; return; }
+    const bool wide = g.M > 128;           // two M128 sub-tiles per CTA share the weight boxes
     switch (epi) {
-      case EPI_NONE: tc_gemm<256, EPI_NONE>(ma, wmap, mres, mout, g); break;
-      case EPI_RELU: tc_gemm<256, EPI_RELU>(ma, wmap, mres, mout, g); break;
-      case EPI_ELU: tc_gemm<256, EPI_ELU>(ma, wmap, mres, mout, g); break;
-      default: tc_gemm<512, EPI_LN>(ma, wmap, mres, mout, g); break;
+      case EPI_NONE: wide ? tc_gemm<256, 2, EPI_NONE>(ma, wmap, mres, mout, g) : tc_gemm<256, 1, EPI_NONE>(ma, wmap, mres, mout, g); break;
+      case EPI_RELU: wide ? tc_gemm<256, 2, EPI_RELU>(ma, wmap, mres, mout, g) : tc_gemm<256, 1, EPI_RELU>(ma, wmap, mres, mout, g); break;
+      case EPI_ELU: wide ? tc_gemm<256, 2, EPI_ELU>(ma, wmap, mres, mout, g) : tc_gemm<256, 1, EPI_ELU>(ma, wmap, mres, mout, g); break;
+      default: tc_gemm<512, 1, EPI_LN>(ma, wmap, mres, mout, g); break;
     }
     end("mtio_gemm_kernel");
   }
@@ -811,7 +857,8 @@ GemmArgs gemm_args(int M, int N, int K, const float *bias) {
 }
 
 // one pass over n <= max_batch samples
-int run_chunk(mansy_mtio *m, const float *hist, const float *cur, int n, int flags, float *pred, float *tokens_out, cudaStream_t s) {
+int run_chunk(mansy_mtio *m, const float *hist, const float *cur, int n, int n_steps, int flags, float *pred, float *tokens_out,
+              cudaStream_t s) {
   Launcher L{m, s, (flags & MANSY_MTIO_FP32) != 0};
   if (!L.fp32 && !m->tc_ok) return set_error(MANSY_E_STATE, "tensor maps unavailable (cuTensorMapEncodeTiled missing); use MANSY_MTIO_FP32");
   const int T = m->T, F = m->F, Tm = m->Tm;
@@ -872,7 +919,7 @@ int run_chunk(mansy_mtio *m, const float *hist, const float *cur, int n, int fla
                                                                                        m->tokens, (int64_t)(F + 1) * kTok);
     L.end("mtio_embed_kernel");
   }
-  for (int t = 0; t < F; ++t) {
+  for (int t = 0; t < n_steps; ++t) {
     for (int l = 0; l < m->n_dec; ++l) {
       LayerDev &D = m->dec[l];
       GemmArgs g = gemm_args(n, 3 * kD, kD, D.sa.b);
@@ -1041,27 +1088,31 @@ int mansy_mtio_create(const mansy_mtio_weights_t *w, int device, int32_t max_bat
   return MANSY_OK;
 }
 
-int mansy_mtio_sample(mansy_mtio_t m, const float *history_dev, const float *current_dev, int32_t n, int32_t flags,
+int mansy_mtio_sample(mansy_mtio_t m, const float *history_dev, const float *current_dev, int32_t n, int32_t n_steps, int32_t flags,
                       float *pred_dev, float *tokens_dev, void *stream) {
   if (!m || !history_dev || !current_dev || !pred_dev) return set_error(MANSY_E_INVALID, "NULL argument");
   if (n < 0) return set_error(MANSY_E_INVALID, "n must be >= 0");
+  if (n_steps < 0 || n_steps > m->F) return set_error(MANSY_E_INVALID, "n_steps must be 0 (= fut_window) .. fut_window");
+  if (n_steps == 0) n_steps = m->F;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   m->timed = (flags & MANSY_MTIO_TIME_KERNELS) != 0;
   m->ev_used = 0;
   m->ev_class.clear();
   for (int64_t off = 0; off < n; off += m->max_batch) {
     const int c = (int)((n - off) < m->max_batch ? (n - off) : m->max_batch);
-    int rc = run_chunk(m, history_dev + off * m->T * 2, current_dev + off * 2, c, flags, pred_dev + off * m->F * 2,
+    int rc = run_chunk(m, history_dev + off * m->T * 2, current_dev + off * 2, c, n_steps, flags, pred_dev + off * m->F * 2,
                        tokens_dev ? tokens_dev + off * (m->F + 1) * kTok : nullptr, s);
     if (rc) return rc;
   }
   return MANSY_OK;
 }
 
-int mansy_mtio_sample_host(mansy_mtio_t m, const float *history_host, const float *current_host, int32_t n, int32_t flags,
-                           float *pred_host, void *stream) {
+int mansy_mtio_sample_host(mansy_mtio_t m, const float *history_host, const float *current_host, int32_t n, int32_t n_steps,
+                           int32_t flags, float *pred_host, void *stream) {
   if (!m || !history_host || !current_host || !pred_host) return set_error(MANSY_E_INVALID, "NULL argument");
   if (n < 0) return set_error(MANSY_E_INVALID, "n must be >= 0");
+  if (n_steps < 0 || n_steps > m->F) return set_error(MANSY_E_INVALID, "n_steps must be 0 (= fut_window) .. fut_window");
+  if (n_steps == 0) n_steps = m->F;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!m->io_hist) {
     const size_t B = (size_t)m->max_batch;
@@ -1075,7 +1126,7 @@ int mansy_mtio_sample_host(mansy_mtio_t m, const float *history_host, const floa
     const int c = (int)((n - off) < m->max_batch ? (n - off) : m->max_batch);
     MTIO_CUDA(cudaMemcpyAsync(m->io_hist, history_host + off * m->T * 2, (size_t)c * m->T * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
     MTIO_CUDA(cudaMemcpyAsync(m->io_cur, current_host + off * 2, (size_t)c * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = run_chunk(m, m->io_hist, m->io_cur, c, flags & ~MANSY_MTIO_TIME_KERNELS, m->io_pred, nullptr, s);
+    int rc = run_chunk(m, m->io_hist, m->io_cur, c, n_steps, flags & ~MANSY_MTIO_TIME_KERNELS, m->io_pred, nullptr, s);
     if (rc) return rc;
     MTIO_CUDA(cudaMemcpyAsync(pred_host + off * m->F * 2, m->io_pred, (size_t)c * m->F * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
   }

@@ -155,10 +155,11 @@ class ViewportTransformerMTIO:
             raise MansyError("load_state_dict() first: the model has no weights")
         return self._h
 
-    def sample(self, history, current, return_tokens: bool = False, timed: bool = False):
+    def sample(self, history, current, return_tokens: bool = False, timed: bool = False, steps: int = 0):
         """history ``[B, his_window, 2]``, current ``[B, 1, 2]`` -> ensembled, wrapped viewports ``[B, fut_window, 2]``
         (mtio.py:106-133).  CUDA tensors run in place on the current stream; numpy / CPU tensors go through the
-        host-buffer entry point (copies + synchronise) and come back as the input's kind."""
+        host-buffer entry point (copies + synchronise) and come back as the input's kind.  ``steps`` (0 = all) stops
+        the autoregression early; later rows of the result are then zero."""
         h = self._handle()
         flags = (_capi.MTIO_FP32 if self.fp32 else 0) | (_capi.MTIO_TIME_KERNELS if timed else 0)
         on_device = isinstance(history, torch.Tensor) and history.is_cuda
@@ -168,9 +169,10 @@ class ViewportTransformerMTIO:
             n = hist.shape[0]
             if hist.shape[1:] != (self.his_window, 2) or cur.shape != (n, 1, 2):
                 raise ValueError("history must be [B, his_window, 2] and current [B, 1, 2]")
-            pred = torch.empty((n, self.fut_window, 2), dtype=torch.float32, device=self.device)
-            tokens = torch.empty((n, self.fut_window + 1, TOKEN), dtype=torch.float32, device=self.device) if return_tokens else None
-            check(self.lib.mansy_mtio_sample(h, hist.data_ptr(), cur.data_ptr(), n, flags, pred.data_ptr(),
+            alloc = torch.zeros if steps else torch.empty
+            pred = alloc((n, self.fut_window, 2), dtype=torch.float32, device=self.device)
+            tokens = alloc((n, self.fut_window + 1, TOKEN), dtype=torch.float32, device=self.device) if return_tokens else None
+            check(self.lib.mansy_mtio_sample(h, hist.data_ptr(), cur.data_ptr(), n, int(steps), flags, pred.data_ptr(),
                                              None if tokens is None else tokens.data_ptr(), self._stream()))
             return (pred, tokens) if return_tokens else pred
         as_numpy = not isinstance(history, torch.Tensor)
@@ -178,16 +180,16 @@ class ViewportTransformerMTIO:
         n = hist.shape[0]
         if hist.shape[1:] != (self.his_window, 2) or cur.shape != (n, 1, 2):
             raise ValueError("history must be [B, his_window, 2] and current [B, 1, 2]")
-        pred = np.empty((n, self.fut_window, 2), dtype=np.float32)
-        check(self.lib.mansy_mtio_sample_host(h, hist.ctypes.data, cur.ctypes.data, n, flags & ~_capi.MTIO_TIME_KERNELS,
+        pred = np.zeros((n, self.fut_window, 2), dtype=np.float32)
+        check(self.lib.mansy_mtio_sample_host(h, hist.ctypes.data, cur.ctypes.data, n, int(steps), flags & ~_capi.MTIO_TIME_KERNELS,
                                               pred.ctypes.data, self._stream()))
         return pred if as_numpy else torch.from_numpy(pred)
 
-    def sample_host(self, history: torch.Tensor, current: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    def sample_host(self, history: torch.Tensor, current: torch.Tensor, out: torch.Tensor, steps: int = 0) -> torch.Tensor:
         """Pinned host tensors in / out (the end-to-end path of bench.py)."""
         n = history.shape[0]
         flags = _capi.MTIO_FP32 if self.fp32 else 0
-        check(self.lib.mansy_mtio_sample_host(self._handle(), history.data_ptr(), current.data_ptr(), n, flags, out.data_ptr(),
+        check(self.lib.mansy_mtio_sample_host(self._handle(), history.data_ptr(), current.data_ptr(), n, int(steps), flags, out.data_ptr(),
                                               self._stream()))
         return out
 
@@ -197,12 +199,14 @@ class ViewportTransformerMTIO:
         check(self.lib.mansy_mtio_kernel_ms(self._handle(), C.byref(ms), C.byref(cnt)))
         return np.array(ms[:]), np.array(cnt[:])
 
-    def predict_chunk_masks(self, history, current, gt_future, tiler: Optional[ViewportTiler] = None, frequency: int = 5):
+    def predict_chunk_masks(self, history, current, gt_future, tiler: Optional[ViewportTiler] = None, frequency: int = 5,
+                            short: bool = True):
         """predict.py:27-48 on the device: sample, then OR the tile masks of the first ``frequency`` ground-truth and
         predicted points and take their IoU.  ``gt_future [B, >= frequency, 2]`` -> (gt masks int64 [B], predicted
-        masks int64 [B], IoU float64 [B], predictions [B, fut_window, 2])."""
+        masks int64 [B], IoU float64 [B], predictions [B, fut_window, 2]).  ``short`` (default) stops the autoregression
+        after the ``frequency`` steps the masks use (rows beyond are zero); a prediction never depends on later steps."""
         tiler = tiler or ViewportTiler(device=self.device.index)
-        pred = self.sample(history.to(self.device), current.to(self.device))
+        pred = self.sample(history.to(self.device), current.to(self.device), steps=min(frequency, self.fut_window) if short else 0)
         gt = gt_future.to(device=self.device, dtype=torch.float32)[:, :frequency].contiguous()
         gt_m, pred_m, acc = tiler.chunk_masks_device(gt, pred[:, :frequency].contiguous())
         return gt_m, pred_m, acc, pred

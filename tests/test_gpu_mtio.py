@@ -117,3 +117,16 @@ def test_kernel_timing_hook():
     # 2 enc layers x 4 + conv + 2 memory kv + 15 steps x 2 layers x 6 GEMMs; attention 2 + 15 x 2 x 2
     assert cnt[0] == 2 * 4 + 1 + 2 + 15 * 2 * 6 and cnt[1] == 2 + 15 * 2 * 2 and cnt[2] == 5 + 15
     assert (ms > 0).all()
+
+
+def test_early_stop_equals_prefix_of_full_run():
+    """n_steps < fut_window: the first steps are bit-identical to a full run (a prediction never depends on later steps)."""
+    sd = mo.seeded_mtio_state_dict(26, bias=True)
+    hist, cur = mo.synthetic_history(200, 38)
+    net = make_model(sd)
+    h, c = torch.from_numpy(hist).cuda(), torch.from_numpy(cur).cuda()
+    full = net.sample(h, c).cpu().numpy()
+    short = net.sample(h, c, steps=5).cpu().numpy()
+    assert np.array_equal(short[:, :5], full[:, :5]) and not short[:, 5:].any()
+    host = net.sample(hist, cur, steps=5)
+    assert np.array_equal(host, short)

@@ -63,6 +63,16 @@ def main():
         kms, cnt = net.kernel_ms()
         print(f"   serialised: gemm {kms[0]:.3f} ms / {cnt[0]} launches, attention {kms[1]:.3f} ms / {cnt[1]}, other {kms[2]:.3f} ms / {cnt[2]}",
               flush=True)
+    net.fp32 = False
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    net.sample(h, c, steps=5)
+    e0.record()
+    for _ in range(reps):
+        net.sample(h, c, steps=5)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"tf32 batch {n}, 5 of 15 steps (what predict.py's masks use): {ms:.3f} ms  {n / ms * 1e3:.3e} samples/s", flush=True)
     # host round trip
     net.fp32 = False
     hp, cp = torch.from_numpy(hist).pin_memory(), torch.from_numpy(cur).pin_memory()
