@@ -44,6 +44,11 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     p.add_argument("--sweep", action="store_true", help="also time the simulator-only kernel at larger env counts")
+    p.add_argument("--workload", default="rollout", choices=["rollout", "mtio"],
+                   help="rollout = BASELINE configs[1] (the bench line the driver records); mtio = BASELINE configs[4], the "
+                        "MTIO viewport-prediction inference feeding predicted tile masks to the environments")
+    p.add_argument("--mtio-samples", type=int, default=16384)
+    p.add_argument("--no-mtio", action="store_true", help="leave the viewport_prediction section out of the rollout line")
     p.add_argument("--profile-sim", type=int, default=0,
                    help="only run a few simulator-only launches at this env count (for ncu captures); prints no bench line")
     return p.parse_args()
@@ -358,9 +363,147 @@ def run_ours(args):
     }
     if sweep:
         line["simulator_sweep"] = sweep
+    if not args.no_mtio:
+        sim.close(); e2e_sim.close()
+        del roll, e2e_roll, host
+        torch.cuda.empty_cache()
+        line["viewport_prediction"] = mtio_section(local, args.mtio_samples,
+                                                   cpu_seconds=0.0 if (world > 1 or args.no_cpu_baseline) else 6.0)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_baseline_seconds, os.cpu_count() or 1)
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# MTIO viewport prediction (BASELINE configs[4])
+# ---------------------------------------------------------------------------------------------
+def mtio_flop_per_sample(T=5, Tm=3, F=15, n_enc=2, n_dec=2, d=512):
+    """Multiply-adds x 2 of the key/value-cached formulation; attention itself is < 1 %."""
+    mac = n_enc * T * 6 * d * d + T * 3 * d * d + n_dec * Tm * 2 * d * d + F * n_dec * 8 * d * d
+    return 2 * mac
+
+
+def mtio_cpu_baseline(seconds: float = 10.0):
+    """The numpy oracle port of ViewportTransformerMTIO.sample (re-decodes the prefix every step like the reference,
+    BLAS threads as numpy sees fit) on a bounded sample."""
+    from oracle import mtio_oracle as mo
+    sd = mo.seeded_mtio_state_dict(3, bias=True)
+    n, done = 64, 0
+    hist, cur = mo.synthetic_history(n, 4)
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        mo.sample(sd, hist, cur, 15)
+        done += n
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "viewport samples/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{done} samples in batches of {n} through the numpy restatement of model.sample (15 autoregressive "
+                      f"steps, whole-prefix decoding as mtio.py:120-123; numpy/BLAS threading)", "wall_s": dt}
+
+
+def mtio_section(device_index: int, n: int, reps: int = 5, cpu_seconds: float = 0.0):
+    """16,384 viewport histories -> 15 predicted points each (model.sample), and the predict.py mask pipeline."""
+    import numpy as np
+    import torch
+    from mansy_immersivevideostreaming_b200.mtio import ViewportTransformerMTIO
+    from mansy_immersivevideostreaming_b200.simulator import ViewportTiler
+    from oracle import mtio_oracle as mo      # seeded weights / synthetic walks only (numpy); the checker, not the product
+    _, tflops, _ = measured_peaks()
+    sd = mo.seeded_mtio_state_dict(3, bias=True)
+    net = ViewportTransformerMTIO(device=f"cuda:{device_index}", max_batch=n).load_state_dict(sd)
+    hist, cur = mo.synthetic_history(n, 4)
+    h, c = torch.from_numpy(hist).cuda(device_index), torch.from_numpy(cur).cuda(device_index)
+    for _ in range(3):
+        net.sample(h, c)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        net.sample(h, c)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    net.sample(h, c, timed=True)
+    torch.cuda.synchronize()
+    kms, cnt = net.kernel_ms()
+    flop = n * mtio_flop_per_sample()
+    gemm_tflops = flop / (kms[0] * 1e-3) / 1e12
+    # predict.py pipeline: 5 steps, OR of the tile masks of 5 points, IoU against the ground truth (a13-a16)
+    tiler = ViewportTiler(device=device_index)
+    gt = torch.from_numpy(np.mod(cur + np.cumsum(np.random.default_rng(1).normal(0, 0.03, size=(n, 15, 2)), axis=1), 1.0)
+                          .astype(np.float32)).cuda(device_index)
+    net.predict_chunk_masks(h, c, gt, tiler)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        net.predict_chunk_masks(h, c, gt, tiler)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_masks = e0.elapsed_time(e1) / reps
+    # end to end: pinned host histories in, predictions out
+    hp, cp = torch.from_numpy(hist).pin_memory(), torch.from_numpy(cur).pin_memory()
+    out = torch.empty((n, 15, 2), dtype=torch.float32).pin_memory()
+    net.sample_host(hp, cp, out)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        net.sample_host(hp, cp, out)
+    e2e_s = (time.perf_counter() - t0) / reps
+    sec = {
+        "workload": f"mtio_sample_{n} (his 5, fut 15, d_model 512, 2+2 layers: predict.py defaults)",
+        "metric": "viewport samples/s", "value": n / (ms * 1e-3), "ms_per_batch": ms, "dtype": "tf32 (fp32 accumulate)",
+        "flop_per_sample": mtio_flop_per_sample(),
+        "kernel_ms": {"gemm": kms[0], "attention": kms[1], "other": kms[2]},
+        "kernel_launches": {"gemm": int(cnt[0]), "attention": int(cnt[1]), "other": int(cnt[2])},
+        "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": tflops / 2.0, "unit": "TFLOP/s",
+                     "frac": gemm_tflops / (tflops / 2.0), "kernel": "mtio_gemm_kernel (tcgen05 kind::tf32; all 191 launches of a batch)",
+                     "avg_launch_ms": kms[0] / max(int(cnt[0]), 1),
+                     "peak_source": "1/2 x measured bf16 cuBLAS burst (MEASURED_PEAKS.json); TF32 runs at half the bf16 rate",
+                     "traffic": None},
+        "mask_pipeline": {"value": n / (ms_masks * 1e-3), "unit": "viewport samples/s", "ms_per_batch": ms_masks,
+                          "what": "5 of 15 autoregressive steps + tile masks + IoU (predict.py:33-48 uses the first 5 points)"},
+        "e2e": {"value": n / e2e_s, "unit": "viewport samples/s", "h2d_bytes_per_step": n * 48, "d2h_bytes_per_step": n * 120},
+    }
+    if cpu_seconds > 0:
+        sec["cpu_baseline"] = mtio_cpu_baseline(cpu_seconds)
+    net.close()
+    return sec
+
+
+def run_mtio(args):
+    """Stand-alone line for the MTIO workload (one process per GPU, samples sharded, no collective)."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    sec = mtio_section(local, args.mtio_samples, reps=max(args.steps if args.steps < 100 else 10, 3),
+                       cpu_seconds=0.0 if (args.no_cpu_baseline or world > 1 or rank != 0) else args.cpu_baseline_seconds)
+    clk = clocks.stop() if rank == 0 else None
+    ms = sec["ms_per_batch"]
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    if rank == 0:
+        line = {"metric": "viewport samples/s", "value": world * args.mtio_samples / (ms * 1e-3), "unit": "viewport samples/s",
+                "n_gpus": world, "steps": max(args.steps if args.steps < 100 else 10, 3), "warmup": 3, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": sec["dtype"], "data": "synthetic",
+                "config": {"workload": sec["workload"], "samples_per_gpu": args.mtio_samples,
+                           "l2": "activations + key/value cache of a batch: 3.3 GB (>> L2)"},
+                "roofline": sec["roofline"], "e2e": sec["e2e"], "mask_pipeline": sec["mask_pipeline"],
+                "kernel_ms": sec["kernel_ms"], "gpu_launches": sum(sec["kernel_launches"].values()), "clocks": clk}
+        if "cpu_baseline" in sec:
+            line["cpu_baseline"] = sec["cpu_baseline"]
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -428,6 +571,8 @@ def main():
         return
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "mtio":
+        run_mtio(args)
     else:
         run_ours(args)
 

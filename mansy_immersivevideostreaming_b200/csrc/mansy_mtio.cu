@@ -510,16 +510,14 @@ __global__ void __launch_bounds__(256) mtio_embed_kernel(const float *__restrict
     for (int o = 0; o < kTok; ++o) tok_out[row * tok_out_stride + o] = t[o];
   }
   const int pos = pos_base + (int)(row % pos_mod);
-  float r[4];
+  float4 r = *reinterpret_cast<const float4 *>(emb_b + c4 * 4);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = c4 * 4 + k;
-    float acc = 0.f;
-#pragma unroll
-    for (int o = 0; o < kTok; ++o) acc = fmaf(emb_w[o * kD + c], t[o], acc);      // emb_w: transposed [6][512] copy
-    r[k] = (acc + emb_b[c]) + pe[(size_t)pos * kD + c];
+  for (int o = 0; o < kTok; ++o) {      // emb_w: transposed [6][512] copy, one 16-byte load per input column
+    const float4 w = *reinterpret_cast<const float4 *>(emb_w + o * kD + c4 * 4);
+    r.x = fmaf(w.x, t[o], r.x); r.y = fmaf(w.y, t[o], r.y); r.z = fmaf(w.z, t[o], r.z); r.w = fmaf(w.w, t[o], r.w);
   }
-  *reinterpret_cast<float4 *>(out + row * kD + c4 * 4) = make_float4(r[0], r[1], r[2], r[3]);
+  const float4 pp = *reinterpret_cast<const float4 *>(pe + (size_t)pos * kD + c4 * 4);
+  *reinterpret_cast<float4 *>(out + row * kD + c4 * 4) = make_float4(r.x + pp.x, r.y + pp.y, r.z + pp.z, r.w + pp.w);
 }
 
 // DistillLayer conv input (customized_transformer.py:21-25,32): row (b, t) -> [x[t-1] | x[t] | x[t+1]] with circular wrap
@@ -656,16 +654,15 @@ __global__ void __launch_bounds__(256) mtio_head_kernel(const HeadArgs h) {
   if (h.t + 1 >= h.F) return;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float r[4];
+    const int c = i * 128 + lane * 4;
+    float4 r = *reinterpret_cast<const float4 *>(h.emb_b + c);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = i * 128 + lane * 4 + k;
-      float acc = 0.f;
-#pragma unroll
-      for (int o = 0; o < kTok; ++o) acc = fmaf(h.emb_w[o * kD + c], p[o], acc);      // transposed [6][512] copy
-      r[k] = (acc + h.emb_b[c]) + h.pe[(size_t)(h.t + 1) * kD + c];
+    for (int o = 0; o < kTok; ++o) {    // transposed [6][512] copy
+      const float4 w = *reinterpret_cast<const float4 *>(h.emb_w + o * kD + c);
+      r.x = fmaf(w.x, p[o], r.x); r.y = fmaf(w.y, p[o], r.y); r.z = fmaf(w.z, p[o], r.z); r.w = fmaf(w.w, p[o], r.w);
     }
-    *reinterpret_cast<float4 *>(h.x + b * kD + i * 128 + lane * 4) = make_float4(r[0], r[1], r[2], r[3]);
+    const float4 pp = *reinterpret_cast<const float4 *>(h.pe + (size_t)(h.t + 1) * kD + c);
+    *reinterpret_cast<float4 *>(h.x + b * kD + c) = make_float4(r.x + pp.x, r.y + pp.y, r.z + pp.z, r.w + pp.w);
   }
 }
 
