@@ -210,3 +210,41 @@ class ViewportTransformerMTIO:
         gt = gt_future.to(device=self.device, dtype=torch.float32)[:, :frequency].contiguous()
         gt_m, pred_m, acc = tiler.chunk_masks_device(gt, pred[:, :frequency].contiguous())
         return gt_m, pred_m, acc, pred
+
+
+def viewport_windows(gt_xy: np.ndarray, his_window: int = 5) -> Tuple[np.ndarray, np.ndarray]:
+    """Cut the samples ``predict.py`` feeds the model out of continuous 5 Hz viewport traces.
+
+    ``gt_xy [P, CV, F, 2]`` holds, per (video, user) pair, the ``F`` ground-truth points of each of ``CV`` consecutive
+    chunks.  ``ViewportDataset.__getitem__`` (viewport_prediction/utils/load_dataset.py:48-57) with
+    ``sample_step = frequency`` makes the sample of a chunk end right before it: ``current`` = the last point of the
+    previous chunk, ``history`` = the ``his_window`` points before that.  The points a real trace has ahead of the
+    first chunk (``trim_head``, config.yml:147) are not part of the synthetic tables; the first point is repeated
+    there.  Returns ``history [P*CV, his_window, 2]``, ``current [P*CV, 1, 2]``.
+    """
+    P, CV, F, _ = gt_xy.shape
+    pts = np.ascontiguousarray(gt_xy, dtype=np.float32).reshape(P, CV * F, 2)
+    full = np.concatenate([np.repeat(pts[:, :1], his_window + 1, axis=1), pts], axis=1)
+    idx = np.arange(CV) * F                               # chunk i starts at full[:, his_window + 1 + F * i]
+    hist = np.stack([full[:, idx + k] for k in range(his_window)], axis=2)
+    cur = full[:, idx + his_window][:, :, None, :]
+    return hist.reshape(P * CV, his_window, 2).copy(), cur.reshape(P * CV, 1, 2).copy()
+
+
+class MtioMaskFn:
+    """``mask_fn`` of ``synth.make_synthetic_tables`` whose predicted-viewport column comes from the MTIO model
+    instead of a noise model: BASELINE config 5 (MTIO inference feeding predicted viewports into the environments).
+    Ground-truth masks, predicted masks and IoU are those of predict.py:33-48."""
+
+    def __init__(self, net: ViewportTransformerMTIO, n_vp_chunks: int, tiler: Optional[ViewportTiler] = None):
+        self.net, self.cv = net, int(n_vp_chunks)
+        self.tiler = tiler or ViewportTiler(device=net.device.index)
+        self.last_pred: Optional[np.ndarray] = None
+
+    def __call__(self, gt_xy: np.ndarray, pred_xy: np.ndarray):
+        n, F, _ = gt_xy.shape
+        hist, cur = viewport_windows(np.asarray(gt_xy).reshape(n // self.cv, self.cv, F, 2), self.net.his_window)
+        gt_m, pred_m, acc, pred = self.net.predict_chunk_masks(torch.from_numpy(hist), torch.from_numpy(cur),
+                                                               torch.from_numpy(np.ascontiguousarray(gt_xy)), self.tiler, frequency=F)
+        self.last_pred = pred[:, :F].cpu().numpy()
+        return gt_m.cpu().numpy().view(np.uint64), pred_m.cpu().numpy().view(np.uint64), acc.cpu().numpy()

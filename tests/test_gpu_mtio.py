@@ -130,3 +130,40 @@ def test_early_stop_equals_prefix_of_full_run():
     assert np.array_equal(short[:, :5], full[:, :5]) and not short[:, 5:].any()
     host = net.sample(hist, cur, steps=5)
     assert np.array_equal(host, short)
+
+
+def test_config5_predicted_tables_drive_the_environments():
+    """BASELINE config 5 end to end at test size: MTIO predictions -> tile masks -> the simulator's tables -> lock-step
+    MANSY envs; the CUDA envs on those tables equal the oracle envs on the same tables."""
+    from mansy_immersivevideostreaming_b200 import synth
+    from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, REWARD_QOE, SimConfig
+    from mansy_immersivevideostreaming_b200.mtio import MtioMaskFn, viewport_windows
+    from mansy_immersivevideostreaming_b200.simulator import BatchSimulator
+    sd = mo.seeded_mtio_state_dict(27, bias=True)
+    net = make_model(sd)
+    fn = MtioMaskFn(net, n_vp_chunks=54)
+    tables, gt_xy, _ = synth.make_synthetic_tables(fn, n_videos=2, n_users=3, n_traces=4, seed=5, trace_len_range=(40, 90),
+                                                   return_centres=True)
+    # the masks in the tables are the oracle's masks of the positions the kernels predicted
+    hist, cur = viewport_windows(gt_xy)
+    assert hist.shape == (6 * 54, 5, 2) and np.array_equal(cur[1, 0], gt_xy[0, 0, 4]) and np.array_equal(hist[2, 4], gt_xy[0, 1, 3])
+    ogt, opred, oacc = so.chunk_masks(gt_xy.reshape(-1, 5, 2), fn.last_pred, SimConfig())
+    valid = (np.arange(54)[None, :] <= (tables.vp_end - tables.vp_start)[:, None]).reshape(-1)
+    assert np.array_equal(tables.vp_gt.reshape(-1)[valid], ogt[valid])
+    assert np.array_equal(tables.vp_pred.reshape(-1)[valid], opred[valid])
+    assert np.array_equal(tables.vp_acc.reshape(-1)[valid], oacc[valid])
+    want = mo.sample(sd, hist, cur, 5)
+    np.testing.assert_allclose(fn.last_pred, want, rtol=0, atol=TF32_ATOL)
+    # and the environments run on them
+    n = 32
+    tables = tables.with_samples(synth.per_env_samples(tables, n))
+    sim = BatchSimulator(tables, n, OBS_MODE_MANSY, REWARD_QOE, seed=1)
+    orc = so.OracleVectorEnv(tables, n, OBS_MODE_MANSY, REWARD_QOE, chain="f64", seed=1)
+    assert np.array_equal(sim.reset().cpu().numpy(), orc.reset())
+    for t in range(55):
+        acts = synth.synthetic_actions(n, t, seed=3)
+        obs, rew, done = sim.step(torch.from_numpy(acts), auto_reset=True)
+        oobs, orew, odone, _ = orc.step(acts, auto_reset=True)
+        np.testing.assert_allclose(obs.cpu().numpy(), oobs, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(rew.cpu().numpy(), orew, rtol=1e-5, atol=1e-6)
+        assert np.array_equal(done.cpu().numpy().astype(bool), odone)

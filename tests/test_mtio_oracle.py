@@ -66,3 +66,19 @@ def test_mtio_refuses_without_gpu(built_library):
         mtio.ViewportTransformerMTIO(device="cuda")
     with pytest.raises(_capi.MansyError):
         mtio.ViewportTransformerMTIO(device="cpu")
+
+
+def test_viewport_windows_follow_the_dataset_cut():
+    """load_dataset.py:48-57 with sample_step == frequency: the sample of a chunk ends right before the chunk."""
+    from mansy_immersivevideostreaming_b200.mtio import viewport_windows
+    g = np.random.default_rng(0).random((2, 4, 5, 2)).astype(np.float32)
+    h, c = viewport_windows(g)
+    assert h.shape == (8, 5, 2) and c.shape == (8, 1, 2)
+    pts = g.reshape(2, 20, 2)
+    for p in range(2):
+        for i in range(1, 4):
+            t = 5 * i - 1                                   # `current` = last point of the previous chunk
+            assert np.array_equal(c[p * 4 + i, 0], pts[p, t])
+            if i >= 2:
+                assert np.array_equal(h[p * 4 + i], pts[p, t - 5:t])
+    assert np.array_equal(c[0, 0], pts[0, 0]) and np.array_equal(h[0], np.repeat(pts[0, :1], 5, axis=0))
