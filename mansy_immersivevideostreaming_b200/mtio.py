@@ -248,3 +248,36 @@ class MtioMaskFn:
                                                                torch.from_numpy(np.ascontiguousarray(gt_xy)), self.tiler, frequency=F)
         self.last_pred = pred[:, :F].cpu().numpy()
         return gt_m.cpu().numpy().view(np.uint64), pred_m.cpu().numpy().view(np.uint64), acc.cpu().numpy()
+
+
+def write_prediction_files(results_dir: str, video: int, user: int, first_chunk: int, gt_masks, pred_masks, accuracy) -> str:
+    """Write one (video, user) pair's per-chunk viewports in the reference's on-disk formats (predict.py:50-65):
+    ``video{v}/user{u}.pkl`` -- the list of ``(chunk, gt uint8[64], pred uint8[64], accuracy float64)`` tuples that
+    ``simulators/hmdtrace.py:5-23`` (and ``tables.pack_from_reference_layout``) load -- and the ``.csv`` twin.
+    ``gt_masks`` / ``pred_masks`` are 64-bit tile masks (bit t = tile t) as the kernels produce them."""
+    import os
+    import pickle
+
+    from .tables import u64_to_masks
+    def bits(x):
+        if isinstance(x, torch.Tensor):
+            x = x.detach().cpu().numpy()
+        if isinstance(x, np.ndarray) and x.dtype == np.int64:       # the kernels' masks come back as int64 tensors
+            return x.reshape(-1).view(np.uint64)
+        return np.array(x, dtype=np.uint64).reshape(-1)             # python ints: no detour through float64
+
+    gt = u64_to_masks(bits(gt_masks))
+    pred = u64_to_masks(bits(pred_masks))
+    acc = np.asarray(accuracy, dtype=np.float64).reshape(-1)
+    value = [(int(first_chunk + i), gt[i].reshape(-1).astype(np.uint8), pred[i].reshape(-1).astype(np.uint8), np.float64(acc[i]))
+             for i in range(len(acc))]
+    base = os.path.join(results_dir, f"video{video}")
+    os.makedirs(base, exist_ok=True)
+    path = os.path.join(base, f"user{user}.pkl")
+    with open(path, "wb") as fh:
+        pickle.dump(value, fh)
+    with open(os.path.join(base, f"user{user}.csv"), "w", encoding="utf-8") as fh:
+        fh.write("chunk,gt,pred,accuracy\n")
+        for chunk, g, p, a in value:
+            fh.write(f"{chunk},{','.join(map(str, list(g)))},{','.join(map(str, list(p)))},{a}\n")
+    return path

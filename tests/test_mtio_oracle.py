@@ -82,3 +82,46 @@ def test_viewport_windows_follow_the_dataset_cut():
             if i >= 2:
                 assert np.array_equal(h[p * 4 + i], pts[p, t - 5:t])
     assert np.array_equal(c[0, 0], pts[0, 0]) and np.array_equal(h[0], np.repeat(pts[0, :1], 5, axis=0))
+
+
+def test_prediction_files_round_trip(tmp_path):
+    """predict.py:50-65 formats: the pickle holds (chunk, gt uint8[64], pred uint8[64], float64) tuples that hmdtrace.py
+    indexes, the csv the same rows as text."""
+    import os
+    import pickle
+    from mansy_immersivevideostreaming_b200.mtio import write_prediction_files
+    from mansy_immersivevideostreaming_b200.tables import mask_to_bits
+    rng = np.random.default_rng(3)
+    gt = rng.integers(0, 2, size=(7, 64)).astype(np.uint8)
+    pred = rng.integers(0, 2, size=(7, 64)).astype(np.uint8)
+    acc = rng.random(7)
+    path = write_prediction_files(str(tmp_path), 4, 9, 3, [mask_to_bits(m) for m in gt], [mask_to_bits(m) for m in pred], acc)
+    assert path.endswith(os.path.join("video4", "user9.pkl"))
+    rows = pickle.load(open(path, "rb"))
+    assert [r[0] for r in rows] == list(range(3, 10))
+    for i, (chunk, g, p, a) in enumerate(rows):
+        assert g.dtype == np.uint8 and g.shape == (64,) and np.array_equal(g, gt[i]) and np.array_equal(p, pred[i]) and a == acc[i]
+    lines = open(path.replace(".pkl", ".csv")).read().splitlines()
+    assert lines[0] == "chunk,gt,pred,accuracy" and len(lines) == 8
+    f = lines[1].split(",")
+    assert int(f[0]) == 3 and [int(x) for x in f[1:65]] == list(gt[0]) and [int(x) for x in f[65:129]] == list(pred[0])
+    assert float(f[129]) == acc[0]
+
+
+def test_prediction_files_reproduce_a_shipped_file(tmp_path):
+    import os
+    import pickle
+    src = "/root/reference/datasets/Jin2022/viewports/prediction/video1/user1.pkl"
+    if not os.path.exists(src):
+        pytest.skip("reference dataset not present (build container only)")
+    from mansy_immersivevideostreaming_b200.mtio import write_prediction_files
+    from mansy_immersivevideostreaming_b200.tables import mask_to_bits
+    rows = pickle.load(open(src, "rb"))
+    path = write_prediction_files(str(tmp_path), 1, 1, rows[0][0], [mask_to_bits(r[1]) for r in rows],
+                                  [mask_to_bits(r[2]) for r in rows], [r[3] for r in rows])
+    back = pickle.load(open(path, "rb"))
+    assert len(back) == len(rows)
+    for a, b in zip(rows, back):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3] and b[1].dtype == a[1].dtype
+    if os.path.exists(src.replace(".pkl", ".csv")):
+        assert open(src.replace(".pkl", ".csv")).read() == open(path.replace(".pkl", ".csv")).read()
