@@ -347,6 +347,15 @@ int mansy_rollout_kernel_ms(mansy_handle_t h, double *policy_ms, double *step_ms
  * (current_video / current_user / ... attributes of the gym envs) and tests. */
 int mansy_state_snapshot(mansy_handle_t h, void *state_dev, void *stream);
 
+/*
+ * MPC expert: ExpertEnv.choose_action (bitrate_selection/envs/expert_env.py:358-422 with ExpertSimulator's virtual
+ * downloads, simulators/simulator.py:125-144, and QoEModelExpert, utils/qoe.py:50-60) for every environment of the
+ * handle at its current state: exhaustive search over the 15^H action sequences of the next H = min(horizon, chunks
+ * left) chunks, first action of the first best sequence.  actions_dev int32 [n_envs]; best_value_dev (float64 [n_envs],
+ * may be NULL) receives the winning QoE sum.  horizon 1..6 (run_expert.py:169 default 4).  The state is not modified.
+ */
+int mansy_expert_actions(mansy_handle_t h, int32_t horizon, int32_t *actions_dev, double *best_value_dev, void *stream);
+
 /* Non-zero once a kernel met a data error (a trace that can never finish a download). */
 int mansy_error_flag(mansy_handle_t h, int32_t *flag_host);
 

@@ -141,6 +141,7 @@ SIGNATURES = {
     "mansy_stats_clear": (C.c_int, [_vp, _vp]),
     "mansy_state_snapshot": (C.c_int, [_vp, _vp, _vp]),
     "mansy_error_flag": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    "mansy_expert_actions": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp]),
     "mansy_viewport_tiles": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        _vp, _vp, _vp, _vp]),
     "mansy_allocate_tile_versions": (C.c_int, [_vp, _vp, C.c_int64, C.POINTER(C.c_int32 * 5), _vp, _vp]),

@@ -135,6 +135,134 @@ reset_kernel(const __grid_constant__ SimDev S, const int32_t *__restrict__ env_i
   store_state(S, e, st, sub);
 }
 
+// ------------------------------------------------------------------------------------------
+// MPC expert: ExpertEnv.choose_action, bitrate_selection/envs/expert_env.py:358-422
+// ------------------------------------------------------------------------------------------
+// One CTA per environment.  The reference scores all 15^horizon action sequences of the next H = min(horizon, chunks
+// left) chunks with virtual downloads from the environment's trace / buffer state (simulator.py:125-144) and the
+// QoE of utils/qoe.py:50-60 on cached per-(chunk, action) statistics (expert_env.py:121-160), and returns the first
+// action of the first sequence with the largest sum.  Here: phase 0 computes the <= 6 x 15 statistics the search
+// needs (tiles allocated from the predicted viewport, quality over the actual viewport -- the same numbers step_env
+// produces for that chunk and action); phase 1 gives every thread prefixes (a_0 .. a_{H-2}) of the sequence tree,
+// each followed by its 15 leaves, so a leaf costs 1 + (H-1)/15 virtual downloads instead of H; a CTA-wide arg-max
+// with the reference's tie rule (lowest sequence index, digit t = action of step t) picks the action.
+// float64 chain like step_env (the pinned numpy 1.24 stack).
+constexpr int kExpertThreads = 256;
+constexpr int kExpertMaxHorizon = 6;
+
+struct ExpertProf { double size, vq, dev; };
+
+__device__ __forceinline__ void expert_virtual_step(const SimDev &S, const ExpertProf &p, double sm, const double *__restrict__ tr,
+                                                    int tlen, int &cur_idx, double &cur_time, double &buf, double &prev_vq,
+                                                    bool first, double w0, double w1, double w2, double &sum, bool &ok) {
+  const double dl = trace_download(p.size, [tr](int i) { return __ldg(tr + i); }, tlen, cur_idx, cur_time, ok);
+  const double rebuf = buffer_push(buf, S.chunk_length, dl);
+  const QoE r = qoe_from_sums(p.vq, p.dev, sm, rebuf, first, prev_vq, w0, w1, w2, S.max_quality);
+  sum = dadd(sum, r.qoe);
+}
+
+__global__ void __launch_bounds__(kExpertThreads, 2) expert_mpc_kernel(const SimDev S, int horizon, int32_t *__restrict__ actions,
+                                                                    double *__restrict__ best_value) {
+  __shared__ ExpertProf prof[kExpertMaxHorizon][16];
+  __shared__ double s_sm[kExpertMaxHorizon];
+  __shared__ double red_val[kExpertThreads / 32];
+  __shared__ int red_idx[kExpertThreads / 32];
+  const int e = blockIdx.x;
+  const EnvState st = S.state[e];
+  const int H = min(horizon, st.end_chunk - st.next_chunk + 1);
+  if ((st.flags & kFlagFinished) || H <= 0) {     // no chunk left: every sequence scores 0, the reference returns action 0
+    if (threadIdx.x == 0) {
+      actions[e] = 0;
+      if (best_value) best_value[e] = 0.0;
+    }
+    return;
+  }
+  // ---- phase 0: chunk_pred_sizes / viewport qualities / intra variance of (chunk next + t, action a) ----
+  for (int k = threadIdx.x; k < H * kActions; k += kExpertThreads) {
+    const int t = k / kActions, a = k % kActions;
+    const int c = st.next_chunk + t;
+    const size_t vi = (size_t)st.pair * S.n_vp_chunks + (c - st.start_chunk);
+    const uint64_t gt = __ldg(S.vp_gt + vi);
+    const size_t tab = ((size_t)st.video * S.n_chunks + c) * kTableRow;
+    int rin, rout;
+    action_to_rates(a, rin, rout);
+    const uint32_t vtab = (S.lut[rout] & ~7u) | (uint32_t)rin;
+    int sz = 0;
+    double mq = 0.0;
+    for (int row = 0; row < 8; ++row) {
+      const uint32_t scales = __ldg(S.vp_scale + vi * 8 + row);
+      for (int i = 0; i < 8; ++i) {
+        const int tile = row * 8 + i;
+        const int ver = (int)((vtab >> (3u * ((scales >> (4 * i)) & 7u))) & 7u);
+        sz += __ldg(S.size + tab + ver * kTiles + tile);
+        if ((gt >> tile) & 1ULL) mq = dadd(mq, (double)__ldg(S.quality + tab + ver * kTiles + tile));
+      }
+    }
+    const double sm = (double)__popcll(gt);
+    const double vq = ddiv(mq, sm);
+    const float vq32 = (float)vq;
+    double dev = 0.0;
+    for (int row = 0; row < 8; ++row) {
+      const uint32_t scales = __ldg(S.vp_scale + vi * 8 + row);
+      for (int i = 0; i < 8; ++i) {
+        const int tile = row * 8 + i;
+        if (!((gt >> tile) & 1ULL)) continue;
+        const int ver = (int)((vtab >> (3u * ((scales >> (4 * i)) & 7u))) & 7u);
+        dev = dadd(dev, (double)fabsf(fsub(__ldg(S.quality + tab + ver * kTiles + tile), vq32)));
+      }
+    }
+    prof[t][a].size = (double)sz;
+    prof[t][a].vq = vq;
+    prof[t][a].dev = dev;
+    if (a == 0) s_sm[t] = sm;
+  }
+  __syncthreads();
+  // ---- phase 1: sequence tree ----
+  const double *tr = S.trace + (size_t)st.trace * S.trace_stride;
+  const int tlen = __ldg(S.trace_len + st.trace);
+  const double w0 = (double)st.w0, w1 = (double)st.w1, w2 = (double)st.w2;
+  int n_prefix = 1;
+  for (int t = 0; t < H - 1; ++t) n_prefix *= kActions;
+  double bv = -INFINITY;
+  int bi = 0x7FFFFFFF;
+  bool ok = true;
+  for (int p = threadIdx.x; p < n_prefix; p += kExpertThreads) {
+    int cur_idx = st.cur_idx;
+    double cur_time = st.cur_time, buf = st.buf, prev = st.prev_vq, sum = 0.0;
+    bool first = st.ep_step == 0;
+    int tmp = p;
+    for (int t = 0; t < H - 1; ++t) {
+      const int a = tmp % kActions;
+      tmp /= kActions;
+      expert_virtual_step(S, prof[t][a], s_sm[t], tr, tlen, cur_idx, cur_time, buf, prev, first, w0, w1, w2, sum, ok);
+      first = false;
+    }
+    for (int a = 0; a < kActions; ++a) {
+      int li = cur_idx;
+      double lt = cur_time, lb = buf, lp = prev, ls = sum;
+      expert_virtual_step(S, prof[H - 1][a], s_sm[H - 1], tr, tlen, li, lt, lb, lp, first, w0, w1, w2, ls, ok);
+      const int idx = p + a * n_prefix;
+      if (ls > bv || (ls == bv && idx < bi)) { bv = ls; bi = idx; }
+    }
+  }
+  if (!ok) atomicExch(S.error_flag, 1);
+  // ---- arg-max, lowest index on ties (expert_env.py:408-410: strict '<' keeps the first maximum) ----
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { red_val[threadIdx.x >> 5] = bv; red_idx[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kExpertThreads / 32; ++w)
+      if (red_val[w] > bv || (red_val[w] == bv && red_idx[w] < bi)) { bv = red_val[w]; bi = red_idx[w]; }
+    actions[e] = bi % kActions;                   // rates2action(action2rates(a)) == a (utils/common.py:101-139)
+    if (best_value) best_value[e] = bv;
+  }
+}
+
 __global__ void seed_kernel(const SimDev S, int32_t seed) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= S.n_envs) return;
@@ -750,6 +878,16 @@ int mansy_stats_clear(mansy_handle_t h, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
   const size_t n = (size_t)h->dev.n_envs * MANSY_STATS_DOUBLES;
   stats_clear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(h->dev.stats, n);
+  count_launch();
+  MANSY_CUDA(cudaGetLastError());
+  return MANSY_OK;
+}
+
+int mansy_expert_actions(mansy_handle_t h, int32_t horizon, int32_t *actions_dev, double *best_value_dev, void *stream) {
+  if (!h || !actions_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (horizon < 1 || horizon > kExpertMaxHorizon) return set_error(MANSY_E_INVALID, "horizon must be 1..6");
+  expert_mpc_kernel<<<(unsigned)h->dev.n_envs, kExpertThreads, 0, static_cast<cudaStream_t>(stream)>>>(h->dev, horizon, actions_dev,
+                                                                                                       best_value_dev);
   count_launch();
   MANSY_CUDA(cudaGetLastError());
   return MANSY_OK;

@@ -191,6 +191,16 @@ class BatchSimulator:
         check(self.lib.mansy_state_snapshot(self._h, raw.data_ptr(), self._stream()))
         return raw.cpu().numpy().view(np.dtype(_capi.ENV_STATE_FIELDS)).reshape(self.n_envs)
 
+    def expert_actions(self, horizon: int = 4, actions: Optional[torch.Tensor] = None, return_value: bool = False):
+        """``ExpertEnv.choose_action`` (envs/expert_env.py:358-422) for every environment at its current state: the
+        first action of the best of the ``15 ** horizon`` sequences over the next chunks (``mansy_expert_actions``).
+        Returns int32 ``[N]`` on the device (and the winning QoE sums, float64 ``[N]``, with ``return_value``)."""
+        if actions is None:
+            actions = torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+        value = torch.empty(self.n_envs, dtype=torch.float64, device=self.device) if return_value else None
+        check(self.lib.mansy_expert_actions(self._h, int(horizon), actions.data_ptr(), self._ptr(value), self._stream()))
+        return (actions, value) if return_value else actions
+
     def error_flag(self) -> int:
         flag = C.c_int32(0)
         check(self.lib.mansy_error_flag(self._h, C.byref(flag)))

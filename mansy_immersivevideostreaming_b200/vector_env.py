@@ -117,6 +117,11 @@ class B200VectorEnv:
             return self._package(rows), rew, done.bool(), info
         return self._package(rows), rew.cpu().numpy().astype(np.float64), done_h, info
 
+    def choose_actions(self, horizon: int = 4) -> np.ndarray:
+        """The MPC expert's action for every environment (``ExpertEnv.choose_action``, envs/expert_env.py:358-422)."""
+        a = self.sim.expert_actions(horizon)
+        return a if self.output == "torch" else a.cpu().numpy()
+
     def _log_finished(self, env_ids: Sequence[int]) -> None:
         if self.log_path is None:
             return
@@ -176,6 +181,10 @@ class SingleEnv:
         obs, rew, done, _ = self._venv.step([int(action)])
         self.state.update({k: v[0] for k, v in obs.items()})
         return self.state, float(rew[0]), bool(done[0]), {}
+
+    def choose_action(self, horizon: Optional[int] = None) -> int:
+        """``ExpertEnv.choose_action`` (envs/expert_env.py:358-422)."""
+        return int(self._venv.sim.expert_actions(int(horizon if horizon is not None else getattr(self, "horizon", 4))).cpu()[0])
 
     def sample_count(self) -> int:
         return self.tables.n_samples

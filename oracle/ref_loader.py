@@ -93,6 +93,10 @@ def load_reference() -> "_Ref":
     try:
         ref.mansy_env = importlib.import_module("envs.mansy_env")
         ref.simple_rl_env = importlib.import_module("envs.simple_rl_env")
+        try:                             # needs tqdm (present in this image); only the expert golden uses it
+            ref.expert_env = importlib.import_module("envs.expert_env")
+        except ImportError:
+            ref.expert_env = None
         ref.common = importlib.import_module("utils.common")
         ref.qoe = importlib.import_module("utils.qoe")
         ref.simulator = importlib.import_module("simulators.simulator")

@@ -457,3 +457,89 @@ class OracleVectorEnv:
                 obs = env.reset()
             rows.append(flatten_obs(obs, self.obs_mode)); rews.append(float(r)); dones.append(d); auxs.append(aux)
         return np.stack(rows), np.asarray(rews, dtype=np.float64), np.asarray(dones, dtype=bool), auxs
+
+
+# ---------------------------------------------------------------------------
+# the MPC expert (bitrate_selection/envs/expert_env.py:358-422)
+# ---------------------------------------------------------------------------
+def expert_profile(env: "OracleEnv", chunk: int, action: int):
+    """One entry of the expert's cache (expert_env.py:121-160, ``chunk_pred_*``): tiles allocated from the PREDICTED
+    viewport, quality statistics taken over the ACTUAL viewport (simulator.py:146-158).  Returns
+    ``(chunk_size, viewport_quality, intra_viewport_quality_variance)`` (not normalised) in the env's numeric chain."""
+    rates = env.cfg.video_rates
+    rate_in, rate_out = action_to_rates(action)
+    gt_bits, pred_bits, _ = env._viewport(chunk)
+    versions = allocate_tile_versions(rate_in, rate_out, pred_bits, rates)
+    size, quality = env._chunk_tables(chunk)
+    chunk_size = int(sum(int(size[versions[t], t]) for t in range(64)))
+    tile_q = np.array([quality[versions[t], t] for t in range(64)], dtype=np.float32)
+    if env.chain == "f64":
+        m = [(gt_bits >> t) & 1 for t in range(64)]
+        s_m = s_mq = 0.0
+        for t in range(64):
+            s_mq += float(F32(m[t]) * F32(tile_q[t]))
+            s_m += float(m[t])
+        vq = s_mq / s_m
+        vq32 = F32(vq)
+        s_dev = 0.0
+        for t in range(64):
+            s_dev += float(F32(m[t]) * F32(abs(F32(tile_q[t]) - vq32)))
+        return chunk_size, vq, s_dev / s_m
+    m = [F32((gt_bits >> t) & 1) for t in range(64)]
+    s_m = s_mq = F32(0)
+    for t in range(64):
+        s_mq = F32(s_mq + F32(m[t] * F32(tile_q[t])))
+        s_m = F32(s_m + m[t])
+    vq = F32(s_mq / s_m)
+    s_dev = F32(0)
+    for t in range(64):
+        s_dev = F32(s_dev + F32(m[t] * F32(abs(F32(F32(tile_q[t]) - vq)))))
+    return chunk_size, vq, F32(s_dev / s_m)
+
+
+def _expert_qoe(env: "OracleEnv", vq, intra, rebuffer: float, prev_vq):
+    """``QoEModelExpert.calculate_qoe_with_given_quality`` (utils/qoe.py:50-60)."""
+    max_q = env.cfg.video_rates[-1]
+    w = env.w
+    if env.chain == "f64":
+        vqn = vq / max_q
+        intra_n = intra / max_q
+        inter = abs(vqn - prev_vq) if prev_vq is not None else 0.0
+        q3 = intra_n + inter
+        return float(w[0]) * vqn - float(w[1]) * float(rebuffer) - float(w[2]) * q3, vqn
+    vqn = F32(vq / F32(max_q))
+    intra_n = F32(intra / F32(max_q))
+    inter = F32(abs(F32(vqn - prev_vq))) if prev_vq is not None else F32(0.0)
+    q3 = F32(intra_n + inter)
+    qoe = F32(F32(F32(w[0]) * vqn) - F32(F32(w[1]) * F32(rebuffer))) - F32(F32(w[2]) * q3)
+    return F32(qoe), vqn
+
+
+def expert_choose_action(env: "OracleEnv", horizon: int, return_value: bool = False):
+    """``ExpertEnv.choose_action`` (expert_env.py:358-422): exhaustive search over action sequences of the next
+    ``min(horizon, chunks left)`` chunks on virtual downloads from the current trace / buffer state
+    (simulator.py:125-144); the first sequence (lowest index, first digit = first action) with the largest QoE sum wins.
+    The reference enumerates ``15 ** horizon`` sequences even when fewer chunks are left; the extra digits are unused
+    there and ties resolve to the lowest index, which is the enumeration of ``15 ** H`` done here."""
+    H = min(int(horizon), env.end_chunk - env.next_chunk + 1)
+    if H <= 0:
+        return (0, 0.0) if return_value else 0
+    prof = [[expert_profile(env, env.next_chunk + t, a) for a in range(15)] for t in range(H)]
+    thr = env.t.trace[env.trace]
+    tlen = int(env.t.trace_len[env.trace])
+    best, best_i = float("-inf"), 0
+    for i in range(15 ** H):
+        cur_idx, cur_time, buf, prev = env.cur_idx, env.cur_time, env.buf, env.prev_vq
+        qoe_sum = 0
+        tmp = i
+        for t in range(H):
+            a = tmp % 15
+            tmp //= 15
+            size, vq, intra = prof[t][a]
+            dl, cur_idx, cur_time = trace_download(size, thr, tlen, cur_idx, cur_time)
+            rebuf, buf = buffer_push(buf, env.cfg.chunk_length, dl)
+            qoe, prev = _expert_qoe(env, vq, intra, rebuf, prev)
+            qoe_sum = qoe_sum + qoe if env.chain == "f64" else F32(qoe_sum + qoe)
+        if best < qoe_sum:
+            best, best_i = qoe_sum, i
+    return (best_i % 15, float(best)) if return_value else best_i % 15
