@@ -35,6 +35,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -62,6 +63,7 @@ struct GemmArgs {
   const float *res;        // EPI_LN: residual rows [M][res_ld]
   int64_t res_ld;
   const float *gamma, *beta;
+  int32_t w_box_rows;      // rows of the weight tensor map's box: 128, or 256 (two adjacent boxes per TMA operation)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -112,6 +114,26 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Cluster launch (runtime attribute): the CTAs of a cluster own consecutive M tiles of the same N tile, so they need the
+// same weight boxes.  Box b of a stage is fetched by CTA rank b % cluster_size and multicast into every CTA of the
+// cluster (same shared-memory offset, each CTA's own `full` barrier gets the bytes); a stage is free again when the MMAs
+// of ALL CTAs have read it (commit multicast onto every CTA's `empty` barrier, which counts cluster_size arrivals).
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
 template <int BN, int MT, int EPI>
 __global__ void __launch_bounds__(GemmCfg<BN, MT>::kThreads, GemmCfg<BN, MT>::kCtasPerSm)
 mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
@@ -141,12 +163,14 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int m0 = blockIdx.x * (128 * MT), n0 = blockIdx.y * BN;
   const int nk = g.K >> 5;
+  const uint32_t crank = cluster_rank(), csize = cluster_size();
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 16 * s, 1);
       mbar_init(bar_full + 16 * s + 8, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, csize);
     }
     mbar_init(bar_d, 1);
     if (EPI == EPI_LN) {
@@ -171,6 +195,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_barrier();       // every CTA's barriers exist before a peer's multicast / commit can reach them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -213,24 +238,42 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int it = s; it < nk; it += kStages) {
       mbar_wait(bar_empty + 8 * s, ((uint32_t)(it / kStages) & 1u) ^ 1u);
       if (elect_one()) {
+        auto load_w = [&](int b) {          // weight box b (rows n0 + 128 b ..) of this K-chunk
+          const uint32_t at = dst + kWOff + kABoxBytes * b;
+          if (g.w_box_rows == 256) {        // the tensor map's box is [256 x 32 floats]: boxes (b, b + 1) in one operation
+            if (!(b & 1)) tma_load_2d(at, &map_w, it * 32, n0 + b * 128, full);
+          } else if (csize == 1) {
+            tma_load_2d(at, &map_w, it * 32, n0 + b * 128, full);
+          } else if ((uint32_t)b % csize == crank) {
+            tma_load_2d_mc(at, &map_w, it * 32, n0 + b * 128, full, cmask);
+          }
+        };
         if (MT == 2) {
           mbar_expect_tx(full, 2 * kABoxBytes);
           if (h == 0) {
             tma_load_2d(dst, &map_a, it * 32, m0, full);
             tma_load_2d(dst + kABoxBytes, &map_a, it * 32, m0 + 128, full);
           } else {
-            tma_load_2d(dst + kWOff, &map_w, it * 32, n0, full);
-            tma_load_2d(dst + kWOff + kABoxBytes, &map_w, it * 32, n0 + 128, full);
+            load_w(0);
+            load_w(1);
+          }
+        } else if (NB == 2 && g.w_box_rows == 256) {      // one 256-row operation brings both weight boxes: all on half 0
+          if (h == 0) {
+            mbar_expect_tx(full, 3 * kABoxBytes);
+            tma_load_2d(dst, &map_a, it * 32, m0, full);
+            load_w(0);
+          } else {
+            mbar_arrive(full);
           }
         } else if (h == 0) {
           mbar_expect_tx(full, kABoxBytes * (1 + NB / 2));
           tma_load_2d(dst, &map_a, it * 32, m0, full);
 #pragma unroll
-          for (int b = 0; b < NB / 2; ++b) tma_load_2d(dst + kWOff + kABoxBytes * b, &map_w, it * 32, n0 + b * 128, full);
+          for (int b = 0; b < NB / 2; ++b) load_w(b);
         } else {
           mbar_expect_tx(full, kABoxBytes * (NB / 2));
 #pragma unroll
-          for (int b = NB / 2; b < NB; ++b) tma_load_2d(dst + kWOff + kABoxBytes * b, &map_w, it * 32, n0 + b * 128, full);
+          for (int b = NB / 2; b < NB; ++b) load_w(b);
         }
       }
       __syncwarp();
@@ -270,7 +313,8 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
       if (elect_one()) {
-        umma_commit(bar_empty + 8 * s);
+        if (csize == 1) umma_commit(bar_empty + 8 * s);
+        else umma_commit_mc(bar_empty + 8 * s, cmask);
         if (it == nk - 1) umma_commit(bar_d);
       }
       __syncwarp();
@@ -379,6 +423,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_barrier();       // no CTA leaves while a peer's commit may still target its barriers
   if (warp == kGemmMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN * MT) : "memory");
@@ -697,6 +742,8 @@ struct mansy_mtio {
   int device = 0;
   int n_enc = 0, n_dec = 0, T = 0, F = 0, Tm = 0, max_batch = 0;
   bool tc_ok = false;
+  int cluster_ln = 1, cluster_wide = 1;      // CTAs sharing weight boxes by TMA multicast (MANSY_MTIO_CLUSTER_LN / _WIDE)
+  int w_box_rows = 128;                      // rows per weight TMA operation (MANSY_MTIO_WBOX = 128 | 256)
   std::vector<void *> allocs;
   LayerDev enc[MANSY_MTIO_MAX_LAYERS], dec[MANSY_MTIO_MAX_LAYERS];
   float *emb_w = nullptr, *emb_b = nullptr, *pe = nullptr;
@@ -746,11 +793,11 @@ int upload_attn(mansy_mtio *m, AttnDev *d, const mansy_mtio_attn_t *a, const cha
   return rc;
 }
 
-int make_attn_maps(AttnDev *d) {
-  int rc = tc_make_map(&d->map_qkv, d->w, kD, 3 * kD, kD, 128);
-  if (!rc) rc = tc_make_map(&d->map_q, d->w, kD, kD, kD, 128);
-  if (!rc) rc = tc_make_map(&d->map_kv, d->w + (size_t)kD * kD, kD, 2 * kD, kD, 128);
-  if (!rc) rc = tc_make_map(&d->map_o, d->ow, kD, kD, kD, 128);
+int make_attn_maps(AttnDev *d, uint32_t box_rows) {
+  int rc = tc_make_map(&d->map_qkv, d->w, kD, 3 * kD, kD, box_rows);
+  if (!rc) rc = tc_make_map(&d->map_q, d->w, kD, kD, kD, box_rows);
+  if (!rc) rc = tc_make_map(&d->map_kv, d->w + (size_t)kD * kD, kD, 2 * kD, kD, box_rows);
+  if (!rc) rc = tc_make_map(&d->map_o, d->ow, kD, kD, kD, box_rows);
   return rc;
 }
 
@@ -792,8 +839,24 @@ struct Launcher {
       if (e != cudaSuccess) { rc = set_error(MANSY_E_CUDA, std::string("mtio_gemm_kernel attribute: ") + cudaGetErrorString(e)); return; }
       attr_done = true;
     }
-    dim3 grid((unsigned)((g.M + 128 * MT - 1) / (128 * MT)), (unsigned)(g.N / BN), 1);
-    mtio_gemm_kernel<BN, MT, EPI><<<grid, Cfg::kThreads, Cfg::kSmem, s>>>(ma, mw, mres, mout, g);
+    unsigned tiles = (unsigned)((g.M + 128 * MT - 1) / (128 * MT));
+    int cl = EPI == EPI_LN ? m->cluster_ln : m->cluster_wide;
+    if (cl > (int)tiles) cl = 1;
+    if (Cfg::kCtasPerSm > 1) cl = 1;
+    tiles = (tiles + cl - 1) / cl * cl;              // whole clusters: surplus CTAs run on zero-filled / clipped rows
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(tiles, (unsigned)(g.N / BN), 1);
+    cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cl > 1 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, mtio_gemm_kernel<BN, MT, EPI>, ma, mw, mres, mout, g);
+    if (e != cudaSuccess && !rc) rc = set_error(MANSY_E_CUDA, std::string("mtio_gemm_kernel launch: ") + cudaGetErrorString(e));
   }
 
   // C[M][N] = epi(A[M][K] W[N][K]^T + bias): `wmap` / `W` describe the same torch-layout weight rows
@@ -814,6 +877,7 @@ struct Launcher {
       }
       return;
     }
+    g.w_box_rows = m->w_box_rows;
     CUtensorMap ma;
     if (int e = tc_make_map(&ma, A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda, 128)) { rc = e; return; }
     CUtensorMap mres = ma;                 // only the LayerNorm epilogue reads it
@@ -993,6 +1057,9 @@ int mansy_mtio_create(const mansy_mtio_weights_t *w, int device, int32_t max_bat
   m->n_enc = w->n_enc; m->n_dec = w->n_dec; m->T = w->his_window; m->F = w->fut_window;
   m->Tm = (m->T + 2 - 3) / 2 + 1;
   m->max_batch = max_batch;
+  if (const char *v = getenv("MANSY_MTIO_CLUSTER_LN")) m->cluster_ln = atoi(v) == 4 ? 4 : (atoi(v) == 2 ? 2 : 1);
+  if (const char *v = getenv("MANSY_MTIO_CLUSTER_WIDE")) m->cluster_wide = atoi(v) == 2 ? 2 : 1;
+  if (const char *v = getenv("MANSY_MTIO_WBOX")) m->w_box_rows = atoi(v) == 256 ? 256 : 128;
   int rc = MANSY_OK;
 #define MTIO_TRY(expr) do { if (!rc) rc = (expr); } while (0)
   {   // embedding.linear.weight [512][6] -> [6][512]: a warp reads 32 consecutive outputs of one input column
@@ -1068,18 +1135,19 @@ int mansy_mtio_create(const mansy_mtio_weights_t *w, int device, int32_t max_bat
   if (rc) { mansy_mtio_destroy(m); return rc; }
   // tensor maps of the weights (the fp32 path works without them)
   int mrc = MANSY_OK;
+  const uint32_t wb = (uint32_t)m->w_box_rows;
   for (int l = 0; l < m->n_enc && !mrc; ++l) {
-    mrc = make_attn_maps(&m->enc[l].sa);
-    if (!mrc) mrc = tc_make_map(&m->enc[l].map_w1, m->enc[l].w1, kD, kD, kD, 128);
-    if (!mrc) mrc = tc_make_map(&m->enc[l].map_w2, m->enc[l].w2, kD, kD, kD, 128);
+    mrc = make_attn_maps(&m->enc[l].sa, wb);
+    if (!mrc) mrc = tc_make_map(&m->enc[l].map_w1, m->enc[l].w1, kD, kD, kD, wb);
+    if (!mrc) mrc = tc_make_map(&m->enc[l].map_w2, m->enc[l].w2, kD, kD, kD, wb);
   }
   for (int l = 0; l < m->n_dec && !mrc; ++l) {
-    mrc = make_attn_maps(&m->dec[l].sa);
-    if (!mrc) mrc = make_attn_maps(&m->dec[l].ca);
-    if (!mrc) mrc = tc_make_map(&m->dec[l].map_w1, m->dec[l].w1, kD, kD, kD, 128);
-    if (!mrc) mrc = tc_make_map(&m->dec[l].map_w2, m->dec[l].w2, kD, kD, kD, 128);
+    mrc = make_attn_maps(&m->dec[l].sa, wb);
+    if (!mrc) mrc = make_attn_maps(&m->dec[l].ca, wb);
+    if (!mrc) mrc = tc_make_map(&m->dec[l].map_w1, m->dec[l].w1, kD, kD, kD, wb);
+    if (!mrc) mrc = tc_make_map(&m->dec[l].map_w2, m->dec[l].w2, kD, kD, kD, wb);
   }
-  if (!mrc) mrc = tc_make_map(&m->map_conv, m->conv_w, 3 * kD, kD, 3 * kD, 128);
+  if (!mrc) mrc = tc_make_map(&m->map_conv, m->conv_w, 3 * kD, kD, 3 * kD, wb);
   m->tc_ok = (mrc == MANSY_OK);
   *out = m;
   return MANSY_OK;
