@@ -1,4 +1,8 @@
 export PYTHONUNBUFFERED=1
-echo "== wbox=256"
-MANSY_MTIO_WBOX=256 timeout 60 python tools/mtio_bench.py 16384 5 2>&1 | grep -E "tf32 max|tf32 batch 16384:|serialised" | head -3
-MANSY_MTIO_WBOX=256 timeout 120 python -m pytest tests/test_gpu_mtio.py -x -q 2>&1 | tail -3
+# launch list of the bench command (cold-cache, serialised: compare shares)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r01z_launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+# --set full captures: MTIO GEMM tiles and attention (decode steady state), expert kernel
+MTIO_BENCH_PROFILE=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:mtio_gemm --launch-skip 250 --launch-count 6 -o gpurun_out/r01z_mtio_gemm python tools/mtio_bench.py 16384 1 > /dev/null 2>&1
+MTIO_BENCH_PROFILE=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:mtio_attn --launch-skip 84 --launch-count 2 -o gpurun_out/r01z_mtio_attn python tools/mtio_bench.py 16384 1 > /dev/null 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:expert_mpc --launch-skip 12 --launch-count 1 -o gpurun_out/r01z_expert python tools/expert_bench.py 4096 > /dev/null 2>&1
+ls -la gpurun_out | tail -8
