@@ -435,6 +435,12 @@ int mansy_mtio_sample_host(mansy_mtio_t m, const float *history_host, const floa
  * [0] the GEMM kernels, [1] the attention kernels, [2] everything else (embedding, norms, distillation, head). */
 int mansy_mtio_kernel_ms(mansy_mtio_t m, double ms[3], int32_t launches[3]);
 
+/* The `--model regression` predictor of predict.py: LinearRegression.sample
+ * (viewport_prediction/models/linear_regression.py:16-33), an ordinary least-squares line per sample and coordinate
+ * through history + current (his_window + 1 points), extrapolated fut_window steps.  Device pointers, layouts as above. */
+int mansy_linreg_sample(const float *history_dev, const float *current_dev, int64_t n, int32_t his_window, int32_t fut_window,
+                        float *pred_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,6 +173,7 @@ SIGNATURES = {
     "mansy_mtio_destroy": (C.c_int, [_vp]),
     "mansy_mtio_sample": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "mansy_mtio_sample_host": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
+    "mansy_linreg_sample": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp]),
     "mansy_mtio_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_double * 3), C.POINTER(C.c_int32 * 3)]),
 }
 

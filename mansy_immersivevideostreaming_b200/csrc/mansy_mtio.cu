@@ -711,6 +711,31 @@ __global__ void __launch_bounds__(256) mtio_head_kernel(const HeadArgs h) {
   }
 }
 
+// LinearRegression.sample (viewport_prediction/models/linear_regression.py:16-33): per sample and coordinate an
+// ordinary least-squares line through the his_window + 1 known points (x = 0, 1, ...), evaluated at the next fut_window
+// positions; float64 like sklearn, stored as float32; no wrap into the unit square (the reference applies none here).
+__global__ void __launch_bounds__(256) linreg_kernel(const float *__restrict__ hist, const float *__restrict__ cur, int64_t n, int T, int F,
+                                                     float *__restrict__ pred) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * n) return;
+  const int64_t b = idx >> 1;
+  const int c = (int)(idx & 1);
+  const int P = T + 1;
+  const double xbar = 0.5 * (double)(P - 1);
+  double ybar = 0.0;
+  for (int j = 0; j < P; ++j) ybar += (double)(j < T ? hist[(b * T + j) * 2 + c] : cur[b * 2 + c]);
+  ybar /= (double)P;
+  double sxy = 0.0, sxx = 0.0;
+  for (int j = 0; j < P; ++j) {
+    const double dx = (double)j - xbar;
+    const double y = (double)(j < T ? hist[(b * T + j) * 2 + c] : cur[b * 2 + c]);
+    sxy += dx * (y - ybar);
+    sxx += dx * dx;
+  }
+  const double slope = sxy / sxx, icpt = ybar - slope * xbar;
+  for (int f = 0; f < F; ++f) pred[(b * F + f) * 2 + c] = (float)(icpt + slope * (double)(P + f));
+}
+
 }  // namespace mansy
 
 // ------------------------------------------------------------------------------------------
@@ -1196,6 +1221,18 @@ int mansy_mtio_sample_host(mansy_mtio_t m, const float *history_host, const floa
     MTIO_CUDA(cudaMemcpyAsync(pred_host + off * m->F * 2, m->io_pred, (size_t)c * m->F * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
   MTIO_CUDA(cudaStreamSynchronize(s));
+  return MANSY_OK;
+}
+
+int mansy_linreg_sample(const float *history_dev, const float *current_dev, int64_t n, int32_t his_window, int32_t fut_window,
+                        float *pred_dev, void *stream) {
+  if (!history_dev || !current_dev || !pred_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  if (n < 0 || his_window < 1 || fut_window < 1) return set_error(MANSY_E_INVALID, "n >= 0, his_window >= 1, fut_window >= 1");
+  if (n == 0) return MANSY_OK;
+  linreg_kernel<<<(unsigned)((2 * n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(history_dev, current_dev, n, his_window,
+                                                                                              fut_window, pred_dev);
+  count_launch();
+  MTIO_CUDA(cudaGetLastError());
   return MANSY_OK;
 }
 

@@ -212,6 +212,38 @@ class ViewportTransformerMTIO:
         return gt_m, pred_m, acc, pred
 
 
+class LinearRegression:
+    """The ``--model regression`` predictor of predict.py (viewport_prediction/models/linear_regression.py): same
+    constructor and ``sample(history, current)``; a least-squares line per sample and coordinate on the GPU instead of
+    two sklearn fits per sample in a Python loop."""
+
+    def __init__(self, fut_window: int, device="cuda"):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise MansyError("the B200 path has no CPU fallback (device must be cuda)")
+        _require_cuda(0 if dev.index is None else dev.index)
+        self.lib = _capi.load_library()
+        self.device = torch.device("cuda", 0 if dev.index is None else dev.index)
+        self.fut_window = int(fut_window)
+
+    def to(self, device):
+        return self
+
+    def eval(self):
+        return self
+
+    def sample(self, history, current) -> torch.Tensor:
+        hist = torch.as_tensor(history).to(device=self.device, dtype=torch.float32).contiguous()
+        cur = torch.as_tensor(current).to(device=self.device, dtype=torch.float32).contiguous()
+        n, his = hist.shape[0], hist.shape[1]
+        if hist.shape[2:] != (2,) or cur.shape != (n, 1, 2):
+            raise ValueError("history must be [B, his_window, 2] and current [B, 1, 2]")
+        pred = torch.empty((n, self.fut_window, 2), dtype=torch.float32, device=self.device)
+        check(self.lib.mansy_linreg_sample(hist.data_ptr(), cur.data_ptr(), n, his, self.fut_window, pred.data_ptr(),
+                                           torch.cuda.current_stream(self.device).cuda_stream))
+        return pred
+
+
 def viewport_windows(gt_xy: np.ndarray, his_window: int = 5) -> Tuple[np.ndarray, np.ndarray]:
     """Cut the samples ``predict.py`` feeds the model out of continuous 5 Hz viewport traces.
 

@@ -108,6 +108,25 @@ def main() -> None:
     path = os.path.join(ROOT, "tests", "golden", "mtio_kat.npz")
     np.savez_compressed(path, **out)
     print("wrote", path)
+    make_linreg_golden()
+
+
+def make_linreg_golden() -> None:
+    """``--model regression``: the reference's LinearRegression.sample (sklearn fits in a Python loop) on seeded walks."""
+    import importlib.util
+
+    import torch
+    spec = importlib.util.spec_from_file_location(
+        "_ref_linreg", os.path.join(REFERENCE_ROOT, "viewport_prediction", "models", "linear_regression.py"))
+    lr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lr)
+    hist, cur = mo.synthetic_history(64, 5)
+    ref = lr.LinearRegression(15).sample(torch.from_numpy(hist), torch.from_numpy(cur)).numpy()
+    err = float(np.max(np.abs(ref - mo.linreg_sample(hist, cur, 15))))
+    assert err <= 5e-7, err
+    path = os.path.join(ROOT, "tests", "golden", "linreg_kat.npz")
+    np.savez_compressed(path, history=hist, current=cur, pred=ref)
+    print(f"linreg: reference vs closed form max abs err {err:.2e}; wrote {path}")
 
 
 if __name__ == "__main__":

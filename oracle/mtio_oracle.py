@@ -257,3 +257,18 @@ def synthetic_history(n: int, seed: int, his_window: int = 5):
     steps = rng.normal(0.0, 0.03, size=(n, his_window + 1, 2))
     walk = np.mod(start + np.cumsum(steps, axis=1), 1.0).astype(F32)
     return walk[:, :his_window].copy(), walk[:, his_window:].copy()
+
+
+def linreg_sample(history: np.ndarray, current: np.ndarray, fut_window: int = 15) -> np.ndarray:
+    """``LinearRegression.sample`` (viewport_prediction/models/linear_regression.py:16-33): sklearn's
+    ``LinearRegression(fit_intercept=True)`` over x = 0..P-1 per sample and coordinate, predictions at P..P+F-1, float64
+    arithmetic stored into a float32 tensor.  Restated as the closed-form least-squares line."""
+    merge = np.concatenate([np.asarray(history, F32), np.asarray(current, F32)], axis=1).astype(np.float64)    # [B, P, 2]
+    P = merge.shape[1]
+    x = np.arange(P, dtype=np.float64)
+    xbar, ybar = x.mean(), merge.mean(axis=1, keepdims=True)
+    dx = (x - xbar)[None, :, None]
+    slope = (dx * (merge - ybar)).sum(axis=1) / (dx ** 2).sum()
+    icpt = ybar[:, 0] - slope * xbar
+    fx = np.arange(P, P + fut_window, dtype=np.float64)[None, :, None]
+    return (icpt[:, None, :] + slope[:, None, :] * fx).astype(F32)

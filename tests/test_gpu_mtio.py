@@ -167,3 +167,16 @@ def test_config5_predicted_tables_drive_the_environments():
         np.testing.assert_allclose(obs.cpu().numpy(), oobs, rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(rew.cpu().numpy(), orew, rtol=1e-5, atol=1e-6)
         assert np.array_equal(done.cpu().numpy().astype(bool), odone)
+
+
+def test_linear_regression_predictor():
+    """predict.py --model regression: the least-squares extrapolation kernel vs the reference golden and the oracle."""
+    from mansy_immersivevideostreaming_b200.mtio import LinearRegression
+    g = load_golden("linreg_kat.npz")
+    net = LinearRegression(fut_window=15, device="cuda:0")
+    got = net.sample(torch.from_numpy(g["history"]), torch.from_numpy(g["current"])).cpu().numpy()
+    np.testing.assert_allclose(got, g["pred"], rtol=0, atol=5e-7)
+    hist, cur = mo.synthetic_history(5000, 77, his_window=7)
+    got = LinearRegression(9, "cuda:0").sample(hist, cur).cpu().numpy()
+    np.testing.assert_allclose(got, mo.linreg_sample(hist, cur, 9), rtol=0, atol=5e-7)
+    assert got.shape == (5000, 9, 2)

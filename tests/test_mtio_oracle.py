@@ -125,3 +125,9 @@ def test_prediction_files_reproduce_a_shipped_file(tmp_path):
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3] and b[1].dtype == a[1].dtype
     if os.path.exists(src.replace(".pkl", ".csv")):
         assert open(src.replace(".pkl", ".csv")).read() == open(path.replace(".pkl", ".csv")).read()
+
+
+def test_linreg_oracle_matches_reference_golden():
+    g = load_golden("linreg_kat.npz")
+    got = mo.linreg_sample(g["history"], g["current"], 15)
+    np.testing.assert_allclose(got, g["pred"], rtol=0, atol=5e-7)       # sklearn lstsq vs closed form, float32 storage
