@@ -354,9 +354,9 @@ def run_ours(args):
                             "peak_source": "1/2 x measured bf16 cuBLAS burst (MEASURED_PEAKS.json); TF32 runs at half the bf16 rate"},
         "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps,
-                "path": "mansy_rollout_policy_host: per step policy launch, D2H actions + sync, H2D actions, step launch, "
-                        "D2H obs+reward+done+logp+value into pinned host slabs on a copy stream (overlaps the next step); "
-                        "all copies complete inside the timed region"},
+                "path": "mansy_rollout_policy_host: per step policy launch, actions to the host (store kernel into the mapped "
+                        "pinned buffer) + sync, H2D actions, step launch, D2H obs+reward+done+logp+value into pinned host slabs "
+                        "on a copy stream (overlaps the next step); all copies complete inside the timed region"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "rollout_summary": summary,

@@ -80,6 +80,7 @@ ROLLOUT_FP32_POLICY = 1
 ROLLOUT_TIME_KERNELS = 2
 ROLLOUT_NO_PDL = 4
 ROLLOUT_TWO_KERNELS = 8
+ROLLOUT_NO_ZERO_COPY = 16
 
 
 class PolicyWeights(C.Structure):

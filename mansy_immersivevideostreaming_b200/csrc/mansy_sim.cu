@@ -263,6 +263,12 @@ __global__ void __launch_bounds__(kExpertThreads, 2) expert_mpc_kernel(const Sim
   }
 }
 
+__global__ void copy_i32_kernel(int32_t *__restrict__ dst, const int32_t *__restrict__ src, int32_t n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+  __threadfence_system();
+}
+
 __global__ void seed_kernel(const SimDev S, int32_t seed) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= S.n_envs) return;
@@ -830,7 +836,22 @@ int mansy_rollout_policy_host(mansy_handle_t h, mansy_policy_t p, const mansy_ro
                                    b->logp + cur * n, seed, t, h->dev.env_offset, nullptr, nullptr, stream);
     }
     if (rc) return rc;
-    MANSY_CUDA(cudaMemcpyAsync(host->actions + hs * n, b->actions + cur * n, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    // act_t -> host.  The device-to-host copy engine is busy with the previous step's 12.9 MB observation slab (copy
+    // stream), and a 16 KB cudaMemcpyAsync would queue behind it: ~40 us of copy-engine idle time per step once the
+    // step that needs the actions has run.  When the caller's pinned buffer is mapped into the device address space
+    // (cudaHostAlloc memory under unified addressing), a small kernel stores the actions straight into it instead.
+    int32_t *act_mapped = nullptr;
+    if (!(flags & MANSY_ROLLOUT_NO_ZERO_COPY) &&
+        cudaHostGetDevicePointer(reinterpret_cast<void **>(&act_mapped), host->actions + hs * n, 0) != cudaSuccess) {
+      cudaGetLastError();
+      act_mapped = nullptr;
+    }
+    if (act_mapped) {
+      copy_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(act_mapped, b->actions + cur * n, (int32_t)n);
+      count_launch();
+    } else {
+      MANSY_CUDA(cudaMemcpyAsync(host->actions + hs * n, b->actions + cur * n, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
     MANSY_CUDA(cudaStreamSynchronize(s));                       // the host now holds act_t
     MANSY_CUDA(cudaMemcpyAsync(b->actions + cur * n, host->actions + hs * n, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     StepArgs a;

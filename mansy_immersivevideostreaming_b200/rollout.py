@@ -16,7 +16,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-from ._capi import (ROLLOUT_FP32_POLICY, ROLLOUT_NO_PDL, ROLLOUT_TIME_KERNELS, ROLLOUT_TWO_KERNELS, Rollout, RolloutHost,
+from ._capi import (ROLLOUT_FP32_POLICY, ROLLOUT_NO_PDL, ROLLOUT_NO_ZERO_COPY, ROLLOUT_TIME_KERNELS, ROLLOUT_TWO_KERNELS, Rollout, RolloutHost,
                     check)
 from .config import OBS_MODE_NONE
 from .policy import PolicyNet
@@ -106,12 +106,15 @@ class PolicyRollout:
                 "logp": pin(host_slabs, n, dtype=torch.float32), "value": pin(host_slabs, n, dtype=torch.float32),
                 "reward": pin(host_slabs, n, dtype=torch.float32), "done": pin(host_slabs, n, dtype=torch.uint8)}
 
-    def run_host(self, n_steps: int, host: Dict[str, torch.Tensor]) -> None:
-        """Rollout with host storage: per step D2H actions + sync, H2D actions, step, D2H results + sync."""
+    def run_host(self, n_steps: int, host: Dict[str, torch.Tensor], zero_copy: bool = True) -> None:
+        """Rollout with host storage: per step actions to the host + sync, H2D actions, step, D2H results + sync.
+        ``zero_copy``: the actions reach the (device-mapped) pinned host buffer through a store kernel instead of a
+        cudaMemcpyAsync that would queue behind the previous step's observation copy."""
         hc = RolloutHost(host["obs"].shape[0], host["obs"].data_ptr(), host["actions"].data_ptr(), host["logp"].data_ptr(),
                          host["value"].data_ptr(), host["reward"].data_ptr(), host["done"].data_ptr())
         check(self.sim.lib.mansy_rollout_policy_host(self.sim._h, self.policy._h, C.byref(self._c), C.byref(hc), int(n_steps),
-                                                     self.t, self.seed, self._flags(), self.sim._stream()))
+                                                     self.t, self.seed, self._flags() | (0 if zero_copy else ROLLOUT_NO_ZERO_COPY),
+                                                     self.sim._stream()))
         self.t += int(n_steps)
 
     def host_bytes_per_step(self) -> Tuple[int, int]:
