@@ -367,6 +367,7 @@ def run_ours(args):
         sim.close(); e2e_sim.close()
         del roll, e2e_roll, host
         torch.cuda.empty_cache()
+        line["expert_mpc"] = expert_section(tables, local, n_local)
         line["viewport_prediction"] = mtio_section(local, args.mtio_samples,
                                                    cpu_seconds=0.0 if (world > 1 or args.no_cpu_baseline) else 6.0)
     if world == 1 and not args.no_cpu_baseline:
@@ -468,6 +469,30 @@ def mtio_section(device_index: int, n: int, reps: int = 5, cpu_seconds: float = 
         sec["cpu_baseline"] = mtio_cpu_baseline(cpu_seconds)
     net.close()
     return sec
+
+
+def expert_section(tables, device_index: int, n: int):
+    """MPC expert: decisions/s of ExpertEnv.choose_action for n environments, horizons 2 and 4."""
+    import torch
+    from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, REWARD_QOE
+    from mansy_immersivevideostreaming_b200.simulator import BatchSimulator
+    sim = BatchSimulator(tables, n, OBS_MODE_MANSY, REWARD_QOE, seed=0, device=device_index)
+    sim.reset()
+    sim.rollout_random(10, seed=3)            # desynchronise trace positions / buffers
+    out = {"envs": n, "what": "ExpertEnv.choose_action (expert_env.py:358-422): exhaustive search over 15^horizon action sequences"}
+    for h in (2, 4):
+        sim.expert_actions(h)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            sim.expert_actions(h)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out[f"horizon_{h}"] = {"ms": ms, "decisions_per_s": n / (ms * 1e-3), "sequences_per_s": n * 15 ** h / (ms * 1e-3)}
+    sim.close()
+    return out
 
 
 def run_mtio(args):
