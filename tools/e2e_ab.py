@@ -16,6 +16,18 @@ n = 4096
 tables = workload_tables(ViewportTiler().chunk_masks, n)
 a, c = mansy_state_dict_shapes()
 policy = PolicyNet(seeded_state_dict(a, 1), seeded_state_dict(c, 2), OBS_MODE_MANSY)
+if "--after-fused" in sys.argv:          # what bench.py does before its e2e section
+    sim0 = BatchSimulator(tables, n, OBS_MODE_MANSY, REWARD_QOE, seed=0)
+    slabs = -(-(320 << 20) // (n * sim0.obs_stride * 4))
+    roll0 = PolicyRollout(sim0, policy, slabs, seed=1234)
+    if "--reserve" in sys.argv:
+        roll0.reserve_timing(2000)
+    roll0.run(50)
+    roll0.run(2000)
+    if "--timed" in sys.argv:
+        roll0.run(2000, timed=True)
+    torch.cuda.synchronize()
+    print("fused rollout done", flush=True)
 for zc in (False, True, False, True):
     sim = BatchSimulator(tables, n, OBS_MODE_MANSY, REWARD_QOE, seed=0)
     roll = PolicyRollout(sim, policy, 4, seed=1234)
