@@ -129,3 +129,29 @@ def test_hashed_action_stream_matches_numpy(lib):
             for k in (0, 5, 63):
                 assert lib.mansy_selftest_hashed_action(seed, 1000 + k, step) == int(acts[k])
     assert set(np.unique(synthetic_actions(4096, 3))) == set(range(15))
+
+
+def test_new_entry_points_validate_arguments_without_a_device(lib):
+    """MTIO / expert / regression entry points reject bad arguments with MANSY_E_INVALID (-1) before touching CUDA, and
+    mansy_mtio_create refuses to run without a device (no CPU fallback)."""
+    import torch
+    w, h = _capi.MtioWeights(), C.c_void_p()
+    assert lib.mansy_mtio_create(None, 0, 16, C.byref(h)) == -1
+    w.n_enc, w.n_dec, w.his_window, w.fut_window, w.pe_rows = 0, 2, 5, 15, 16
+    assert lib.mansy_mtio_create(C.byref(w), 0, 16, C.byref(h)) == -1 and b"n_enc" in lib.mansy_last_error()
+    w.n_enc, w.fut_window = 2, 40
+    assert lib.mansy_mtio_create(C.byref(w), 0, 16, C.byref(h)) == -1 and b"fut_window" in lib.mansy_last_error()
+    w.fut_window = 15
+    assert lib.mansy_mtio_create(C.byref(w), 0, 16, C.byref(h)) == -1 and b"NULL" in lib.mansy_last_error()   # no weights
+    assert lib.mansy_mtio_sample(None, None, None, 1, 0, 0, None, None, None) == -1
+    assert lib.mansy_mtio_sample_host(None, None, None, 1, 0, 0, None, None) == -1
+    assert lib.mansy_expert_actions(None, 4, None, None, None) == -1
+    assert lib.mansy_linreg_sample(None, None, 1, 5, 15, None, None) == -1
+    assert lib.mansy_mtio_destroy(None) == 0
+    if not torch.cuda.is_available():
+        keep = [np.zeros(8, np.float32)]
+        for name, _ in _capi.MtioWeights._fields_:
+            if name in ("emb_w", "emb_b", "pe", "enc_norm_w", "dec_norm_w", "conv_w", "conv_b", "bn_w", "bn_b", "bn_mean",
+                        "bn_var", "pred_w", "pred_b"):
+                setattr(w, name, keep[0].ctypes.data)
+        assert lib.mansy_mtio_create(C.byref(w), 0, 16, C.byref(h)) == -2       # MANSY_E_CUDA: no device
