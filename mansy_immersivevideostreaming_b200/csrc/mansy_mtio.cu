@@ -1040,8 +1040,9 @@ int run_chunk(mansy_mtio *m, const float *hist, const float *cur, int n, int n_s
     }
   }
   if (L.rc) return L.rc;
-  if (tokens_out)
-    MTIO_CUDA(cudaMemcpyAsync(tokens_out, m->tokens, (size_t)n * (F + 1) * kTok * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (tokens_out)     // tokens 0 .. n_steps of every sample; later rows of the caller's buffer stay untouched
+    MTIO_CUDA(cudaMemcpy2DAsync(tokens_out, (size_t)(F + 1) * kTok * sizeof(float), m->tokens, (size_t)(F + 1) * kTok * sizeof(float),
+                                (size_t)(n_steps + 1) * kTok * sizeof(float), (size_t)n, cudaMemcpyDeviceToDevice, s));
   return MANSY_OK;
 }
 
@@ -1218,7 +1219,9 @@ int mansy_mtio_sample_host(mansy_mtio_t m, const float *history_host, const floa
     MTIO_CUDA(cudaMemcpyAsync(m->io_cur, current_host + off * 2, (size_t)c * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
     int rc = run_chunk(m, m->io_hist, m->io_cur, c, n_steps, flags & ~MANSY_MTIO_TIME_KERNELS, m->io_pred, nullptr, s);
     if (rc) return rc;
-    MTIO_CUDA(cudaMemcpyAsync(pred_host + off * m->F * 2, m->io_pred, (size_t)c * m->F * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    // rows 0 .. n_steps - 1 of every sample (the rest of the caller's buffer stays untouched)
+    MTIO_CUDA(cudaMemcpy2DAsync(pred_host + off * m->F * 2, (size_t)m->F * 2 * sizeof(float), m->io_pred, (size_t)m->F * 2 * sizeof(float),
+                                (size_t)n_steps * 2 * sizeof(float), (size_t)c, cudaMemcpyDeviceToHost, s));
   }
   MTIO_CUDA(cudaStreamSynchronize(s));
   return MANSY_OK;

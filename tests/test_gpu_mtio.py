@@ -128,8 +128,13 @@ def test_early_stop_equals_prefix_of_full_run():
     full = net.sample(h, c).cpu().numpy()
     short = net.sample(h, c, steps=5).cpu().numpy()
     assert np.array_equal(short[:, :5], full[:, :5]) and not short[:, 5:].any()
+    assert np.array_equal(net.sample(hist, cur), full)       # host path, all steps: fills the library's staging buffers
     host = net.sample(hist, cur, steps=5)
-    assert np.array_equal(host, short)
+    assert np.array_equal(host, short)                       # rows >= 5 of the caller's (zeroed) buffer stay untouched
+    _, tok_full = net.sample(h, c, return_tokens=True)
+    _, tok_short = net.sample(h, c, return_tokens=True, steps=5)
+    tok_full, tok_short = tok_full.cpu().numpy(), tok_short.cpu().numpy()
+    assert np.array_equal(tok_short[:, :6], tok_full[:, :6]) and not tok_short[:, 6:].any()
 
 
 def test_config5_predicted_tables_drive_the_environments():
