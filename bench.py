@@ -409,7 +409,7 @@ def mtio_section(device_index: int, n: int, reps: int = 5, cpu_seconds: float = 
     import torch
     from mansy_immersivevideostreaming_b200.mtio import ViewportTransformerMTIO
     from mansy_immersivevideostreaming_b200.simulator import ViewportTiler
-    from oracle import mtio_oracle as mo      # seeded weights / synthetic walks only (numpy); the checker, not the product
+    from mansy_immersivevideostreaming_b200 import mtio as mo      # seeded weights / synthetic walks (numpy)
     _, tflops, _ = measured_peaks()
     sd = mo.seeded_mtio_state_dict(3, bias=True)
     net = ViewportTransformerMTIO(device=f"cuda:{device_index}", max_batch=n).load_state_dict(sd)

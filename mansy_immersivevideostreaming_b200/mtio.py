@@ -44,6 +44,70 @@ def positional_encoding(n: int, d: int = D_MODEL) -> np.ndarray:
     return pe
 
 
+# ---- deterministic weights and synthetic inputs (numpy only: identical in the build container and on the GPU box) ----
+def mtio_state_dict_shapes(n_enc: int = 2, n_dec: int = 2, d: int = D_MODEL, ff: int = D_MODEL, bias: bool = True):
+    s = [("embedding.linear.weight", (d, TOKEN)), ("embedding.linear.bias", (d,))]
+
+    def attn(p):
+        out = [(p + "in_proj_weight", (3 * d, d))]
+        if bias:
+            out.append((p + "in_proj_bias", (3 * d,)))
+        out.append((p + "out_proj.weight", (d, d)))
+        if bias:
+            out.append((p + "out_proj.bias", (d,)))
+        return out
+
+    def lin(p, o, i):
+        return [(p + ".weight", (o, i))] + ([(p + ".bias", (o,))] if bias else [])
+
+    def norm(p):
+        return [(p + ".weight", (d,))] + ([(p + ".bias", (d,))] if bias else [])
+
+    for l in range(n_enc):
+        p = f"transformer.encoder.layers.{l}."
+        s += attn(p + "self_attn.") + lin(p + "linear1", ff, d) + lin(p + "linear2", d, ff) + norm(p + "norm1") + norm(p + "norm2")
+    s += norm("transformer.encoder.norm")
+    for l in range(n_dec):
+        p = f"transformer.decoder.layers.{l}."
+        s += (attn(p + "self_attn.") + attn(p + "multihead_attn.") + lin(p + "linear1", ff, d) + lin(p + "linear2", d, ff)
+              + norm(p + "norm1") + norm(p + "norm2") + norm(p + "norm3"))
+    s += norm("transformer.decoder.norm")
+    s += [("transformer.distill_layer.downConv.weight", (d, d, 3)), ("transformer.distill_layer.downConv.bias", (d,)),
+          ("transformer.distill_layer.norm.weight", (d,)), ("transformer.distill_layer.norm.bias", (d,)),
+          ("transformer.distill_layer.norm.running_mean", (d,)), ("transformer.distill_layer.norm.running_var", (d,)),
+          ("predictor.0.weight", (TOKEN, d)), ("predictor.0.bias", (TOKEN,))]
+    return s
+
+
+def seeded_mtio_state_dict(seed: int, bias: bool = True, n_enc: int = 2, n_dec: int = 2) -> dict:
+    """Matrices uniform(+-1/sqrt(fan_in)); norm gains 1 + 0.1u, norm / linear biases 0.1u; BatchNorm running
+    statistics away from (0, 1) so that the eval-mode affine is exercised."""
+    rng = np.random.default_rng(seed)
+    sd: dict = {}
+    for name, shape in mtio_state_dict_shapes(n_enc, n_dec, bias=bias):
+        u = rng.uniform(-1.0, 1.0, size=shape)
+        if len(shape) > 1:
+            v = u / math.sqrt(float(np.prod(shape[1:])))
+        elif name.endswith("running_var"):
+            v = 1.0 + 0.5 * np.abs(u)
+        elif "norm" in name and name.endswith("weight"):
+            v = 1.0 + 0.1 * u
+        else:
+            v = 0.1 * u
+        sd[name] = v.astype(np.float32)
+    return sd
+
+
+def synthetic_history(n: int, seed: int, his_window: int = 5):
+    """5 Hz random walk of viewport centres on the unit torus: history [n,M,2], current [n,1,2]."""
+    rng = np.random.default_rng(seed)
+    start = rng.uniform(0.05, 0.95, size=(n, 1, 2))
+    steps = rng.normal(0.0, 0.03, size=(n, his_window + 1, 2))
+    walk = np.mod(start + np.cumsum(steps, axis=1), 1.0).astype(np.float32)
+    return walk[:, :his_window].copy(), walk[:, his_window:].copy()
+
+
+
 class ViewportTransformerMTIO:
     """Same constructor arguments as the reference class (mtio.py:48-50); only the configuration the reference's
     own scripts build is supported: ``in_channel=2``, ``num_head=3``, ``d_model = dim_feedforward = 512``."""
