@@ -185,3 +185,21 @@ def test_linear_regression_predictor():
     got = LinearRegression(9, "cuda:0").sample(hist, cur).cpu().numpy()
     np.testing.assert_allclose(got, mo.linreg_sample(hist, cur, 9), rtol=0, atol=5e-7)
     assert got.shape == (5000, 9, 2)
+
+
+def test_two_lane_pass_equals_single_lane(monkeypatch):
+    """>= 1024 samples run as two halves on two streams (attention of one half under the GEMMs of the other); rows are
+    independent, so the result equals the single-stream pass bit for bit, and a sub-sample equals the oracle."""
+    sd = mo.seeded_mtio_state_dict(28, bias=True)
+    hist, cur = mo.synthetic_history(1300, 39)
+    h, c = torch.from_numpy(hist).cuda(), torch.from_numpy(cur).cuda()
+    monkeypatch.setenv("MANSY_MTIO_LANES", "1")
+    one = make_model(sd).sample(h, c, return_tokens=True)
+    monkeypatch.setenv("MANSY_MTIO_LANES", "2")
+    net2 = make_model(sd)
+    two = net2.sample(h, c, return_tokens=True)
+    assert torch.equal(one[0], two[0]) and torch.equal(one[1], two[1])
+    host = net2.sample(hist, cur)
+    assert np.array_equal(host, two[0].cpu().numpy())
+    idx = np.r_[0:8, 760:776, 1292:1300]              # both lanes, around the cut at row 768
+    np.testing.assert_allclose(two[0].cpu().numpy()[idx], mo.sample(sd, hist[idx], cur[idx], 15), rtol=0, atol=TF32_ATOL)
