@@ -136,6 +136,30 @@ def all_gather_stats(local: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
+def broadcast_state_dict(sd, src: int = 0, device=None, group=None):
+    """The optional weight broadcast of SURVEY 8(e): every rank gets rank ``src``'s policy (or MTIO) state dict before a
+    rollout, as ONE flat float32 buffer (1.31 M parameters = 5.2 MB for the MANSY policy) through
+    ``torch.distributed.broadcast`` (NCCL on GPUs, gloo in the CPU tests).  Keys, shapes and order must agree on all
+    ranks (they come from the same architecture); returns ``{name: float32 numpy array}`` for ``PolicyNet`` / ``load_state_dict``."""
+    import numpy as np
+    import torch.distributed as dist
+    names = list(sd.keys())
+    arrs = [np.ascontiguousarray(np.asarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32))
+            for v in sd.values()]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dict(zip(names, arrs))
+    flat = torch.from_numpy(np.concatenate([a.reshape(-1) for a in arrs]))
+    if device is not None:
+        flat = flat.to(device)
+    dist.broadcast(flat, src=src, group=group)
+    flat = flat.cpu().numpy()
+    out, off = {}, 0
+    for name, a in zip(names, arrs):
+        out[name] = flat[off:off + a.size].reshape(a.shape).copy()
+        off += a.size
+    return out
+
+
 def gather_episode_stats(sim: BatchSimulator, group=None) -> torch.Tensor:
     """The one collective of a rollout: all-gather ``[N_local, 6]`` float64 episode statistics
     (sum qoe, qoe1, qoe2, qoe3, steps, episodes per env) into ``[N_global, 6]`` on every rank."""

@@ -12,7 +12,7 @@ from mansy_immersivevideostreaming_b200 import synth
 from mansy_immersivevideostreaming_b200.config import (MANSY_OBS_FLOATS, MANSY_OBS_SEGMENTS, MANSY_OBS_STRIDE,
                                                        SIMPLE_OBS_FLOATS, SIMPLE_OBS_SEGMENTS, SIMPLE_OBS_STRIDE,
                                                        SimConfig, rate_out_lut)
-from mansy_immersivevideostreaming_b200.rollout import all_gather_stats, shard_range, summarise_stats
+from mansy_immersivevideostreaming_b200.rollout import all_gather_stats, broadcast_state_dict, shard_range, summarise_stats
 from mansy_immersivevideostreaming_b200.tables import (SimTables, environment_samples, environment_test_samples,
                                                        masks_to_u64, u64_to_masks)
 from mansy_immersivevideostreaming_b200.vector_env import episode_log_line
@@ -143,6 +143,13 @@ def _gloo_worker(rank, world, port, out_dir):
     local = torch.arange(start * 6, (start + per) * 6, dtype=torch.float64).reshape(per, 6)   # rank-ordered rows
     full = all_gather_stats(local)
     torch.save(full, os.path.join(out_dir, f"r{rank}.pt"))
+    # weight broadcast: every rank ends up with rank 0's policy state dict
+    from mansy_immersivevideostreaming_b200.policy import mansy_state_dict_shapes, seeded_state_dict
+    sd = seeded_state_dict(mansy_state_dict_shapes()[0], 100 + rank)          # ranks start with DIFFERENT weights
+    got = broadcast_state_dict(sd, src=0)
+    want = seeded_state_dict(mansy_state_dict_shapes()[0], 100)
+    ok = list(got) == list(want) and all(np.array_equal(got[k], want[k]) and got[k].shape == want[k].shape for k in want)
+    torch.save(torch.tensor(ok), os.path.join(out_dir, f"b{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -158,3 +165,4 @@ def test_all_gather_stats_world_size_2_gloo():
     expect = torch.arange(16 * 6, dtype=torch.float64).reshape(16, 6)
     for r in range(2):
         assert torch.equal(torch.load(os.path.join(out_dir, f"r{r}.pt")), expect)   # sharded == unsharded order
+        assert bool(torch.load(os.path.join(out_dir, f"b{r}.pt")))                  # broadcast weights == rank 0's
