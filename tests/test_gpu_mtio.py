@@ -203,3 +203,19 @@ def test_two_lane_pass_equals_single_lane(monkeypatch):
     assert np.array_equal(host, two[0].cpu().numpy())
     idx = np.r_[0:8, 760:776, 1292:1300]              # both lanes, around the cut at row 768
     np.testing.assert_allclose(two[0].cpu().numpy()[idx], mo.sample(sd, hist[idx], cur[idx], 15), rtol=0, atol=TF32_ATOL)
+
+
+def test_full_size_properties():
+    """BASELINE configs[4] size (16,384 samples): results do not depend on how the batch is tiled (one two-lane pass vs
+    four sequential passes of 4,096), stay inside the unit square, and a spread of rows equals the oracle."""
+    sd = mo.seeded_mtio_state_dict(29, bias=True)
+    n = 16384
+    hist, cur = mo.synthetic_history(n, 40)
+    h, c = torch.from_numpy(hist).cuda(), torch.from_numpy(cur).cuda()
+    whole = make_model(sd, max_batch=n).sample(h, c)
+    parts = make_model(sd, max_batch=4096).sample(h, c)
+    assert torch.equal(whole, parts)
+    w = whole.cpu().numpy()
+    assert w.shape == (n, 15, 2) and np.isfinite(w).all() and w.min() >= 0.0 and w.max() <= 1.0
+    idx = np.arange(0, n, 683)                       # 24 rows across tiles, lanes and passes
+    np.testing.assert_allclose(w[idx], mo.sample(sd, hist[idx], cur[idx], 15), rtol=0, atol=TF32_ATOL)
