@@ -913,7 +913,10 @@ struct Launcher {
     }
     if (epi == EPI_LN)
       if (int e = tc_make_map(&mres, g.res, kD, (uint64_t)g.M, (uint64_t)g.res_ld, 128)) { rc = e; return; }
-    const bool wide = g.M > 128;           // two M128 sub-tiles per CTA share the weight boxes
+    // two M128 sub-tiles per CTA share the weight boxes -- when that still leaves enough CTAs to occupy the SMs; small
+    // batches (e.g. 2 048 samples per GPU in BASELINE config 5) keep [128 x 256] tiles, two CTAs per SM
+    static const int wide_min = getenv("MANSY_MTIO_WIDE_MIN_CTAS") ? atoi(getenv("MANSY_MTIO_WIDE_MIN_CTAS")) : 64;
+    const bool wide = g.M > 128 && ((g.M + 255) / 256) * (g.N / 256) >= wide_min;
     switch (epi) {
       case EPI_NONE: wide ? tc_gemm<256, 2, EPI_NONE>(ma, wmap, mres, mout, g) : tc_gemm<256, 1, EPI_NONE>(ma, wmap, mres, mout, g); break;
       case EPI_RELU: wide ? tc_gemm<256, 2, EPI_RELU>(ma, wmap, mres, mout, g) : tc_gemm<256, 1, EPI_RELU>(ma, wmap, mres, mout, g); break;
