@@ -54,7 +54,7 @@ constexpr int kDh = kD / kMtioHeads;
 constexpr int kTok = 6;        // in_channel 2 x 3 MTIO heads (mtio.py:49,55)
 constexpr float kLnEps = 1e-5f;
 
-enum { EPI_NONE = 0, EPI_RELU = 1, EPI_ELU = 2, EPI_LN = 3 };
+enum { EPI_NONE = 0, EPI_RELU = 1, EPI_ELU = 2, EPI_LN = 3, EPI_LN2 = 4 };   // LN2: LayerNorm row split over a 2-CTA cluster
 
 struct GemmArgs {
   int32_t M, N, K;
@@ -89,7 +89,7 @@ struct GemmCfg {
   static constexpr int kResWarp = kGemmProd0 + 2 * kStages;
   static constexpr int kThreads = 32 * (kResWarp + 1);
   static constexpr uint32_t kRing = BN == 512 ? kResRing * kABoxBytes : 0u;
-  static constexpr uint32_t kSmem = 1024u + kStages * kStage + kRing + kGemmBarBytes + 3u * BN * 4u;
+  static constexpr uint32_t kSmem = 1024u + kStages * kStage + kRing + kGemmBarBytes + 3u * BN * 4u + 1024u /* LN2 statistics */;
   static constexpr int kCtasPerSm = (BN == 256 && MT == 1) ? 2 : 1;
   static constexpr int kOutSlots = BN == 512 ? 8 : 4;       // output staging boxes carved out of the operand stages
 };
@@ -142,6 +142,13 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   using Cfg = GemmCfg<BN, MT>;
   static_assert((BN == 256 && (MT == 1 || MT == 2)) || (BN == 512 && MT == 1), "tile shape");
   static_assert(EPI != EPI_LN || BN == 512, "the LayerNorm epilogue needs the whole d_model row in one tile");
+  static_assert(EPI != EPI_LN2 || (BN == 256 && MT == 1), "split LayerNorm: two [128 x 256] halves in a 2-CTA cluster");
+  constexpr bool kLn = EPI == EPI_LN || EPI == EPI_LN2;        // epilogues with residual + LayerNorm
+  constexpr bool kLn2 = EPI == EPI_LN2;
+  constexpr int kBoxes = BN / 32;                                // residual / output boxes of 32 columns per tile row block
+  constexpr int kRingBoxes = (int)(Cfg::kRing / kABoxBytes);     // residual boxes with a buffer of their own (BN = 512: 3)
+  constexpr int kStageBoxes = (int)(Cfg::kStages * Cfg::kStage / kABoxBytes);   // residual boxes that fit the freed operand stages
+  constexpr int kReuse = kBoxes - kRingBoxes - kStageBoxes > 0 ? kBoxes - kRingBoxes - kStageBoxes : 0;   // boxes that wait for a consumed buffer
   static_assert(BN * MT <= 512, "tensor memory columns");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kStage = Cfg::kStage;
@@ -160,11 +167,15 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t bar_ring_free = bars + 216;     // [kResRing] ring box consumed by the 128 epilogue threads
   float *s_bias = reinterpret_cast<float *>(smem_raw + (bars + kGemmBarBytes - raw));
   float *s_gamma = s_bias + BN, *s_beta = s_gamma + BN;
+  const uint32_t xch = bars + kGemmBarBytes + 3u * BN * 4u;      // LN2: [128 rows] x (sum, centred squares) written by the peer CTA
 
   const int warp = threadIdx.x >> 5;
-  const int m0 = blockIdx.x * (128 * MT), n0 = blockIdx.y * BN;
+  const uint32_t crank = cluster_rank(), csize_hw = cluster_size();
+  // LN2: the two CTAs of a cluster own the two 256-column halves of the same 128 rows (nothing is multicast)
+  const uint32_t csize = kLn2 ? 1u : csize_hw;
+  const int m0 = kLn2 ? (int)(blockIdx.x >> 1) * 128 : blockIdx.x * (128 * MT);
+  const int n0 = kLn2 ? (int)crank * BN : blockIdx.y * BN;
   const int nk = g.K >> 5;
-  const uint32_t crank = cluster_rank(), csize = cluster_size();
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
   if (threadIdx.x == 0) {
@@ -174,9 +185,9 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(bar_empty + 8 * s, csize);
     }
     mbar_init(bar_d, 1);
-    if (EPI == EPI_LN) {
-      for (int c = 0; c < 16; ++c) mbar_init(bar_res_full + 8 * c, 1);
-      for (int c = 0; c < kResRing; ++c) mbar_init(bar_ring_free + 8 * c, 128);
+    if (kLn) {
+      for (int c = 0; c < kBoxes; ++c) mbar_init(bar_res_full + 8 * c, 1);
+      for (int c = 0; c < kReuse; ++c) mbar_init(bar_ring_free + 8 * c, 128);
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_res) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -191,7 +202,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp < 4) {
     for (int i = threadIdx.x; i < BN; i += 128) {
       s_bias[i] = g.bias[n0 + i];
-      if (EPI == EPI_LN) { s_gamma[i] = g.gamma[i]; s_beta[i] = g.beta[i]; }
+      if (kLn) { s_gamma[i] = g.gamma[n0 + i]; s_beta[i] = g.beta[n0 + i]; }
     }
   }
   tc_fence_before();
@@ -205,31 +216,36 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===== residual producer (LayerNorm epilogue): the [128 x 512] residual tile as 16 boxes of 32 columns.  Boxes 0..2
     // land in the ring while the main loop runs, 3..12 in the operand stages once the last MMA has retired, 13..15 in
     // the ring again as the epilogue frees it. =====
-    if (EPI == EPI_LN) {
+    if (kLn) {
+      auto buffer_of = [&](int c) -> uint32_t {      // residual box c: own ring box, a freed operand-stage box, or a consumed buffer
+        const int j = c < kRingBoxes + kStageBoxes ? c : c - kRingBoxes - kStageBoxes;
+        return j < kRingBoxes ? ring + j * kABoxBytes : base + (j - kRingBoxes) * kABoxBytes;
+      };
       if (elect_one()) {
-        for (int c = 0; c < kResRing; ++c) {
+        for (int c = 0; c < kRingBoxes; ++c) {
           mbar_expect_tx(bar_res_full + 8 * c, kABoxBytes);
-          tma_load_2d(ring + c * kABoxBytes, &map_res, c * 32, m0, bar_res_full + 8 * c);
+          tma_load_2d(buffer_of(c), &map_res, n0 + c * 32, m0, bar_res_full + 8 * c);
         }
       }
       __syncwarp();
       mbar_wait(bar_d, 0);
       if (elect_one()) {
-        for (int c = kResRing; c < 16 - kResRing; ++c) {
+        for (int c = kRingBoxes; c < kBoxes - kReuse; ++c) {
           mbar_expect_tx(bar_res_full + 8 * c, kABoxBytes);
-          tma_load_2d(base + (c - kResRing) * kABoxBytes, &map_res, c * 32, m0, bar_res_full + 8 * c);
+          tma_load_2d(buffer_of(c), &map_res, n0 + c * 32, m0, bar_res_full + 8 * c);
         }
       }
       __syncwarp();
-      for (int c = 16 - kResRing; c < 16; ++c) {
-        mbar_wait(bar_ring_free + 8 * (c - (16 - kResRing)), 0);
+      for (int c = kBoxes - kReuse; c < kBoxes; ++c) {
+        mbar_wait(bar_ring_free + 8 * (c - (kBoxes - kReuse)), 0);
         if (elect_one()) {
           mbar_expect_tx(bar_res_full + 8 * c, kABoxBytes);
-          tma_load_2d(ring + (c - (16 - kResRing)) * kABoxBytes, &map_res, c * 32, m0, bar_res_full + 8 * c);
+          tma_load_2d(buffer_of(c), &map_res, n0 + c * 32, m0, bar_res_full + 8 * c);
         }
         __syncwarp();
       }
     }
+    if (kLn2) cluster_barrier();           // every thread of both CTAs meets here once (statistics exchange below)
   } else if (warp >= kGemmProd0) {
     // ===== TMA producers: warp p fills half (p & 1) of stage (p >> 1).
     // MT = 1: half 0 = A box + first NB/2 weight boxes, half 1 = the other weight boxes;  MT = 2: half 0 = both A boxes,
@@ -279,6 +295,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       __syncwarp();
     }
+    if (kLn2) cluster_barrier();
   } else if (warp == kGemmMmaWarp) {
     // ===== MMA issuer: per stage four K8 steps of M128 x N256 MMAs =====
     constexpr uint32_t kIdesc = idesc_tf32(256);
@@ -321,6 +338,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       __syncwarp();
       if (++s == kStages) { s = 0; ph ^= 1u; }
     }
+    if (kLn2) cluster_barrier();
   } else {
     // ===== epilogue warps 0..3: thread = output row.  Output (and residual) boxes are [128 rows x 128 B] SWIZZLE_128B
     // tiles: row r keeps its 16-byte piece j at r * 128 + ((j ^ (r & 7)) << 4), so the 8 lanes of a shared-memory phase
@@ -333,7 +351,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     constexpr int NS = Cfg::kOutSlots;
     mbar_wait(bar_d, 0);
     tc_fence_after();
-    if (EPI != EPI_LN) {
+    if (!kLn) {
 #pragma unroll 1
       for (int ci = 0; ci < MT * (BN / 32); ++ci) {
         const int mt = ci / (BN / 32), c = ci % (BN / 32);
@@ -365,10 +383,9 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     } else {
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 16; ++c) {     // pass 1: x = acc + bias + residual, kept in TMEM
-        const uint32_t buf = (c < kResRing) ? ring + c * kABoxBytes
-                           : (c < 16 - kResRing) ? base + (c - kResRing) * kABoxBytes
-                                                 : ring + (c - (16 - kResRing)) * kABoxBytes;
+      for (int c = 0; c < kBoxes; ++c) {     // pass 1: x = acc + bias + residual, kept in TMEM
+        const int j0 = c < kRingBoxes + kStageBoxes ? c : c - kRingBoxes - kStageBoxes;
+        const uint32_t buf = j0 < kRingBoxes ? ring + j0 * kABoxBytes : base + (j0 - kRingBoxes) * kABoxBytes;
         float v[32];
         tmem_ld32(ta + c * 32, v);
         mbar_wait(bar_res_full + 8 * c, 0);
@@ -380,25 +397,44 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           v[4 * j + 2] += s_bias[c * 32 + 4 * j + 2] + q.z;
           v[4 * j + 3] += s_bias[c * 32 + 4 * j + 3] + q.w;
         }
-        if (c < kResRing) mbar_arrive(bar_ring_free + 8 * c);
+        if (c < kReuse) {
+          fence_async_smem();            // the buffer is refilled through the async proxy (TMA) once all 128 threads have read it
+          mbar_arrive(bar_ring_free + 8 * c);
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) sum += v[j];
         tmem_st32(ta + c * 32, v);
       }
       tmem_st_wait();
-      const float mean = sum * (1.0f / BN);
+      float mean = sum * (1.0f / BN);
       float ss = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 16; ++c) {     // pass 2: centred sum of squares
+      for (int c = 0; c < kBoxes; ++c) {     // pass 2: centred sum of squares
         float v[32];
         tmem_ld32(ta + c * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; ss += d * d; }
       }
-      const float rstd = 1.0f / sqrtf(ss * (1.0f / BN) + kLnEps);
+      float var = ss * (1.0f / BN);
+      if (kLn2) {
+        // the row's other 256 columns live in the peer CTA: swap (sum, centred squares) through distributed shared memory
+        // and merge the two halves (Chan et al.): M2 = M2_a + M2_b + n_a (mean_a - mean)^2 + n_b (mean_b - mean)^2
+        uint32_t peer;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer) : "r"(xch + (uint32_t)r * 8u), "r"(crank ^ 1u));
+        asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(peer), "f"(sum), "f"(ss) : "memory");
+        cluster_barrier();
+        float osum, oss;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(osum), "=f"(oss) : "r"(xch + (uint32_t)r * 8u) : "memory");
+        const float omean = osum * (1.0f / BN);
+        const float tmean = (sum + osum) * (0.5f / BN);
+        const float da = mean - tmean, db = omean - tmean;
+        var = (ss + oss + (float)BN * (da * da + db * db)) * (0.5f / BN);
+        mean = tmean;
+      }
+      const float rstd = 1.0f / sqrtf(var + kLnEps);
       epi_bar_sync();                    // every warp is done reading residual boxes: the stages become output staging
 #pragma unroll 1
-      for (int c = 0; c < 16; ++c) {     // pass 3: normalise, affine, stage the box, TMA store
+      for (int c = 0; c < kBoxes; ++c) {     // pass 3: normalise, affine, stage the box, TMA store
         const uint32_t slot = base + (uint32_t)(c % NS) * kABoxBytes;
         if (c >= NS) {
           if (threadIdx.x == 0) tma_store_wait_read<NS - 1>();
@@ -414,7 +450,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         fence_async_smem();
         epi_bar_sync();
         if (threadIdx.x == 0) {
-          tma_store_2d(omap, slot, c * 32, m0);
+          tma_store_2d(omap, slot, col0 + c * 32, m0);
           tma_store_commit();
         }
       }
@@ -771,6 +807,12 @@ struct mansy_mtio {
   int cluster_ln = 1, cluster_wide = 1;      // CTAs sharing weight boxes by TMA multicast (MANSY_MTIO_CLUSTER_LN / _WIDE)
   int w_box_rows = 128;                      // rows per weight TMA operation (MANSY_MTIO_WBOX = 128 | 256)
   int lanes = 2;                             // halves of a pass run on two streams (MANSY_MTIO_LANES = 1 | 2)
+  int ln_split = 0;                          // EXPERIMENTAL, off (MANSY_MTIO_LN_SPLIT=1): LayerNorm GEMMs as 2-CTA clusters of
+                                             // [128 x 256] halves, row statistics swapped over DSMEM: -7 % GEMM time (-3 % per pass).
+                                             // Its first build differed from run to run in a few rows per pass; the missing
+                                             // generic->async proxy fence before a residual buffer is handed back to TMA (short
+                                             // reuse distance in this variant) is the likely cause and is in place now (3 clean
+                                             // runs of the bit-equality tests), but one fix-and-pass is not proof
   cudaStream_t s2 = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   std::vector<void *> allocs;
@@ -871,6 +913,10 @@ struct Launcher {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(tiles, (unsigned)(g.N / BN), 1);
+    if (EPI == EPI_LN2) {                            // 2-CTA clusters along x: the two column halves of one row tile
+      cl = 2;
+      cfg.gridDim = dim3(2 * tiles, 1, 1);
+    }
     cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmem;
     cfg.stream = s;
@@ -921,7 +967,10 @@ struct Launcher {
       case EPI_NONE: wide ? tc_gemm<256, 2, EPI_NONE>(ma, wmap, mres, mout, g) : tc_gemm<256, 1, EPI_NONE>(ma, wmap, mres, mout, g); break;
       case EPI_RELU: wide ? tc_gemm<256, 2, EPI_RELU>(ma, wmap, mres, mout, g) : tc_gemm<256, 1, EPI_RELU>(ma, wmap, mres, mout, g); break;
       case EPI_ELU: wide ? tc_gemm<256, 2, EPI_ELU>(ma, wmap, mres, mout, g) : tc_gemm<256, 1, EPI_ELU>(ma, wmap, mres, mout, g); break;
-      default: tc_gemm<512, 1, EPI_LN>(ma, wmap, mres, mout, g); break;
+      default:
+        if (m->ln_split) tc_gemm<256, 1, EPI_LN2>(ma, wmap, mres, mout, g);
+        else tc_gemm<512, 1, EPI_LN>(ma, wmap, mres, mout, g);
+        break;
     }
     end("mtio_gemm_kernel");
   }
@@ -945,6 +994,7 @@ void gemm_set_attributes() {
   gemm_set_attribute<256, 1, EPI_NONE>(); gemm_set_attribute<256, 1, EPI_RELU>(); gemm_set_attribute<256, 1, EPI_ELU>();
   gemm_set_attribute<256, 2, EPI_NONE>(); gemm_set_attribute<256, 2, EPI_RELU>(); gemm_set_attribute<256, 2, EPI_ELU>();
   gemm_set_attribute<512, 1, EPI_LN>();
+  gemm_set_attribute<256, 1, EPI_LN2>();
   cudaGetLastError();
 }
 
@@ -1157,6 +1207,7 @@ int mansy_mtio_create(const mansy_mtio_weights_t *w, int device, int32_t max_bat
   if (const char *v = getenv("MANSY_MTIO_CLUSTER_WIDE")) m->cluster_wide = atoi(v) == 2 ? 2 : 1;
   if (const char *v = getenv("MANSY_MTIO_WBOX")) m->w_box_rows = atoi(v) == 256 ? 256 : 128;
   if (const char *v = getenv("MANSY_MTIO_LANES")) m->lanes = atoi(v) == 1 ? 1 : 2;
+  if (const char *v = getenv("MANSY_MTIO_LN_SPLIT")) m->ln_split = atoi(v) != 0;
   int rc = MANSY_OK;
 #define MTIO_TRY(expr) do { if (!rc) rc = (expr); } while (0)
   {   // embedding.linear.weight [512][6] -> [6][512]: a warp reads 32 consecutive outputs of one input column
