@@ -807,12 +807,8 @@ struct mansy_mtio {
   int cluster_ln = 1, cluster_wide = 1;      // CTAs sharing weight boxes by TMA multicast (MANSY_MTIO_CLUSTER_LN / _WIDE)
   int w_box_rows = 128;                      // rows per weight TMA operation (MANSY_MTIO_WBOX = 128 | 256)
   int lanes = 2;                             // halves of a pass run on two streams (MANSY_MTIO_LANES = 1 | 2)
-  int ln_split = 0;                          // EXPERIMENTAL, off (MANSY_MTIO_LN_SPLIT=1): LayerNorm GEMMs as 2-CTA clusters of
-                                             // [128 x 256] halves, row statistics swapped over DSMEM: -7 % GEMM time (-3 % per pass).
-                                             // Its first build differed from run to run in a few rows per pass; the missing
-                                             // generic->async proxy fence before a residual buffer is handed back to TMA (short
-                                             // reuse distance in this variant) is the likely cause and is in place now (3 clean
-                                             // runs of the bit-equality tests), but one fix-and-pass is not proof
+  int ln_split = 1;                          // LayerNorm GEMMs as 2-CTA clusters of [128 x 256] halves, row statistics swapped over
+                                             // DSMEM (MANSY_MTIO_LN_SPLIT=0: one [128 x 512] CTA per row tile)
   cudaStream_t s2 = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   std::vector<void *> allocs;
