@@ -123,18 +123,19 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     per_step_seconds = max(2.0, min(10.0, 60.0 / max(args.steps + args.warmup, 1)))
     # a "step" of this arm = a bounded sample (per_step_seconds of all-core stepping); K steps are averaged
+    # bounded: at most one warm-up sample and three timed samples, whatever --steps / --warmup say (the whole run must end
+    # within a few minutes; the line reports the counts actually used)
+    warm, steps = min(args.warmup, 1), max(1, min(args.steps, 3))
     rates = []
-    for i in range(args.warmup + args.steps):
+    for i in range(warm + steps):
         r = cpu_baseline(per_step_seconds, cores)
-        if i >= args.warmup:
+        if i >= warm:
             rates.append(r)
-        if len(rates) >= 3:          # keep the whole run within a few minutes
-            break
     value = sum(r["value"] for r in rates) / len(rates)
     n_env = args.envs_per_gpu * args.gpus
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(rates), "warmup": args.warmup, "ms_per_step": 1e3 * n_env / value,
+        "steps": len(rates), "warmup": warm, "ms_per_step": 1e3 * n_env / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"mansy_ppo_rollout_{args.envs_per_gpu}_envs_per_gpu (simulator step only: the reference's "
                                "policy forward is GPU-side torch and is not part of the CPU arm)",
