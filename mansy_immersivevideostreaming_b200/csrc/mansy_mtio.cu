@@ -35,6 +35,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -65,6 +66,7 @@ struct GemmArgs {
   int64_t res_ld;
   const float *gamma, *beta;
   int32_t w_box_rows;      // rows of the weight tensor map's box: 128, or 256 (two adjacent boxes per TMA operation)
+  long long *timeline;     // profiling hook (MANSY_MTIO_TIMELINE): SM-clock stamps of CTA (0, 0), see mtio_timeline_dump
 };
 
 // ------------------------------------------------------------------------------------------
@@ -211,6 +213,8 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const bool tl = g.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (tl && threadIdx.x == 0) g.timeline[190] = clock64();        // prologue done
 
   if (warp == Cfg::kResWarp) {
     // ===== residual producer (LayerNorm epilogue): the [128 x 512] residual tile as 16 boxes of 32 columns.  Boxes 0..2
@@ -254,6 +258,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t dst = base + s * kStage, full = bar_full + 16 * s + 8 * h;
     for (int it = s; it < nk; it += kStages) {
       mbar_wait(bar_empty + 8 * s, ((uint32_t)(it / kStages) & 1u) ^ 1u);
+      if (tl && h == 0 && (threadIdx.x & 31) == 0 && it < 60) g.timeline[it] = clock64();           // stage free: TMA issue
       if (elect_one()) {
         auto load_w = [&](int b) {          // weight box b (rows n0 + 128 b ..) of this K-chunk
           const uint32_t at = dst + kWOff + kABoxBytes * b;
@@ -306,6 +311,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (BN == 256) {
         mbar_wait(bar_full + 16 * s, ph);
         mbar_wait(bar_full + 16 * s + 8, ph);
+        if (tl && (threadIdx.x & 31) == 0 && it < 60) g.timeline[60 + it] = clock64();              // operands landed
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -336,6 +342,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (it == nk - 1) umma_commit(bar_d);
       }
       __syncwarp();
+      if (tl && (threadIdx.x & 31) == 0 && it < 60) g.timeline[120 + it] = clock64();                 // MMAs issued + committed
       if (++s == kStages) { s = 0; ph ^= 1u; }
     }
     if (kLn2) cluster_barrier();
@@ -351,6 +358,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     constexpr int NS = Cfg::kOutSlots;
     mbar_wait(bar_d, 0);
     tc_fence_after();
+    if (tl && threadIdx.x == 0) g.timeline[191] = clock64();        // accumulators complete
     if (!kLn) {
 #pragma unroll 1
       for (int ci = 0; ci < MT * (BN / 32); ++ci) {
@@ -458,6 +466,7 @@ mtio_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   }
 
+  if (tl && threadIdx.x == 0) g.timeline[192] = clock64();          // epilogue done
   tc_fence_before();
   __syncthreads();
   if (csize > 1) cluster_barrier();       // no CTA leaves while a peer's commit may still target its barriers
@@ -806,6 +815,8 @@ struct mansy_mtio {
   bool tc_ok = false;
   int cluster_ln = 1, cluster_wide = 1;      // CTAs sharing weight boxes by TMA multicast (MANSY_MTIO_CLUSTER_LN / _WIDE)
   int w_box_rows = 128;                      // rows per weight TMA operation (MANSY_MTIO_WBOX = 128 | 256)
+  int timeline_launch = -1, gemm_launches = 0, timeline_shape[4] = {0, 0, 0, 0};   // MANSY_MTIO_TIMELINE=<k>: stamp the k-th GEMM launch
+  long long *timeline_dev = nullptr;
   int lanes = 2;                             // halves of a pass run on two streams (MANSY_MTIO_LANES = 1 | 2)
   int ln_split = 1;                          // LayerNorm GEMMs as 2-CTA clusters of [128 x 256] halves, row statistics swapped over
                                              // DSMEM (MANSY_MTIO_LN_SPLIT=0: one [128 x 512] CTA per row tile)
@@ -944,6 +955,11 @@ struct Launcher {
       return;
     }
     g.w_box_rows = m->w_box_rows;
+    g.timeline = nullptr;
+    if (m->timeline_launch >= 0 && m->gemm_launches++ == m->timeline_launch && m->timeline_dev) {
+      g.timeline = m->timeline_dev;
+      m->timeline_shape[0] = g.M; m->timeline_shape[1] = g.N; m->timeline_shape[2] = g.K; m->timeline_shape[3] = epi;
+    }
     CUtensorMap ma;
     if (int e = tc_make_map(&ma, A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)lda, 128)) { rc = e; return; }
     CUtensorMap mres = ma;                 // only the LayerNorm epilogue reads it
@@ -1203,6 +1219,16 @@ int mansy_mtio_create(const mansy_mtio_weights_t *w, int device, int32_t max_bat
   if (const char *v = getenv("MANSY_MTIO_CLUSTER_WIDE")) m->cluster_wide = atoi(v) == 2 ? 2 : 1;
   if (const char *v = getenv("MANSY_MTIO_WBOX")) m->w_box_rows = atoi(v) == 256 ? 256 : 128;
   if (const char *v = getenv("MANSY_MTIO_LANES")) m->lanes = atoi(v) == 1 ? 1 : 2;
+  if (const char *v = getenv("MANSY_MTIO_TIMELINE")) {
+    m->timeline_launch = atoi(v);
+    m->lanes = 1;
+    void *d = nullptr;
+    if (cudaMalloc(&d, 256 * sizeof(long long)) == cudaSuccess) {
+      cudaMemset(d, 0, 256 * sizeof(long long));
+      m->allocs.push_back(d);
+      m->timeline_dev = static_cast<long long *>(d);
+    }
+  }
   if (const char *v = getenv("MANSY_MTIO_LN_SPLIT")) m->ln_split = atoi(v) != 0;
   int rc = MANSY_OK;
 #define MTIO_TRY(expr) do { if (!rc) rc = (expr); } while (0)
@@ -1319,6 +1345,19 @@ int mansy_mtio_sample(mansy_mtio_t m, const float *history_dev, const float *cur
     int rc = run_lanes(m, history_dev + off * m->T * 2, current_dev + off * 2, c, n_steps, flags, pred_dev + off * m->F * 2,
                        tokens_dev ? tokens_dev + off * (m->F + 1) * kTok : nullptr, s);
     if (rc) return rc;
+  }
+  if (m->timeline_dev && m->gemm_launches > m->timeline_launch && m->timeline_launch >= 0) {
+    long long tl[256];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(tl, m->timeline_dev, sizeof(tl), cudaMemcpyDeviceToHost);
+    const long long t0 = tl[190];
+    fprintf(stderr, "mtio_gemm timeline: launch %d  M %d N %d K %d epi %d  (SM cycles after the prologue of CTA (0,0))\n",
+            m->timeline_launch, m->timeline_shape[0], m->timeline_shape[1], m->timeline_shape[2], m->timeline_shape[3]);
+    for (int it = 0; it < 60 && tl[120 + it]; ++it)
+      fprintf(stderr, "  chunk %2d: stage free / TMA issue %7lld   operands landed %7lld   MMAs issued %7lld\n", it, tl[it] - t0,
+              tl[60 + it] - t0, tl[120 + it] - t0);
+    fprintf(stderr, "  accumulators complete %lld   epilogue done %lld\n", tl[191] - t0, tl[192] - t0);
+    m->timeline_launch = -1;
   }
   return MANSY_OK;
 }
