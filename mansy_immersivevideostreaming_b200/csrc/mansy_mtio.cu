@@ -12,18 +12,20 @@
 // per layer in HBM (the reference re-runs encoder and decoder on the whole prefix every step, mtio.py:120-123:
 // ~10x the FLOPs for the same function).  What is left is a chain of [rows x 512] x [512 x N] products shared
 // by all samples:
-//   * mtio_gemm_kernel<BN, EPI>: tcgen05 kind::tf32, one CTA per [128 rows x BN columns] output tile.  A rows and
-//     torch-layout weight rows ([out][in] = K-major) are TMA-loaded as [128 x 32-float] SWIZZLE_128B boxes into a
-//     2-stage ring (4 producer warps: one per stage half), one elected lane issues M128 x N256 x K8 MMAs into
-//     TMEM, four epilogue warps (one per TMEM lane quarter, thread = output row) apply
-//        EPI_NONE / EPI_RELU / EPI_ELU : + bias (+ activation), rows stored as 128-byte runs
-//        EPI_LN (BN = 512 = d_model: the whole row lives in one CTA's TMEM): + bias + residual row, LayerNorm
-//            over the 512 columns in three TMEM passes (sum, centred squares, normalise) -- the post-norm
-//            "x = norm(x + sublayer(x))" of every transformer sub-block in the producing kernel.
-//     BN = 256 tiles use 256 TMEM columns and 100 KB of shared memory: two CTAs per SM, so one tile's epilogue
-//     overlaps the other's operand stream.  Output columns are routed by 512-column segment (pointer + leading
-//     dimension per segment): the fused QKV projection writes q to a scratch row and k / v straight into step t
-//     of the per-layer cache.
+//   * mtio_gemm_kernel<BN, MT, EPI>: tcgen05 kind::tf32.  A rows and torch-layout weight rows ([out][in] = K-major) are
+//     TMA-loaded as [128 x 32-float] SWIZZLE_128B boxes into a 2-3-stage ring (one producer warp per stage half), one
+//     elected lane issues M128 x N256 x K8 MMAs into TMEM, four epilogue warps (one per TMEM lane quarter, thread =
+//     output row) post-process and stage [128 x 32] output boxes in swizzled shared memory for TMA stores.  Tiles:
+//        <256, 2> [256 rows x 256 columns]: two M128 accumulators share every weight box -- all GEMMs without
+//                 LayerNorm (EPI_NONE / EPI_RELU / EPI_ELU: + bias (+ activation));
+//        <256, 1> [128 x 256], two CTAs per SM: small batches, and EPI_LN2, the LayerNorm GEMM as a 2-CTA cluster whose
+//                 CTAs own the two column halves of the same rows: + bias + residual (TMA-prefetched boxes), per-row
+//                 (sum, centred squares) swapped through distributed shared memory, normalise -- the post-norm
+//                 "x = norm(x + sublayer(x))" of every transformer sub-block in the producing kernel;
+//        <512, 1> [128 x 512] EPI_LN: the same epilogue with the whole d_model row in one CTA (MANSY_MTIO_LN_SPLIT=0).
+//     Output columns are routed by 512-column segment (tensor map per segment): the fused QKV projection writes q to a
+//     scratch row and k / v straight into step t of the per-layer cache.  Passes of >= 1024 samples run as two lanes
+//     (two streams, two launching threads).  DESIGN.md 4.7 has the measurements behind these choices.
 //   * mtio_attn_kernel: one warp per (sample, head); <= 32 keys (5 source tokens, 3 distilled memory tokens,
 //     <= 31 cached target tokens): lane = key for the scores, lane = 2 of the 64 head dims for the output.
 //   * mtio_head_kernel: final decoder LayerNorm + predictor + sigmoid + MTIO-head ensemble + wrap into the unit
