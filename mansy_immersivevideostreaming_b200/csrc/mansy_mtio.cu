@@ -581,13 +581,12 @@ __global__ void __launch_bounds__(256) mtio_ln_kernel(const float *in, float *ou
 
 // ViewportEmbedding + PositionalEncoding (mtio.py:29-45, 11-27): out[row] = W tok + b + pe[pos_base + row % pos_mod].
 // in_dim 2: the viewport centre repeated for the 3 MTIO heads (mtio.py:113-116); in_dim 6: a predicted token.
-__global__ void __launch_bounds__(256) mtio_embed_kernel(const float *__restrict__ tok, int64_t tok_stride, int in_dim, int64_t rows,
+__global__ void __launch_bounds__(128) mtio_embed_kernel(const float *__restrict__ tok, int64_t tok_stride, int in_dim, int64_t rows,
                                                          int pos_mod, int pos_base, const float *__restrict__ emb_w,
                                                          const float *__restrict__ emb_b, const float *__restrict__ pe,
                                                          float *__restrict__ out, float *__restrict__ tok_out, int64_t tok_out_stride) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = idx >> 7;
-  const int c4 = (int)(idx & 127);
+  const int64_t row = blockIdx.x;          // one block of 128 threads per row
+  const int c4 = (int)threadIdx.x;
   if (row >= rows) return;
   float t[kTok];
   const float *tr = tok + row * tok_stride;
@@ -602,7 +601,7 @@ __global__ void __launch_bounds__(256) mtio_embed_kernel(const float *__restrict
 #pragma unroll
     for (int o = 0; o < kTok; ++o) tok_out[row * tok_out_stride + o] = t[o];
   }
-  const int pos = pos_base + (int)(row % pos_mod);
+  const int pos = pos_base + (int)((uint32_t)blockIdx.x % (uint32_t)pos_mod);
   float4 r = *reinterpret_cast<const float4 *>(emb_b + c4 * 4);
 #pragma unroll
   for (int o = 0; o < kTok; ++o) {      // emb_w: transposed [6][512] copy, one 16-byte load per input column
@@ -614,26 +613,24 @@ __global__ void __launch_bounds__(256) mtio_embed_kernel(const float *__restrict
 }
 
 // DistillLayer conv input (customized_transformer.py:21-25,32): row (b, t) -> [x[t-1] | x[t] | x[t+1]] with circular wrap
-__global__ void __launch_bounds__(256) mtio_im2col_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t rows, int T) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t row = idx / 384;
-  const int rem = (int)(idx % 384), k = rem >> 7, c4 = rem & 127;
+__global__ void __launch_bounds__(384) mtio_im2col_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t rows, int T) {
+  const int64_t row = blockIdx.x;          // one block of 384 threads per row: thread = (tap, 16-byte column piece)
+  const int rem = (int)threadIdx.x, k = rem >> 7, c4 = rem & 127;
   if (row >= rows) return;
-  const int64_t b = row / T;
-  const int t = (int)(row % T);
+  const int64_t b = (uint32_t)blockIdx.x / (uint32_t)T;
+  const int t = (int)((uint32_t)blockIdx.x % (uint32_t)T);
   const int src_t = (t + k - 1 + T) % T;
   *reinterpret_cast<float4 *>(out + row * (3 * kD) + k * kD + c4 * 4) =
       *reinterpret_cast<const float4 *>(in + (b * T + src_t) * kD + c4 * 4);
 }
 
 // MaxPool1d(kernel 3, stride 2, padding 1) over the T tokens of a sample (customized_transformer.py:28,35)
-__global__ void __launch_bounds__(256) mtio_maxpool_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t n, int T, int To) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t orow = idx >> 7;
-  const int c4 = (int)(idx & 127);
+__global__ void __launch_bounds__(128) mtio_maxpool_kernel(const float *__restrict__ in, float *__restrict__ out, int64_t n, int T, int To) {
+  const int64_t orow = blockIdx.x;         // one block of 128 threads per output row
+  const int c4 = (int)threadIdx.x;
   if (orow >= n * To) return;
-  const int64_t b = orow / To;
-  const int o = (int)(orow % To);
+  const int64_t b = (uint32_t)blockIdx.x / (uint32_t)To;
+  const int o = (int)((uint32_t)blockIdx.x % (uint32_t)To);
   const int lo = max(2 * o - 1, 0), hi = min(2 * o + 1, T - 1);
   float4 m = *reinterpret_cast<const float4 *>(in + (b * T + lo) * kD + c4 * 4);
   for (int t = lo + 1; t <= hi; ++t) {
@@ -1046,12 +1043,10 @@ int run_chunk(mansy_mtio *m, const Ws &w, const float *hist, const float *cur, i
   if (!L.fp32 && !m->tc_ok) return set_error(MANSY_E_STATE, "tensor maps unavailable (cuTensorMapEncodeTiled missing); use MANSY_MTIO_FP32");
   const int T = m->T, F = m->F, Tm = m->Tm;
   const int rows = n * T;
-  const unsigned g128 = 256;     // threads per block of the element-wise kernels
 
   // ---- encoder (once per sample) ----
   if (L.begin(2)) {
-    mtio_embed_kernel<<<(unsigned)(((int64_t)rows * 128 + g128 - 1) / g128), g128, 0, s>>>(hist, 2, 2, rows, T, 0, m->emb_w, m->emb_b, m->pe,
-                                                                                          w.xs, nullptr, 0);
+    mtio_embed_kernel<<<(unsigned)rows, 128, 0, s>>>(hist, 2, 2, rows, T, 0, m->emb_w, m->emb_b, m->pe, w.xs, nullptr, 0);
     L.end("mtio_embed_kernel");
   }
   for (int l = 0; l < m->n_enc; ++l) {
@@ -1076,7 +1071,7 @@ int run_chunk(mansy_mtio *m, const Ws &w, const float *hist, const float *cur, i
     L.end("mtio_ln_kernel");
   }
   if (L.begin(2)) {
-    mtio_im2col_kernel<<<(unsigned)(((int64_t)rows * 384 + g128 - 1) / g128), g128, 0, s>>>(w.att_e, w.wide_e, rows, T);
+    mtio_im2col_kernel<<<(unsigned)rows, 384, 0, s>>>(w.att_e, w.wide_e, rows, T);
     L.end("mtio_im2col_kernel");
   }
   {
@@ -1085,7 +1080,7 @@ int run_chunk(mansy_mtio *m, const Ws &w, const float *hist, const float *cur, i
     L.gemm(EPI_ELU, w.wide_e, 3 * kD, m->map_conv, m->conv_w, g);
   }
   if (L.begin(2)) {
-    mtio_maxpool_kernel<<<(unsigned)(((int64_t)n * Tm * 128 + g128 - 1) / g128), g128, 0, s>>>(w.x1_e, w.mem, n, T, Tm);
+    mtio_maxpool_kernel<<<(unsigned)(n * Tm), 128, 0, s>>>(w.x1_e, w.mem, n, T, Tm);
     L.end("mtio_maxpool_kernel");
   }
   for (int l = 0; l < m->n_dec; ++l) {   // cross-attention keys / values of the memory, once per layer
@@ -1098,8 +1093,7 @@ int run_chunk(mansy_mtio *m, const Ws &w, const float *hist, const float *cur, i
 
   // ---- decoder: F autoregressive steps, one new token per step ----
   if (L.begin(2)) {
-    mtio_embed_kernel<<<(unsigned)(((int64_t)n * 128 + g128 - 1) / g128), g128, 0, s>>>(cur, 2, 2, n, 1, 0, m->emb_w, m->emb_b, m->pe, w.x,
-                                                                                       w.tokens, (int64_t)(F + 1) * kTok);
+    mtio_embed_kernel<<<(unsigned)n, 128, 0, s>>>(cur, 2, 2, n, 1, 0, m->emb_w, m->emb_b, m->pe, w.x, w.tokens, (int64_t)(F + 1) * kTok);
     L.end("mtio_embed_kernel");
   }
   for (int t = 0; t < n_steps; ++t) {
