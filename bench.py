@@ -42,6 +42,9 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--diverse-qoe", action="store_true",
+                   help="BASELINE configs[2]: one Dirichlet(1,1,1)*9 QoE preference vector per environment (65,536 envs = "
+                        "--envs-per-gpu 8192 on 8 GPUs) instead of the 4 default weights")
     p.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     p.add_argument("--sweep", action="store_true", help="also time the simulator-only kernel at larger env counts")
     p.add_argument("--workload", default="rollout", choices=["rollout", "mtio"],
@@ -57,9 +60,15 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------
 # shared: synthetic workload
 # ---------------------------------------------------------------------------------------------
-def workload_tables(mask_fn, n_slots):
+def workload_tables(mask_fn, n_slots, diverse_qoe=False):
     from mansy_immersivevideostreaming_b200 import synth
     t = synth.make_synthetic_tables(mask_fn, n_videos=24, n_users=60, n_chunks=60, n_traces=40, seed=20260101)
+    if diverse_qoe:      # Q = number of environments, weights ~ Dirichlet(1,1,1) * 9; environment k uses weight k
+        import numpy as np
+        t = t.with_samples(t.samples, qoe_w=synth.diverse_qoe_weights(n_slots))
+        s = synth.per_env_samples(t, n_slots)
+        s[:, 3] = np.arange(n_slots, dtype=s.dtype)
+        return t.with_samples(s)
     return t.with_samples(synth.per_env_samples(t, n_slots))
 
 
@@ -236,7 +245,7 @@ def run_ours(args):
     n_local = args.envs_per_gpu
     n_global = n_local * world
     tiler = ViewportTiler(device=local)
-    tables = workload_tables(tiler.chunk_masks, n_global)        # masks come from the CUDA viewport->tiles kernel
+    tables = workload_tables(tiler.chunk_masks, n_global, args.diverse_qoe)   # masks come from the CUDA viewport->tiles kernel
     sim = BatchSimulator(tables, n_local, OBS_MODE_MANSY, REWARD_QOE, seed=0, worker_num=n_global,
                          env_offset=rank * n_local, device=local)
     actor_shapes, critic_shapes = mansy_state_dict_shapes()
@@ -323,7 +332,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 simulator scalars / f32 observations / tf32 policy (fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": f"mansy_ppo_rollout_{n_local}_envs_per_gpu", "envs": n_global, "envs_per_gpu": n_local,
+        "config": {"workload": f"mansy_ppo_rollout_{n_local}_envs_per_gpu" + ("_diverse_qoe" if args.diverse_qoe else ""),
+                   "envs": n_global, "envs_per_gpu": n_local,
                    "obs_row_bytes": sim.obs_stride * 4,
                    "l2": f"observations stream into a {slabs}-slab rollout buffer of {slabs * slab_bytes >> 20} MiB "
                          "(> L2 126 MB): every step writes a slab last touched >2.5 L2-sizes ago",
