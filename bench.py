@@ -46,7 +46,11 @@ def parse_args():
                    help="BASELINE configs[2]: one Dirichlet(1,1,1)*9 QoE preference vector per environment (65,536 envs = "
                         "--envs-per-gpu 8192 on 8 GPUs) instead of the 4 default weights")
     p.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
-    p.add_argument("--sweep", action="store_true", help="also time the simulator-only kernel at larger env counts")
+    p.add_argument("--no-extras", action="store_true",
+                   help="only the headline rollout line: skip configs[2] (8,192 diverse-QoE envs per GPU), configs[3] (simulator-only "
+                        "sweep at 65,536 / 1,048,576 envs) and configs[4] (MTIO masks feeding the environments)")
+    p.add_argument("--nccl-gather", action="store_true",
+                   help="exchange the episode totals with torch.distributed (NCCL) instead of the NVLink peer-memory kernel")
     p.add_argument("--workload", default="rollout", choices=["rollout", "mtio"],
                    help="rollout = BASELINE configs[1] (the bench line the driver records); mtio = BASELINE configs[4], the "
                         "MTIO viewport-prediction inference feeding predicted tile masks to the environments")
@@ -73,56 +77,124 @@ def workload_tables(mask_fn, n_slots, diverse_qoe=False):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port (Python, like the reference) on all host cores
+# CPU arm: the UNMODIFIED reference (oracle/_ref archive or /root/reference) on all host cores
 # ---------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    seconds, worker, n_workers, tables_path = args
+def _ref_worker(args):
+    """One process = one reference environment driven exactly like the reference's own loop (run_mansy.py:161-175):
+    the reference's MANSYEnv (unmodified file) stepped with actions sampled from the reference's Actor (models/mansy.py,
+    torch on the CPU, batch of 1, Categorical(logits) as run_mansy.py:228-229), resets included.  Returns per interval
+    (steps, seconds) for `intervals` back-to-back intervals of `seconds` each."""
+    worker, n_workers, cfg_path, intervals, seconds, with_policy, kind = args
     import numpy as np
+    out = []
+    if kind == "reference":
+        import torch
+        from torch.distributions import Categorical
+        torch.set_num_threads(1)
+        from oracle.ref_loader import load_reference, silence_prints
+        from mansy_immersivevideostreaming_b200.policy import mansy_state_dict_shapes, seeded_state_dict
+        ref = load_reference()
+        config = ref.common.get_config_from_yml(cfg_path)
+        qoe = config.qoe_split["train"]
+        log = os.path.join(os.path.dirname(cfg_path), f"train_log_{worker}.csv")
+        with silence_prints():
+            env = ref.mansy_env.MANSYEnv(config, "Synth", "SynthNet", qoe, None, 0.5, log, config.startup_download,
+                                         mode="train", seed=worker, worker_num=n_workers, device="cpu")
+        env.seed(worker)
+        M = ref.models_mansy
+        fn = M.FeatureNet(config.past_k, config.tile_total_num, len(config.video_rates), 128, device="cpu")
+        actor = M.Actor(fn, 1280, 128, config.action_space, "cpu")
+        shapes, _ = mansy_state_dict_shapes()
+        actor.load_state_dict({k: torch.from_numpy(v) for k, v in seeded_state_dict(shapes, 1).items()})
+        torch.manual_seed(1234 + worker)
+        rng = np.random.default_rng(worker)
+        state = env.reset()
+        with torch.no_grad():
+            for _ in range(intervals):
+                steps, t0 = 0, time.perf_counter()
+                while time.perf_counter() - t0 < seconds:
+                    for _ in range(10):
+                        if with_policy:
+                            for key, value in state.items():                 # run_mansy.py:167-168
+                                state[key] = np.expand_dims(value, 0)
+                            logits, _ = actor(state)
+                            action = Categorical(logits=logits).sample().item()
+                        else:
+                            action = int(rng.integers(0, 15))
+                        state, _, done, _ = env.step(action)
+                        steps += 1
+                        if done:
+                            state = env.reset()
+                out.append((steps, time.perf_counter() - t0))
+        return out
+    # fallback when no reference archive travelled with the repo: the oracle port (restatement) of the simulator
     from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, REWARD_QOE
     from mansy_immersivevideostreaming_b200.synth import synthetic_actions
     from mansy_immersivevideostreaming_b200.tables import SimTables
     from oracle import sim_oracle as so
-    tables = SimTables.from_npz_dict(np.load(tables_path))
+    tables = SimTables.from_npz_dict(np.load(cfg_path))
     env = so.OracleEnv(tables, OBS_MODE_MANSY, REWARD_QOE, "f64", worker_id=worker, worker_num=n_workers)
     env.reset()
-    actions = [int(a) for a in synthetic_actions(8192, worker, seed=1234)]     # precomputed: not part of the timed work
-    steps = 0
-    t0 = time.perf_counter()
-    while time.perf_counter() - t0 < seconds:
-        for _ in range(50):
-            _, _, done, _ = env.step(actions[steps & 8191])
-            steps += 1
-            if done:
-                env.reset()
-    return steps, time.perf_counter() - t0
+    actions = [int(a) for a in synthetic_actions(8192, worker, seed=1234)]
+    total = 0
+    for _ in range(intervals):
+        steps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(50):
+                _, _, done, _ = env.step(actions[total & 8191])
+                steps += 1; total += 1
+                if done:
+                    env.reset()
+        out.append((steps, time.perf_counter() - t0))
+    return out
 
 
-def cpu_baseline(seconds: float, cores: int):
-    """Chunk-steps/s of the Python oracle port (one env per process, resets included), all cores."""
+def cpu_arm(intervals: int, seconds: float, cores: int, with_policy: bool = True):
+    """Chunk-steps/s of the reference on `cores` processes (one environment each) for `intervals` intervals.
+    Returns (list of per-interval aggregate rates, description dict)."""
     import multiprocessing as mp
     import numpy as np
     from oracle import sim_oracle as so
+    from oracle.ref_loader import code_available
+    from mansy_immersivevideostreaming_b200 import synth
     from mansy_immersivevideostreaming_b200.config import SimConfig
     cfg = SimConfig()
-    # a slice of the workload (the oracle needs the masks; its own geometry makes them)
-    from mansy_immersivevideostreaming_b200 import synth
+    # a slice of the bench workload (same generators and seed): 4 videos x 8 users x 40 traces, 4 default QoE weights
     t = synth.make_synthetic_tables(lambda g, p: so.chunk_masks(g, p, cfg), n_videos=4, n_users=8, n_chunks=60,
                                     n_traces=40, seed=20260101)
-    t = t.with_samples(synth.per_env_samples(t, max(cores, 64)))
-    path = os.path.join(tempfile.mkdtemp(prefix="mansy_cpu_"), "tables.npz")
-    np.savez(path, **t.to_npz_dict())
+    root = tempfile.mkdtemp(prefix="mansy_cpu_")
+    kind = "reference" if code_available() else "port"
+    if kind == "reference":
+        path = synth.write_reference_layout(t, root)          # the reference's own on-disk formats + config.yml
+    else:
+        t = t.with_samples(synth.per_env_samples(t, max(cores, 64)))
+        path = os.path.join(root, "tables.npz")
+        np.savez(path, **t.to_npz_dict())
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(seconds, w, cores, path) for w in range(cores)])
+        res = pool.map(_ref_worker, [(w, cores, path, intervals, seconds, with_policy, kind) for w in range(cores)])
     wall = time.perf_counter() - t0
-    total = sum(r[0] for r in res)
-    rate = sum(r[0] / r[1] for r in res)
-    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{total} chunk-steps: {cores} processes x 1 MANSY env (Python float64 oracle port of the "
-                      f"reference's MANSYEnv.step/reset, resets included) for {seconds:.0f} s each on a 4-video x "
-                      f"8-user x 40-trace slice of the workload",
-            "wall_s": wall}
+    rates = [sum(r[i][0] / r[i][1] for r in res) for i in range(intervals)]
+    steps = [sum(r[i][0] for r in res) for i in range(intervals)]
+    what = ("the UNMODIFIED reference classes (oracle/_ref archive): MANSYEnv.step/reset (envs/mansy_env.py, resets re-read the "
+            "manifest / viewport / trace files as simulators/simulator.py:30-38 does)"
+            + (" + Actor forward and Categorical sample per step (models/mansy.py, torch CPU, batch 1: the loop of "
+               "run_mansy.py:161-175)" if with_policy else " with uniform random actions (simulator only)")
+            if kind == "reference" else
+            "Python float64 oracle port of MANSYEnv.step/reset (no reference archive on this box), simulator only")
+    return rates, {"cores": cores, "kind": kind, "wall_s": wall,
+                   "sample": f"{steps[-1]} chunk-steps per interval: {cores} processes x 1 env, {what}, {seconds:.1f} s per "
+                             f"interval on a 4-video x 8-user x 40-trace slice of the workload written in the reference's "
+                             f"on-disk formats"}
+
+
+def cpu_baseline(seconds: float, cores: int):
+    """`cpu_baseline` of our line: one bounded sample of the reference arm + the simulator-only rate beside it."""
+    rates, d = cpu_arm(1, seconds, cores, with_policy=True)
+    sim_rates, _ = cpu_arm(1, max(2.0, seconds / 3), cores, with_policy=False)
+    d.update(value=rates[0], unit=UNIT, simulator_only_value=sim_rates[0])
+    return d
 
 
 def run_reference_arm(args):
@@ -130,26 +202,23 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step_seconds = max(2.0, min(10.0, 60.0 / max(args.steps + args.warmup, 1)))
-    # a "step" of this arm = a bounded sample (per_step_seconds of all-core stepping); K steps are averaged
-    # bounded: at most one warm-up sample and three timed samples, whatever --steps / --warmup say (the whole run must end
-    # within a few minutes; the line reports the counts actually used)
-    warm, steps = min(args.warmup, 1), max(1, min(args.steps, 3))
-    rates = []
-    for i in range(warm + steps):
-        r = cpu_baseline(per_step_seconds, cores)
-        if i >= warm:
-            rates.append(r)
-    value = sum(r["value"] for r in rates) / len(rates)
+    W, K = max(args.warmup, 0), max(args.steps, 1)
+    # a "step" of this arm = one bounded interval of all-core stepping; the whole run is capped at ~100 s of stepping
+    seconds = max(0.5, min(4.0, 100.0 / (W + K)))
+    rates, d = cpu_arm(W + K, seconds, cores, with_policy=True)
+    timed = rates[W:]
+    value = sum(timed) / len(timed)
     n_env = args.envs_per_gpu * args.gpus
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(rates), "warmup": warm, "ms_per_step": 1e3 * n_env / value,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"mansy_ppo_rollout_{args.envs_per_gpu}_envs_per_gpu (simulator step only: the reference's "
-                               "policy forward is GPU-side torch and is not part of the CPU arm)",
-                   "envs": n_env},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": rates[0]["sample"]},
+        "steps": K, "warmup": W, "ms_per_step": 1e3 * n_env / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 simulator scalars / f32 observations / f32 policy",
+        "data": "synthetic",
+        "config": {"workload": f"mansy_ppo_rollout_{args.envs_per_gpu}_envs_per_gpu", "envs": n_env,
+                   "envs_per_gpu": args.envs_per_gpu,
+                   "how": "CPU arm: one reference env per host core, policy forward + sample + env.step per chunk-step; "
+                          "ms_per_step = time the host cores need for one lock-step of all envs at the measured rate"},
+        "cpu_baseline": dict(d, value=value, unit=UNIT),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -219,16 +288,58 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def _max_over_ranks(x: float, world: int) -> float:
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_rollout(roll, sim, peers, K, W, world):
+    """W warm-up steps, then EXACTLY K rollout steps + the per-rollout gather between CUDA events on the launching
+    stream, bracketed by barrier + synchronize on both sides; the device-side peer barrier right before the start
+    event lines the GPUs up so host launch skew is not part of any rank's region.  Returns (ms max over ranks, stats,
+    launches of our kernels inside the region)."""
+    import torch
+    import torch.distributed as dist
+    from mansy_immersivevideostreaming_b200 import _capi
+    from mansy_immersivevideostreaming_b200.rollout import gather_episode_stats
+    lib = _capi.load_library()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    roll.run(W)
+    gather_episode_stats(sim, peers=peers)       # a warm-up rollout includes its gather
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if peers is not None:
+        peers.barrier()                          # device-side: all GPUs pass this point within microseconds
+    launches0 = lib.mansy_kernel_launches()
+    start.record()
+    roll.run(K)
+    stats = gather_episode_stats(sim, peers=peers)
+    stop.record()
+    launches = lib.mansy_kernel_launches() - launches0
+    barrier()
+    return _max_over_ranks(start.elapsed_time(stop), world), stats, int(launches)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from mansy_immersivevideostreaming_b200 import _capi
-    from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, OBS_MODE_SIMPLE, REWARD_QOE
+    from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, REWARD_QOE
     from mansy_immersivevideostreaming_b200.policy import PolicyNet, mansy_state_dict_shapes, seeded_state_dict
-    from mansy_immersivevideostreaming_b200.rollout import PolicyRollout, gather_episode_stats, summarise_stats
+    from mansy_immersivevideostreaming_b200.rollout import PeerGroup, PolicyRollout, summarise_stats
     from mansy_immersivevideostreaming_b200.simulator import BatchSimulator, ViewportTiler
-    from mansy_immersivevideostreaming_b200.synth import synthetic_actions
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,7 +351,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = _capi.load_library()
+    _capi.load_library()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()                           # before warm-up: the timed regions are shorter than one sampling period
 
     n_local = args.envs_per_gpu
     n_global = n_local * world
@@ -253,40 +367,18 @@ def run_ours(args):
     slab_bytes = n_local * sim.obs_stride * 4
     slabs = max(4, -(-(320 << 20) // slab_bytes))                # rollout buffer > 2.5 x L2 (126 MB)
     roll = PolicyRollout(sim, policy, slabs, seed=1234)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    peers = None
+    if not args.nccl_gather:
+        peers = PeerGroup(n_local, local)        # world 1: a plain pack kernel; world > 1: one NVLink push kernel
 
     W = max(args.warmup, 3)
     K = args.steps
     roll.reserve_timing(K)
-    roll.run(W)
-    gather_episode_stats(sim)       # warm-up rollouts include their all-gather (first use loads torch's index kernels)
-    barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    launches0 = lib.mansy_kernel_launches()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    start.record()
-    roll.run(K)                                                  # ONE launch of the fused policy+step cluster kernel (all tiles resident)
-    stats = gather_episode_stats(sim)                            # the one collective of the rollout
-    stop.record()
-    barrier()
-    elapsed_ms = start.elapsed_time(stop)
-    launches = lib.mansy_kernel_launches() - launches0
+    elapsed_ms, stats, launches = timed_rollout(roll, sim, peers, K, W, world)
     # per-kernel durations for the rooflines: the same K steps again with CUDA events around every launch on the
     # launching stream (events between the launches serialise them, so this pass is not the one `value` is from)
     roll.run(K, timed=True)
-    barrier()
-    if world > 1:
-        tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tmax.item())
-    clk = clocks.stop() if rank == 0 else None
+    torch.cuda.synchronize()
     policy_sum, step_sum, timed_steps = roll.kernel_ms()
     policy_ms, step_ms = policy_sum / timed_steps, step_sum / timed_steps
     summary = summarise_stats(stats)
@@ -299,20 +391,29 @@ def run_ours(args):
     host = e2e_roll.make_host_buffers(host_slabs=8)              # 8 x 12.9 MB pinned ring
     e2e_steps = max(20, min(K, 100))
     e2e_roll.run_host(5, host)
-    barrier()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_roll.run_host(e2e_steps, host)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        tmax = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_s = float(tmax.item())
+    e2e_s = _max_over_ranks(time.perf_counter() - t0, world)
     h2d, d2h = e2e_roll.host_bytes_per_step()
+    e2e_sim.close()
+    del e2e_roll, host
 
-    sweep = None
-    if args.sweep and rank == 0:
-        sweep = simulator_sweep(tables, local)
+    # ---- the other BASELINE configs, each a short measurement of its own (every rank takes part) ----------------
+    extra = {}
+    if not args.no_extras:
+        sim.close()
+        del roll
+        torch.cuda.empty_cache()
+        extra["configs[2]"] = config3_section(args, tiler, policy, rank, world, local)
+        extra["configs[3]"] = {"what": "simulator-only sweep, hashed in-kernel actions, observation materialised, one launch per "
+                                       "lock-step, fresh slab per step; every rank runs its own shard, value = all ranks",
+                               "entries": simulator_sweep(tables, local, world)}
+        extra["configs[4]"] = config5_section(args, tables, policy, tiler, rank, world, local)
+    clk = clocks.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -320,7 +421,7 @@ def run_ours(args):
         return
     hbm_gbs, tflops, peak_src = measured_peaks()
     value = n_global * K / (elapsed_ms * 1e-3)
-    fused = launches == 1
+    fused = launches <= 2                        # the fused rollout kernel + the gather kernel
     # fused kernel: the step's algorithmic bytes (3 513 B) + the policy's outputs (action, logp, value,
     # logits row: 76 B); the observation rows the policy re-reads were written one phase earlier and are not counted
     fused_bytes = n_local * (BYTES_PER_STEP_MANSY + 76)
@@ -339,9 +440,12 @@ def run_ours(args):
                          "(> L2 126 MB): every step writes a slab last touched >2.5 L2-sizes ago",
                    "tables": "24 videos x 60 chunks, 1440 viewport pairs, 40 traces (SURVEY.md 8(d))",
                    "timed": ("ONE launch of the fused cluster kernel: K x (tcgen05 split-K policy forward + sample + simulator "
-                             "step per 128-env tile) (mansy_rollout_policy) + 1 all-gather of episode stats") if fused else
-                            ("K x (tcgen05 policy forward+sample launch, simulator step launch) driven from C "
-                             "(mansy_rollout_policy, programmatic dependent launch) + 1 all-gather of episode stats"),
+                             "step per 128-env tile) (mansy_rollout_policy)" if fused else
+                             "K x (tcgen05 policy forward+sample launch, simulator step launch) driven from C "
+                             "(mansy_rollout_policy, programmatic dependent launch)")
+                            + (" + the per-rollout exchange of episode totals: one kernel storing into every peer's mailbox over "
+                               "NVLink (mansy_peer_allgather_stats)" if peers is not None else
+                               " + 1 NCCL all-gather of episode totals"),
                    "kernel_timing": "roofline launch durations: a second pass of the same K steps with CUDA events "
                                     "around every launch on the launching stream (serialised launches)"},
         "roofline": ({"bound": "hbm", "achieved": fused_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": fused_gbs / hbm_gbs,
@@ -350,7 +454,7 @@ def run_ours(args):
                       "kernel": "policy_tc4_kernel<fused> (policy + sample + simulator step, K steps per launch)",
                       "bytes_per_launch": fused_bytes * K, "avg_launch_ms": elapsed_ms, "peak_source": peak_src,
                       "note": "4096 envs move 14.7 MB per step (2.2 us of HBM time): the step is latency-bound, see "
-                              "roofline_step_kernel / simulator_sweep for the stand-alone kernel at HBM-filling sizes"}
+                              "roofline_step_kernel / configs[3] for the stand-alone kernel at HBM-filling sizes"}
                      if fused else
                      {"bound": "hbm", "achieved": step_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": step_gbs / hbm_gbs,
                       "traffic": None, "kernel": "step_kernel<MANSY>", "bytes_per_launch": n_local * BYTES_PER_STEP_MANSY,
@@ -372,12 +476,8 @@ def run_ours(args):
         "clocks": clk,
         "rollout_summary": summary,
     }
-    if sweep:
-        line["simulator_sweep"] = sweep
-    if not args.no_mtio:
-        sim.close(); e2e_sim.close()
-        del roll, e2e_roll, host
-        torch.cuda.empty_cache()
+    line.update(extra)
+    if not args.no_extras and not args.no_mtio:
         line["expert_mpc"] = expert_section(tables, local, n_local)
         line["viewport_prediction"] = mtio_section(local, args.mtio_samples,
                                                    cpu_seconds=0.0 if (world > 1 or args.no_cpu_baseline) else 6.0)
@@ -386,6 +486,85 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def config3_section(args, tiler, policy, rank, world, local):
+    """BASELINE configs[2]: 8,192 envs per GPU, one Dirichlet QoE preference vector per environment (65,536 envs at 8 GPUs)."""
+    import torch
+    from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, REWARD_QOE
+    from mansy_immersivevideostreaming_b200.rollout import PeerGroup, PolicyRollout
+    from mansy_immersivevideostreaming_b200.simulator import BatchSimulator
+    n_local = 8192
+    n_global = n_local * world
+    tables = workload_tables(tiler.chunk_masks, n_global, diverse_qoe=True)
+    sim = BatchSimulator(tables, n_local, OBS_MODE_MANSY, REWARD_QOE, seed=0, worker_num=n_global,
+                         env_offset=rank * n_local, device=local)
+    slabs = max(4, -(-(320 << 20) // (n_local * sim.obs_stride * 4)))
+    roll = PolicyRollout(sim, policy, slabs, seed=1234)
+    peers = None if args.nccl_gather else PeerGroup(n_local, local)
+    K = max(20, min(args.steps, 200))
+    ms, _, launches = timed_rollout(roll, sim, peers, K, 5, world)
+    out = {"workload": "mansy_ppo_rollout_8192_envs_per_gpu_diverse_qoe", "envs": n_global, "envs_per_gpu": n_local, "steps": K,
+           "ms_per_step": ms / K, "value": n_global * K / (ms * 1e-3), "unit": UNIT, "gpu_launches": launches,
+           "qoe_vectors": n_global}
+    sim.close()
+    if peers is not None:
+        peers.close()
+    del roll
+    torch.cuda.empty_cache()
+    return out
+
+
+def config5_section(args, tables, policy, tiler, rank, world, local):
+    """BASELINE configs[4]: MTIO viewport prediction feeding the environments, 16,384 envs over the job's GPUs.  Per
+    lock-step and GPU: the predict.py mask pipeline (5 autoregressive steps -> 5 predicted points -> tile masks + IoU) for
+    the 16384/N environments of the shard, then one policy + simulator step of those environments."""
+    import numpy as np
+    import torch
+    from mansy_immersivevideostreaming_b200 import mtio as mo
+    from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, REWARD_QOE
+    from mansy_immersivevideostreaming_b200.mtio import ViewportTransformerMTIO
+    from mansy_immersivevideostreaming_b200.rollout import PolicyRollout
+    from mansy_immersivevideostreaming_b200.simulator import BatchSimulator
+    from mansy_immersivevideostreaming_b200 import synth
+    n_global = args.mtio_samples
+    n = max(128, n_global // world)
+    net = ViewportTransformerMTIO(device=f"cuda:{local}", max_batch=n).load_state_dict(mo.seeded_mtio_state_dict(3, bias=True))
+    hist, cur = mo.synthetic_history(n, 4 + rank)
+    h, c = torch.from_numpy(hist).cuda(local), torch.from_numpy(cur).cuda(local)
+    gt = torch.from_numpy(np.mod(cur + np.cumsum(np.random.default_rng(1 + rank).normal(0, 0.03, size=(n, 15, 2)), axis=1), 1.0)
+                          .astype(np.float32)).cuda(local)
+    t = tables.with_samples(synth.per_env_samples(tables, n * world))
+    sim = BatchSimulator(t, n, OBS_MODE_MANSY, REWARD_QOE, seed=0, worker_num=n * world, env_offset=rank * n, device=local)
+    roll = PolicyRollout(sim, policy, 4, seed=1234)
+    for _ in range(3):
+        net.predict_chunk_masks(h, c, gt, tiler)
+        roll.run(1)
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+    reps = 10
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(reps):
+        net.predict_chunk_masks(h, c, gt, tiler)
+    e1.record()
+    for _ in range(reps):
+        net.predict_chunk_masks(h, c, gt, tiler)
+        roll.run(1)
+    e2.record()
+    torch.cuda.synchronize()
+    ms_masks = _max_over_ranks(e0.elapsed_time(e1) / reps, world)
+    ms_chain = _max_over_ranks(e1.elapsed_time(e2) / reps, world)
+    out = {"workload": f"mtio_masks_then_rollout_step_{n}_envs_per_gpu", "envs": n * world, "envs_per_gpu": n,
+           "mask_pipeline_ms": ms_masks, "mask_pipeline_samples_per_s": n * world / (ms_masks * 1e-3),
+           "chain_ms_per_step": ms_chain, "value": n * world / (ms_chain * 1e-3), "unit": "chunk-steps/s with an on-line viewport prediction per step"}
+    sim.close(); net.close()
+    del roll
+    torch.cuda.empty_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -544,9 +723,9 @@ def run_mtio(args):
         dist.destroy_process_group()
 
 
-def simulator_sweep(tables, device_index):
-    """Simulator-only kernel at growing env counts (hashed in-kernel actions, observation
-    materialised, one launch per step, fresh slab per step)."""
+def simulator_sweep(tables, device_index, world=1, sizes=(65536, 1048576)):
+    """Simulator-only kernel at HBM-filling env counts (hashed in-kernel actions, observation
+    materialised, one launch per step, fresh slab per step), both observation layouts."""
     import torch
     from mansy_immersivevideostreaming_b200 import synth
     from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, OBS_MODE_SIMPLE, REWARD_QOE
@@ -554,7 +733,7 @@ def simulator_sweep(tables, device_index):
     hbm_gbs, _, _ = measured_peaks()
     out = []
     for mode, name, bytes_per_step in ((OBS_MODE_MANSY, "mansy", 3513), (OBS_MODE_SIMPLE, "simple_rl", 1805)):
-        for n in (4096, 65536, 262144, 1048576):
+        for n in sizes:
             t = tables.with_samples(synth.per_env_samples(tables, n))
             sim = BatchSimulator(t, n, mode, REWARD_QOE, seed=0, device=device_index)
             slab = n * sim.obs_stride * 4
@@ -574,11 +753,13 @@ def simulator_sweep(tables, device_index):
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
-            gbs = n * bytes_per_step / (ms * 1e-3) / 1e9
-            out.append({"env": name, "envs": n, "ms_per_step": ms, "chunk_steps_per_s": n / (ms * 1e-3),
-                        "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_gbs})
+            gbs = n * bytes_per_step / (ms * 1e-3) / 1e9              # this GPU's kernel against this GPU's HBM peak
+            ms_all = _max_over_ranks(ms, world)
+            out.append({"env": name, "envs_per_gpu": n, "ms_per_step": ms_all, "chunk_steps_per_s": world * n / (ms_all * 1e-3),
+                        "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_gbs, "bytes_per_chunk_step": bytes_per_step})
             sim.close()
             del obs
+            torch.cuda.empty_cache()
     return out
 
 

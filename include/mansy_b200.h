@@ -185,6 +185,32 @@ int mansy_rollout_random(mansy_handle_t h, int32_t n_steps, uint64_t seed, int64
  * running totals for the per-rollout all-gather): stats_dev is [n_envs][MANSY_STATS_DOUBLES]. */
 int mansy_episode_stats(mansy_handle_t h, double *stats_dev, void *stream);
 int mansy_stats_clear(mansy_handle_t h, void *stream);
+/* The six running totals a rollout exchanges (MANSY_STAT_TOT_SUM_QOE .. MANSY_STAT_TOT_EPISODES) packed as
+ * totals_dev[n_envs][6] by one small kernel: the send buffer of the per-rollout all-gather. */
+int mansy_episode_totals(mansy_handle_t h, double *totals_dev, void *stream);
+
+/*
+ * Peer group: the per-rollout all-gather of episode totals as ONE kernel over NVLink peer memory, and a
+ * device-side barrier (csrc/mansy_peer.cu).  One process per GPU; every rank creates a mailbox, exports its CUDA
+ * IPC handle (MANSY_PEER_HANDLE_BYTES bytes), the caller exchanges the handles out of band (torch.distributed
+ * all_gather in rollout.PeerGroup) and passes all `world` of them, rank-ordered, to mansy_peer_connect.
+ * Replaces nothing in the reference (it has no multi-device path); it is the B200 form of
+ * "a single allgather of episode returns and QoE statistics per rollout" (BASELINE.json north_star).
+ *   slot_bytes: bytes each rank contributes per gather = n_envs_local * 6 * 8.
+ *   mansy_peer_allgather_stats: *gathered_dev (device pointer on this GPU, valid until the gather after the next
+ *   one) holds [world * n_envs_local][6] float64 in rank order once the stream has passed the call.
+ *   Every rank must issue the same sequence of barrier / gather calls.  A wait that sees no peer for ~4 s gives
+ *   up and raises the flag mansy_peer_timed_out reports (the data of that gather is then incomplete).
+ */
+#define MANSY_PEER_HANDLE_BYTES 64
+typedef struct mansy_peer *mansy_peer_t;
+int mansy_peer_create(int32_t world, int32_t rank, int64_t slot_bytes, int device, mansy_peer_t *out);
+int mansy_peer_export(mansy_peer_t p, void *handle_out);
+int mansy_peer_connect(mansy_peer_t p, const void *all_handles);
+int mansy_peer_barrier(mansy_peer_t p, void *stream);
+int mansy_peer_allgather_stats(mansy_peer_t p, mansy_handle_t h, void *stream, const double **gathered_dev);
+int mansy_peer_timed_out(mansy_peer_t p, int32_t *flag_host);
+int mansy_peer_destroy(mansy_peer_t p);
 
 /* Field-of-view -> tile masks with per-chunk OR and IoU
  * (viewport_prediction/utils/common.py:37-58,83-127; viewport_prediction/predict.py:33-48).

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmansy_b200.so")
 
 AUX_DOUBLES = 16
 STATS_DOUBLES = 16
+TOTALS_DOUBLES = 6          # mansy_episode_totals / mansy_peer_allgather_stats columns
+PEER_HANDLE_BYTES = 64
 
 
 # csrc/mansy_sim.cuh EnvState (one 128-byte record per environment)
@@ -140,6 +142,14 @@ SIGNATURES = {
     "mansy_rollout_random": (C.c_int, [_vp, C.c_int32, C.c_uint64, C.c_int64, C.c_int32, C.POINTER(Out), _vp]),
     "mansy_episode_stats": (C.c_int, [_vp, _vp, _vp]),
     "mansy_stats_clear": (C.c_int, [_vp, _vp]),
+    "mansy_episode_totals": (C.c_int, [_vp, _vp, _vp]),
+    "mansy_peer_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int, C.POINTER(_vp)]),
+    "mansy_peer_export": (C.c_int, [_vp, _vp]),
+    "mansy_peer_connect": (C.c_int, [_vp, _vp]),
+    "mansy_peer_barrier": (C.c_int, [_vp, _vp]),
+    "mansy_peer_allgather_stats": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "mansy_peer_timed_out": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    "mansy_peer_destroy": (C.c_int, [_vp]),
     "mansy_state_snapshot": (C.c_int, [_vp, _vp, _vp]),
     "mansy_error_flag": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "mansy_expert_actions": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp]),

@@ -116,6 +116,9 @@ struct TcState {
   int split = 0;               // 0 = by batch size, 1 = one CTA per 128-env tile, 4 = split-K cluster of 4 CTAs per tile
   float4 *scratch = nullptr;   // partial-sum exchange of the cluster kernel (128 KB per rank and tile), grown on demand
   int scratch_tiles = 0;
+  // observation tensor maps are encoded once per (pointer, rows, stride): a rollout buffer is reused call after call
+  struct ObsMap { const float *ptr = nullptr; uint64_t rows = 0, stride = 0; CUtensorMap map; } obs_maps[4];
+  int obs_map_next = 0;
 };
 
 
@@ -1213,6 +1216,21 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
   return MANSY_OK;
 }
 
+// Tensor map of an observation tensor [rows][obs_floats] (row stride `stride` floats), cached per policy.
+static int obs_map_for(mansy_policy *p, const float *ptr, uint64_t rows, uint64_t stride, const CUtensorMap **out) {
+  TcState *st = p->tc;
+  for (auto &m : st->obs_maps)
+    if (m.ptr == ptr && m.rows == rows && m.stride == stride) { *out = &m.map; return MANSY_OK; }
+  TcState::ObsMap &m = st->obs_maps[st->obs_map_next];
+  st->obs_map_next = (st->obs_map_next + 1) % 4;
+  m.ptr = nullptr;
+  int rc = make_map(&m.map, ptr, (uint64_t)st->obs_floats, rows, stride, 128);
+  if (rc) return rc;
+  m.ptr = ptr; m.rows = rows; m.stride = stride;
+  *out = &m.map;
+  return MANSY_OK;
+}
+
 // Exchange buffer of the cluster kernel: (re)allocated when a larger batch shows up (not stream-ordered: callers
 // that time launches warm up first).
 static int ensure_scratch(mansy_policy *p, int n_tiles) {
@@ -1259,9 +1277,10 @@ int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs
   if (reinterpret_cast<uintptr_t>(obs_dev) & 15) return set_error(MANSY_E_INVALID, "obs must be 16-byte aligned");
   if (logits_dev && (reinterpret_cast<uintptr_t>(logits_dev) & 15)) return set_error(MANSY_E_INVALID, "logits must be 16-byte aligned");
   if (n == 0) return MANSY_OK;
-  CUtensorMap map_obs;
-  int rc = make_map(&map_obs, obs_dev, (uint64_t)p->tc->obs_floats, (uint64_t)n, (uint64_t)obs_stride, 128);
+  const CUtensorMap *map_obs_p = nullptr;
+  int rc = obs_map_for(p, obs_dev, (uint64_t)n, (uint64_t)obs_stride, &map_obs_p);
   if (rc) return rc;
+  const CUtensorMap &map_obs = *map_obs_p;
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.n = n; a.n_tiles = (n + 127) / 128;
@@ -1355,9 +1374,10 @@ int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t
   cfg.stream = s;
   // (the cluster shape is compiled into the kernel: __cluster_dims__)
 
-  CUtensorMap map_obs;     // all slabs as one row-major tensor: row = slab * n + env
-  int rc = make_map(&map_obs, b->obs, (uint64_t)p->tc->obs_floats, (uint64_t)n * (uint64_t)b->slabs, (uint64_t)b->obs_stride, 128);
+  const CUtensorMap *map_obs_p = nullptr;     // all slabs as one row-major tensor: row = slab * n + env
+  int rc = obs_map_for(p, b->obs, (uint64_t)n * (uint64_t)b->slabs, (uint64_t)b->obs_stride, &map_obs_p);
   if (rc) return rc;
+  const CUtensorMap &map_obs = *map_obs_p;
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.n = n; a.n_tiles = n_tiles;

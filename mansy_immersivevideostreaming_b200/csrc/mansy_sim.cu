@@ -46,6 +46,14 @@ int set_error(int code, const std::string &msg) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// Entry points run on the handle's device whatever the caller's current device is (a process driving several GPUs).
+cudaError_t use_device(int device) {
+  int cur = -1;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e != cudaSuccess) return e;
+  return cur == device ? cudaSuccess : cudaSetDevice(device);
+}
+
 }  // namespace mansy
 
 #include "mansy_step.cuh"  // StepArgs, step_env, emit_obs, reset_episode, finish_episode (device code)
@@ -95,11 +103,16 @@ step_kernel(const __grid_constant__ SimDev S, const __grid_constant__ StepArgs A
   // state, history) may have been written by the kernels before us.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int i = blockIdx.x * kEnvsPerBlock + (threadIdx.x >> 3);   // output row
-  const bool live = i < A.n;                                       // lanes past the end stay for the warp votes below
+  bool live = i < A.n;                                             // lanes past the end stay for the warp votes below
   const int sub = threadIdx.x & 7;
   const unsigned gmask = group_mask();
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int e = live ? (A.env_ids ? __ldg(A.env_ids + i) : i) : 0;
+  int e = live ? (A.env_ids ? __ldg(A.env_ids + i) : i) : 0;
+  if (e < 0 || e >= S.n_envs) {            // the host wrappers validate ids (the reference raises IndexError); never index out of range
+    if (sub == 0) atomicExch(S.error_flag, 2);
+    live = false;
+    e = 0;
+  }
 
   EnvState st;
   float slot[8];
@@ -127,6 +140,10 @@ reset_kernel(const __grid_constant__ SimDev S, const int32_t *__restrict__ env_i
   const int sub = threadIdx.x & 7;
   const unsigned gmask = group_mask();
   const int e = env_ids ? __ldg(env_ids + i) : i;
+  if (e < 0 || e >= S.n_envs) {
+    if (sub == 0) atomicExch(S.error_flag, 2);
+    return;
+  }
   EnvState st;
   load_state(S, e, st);
   reset_episode(S, st);
@@ -269,14 +286,19 @@ __global__ void copy_i32_kernel(int32_t *__restrict__ dst, const int32_t *__rest
   __threadfence_system();
 }
 
-__global__ void seed_kernel(const SimDev S, int32_t seed) {
+__global__ void seed_kernel(const SimDev S, int32_t seed, int full) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= S.n_envs) return;
-  EnvState st;
-  memset(&st, 0, sizeof(st));
-  // mansy_env.py:253-256 with the vector env handing env k the seed `seed + k`
+  // mansy_env.py:253-256 with the vector env handing env k the seed `seed + k`: seed() only moves worker_id, a
+  // running episode is left alone (`full` = the state wipe of mansy_create)
   long long wid = ((long long)seed + S.env_offset + e) % S.worker_num;
   if (wid < 0) wid += S.worker_num;
+  if (!full) {
+    S.state[e].cursor = (int32_t)wid;
+    return;
+  }
+  EnvState st;
+  memset(&st, 0, sizeof(st));
   st.cursor = (int32_t)wid;
   st.flags = kFlagFinished | (kNoAction << 8);     // must be reset before the first step
   st.end_chunk = S.startup_download + 1;
@@ -377,6 +399,10 @@ struct mansy_sim {
 };
 constexpr int kCopyRing = 64;
 
+namespace mansy {
+const SimDev *sim_dev_of(mansy_handle_t h) { return &h->dev; }    // mansy_peer.cu packs the statistics rows
+}
+
 namespace {
 
 template <typename T>
@@ -465,6 +491,8 @@ int ensure_staging(mansy_sim *h) {
 }
 
 }  // namespace
+
+static int launch_seed(mansy_handle_t h, int32_t seed, int full, void *stream);
 
 extern "C" {
 
@@ -611,7 +639,7 @@ int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, ma
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { mansy_destroy(h); return set_error(MANSY_E_CUDA, "cudaMemset failed"); }
   }
 #undef MANSY_TRY
-  rc = mansy_seed(h, cfg->seed, nullptr);
+  rc = launch_seed(h, cfg->seed, 1, nullptr);
   if (rc) { mansy_destroy(h); return rc; }
   cudaError_t e = cudaStreamSynchronize(nullptr);
   if (e != cudaSuccess) { mansy_destroy(h); return set_error(MANSY_E_CUDA, cudaGetErrorString(e)); }
@@ -631,18 +659,28 @@ int mansy_destroy(mansy_handle_t h) {
   return MANSY_OK;
 }
 
-int mansy_seed(mansy_handle_t h, int32_t seed, void *stream) {
-  if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+}  // extern "C"
+
+static int launch_seed(mansy_handle_t h, int32_t seed, int full, void *stream) {
   const int threads = 256, grid = (h->dev.n_envs + threads - 1) / threads;
-  seed_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(h->dev, seed);
+  seed_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(h->dev, seed, full);
   count_launch();
   MANSY_CUDA(cudaGetLastError());
   return MANSY_OK;
 }
 
+extern "C" {
+
+int mansy_seed(mansy_handle_t h, int32_t seed, void *stream) {
+  if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  MANSY_CUDA(use_device(h->device));
+  return launch_seed(h, seed, 0, stream);
+}
+
 int mansy_reset(mansy_handle_t h, const int32_t *env_ids_dev, int32_t n, float *obs_dev, int64_t obs_stride,
                 void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  MANSY_CUDA(use_device(h->device));
   if (n < 0 || (!env_ids_dev && n != h->dev.n_envs))
     return set_error(MANSY_E_INVALID, "n must equal n_envs when env_ids is NULL");
   if (n == 0) return MANSY_OK;
@@ -666,6 +704,7 @@ int mansy_reset(mansy_handle_t h, const int32_t *env_ids_dev, int32_t n, float *
 int mansy_step(mansy_handle_t h, const int32_t *actions_dev, const int32_t *env_ids_dev, int32_t n, int32_t auto_reset,
                const mansy_out_t *out, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  MANSY_CUDA(use_device(h->device));
   if (!actions_dev) return set_error(MANSY_E_INVALID, "actions is NULL");
   if (n < 0 || (!env_ids_dev && n != h->dev.n_envs))
     return set_error(MANSY_E_INVALID, "n must equal n_envs when env_ids is NULL");
@@ -681,6 +720,7 @@ int mansy_step(mansy_handle_t h, const int32_t *actions_dev, const int32_t *env_
 int mansy_rollout_random(mansy_handle_t h, int32_t n_steps, uint64_t seed, int64_t step0, int32_t per_step_outputs,
                          const mansy_out_t *out, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  MANSY_CUDA(use_device(h->device));
   if (n_steps < 1) return set_error(MANSY_E_INVALID, "n_steps must be >= 1");
   int rc = check_out(h, out);
   if (rc) return rc;
@@ -695,6 +735,7 @@ int mansy_rollout_random(mansy_handle_t h, int32_t n_steps, uint64_t seed, int64
 int mansy_step_host(mansy_handle_t h, const int32_t *actions_host, int32_t auto_reset, float *obs_host,
                     float *reward_host, uint8_t *done_host, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  MANSY_CUDA(use_device(h->device));
   if (!actions_host) return set_error(MANSY_E_INVALID, "actions is NULL");
   int rc = ensure_staging(h);
   if (rc) return rc;
@@ -718,6 +759,7 @@ int mansy_step_host(mansy_handle_t h, const int32_t *actions_host, int32_t auto_
 
 int mansy_reset_host(mansy_handle_t h, float *obs_host, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  MANSY_CUDA(use_device(h->device));
   int rc = ensure_staging(h);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -743,6 +785,7 @@ int mansy_rollout_reserve_timing(mansy_handle_t h, int32_t n_steps) {
 int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout_t *b, int32_t n_steps, int64_t t0,
                          uint64_t seed, int32_t flags, void *stream) {
   if (!h || !p || !b) return set_error(MANSY_E_INVALID, "NULL argument");
+  MANSY_CUDA(use_device(h->device));
   if (n_steps < 0 || t0 < 0) return set_error(MANSY_E_INVALID, "n_steps / t0 must be >= 0");
   if (b->slabs < 2) return set_error(MANSY_E_INVALID, "a rollout needs at least 2 observation slabs");
   if (!b->obs || !b->actions || !b->logp || !b->value || !b->reward || !b->done || !b->logits)
@@ -798,6 +841,7 @@ int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout
 int mansy_rollout_policy_host(mansy_handle_t h, mansy_policy_t p, const mansy_rollout_t *b, const mansy_rollout_host_t *host,
                               int32_t n_steps, int64_t t0, uint64_t seed, int32_t flags, void *stream) {
   if (!h || !p || !b || !host) return set_error(MANSY_E_INVALID, "NULL argument");
+  MANSY_CUDA(use_device(h->device));
   if (n_steps < 0 || t0 < 0) return set_error(MANSY_E_INVALID, "n_steps / t0 must be >= 0");
   if (b->slabs < 2 || host->host_slabs < 1) return set_error(MANSY_E_INVALID, "need >= 2 device slabs and >= 1 host slab");
   if (!b->obs || !b->actions || !b->logp || !b->value || !b->reward || !b->done || !b->logits || !host->obs ||
@@ -890,6 +934,7 @@ int mansy_rollout_kernel_ms(mansy_handle_t h, double *policy_ms, double *step_ms
 
 int mansy_episode_stats(mansy_handle_t h, double *stats_dev, void *stream) {
   if (!h || !stats_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  MANSY_CUDA(use_device(h->device));
   MANSY_CUDA(cudaMemcpyAsync(stats_dev, h->dev.stats, (size_t)h->dev.n_envs * MANSY_STATS_DOUBLES * sizeof(double),
                              cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return MANSY_OK;
@@ -897,6 +942,7 @@ int mansy_episode_stats(mansy_handle_t h, double *stats_dev, void *stream) {
 
 int mansy_stats_clear(mansy_handle_t h, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  MANSY_CUDA(use_device(h->device));
   const size_t n = (size_t)h->dev.n_envs * MANSY_STATS_DOUBLES;
   stats_clear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(h->dev.stats, n);
   count_launch();
@@ -906,6 +952,7 @@ int mansy_stats_clear(mansy_handle_t h, void *stream) {
 
 int mansy_expert_actions(mansy_handle_t h, int32_t horizon, int32_t *actions_dev, double *best_value_dev, void *stream) {
   if (!h || !actions_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  MANSY_CUDA(use_device(h->device));
   if (horizon < 1 || horizon > kExpertMaxHorizon) return set_error(MANSY_E_INVALID, "horizon must be 1..6");
   expert_mpc_kernel<<<(unsigned)h->dev.n_envs, kExpertThreads, 0, static_cast<cudaStream_t>(stream)>>>(h->dev, horizon, actions_dev,
                                                                                                        best_value_dev);
@@ -916,6 +963,7 @@ int mansy_expert_actions(mansy_handle_t h, int32_t horizon, int32_t *actions_dev
 
 int mansy_state_snapshot(mansy_handle_t h, void *state_dev, void *stream) {
   if (!h || !state_dev) return set_error(MANSY_E_INVALID, "NULL argument");
+  MANSY_CUDA(use_device(h->device));
   MANSY_CUDA(cudaMemcpyAsync(state_dev, h->dev.state, (size_t)h->dev.n_envs * sizeof(EnvState),
                              cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return MANSY_OK;
@@ -923,6 +971,7 @@ int mansy_state_snapshot(mansy_handle_t h, void *state_dev, void *stream) {
 
 int mansy_error_flag(mansy_handle_t h, int32_t *flag_host) {
   if (!h || !flag_host) return set_error(MANSY_E_INVALID, "NULL argument");
+  MANSY_CUDA(use_device(h->device));
   MANSY_CUDA(cudaMemcpy(flag_host, h->dev.error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost));
   return MANSY_OK;
 }

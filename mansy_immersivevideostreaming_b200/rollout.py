@@ -160,10 +160,84 @@ def broadcast_state_dict(sd, src: int = 0, device=None, group=None):
     return out
 
 
-def gather_episode_stats(sim: BatchSimulator, group=None) -> torch.Tensor:
-    """The one collective of a rollout: all-gather ``[N_local, 6]`` float64 episode statistics
-    (sum qoe, qoe1, qoe2, qoe3, steps, episodes per env) into ``[N_global, 6]`` on every rank."""
-    return all_gather_stats(sim.episode_stats()[:, list(STAT_COLUMNS)].contiguous(), group)
+class _DevArray:
+    """``__cuda_array_interface__`` over library-owned device memory (zero-copy ``torch.as_tensor``)."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+        self._owner = owner           # keeps the allocation alive
+
+
+class PeerGroup:
+    """The job's GPUs as a peer group: the per-rollout all-gather of episode totals as ONE kernel that stores into
+    every peer's mailbox over NVLink (CUDA IPC mapped memory) and a device-side barrier -- ``csrc/mansy_peer.cu``.
+    The 64-byte IPC handles are exchanged once through ``torch.distributed`` (any backend); afterwards nothing on the
+    gather path goes through a collective library.  ``world == 1`` needs no process group."""
+
+    def __init__(self, n_local: int, device: int, group=None):
+        import torch.distributed as dist
+        from . import _capi
+        self.lib = _capi.load_library()
+        on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if on else 1
+        self.rank = dist.get_rank(group) if on else 0
+        self.n_local, self.device = int(n_local), torch.device("cuda", device)
+        h = C.c_void_p()
+        check(self.lib.mansy_peer_create(self.world, self.rank, self.n_local * _capi.TOTALS_DOUBLES * 8, device, C.byref(h)))
+        self._h = h
+        if self.world > 1:
+            mine = (C.c_uint8 * _capi.PEER_HANDLE_BYTES)()
+            check(self.lib.mansy_peer_export(self._h, mine))
+            every = [None] * self.world
+            dist.all_gather_object(every, bytes(mine), group=group)
+            blob = (C.c_uint8 * (_capi.PEER_HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(every))
+            check(self.lib.mansy_peer_connect(self._h, blob))
+            dist.barrier(group)          # every rank has mapped every mailbox before the first store
+
+    def barrier(self, stream: Optional[int] = None) -> None:
+        """Device-side barrier over the group's GPUs on ``stream`` (no host synchronisation)."""
+        check(self.lib.mansy_peer_barrier(self._h, stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream))
+
+    def gather_episode_stats(self, sim: BatchSimulator) -> torch.Tensor:
+        """``[world * N_local, 6]`` float64 in rank order, a zero-copy view of this rank's mailbox (valid until the
+        gather after the next one)."""
+        ptr = C.c_void_p()
+        check(self.lib.mansy_peer_allgather_stats(self._h, sim._h, sim._stream(), C.byref(ptr)))
+        return torch.as_tensor(_DevArray(ptr.value, (self.world * self.n_local, 6), "<f8", self), device=self.device)
+
+    def timed_out(self) -> bool:
+        f = C.c_int32(0)
+        check(self.lib.mansy_peer_timed_out(self._h, C.byref(f)))
+        return bool(f.value)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.mansy_peer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gather_episode_stats(sim: BatchSimulator, group=None, peers: Optional[PeerGroup] = None,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The one exchange of a rollout: all-gather ``[N_local, 6]`` float64 episode totals (sum qoe, qoe1, qoe2, qoe3,
+    steps, episodes per env) into ``[N_global, 6]`` on every rank.  With ``peers`` it is one kernel over NVLink peer
+    memory (:class:`PeerGroup`); otherwise the totals are packed by one kernel and, when a process group is up,
+    exchanged with ``torch.distributed.all_gather_into_tensor`` into the preallocated ``out`` (NCCL on GPUs)."""
+    if peers is not None:
+        return peers.gather_episode_stats(sim)
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return sim.episode_totals(out)
+    local = sim.episode_totals()
+    if out is None:
+        out = torch.empty((dist.get_world_size(group) * local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out
 
 
 def summarise_stats(stats: torch.Tensor) -> Dict[str, float]:

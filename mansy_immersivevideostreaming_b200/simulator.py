@@ -114,10 +114,20 @@ class BatchSimulator:
         return None if t is None else t.data_ptr()
 
     def _ids(self, env_ids) -> Optional[torch.Tensor]:
+        """Device int32 ids of the envs a call touches.  Ids must be unique and in ``[0, n_envs)``: the kernels
+        index state / history / statistics rows with them (two lane groups on one id would race on its 128-byte
+        state line), so the host side raises ``IndexError`` / ``ValueError`` where the reference's list indexing would."""
         if env_ids is None:
             return None
-        ids = torch.as_tensor(env_ids, dtype=torch.int32, device=self.device).contiguous()
-        return ids
+        host = env_ids.detach().cpu().numpy() if isinstance(env_ids, torch.Tensor) else np.asarray(env_ids)
+        host = host.reshape(-1).astype(np.int64)
+        if host.size > self.n_envs:
+            raise ValueError(f"{host.size} env ids for {self.n_envs} environments")
+        if host.size and (host.min() < 0 or host.max() >= self.n_envs):
+            raise IndexError(f"env id out of range [0, {self.n_envs})")
+        if np.unique(host).size != host.size:
+            raise ValueError("env ids must be unique")
+        return torch.as_tensor(host.astype(np.int32), device=self.device).contiguous()
 
     # ------------------------------------------------------------------
     def seed(self, seed: int) -> None:
@@ -180,6 +190,14 @@ class BatchSimulator:
         """[N, 16] float64: last finished episode + totals (include/mansy_b200.h MANSY_STAT_*)."""
         out = torch.empty((self.n_envs, STATS_DOUBLES), dtype=torch.float64, device=self.device)
         check(self.lib.mansy_episode_stats(self._h, out.data_ptr(), self._stream()))
+        return out
+
+    def episode_totals(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[N, 6] float64 running totals (sum qoe, qoe1, qoe2, qoe3, steps, episodes): the per-rollout send buffer,
+        packed by one small kernel (``mansy_episode_totals``)."""
+        if out is None:
+            out = torch.empty((self.n_envs, _capi.TOTALS_DOUBLES), dtype=torch.float64, device=self.device)
+        check(self.lib.mansy_episode_totals(self._h, out.data_ptr(), self._stream()))
         return out
 
     def stats_clear(self) -> None:

@@ -232,42 +232,65 @@ def pack_from_reference_layout(config, dataset: str, network_dataset: str, video
     """
     cfg = sim_cfg or SimConfig.from_reference_config(config)
     R, TT = len(cfg.video_rates), cfg.tile_total_num
-    manifests = []
-    for v in videos:
-        path = os.path.join(config.video_datasets_dir[dataset], f"video{v}.json")
-        with open(path, "r", encoding="utf-8") as fh:
-            manifests.append(json.load(fh))
-    C = max(max(int(k) for k in m["Chunks"].keys()) + 1 for m in manifests)
     V, U = len(videos), len(users)
+    qoe_w = np.asarray(qoe_weights, dtype=np.float32).reshape(-1, 3)
+    if mode == "test":
+        samples = environment_test_samples(V, U, len(traces), qoe_w.shape[0])
+    else:
+        samples = environment_samples(V, U, len(traces), qoe_w.shape[0])
+    # the reference only ever opens the files of sampled combinations (simulator.py:30-38 runs per episode), so a
+    # missing / short file of an unused (video, user) pair must not matter: load exactly the referenced ones
+    used_videos = sorted({int(s[0]) for s in samples})
+    used_pairs = sorted({(int(s[0]), int(s[1])) for s in samples})
+
+    manifests = {}
+    for vi in used_videos:
+        path = os.path.join(config.video_datasets_dir[dataset], f"video{videos[vi]}.json")
+        with open(path, "r", encoding="utf-8") as fh:
+            manifests[vi] = json.load(fh)
+    C = max(max(int(k) for k in m["Chunks"].keys()) + 1 for m in manifests.values())
     size = np.ones((V, C, R, TT), dtype=np.int32)
     quality = np.zeros((V, C, R, TT), dtype=np.float32)
-    video_time = np.zeros(V, dtype=np.int32)
-    for vi, m in enumerate(manifests):
+    filled = np.zeros((V, C), dtype=bool)
+    video_time = np.full(V, cfg.startup_download + 2, dtype=np.int32)      # unused videos: any valid value
+    for vi, m in manifests.items():
         video_time[vi] = int(m["Video_Time"])
         for k, info in m["Chunks"].items():
-            size[vi, int(k)] = np.asarray(info["size"], dtype=np.int64)
+            sz = np.asarray(info["size"])
+            if not np.issubdtype(sz.dtype, np.integer):
+                if not np.all(sz == np.rint(sz)):
+                    raise ValueError(f"video{videos[vi]}.json chunk {k}: tile sizes must be integers (simulator.py:100 sums them)")
+                sz = np.rint(sz)
+            size[vi, int(k)] = sz.astype(np.int64)
             quality[vi, int(k)] = np.asarray(info["quality"], dtype=np.float32)
+            filled[vi, int(k)] = True
 
-    lists = []
-    for v in videos:
-        for u in users:
-            path = os.path.join(config.viewport_datasets_dir[dataset], "prediction", f"video{v}", f"user{u}.pkl")
-            with open(path, "rb") as fh:
-                lists.append(pickle.load(fh))
-    CV = max(len(l) for l in lists)
+    lists = {}
+    for vi, ui in used_pairs:
+        path = os.path.join(config.viewport_datasets_dir[dataset], "prediction", f"video{videos[vi]}", f"user{users[ui]}.pkl")
+        with open(path, "rb") as fh:
+            lists[vi * U + ui] = pickle.load(fh)
+    CV = max(len(l) for l in lists.values())
     P = V * U
     vp_gt = np.zeros((P, CV), dtype=np.uint64)
     vp_pred = np.zeros((P, CV), dtype=np.uint64)
     vp_acc = np.zeros((P, CV), dtype=np.float64)
-    vp_start = np.zeros(P, dtype=np.int32)
-    vp_end = np.zeros(P, dtype=np.int32)
-    for p, l in enumerate(lists):
+    vp_start = np.full(P, cfg.startup_download + 1, dtype=np.int32)      # unused pairs: a valid one-chunk list, never read
+    vp_end = np.full(P, cfg.startup_download + 1, dtype=np.int32)
+    for p, l in lists.items():
         vp_start[p] = int(l[0][0])
         vp_end[p] = int(l[-1][0])       # hmdtrace.py:11 -- taken from the last entry, not a count
         for j, (chunk, gt, pred, acc) in enumerate(l):
             vp_gt[p, j] = mask_to_bits(gt)
             vp_pred[p, j] = mask_to_bits(pred)
             vp_acc[p, j] = float(acc)
+        # chunks an episode of this pair touches: startup+1 .. min(last viewport chunk, Video_Time - 1)
+        # (simulator.py:41-45); the reference raises KeyError from chunk_info[str(chunk)] when one is absent
+        vi = p // U
+        end = min(int(vp_end[p]), int(video_time[vi]) - 1)
+        for c in range(cfg.startup_download + 1, end + 1):
+            if c >= C or not filled[vi, c]:
+                raise KeyError(f"video{videos[vi]}.json has no chunk {c} (needed by user {users[p % U]})")
 
     tr = []
     for t in traces:
@@ -288,11 +311,6 @@ def pack_from_reference_layout(config, dataset: str, network_dataset: str, video
         trace[i, : len(x)] = x
         trace_len[i] = len(x)
 
-    qoe_w = np.asarray(qoe_weights, dtype=np.float32).reshape(-1, 3)
-    if mode == "test":
-        samples = environment_test_samples(V, U, len(traces), qoe_w.shape[0])
-    else:
-        samples = environment_samples(V, U, len(traces), qoe_w.shape[0])
     return SimTables(cfg=cfg, size=size, quality=quality, video_time=video_time, vp_gt=vp_gt, vp_pred=vp_pred,
                      vp_acc=vp_acc, vp_start=vp_start, vp_end=vp_end, trace=trace, trace_len=trace_len,
                      qoe_w=qoe_w, samples=samples, n_users=U, video_ids=np.asarray(videos),

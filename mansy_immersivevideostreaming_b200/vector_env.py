@@ -64,6 +64,7 @@ class B200VectorEnv:
         n_act = tables.cfg.action_space if obs_mode == OBS_MODE_MANSY else len(tables.cfg.video_rates)
         self.action_space = [_Discrete(n_act) for _ in range(self.env_num)]   # simple_rl_env.py:33 quirk kept
         self._obs = self.sim.new_obs()                                         # [N, stride] current observations
+        self._logged = np.zeros(self.env_num, dtype=np.int64)                  # episodes of each env already in the CSV
         self._closed = False
 
     def __len__(self) -> int:
@@ -74,11 +75,18 @@ class B200VectorEnv:
 
     # -- helpers -----------------------------------------------------------
     def _ids(self, id) -> Optional[np.ndarray]:
+        """tianshou passes an int, a list or an array of env indices; out-of-range ids raise ``IndexError`` like the
+        reference's ``self.workers[i]`` list indexing, duplicates ``ValueError`` (BatchSimulator._ids)."""
         if id is None:
             return None
         if np.isscalar(id):
             id = [id]
-        return np.asarray(id, dtype=np.int32).reshape(-1)
+        ids = np.asarray(id, dtype=np.int64).reshape(-1)
+        if ids.size and (ids.min() < 0 or ids.max() >= self.env_num):
+            raise IndexError(f"env id out of range [0, {self.env_num})")
+        if np.unique(ids).size != ids.size:
+            raise ValueError("env ids must be unique")
+        return ids.astype(np.int32)
 
     def _package(self, rows: torch.Tensor):
         if self.output == "torch":
@@ -105,17 +113,20 @@ class B200VectorEnv:
     def step(self, action, id=None):
         ids = self._ids(id)
         act = torch.as_tensor(np.asarray(action, dtype=np.int32).reshape(-1)) if not isinstance(action, torch.Tensor) else action
-        rows, rew, done = self.sim.step(act.to(self.sim.device), env_ids=ids, auto_reset=False)
-        idx = (torch.arange(self.env_num, device=rows.device) if ids is None
-               else torch.as_tensor(ids, dtype=torch.long, device=rows.device))
+        numpy_out = self.output == "numpy"
+        # numpy callers get the reward as the float64 the reference returns (qoe.py:33), not its float32 rounding
+        aux = self.sim.new_aux(self.env_num if ids is None else len(ids)) if numpy_out else None
+        rows, rew, done = self.sim.step(act.to(self.sim.device), env_ids=ids, auto_reset=False, aux=aux)
+        idx_h = np.arange(self.env_num) if ids is None else ids.astype(np.int64)
+        idx = torch.as_tensor(idx_h, dtype=torch.long, device=rows.device)
         self._obs[idx] = rows
         done_h = done.cpu().numpy().astype(bool)
         if done_h.any():
-            self._log_finished(np.asarray(idx.cpu())[done_h])
-        info = np.array([{"env_id": int(i)} for i in np.asarray(idx.cpu())], dtype=object)
-        if self.output == "torch":
+            self._log_finished(idx_h[done_h])
+        info = np.array([{"env_id": int(i)} for i in idx_h], dtype=object)
+        if not numpy_out:
             return self._package(rows), rew, done.bool(), info
-        return self._package(rows), rew.cpu().numpy().astype(np.float64), done_h, info
+        return self._package(rows), aux[:, 13].cpu().numpy(), done_h, info     # MANSY_AUX_REWARD (0 for an env already finished)
 
     def choose_actions(self, horizon: int = 4) -> np.ndarray:
         """The MPC expert's action for every environment (``ExpertEnv.choose_action``, envs/expert_env.py:358-422)."""
@@ -125,13 +136,18 @@ class B200VectorEnv:
     def _log_finished(self, env_ids: Sequence[int]) -> None:
         if self.log_path is None:
             return
-        stats = self.sim.episode_stats().cpu().numpy()
+        ids = torch.as_tensor(np.asarray(env_ids, dtype=np.int64), device=self.sim.device)
+        stats = self.sim.episode_stats()[ids].cpu().numpy()       # rows of the finished envs only
         if not os.path.exists(self.log_path):
             with open(self.log_path, "w", encoding="utf-8") as fh:
                 fh.write(LOG_HEADER)
         with open(self.log_path, "a", encoding="utf-8") as fh:
-            for e in env_ids:
-                s = stats[int(e)]
+            for e, s in zip(env_ids, stats):
+                # a finished env stepped again before its reset reports done once more without a new episode:
+                # one CSV row per FINISHED EPISODE (MANSY_STAT_TOT_EPISODES), like `_log` (mansy_env.py:225)
+                if int(s[11]) <= self._logged[int(e)]:
+                    continue
+                self._logged[int(e)] = int(s[11])
                 fh.write(episode_log_line(self.tables, int(s[5]), s[0], s[1], s[2], s[3], int(s[4])))
 
     def close(self) -> None:

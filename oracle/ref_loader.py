@@ -1,12 +1,14 @@
-"""Import the UNMODIFIED reference from /root/reference -- TEST INFRASTRUCTURE, build container only.
+"""Import the UNMODIFIED reference -- TEST INFRASTRUCTURE (tests, smoke(), bench.py's reference / cpu_baseline legs).
 
 The reference is pure Python but needs ``gym``, ``munch`` and ``prettytable``, none of which is
 installed here.  Minimal stand-ins for exactly the names the reference
-touches are registered in ``sys.modules`` before the import; the reference's own files are used
-where they lie and are never copied.  ``/root/reference`` does not exist on the GPU box: nothing
-that runs there (``-m gpu`` tests, ``smoke()``, ``bench.py``) may call this module -- it is used
-by ``oracle/make_golden.py`` and by container-only cross-check tests that skip when the
-reference tree is absent.
+touches are registered in ``sys.modules`` before the import.  Two sources, in this order:
+
+* ``/root/reference`` (build container): the reference's own files, used where they lie -- code AND datasets
+  (``oracle/make_golden*.py`` need the datasets);
+* ``oracle/_ref/mansy_reference.zip`` (``oracle/make_ref.py``: byte-for-byte members, git-ignored, shipped to the
+  GPU box by gpurun): code and the small shipped fixtures only, imported straight from the archive.  This is what
+  the GPU box uses, where ``/root/reference`` does not exist.
 """
 from __future__ import annotations
 
@@ -16,10 +18,45 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("MANSY_REFERENCE_ROOT", "/root/reference")
+ARCHIVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "mansy_reference.zip")
 
 
 def reference_available() -> bool:
+    """The full reference tree (code + datasets) is present (build container)."""
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "bitrate_selection", "envs"))
+
+
+def archive_available() -> bool:
+    return os.path.isfile(ARCHIVE)
+
+
+def code_available() -> bool:
+    return reference_available() or archive_available()
+
+
+def code_root() -> str:
+    """Directory (or zip path) that holds ``bitrate_selection/`` and ``viewport_prediction/``."""
+    if reference_available():
+        return REFERENCE_ROOT
+    if archive_available():
+        return ARCHIVE
+    raise RuntimeError(f"reference not found: neither {REFERENCE_ROOT} nor {ARCHIVE} (python -m oracle.make_ref) exists")
+
+
+def read_member(rel: str) -> bytes:
+    """Bytes of a reference file: ``rel`` relative to the reference root, or ``fixtures/<name>`` for the shipped
+    example-run files listed in oracle/make_ref.py."""
+    if archive_available():
+        import zipfile
+        with zipfile.ZipFile(ARCHIVE) as z:
+            return z.read(rel)
+    if reference_available():
+        if rel.startswith("fixtures/"):
+            from oracle.make_ref import _members
+            rel = {name: src for src, name in _members()}[rel]
+        with open(os.path.join(REFERENCE_ROOT, rel), "rb") as fh:
+            return fh.read()
+    raise RuntimeError("reference not available")
 
 
 def _install_stubs() -> None:
@@ -79,11 +116,11 @@ def load_reference() -> "_Ref":
     global _cached
     if _cached is not None:
         return _cached
-    if not reference_available():
-        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    root = code_root()
     _install_stubs()
     ref = _Ref()
-    bs = os.path.join(REFERENCE_ROOT, "bitrate_selection")
+    ref.root = root
+    bs = root + "/bitrate_selection"
     # The reference uses top-level package names (envs, simulators, utils, models); import the
     # bitrate-selection side first, then re-import `utils.common` of viewport_prediction under a
     # private name so both geometries are reachable.
@@ -107,10 +144,10 @@ def load_reference() -> "_Ref":
     bs_mods = {k: sys.modules.pop(k) for k in list(sys.modules)
                if k.split(".")[0] in ("envs", "simulators", "utils", "models")}
     ref._bs_mods = bs_mods      # keep alive
-    vp_common = os.path.join(REFERENCE_ROOT, "viewport_prediction", "utils", "common.py")
-    spec = importlib.util.spec_from_file_location("_ref_vp_common", vp_common)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
+    mod = types.ModuleType("_ref_vp_common")        # viewport_prediction/utils/common.py under a private name
+    mod.__file__ = root + "/viewport_prediction/utils/common.py"
+    src = read_member("viewport_prediction/utils/common.py") if root == ARCHIVE else open(mod.__file__, "rb").read()
+    exec(compile(src, mod.__file__, "exec"), mod.__dict__)
     ref.vp_common = mod
     sys.modules.update(saved)
     _cached = ref
