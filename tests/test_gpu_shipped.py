@@ -104,15 +104,16 @@ def test_shipped_logs_pin_the_cursor_per_reset_rule(tmp_path):
                                         seed=5, trace_len_range=(30, 50), short_tail_frac=0.0, vp_last_chunk=19)
         t = dataclasses.replace(t, video_ids=np.asarray(videos), user_ids=np.asarray(users), trace_ids=np.asarray(traces),
                                 qoe_w=np.asarray(qoe, dtype=np.float32)).with_samples(environment_samples(V, U, T, Q))
-        ep_len = int(min(t.vp_end.min(), t.video_time.min() - 1)) - scfg.startup_download     # every episode: chunks 6 .. end
         venv = B200VectorEnv(t, n_envs, OBS_MODE_MANSY, REWARD_QOE, seed=0, worker_num=n_envs, log_path=str(log))
         venv.seed(seed)                                        # run_mansy.py:55-56
         for _ in range(resets_before_play):
             venv.reset()
         rng = np.random.default_rng(0)
         for _ in range(n_rounds):
-            for _ in range(ep_len):
-                _, _, done, _ = venv.step(rng.integers(0, 15, size=n_envs))
+            done = np.zeros(n_envs, bool)
+            for _ in range(t.n_chunks):                        # a finished env stepped again stays finished (logged once)
+                _, _, d, _ = venv.step(rng.integers(0, 15, size=n_envs))
+                done |= d
             assert done.all()
             venv.reset(np.flatnonzero(done))                   # Collector: reset the finished ids
         venv.close()
