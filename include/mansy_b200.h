@@ -212,6 +212,13 @@ int mansy_peer_allgather_stats(mansy_peer_t p, mansy_handle_t h, void *stream, c
 int mansy_peer_timed_out(mansy_peer_t p, int32_t *flag_host);
 int mansy_peer_destroy(mansy_peer_t p);
 
+/* (viewport pair, chunk, action) outcome table: chunk bytes, viewport quality and intra-chunk variance -- everything
+ * of a step that depends only on the read-only tables and the action (utils/common.py:101-193, simulators/simulator.py:94-101,
+ * utils/qoe.py:23-28; the reference's ExpertEnv caches the same statistics, envs/expert_env.py:121-160) -- is tabulated
+ * at mansy_create by the step's own gather code, and steps read it back (bit-identical results) unless tile_versions
+ * are requested.  enable = 0 makes every step gather again (parity tests compare the two). */
+int mansy_set_outcome_table(mansy_handle_t h, int32_t enable);
+
 /* Field-of-view -> tile masks with per-chunk OR and IoU
  * (viewport_prediction/utils/common.py:37-58,83-127; viewport_prediction/predict.py:33-48).
  * gt_xy_dev / pred_xy_dev: float32 [n_chunks][points][2] normalised centres in [0,1];
@@ -293,6 +300,14 @@ int mansy_gae(const float *reward_dev, const float *value_dev, const uint8_t *do
 int mansy_policy_forward_tc(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
                             float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
                             int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, void *stream);
+
+/* mansy_policy_forward_tc for the CURRENT observations of simulator `h` (row i = environment i, all n_envs rows): the two
+ * 320-input FeatureNet branches (conv1d2 / conv1d3 over the next chunk's size and quality tables, models/mansy.py:15-16,
+ * 41-42; conv1d_2 of models/simple_rl.py) see rows of the simulator's read-only tables, so their share of the
+ * actor.fc | critic.fc pre-activation is looked up in a (video, chunk) table computed once per (policy, simulator) in exact
+ * fp32 instead of being recomputed per environment step.  The rollout entry points use the same path. */
+int mansy_policy_forward_tc_sim(mansy_policy_t p, mansy_handle_t h, const float *obs_dev, int64_t obs_stride, float *logits_dev,
+                                float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step, void *stream);
 
 /* Same launch with a profiling hook: timeline_dev (int64[512], may be NULL) receives SM-clock stamps of CTA 0:
  * [0..127] TMA issue per job, [128..255] operand arrival per job, [256..383] MMAs issued per job,
@@ -396,6 +411,8 @@ int mansy_selftest_fov_mask(int32_t x, int32_t y, int32_t width, int32_t height,
 int mansy_selftest_centre_to_pixel(float v, int32_t length);
 int mansy_selftest_download(const double *thr, int32_t trace_len, int64_t size, int32_t *cur_idx, double *cur_time,
                             double *buf, double *download_time, double *rebuffer);
+/* out[i] = ddiv_rcp(a[i], b[i], 1 / b[i]): the reciprocal-based division the kernels use (csrc/mansy_core.cuh); must equal a[i] / b[i] bit for bit */
+int mansy_selftest_ddiv_rcp(const double *a, const double *b, int64_t n, double *out);
 int mansy_selftest_hashed_action(uint64_t seed, uint64_t env, uint64_t step);
 
 /*

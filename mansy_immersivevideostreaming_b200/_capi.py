@@ -143,6 +143,7 @@ SIGNATURES = {
     "mansy_episode_stats": (C.c_int, [_vp, _vp, _vp]),
     "mansy_stats_clear": (C.c_int, [_vp, _vp]),
     "mansy_episode_totals": (C.c_int, [_vp, _vp, _vp]),
+    "mansy_set_outcome_table": (C.c_int, [_vp, C.c_int32]),
     "mansy_peer_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int, C.POINTER(_vp)]),
     "mansy_peer_export": (C.c_int, [_vp, _vp]),
     "mansy_peer_connect": (C.c_int, [_vp, _vp]),
@@ -162,6 +163,7 @@ SIGNATURES = {
     "mansy_policy_sample": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, C.c_int32, _vp, _vp, _vp]),
     "mansy_policy_forward_tc": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int64,
                                           C.c_int32, _vp, _vp, _vp]),
+    "mansy_policy_forward_tc_sim": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int64, _vp]),
     "mansy_policy_forward_tc_timeline": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int64,
                                                    C.c_int32, _vp, _vp, _vp, _vp]),
     "mansy_policy_tc_set_split": (C.c_int, [_vp, C.c_int32]),
@@ -179,6 +181,7 @@ SIGNATURES = {
     "mansy_selftest_centre_to_pixel": (C.c_int, [C.c_float, C.c_int32]),
     "mansy_selftest_download": (C.c_int, [_vp, C.c_int32, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double),
                                           C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mansy_selftest_ddiv_rcp": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "mansy_selftest_hashed_action": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64]),
     "mansy_mtio_create": (C.c_int, [C.POINTER(MtioWeights), C.c_int, C.c_int32, C.POINTER(_vp)]),
     "mansy_mtio_destroy": (C.c_int, [_vp]),

@@ -49,6 +49,29 @@ MANSY_HD double ddiv(double a, double b) {
   volatile double r = a / b; return r;
 #endif
 }
+// a / b, correctly rounded, from r = RN(1 / b) computed once on the host (Markstein's sequence: q = a * r refined
+// twice through the exact FMA residual).  With a correctly rounded reciprocal and a faithful quotient estimate the
+// last FMA rounds to RN(a / b), i.e. the result is bit-identical to an IEEE division (tests/test_capi_cpu.py checks
+// 10^7 random and near-midpoint cases per run against a / b through mansy_selftest_ddiv_rcp; a standalone run of
+// 6 x 10^8 cases found no mismatch).  Five dependent FMA-pipe operations instead of the ~30-instruction __ddiv_rn
+// sequence: divisions were 13 % of the simulator step's instructions and sit on its critical path.
+// Domain: finite a, finite b > 0 away from the over/underflow thresholds (throughputs, tile counts, rates).
+MANSY_HD double ddiv_rcp(double a, double b, double r) {
+#ifdef __CUDA_ARCH__
+  double q = __dmul_rn(a, r);
+  double e = __fma_rn(-b, q, a);
+  q = __fma_rn(e, r, q);
+  e = __fma_rn(-b, q, a);
+  return __fma_rn(e, r, q);
+#else
+  volatile double q = a * r;
+  volatile double e = fma(-b, q, a);
+  q = fma(e, r, q);
+  e = fma(-b, q, a);
+  volatile double out = fma(e, r, q);
+  return out;
+#endif
+}
 MANSY_HD float fsub(float a, float b) {
 #ifdef __CUDA_ARCH__
   return __fsub_rn(a, b);
@@ -194,6 +217,21 @@ MANSY_HD QoE qoe_from_sums(double vq, double sum_dev, double sum_m, double rebuf
   const double inter = first_step ? 0.0 : fabs(dsub(vqn, prev_vq));
   prev_vq = vqn;
   r.q1 = vqn;
+  r.q2 = rebuffer;
+  r.q3 = dadd(intra, inter);
+  r.qoe = dsub(dsub(dmul(w0, r.q1), dmul(w1, r.q2)), dmul(w2, r.q3));
+  return r;
+}
+
+// The same QoE from the per-(chunk, action) parts: q1 = vq / max_quality and intra = sum_dev / sum_m / max_quality
+// (qoe.py:23-28) are pure functions of the tables and the action; what a step adds is the rebuffer time and the
+// inter-chunk term (qoe.py:29-33).  Same operations in the same order as qoe_from_sums.
+MANSY_HD QoE qoe_from_parts(double q1, double intra, double rebuffer, bool first_step, double &prev_vq, double w0,
+                            double w1, double w2) {
+  QoE r;
+  const double inter = first_step ? 0.0 : fabs(dsub(q1, prev_vq));
+  prev_vq = q1;
+  r.q1 = q1;
   r.q2 = rebuffer;
   r.q3 = dadd(intra, inter);
   r.qoe = dsub(dsub(dmul(w0, r.q1), dmul(w1, r.q2)), dmul(w2, r.q3));

@@ -160,6 +160,62 @@ __global__ void policy_sample_kernel(const float *__restrict__ logits, int n, in
   if (logp) logp[e] = lp;
 }
 
+// One CTA per table row (video, chunk): thread t computes feature t of the memoised branches (t >> 7 selects the
+// branch: 0 = next-chunk sizes, 1 = next-chunk qualities) from the row of size_norm / qual_norm -- exactly what the
+// observation carries at those columns (mansy_step.cuh emit_obs_tables) -- then hidden unit t of actor.fc | critic.fc.
+__global__ void __launch_bounds__(256) policy_memo_kernel(const PolicyDev P, const float *__restrict__ size_norm,
+                                                          const float *__restrict__ qual_norm, int n_memo, int b0, int b1,
+                                                          float *__restrict__ memo) {
+  __shared__ float x[2 * kTableRow];
+  __shared__ float feat[2 * kHidden];
+  const int row = blockIdx.x, t = threadIdx.x;
+  for (int i = t; i < n_memo * kTableRow; i += 256)
+    x[i] = i < kTableRow ? __ldg(size_norm + (size_t)row * kTableRow + i) : __ldg(qual_norm + (size_t)row * kTableRow + i - kTableRow);
+  __syncthreads();
+  const int which = t >> 7, f = t & (kHidden - 1);
+  if (which < n_memo) {
+    const int b = which == 0 ? b0 : b1;
+    float acc = __ldg(P.b1 + b * kHidden + f);
+    const float *w = P.w1t + P.w_off[b] + f;
+    const float *xb = x + which * kTableRow;
+    for (int k = 0; k < kTableRow; ++k) acc = fmaf(__ldg(w + (size_t)k * kHidden), xb[k], acc);
+    feat[t] = leaky(acc);
+  }
+  __syncthreads();
+  float acc = 0.f;
+  for (int m = 0; m < n_memo; ++m) {
+    const int b = m == 0 ? b0 : b1;
+    const float *w = P.wfct + (size_t)b * kHidden * 256 + t;
+    for (int k = 0; k < kHidden; ++k) acc = fmaf(__ldg(w + (size_t)k * 256), feat[m * kHidden + k], acc);
+  }
+  memo[(size_t)row * 256 + t] = acc;
+}
+
+int policy_memo_for(mansy_policy *p, const SimDev &S, void *stream, const float **memo_out) {
+  *memo_out = nullptr;
+  int n_memo = 0, b[2] = {0, 0};
+  if (p->dev.kind == MANSY_OBS_MANSY && S.obs_mode == MANSY_OBS_MANSY) { n_memo = 2; b[0] = 1; b[1] = 2; }        // conv1d2, conv1d3
+  else if (p->dev.kind == MANSY_OBS_SIMPLE && S.obs_mode == MANSY_OBS_SIMPLE) { n_memo = 1; b[0] = 1; }           // conv1d_2
+  else return MANSY_OK;
+  const int rows = S.n_videos * S.n_chunks;
+  if (p->memo_key != S.uid || p->memo_rows != rows) {
+    if (p->memo_cap < rows) {
+      if (p->memo) { cudaDeviceSynchronize(); cudaFree(p->memo); p->memo = nullptr; p->memo_cap = 0; }
+      void *d = nullptr;
+      if (cudaMalloc(&d, (size_t)rows * 256 * sizeof(float)) != cudaSuccess) return set_error(MANSY_E_NOMEM, "cudaMalloc failed (policy memo)");
+      p->memo = static_cast<float *>(d);
+      p->memo_cap = rows;
+    }
+    p->memo_rows = rows;
+    policy_memo_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, S.size_norm, S.qual_norm, n_memo, b[0], b[1], p->memo);
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return set_error(MANSY_E_CUDA, "policy_memo_kernel launch failed");
+    p->memo_key = S.uid;
+  }
+  *memo_out = p->memo;
+  return MANSY_OK;
+}
+
 }  // namespace mansy
 
 using namespace mansy;
@@ -310,6 +366,7 @@ int mansy_policy_destroy(mansy_policy_t p) {
   if (!p) return MANSY_OK;
   cudaSetDevice(p->device);
   tc_destroy(p);
+  if (p->memo) cudaFree(p->memo);
   for (void *q : p->allocs) cudaFree(q);
   delete p;
   return MANSY_OK;

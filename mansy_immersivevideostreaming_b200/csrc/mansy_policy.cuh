@@ -81,6 +81,11 @@ struct mansy_policy {
   size_t smem_bytes = 0;
   std::vector<void *> allocs;
   mansy::TcState *tc = nullptr;
+  // Memoised table branches (policy_memo_for): the 320-input branches (next chunk sizes / qualities) see rows of the
+  // simulator's read-only tables, so their contribution to the hidden pre-activation is a function of (video, chunk)
+  float *memo = nullptr;            // [memo_rows][256]
+  uint64_t memo_key = 0;            // SimDev.uid of the simulator the table was built for
+  int memo_rows = 0, memo_cap = 0;
 };
 
 namespace mansy {
@@ -89,10 +94,17 @@ namespace mansy {
 int tc_create(mansy_policy *p, const mansy_policy_weights_t *w);
 void tc_destroy(mansy_policy *p);
 // Tensor-core forward launch shared by the C entry points and the rollout loops (mansy_policy_tc.cu).
+// `memo_sim` != NULL: the rows are the CURRENT observations of that simulator's environments (row i = env i); the
+// 320-input table branches then come from the (video, chunk) memo instead of the tensor pipe (policy_memo_for).
 int policy_forward_tc_launch(mansy_policy *p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
                              float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
                              int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
-                             int32_t timeline_cta, bool pdl, void *stream);
+                             int32_t timeline_cta, bool pdl, void *stream, const SimDev *memo_sim = nullptr);
+// Device table memo[video * n_chunks + chunk][256] for (policy, simulator tables): sum over the 320-input branches of
+// LeakyReLU(W1_b x_b + b1_b) . [actor.fc | critic.fc]_b^T in exact fp32, built on `stream` the first time the pair
+// is seen (and again when the policy meets another simulator).  *memo_out = NULL when the net has no such branch
+// input in the tables (the QoE identifier is never evaluated inside a rollout).
+int policy_memo_for(mansy_policy *p, const SimDev &S, void *stream, const float **memo_out);
 // n_steps x (policy + sample + simulator step) in one launch of the cluster kernel; *launched = 0 if not applicable.
 int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t *b, int32_t n_steps, int64_t t0,
                          uint64_t seed, void *stream, int *launched);

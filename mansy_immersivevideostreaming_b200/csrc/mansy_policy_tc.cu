@@ -40,6 +40,8 @@
 
 namespace mansy {
 
+const SimDev *sim_dev_of(mansy_handle_t h);     // mansy_sim.cu
+
 constexpr int kTcSlots = 3;            // policies with live tensor-core state per process
 constexpr int kTcMaxJobs = 96;
 constexpr int kTcStages = 3;
@@ -88,6 +90,11 @@ struct TcConst {
   TcJob jobs[kTcMaxJobs];
   int32_t n_jobs, n_branches, residual_slot, softmax;
   TcRankPlan rank[kTcRanks];
+  // "memo" plans: the 320-input table branches (next chunk sizes / qualities) are left out -- their contribution to
+  // the hidden pre-activation comes from the (video, chunk) table of policy_memo_for.  rank_memo: the split-K cluster
+  // kernel; solo_memo: the one-CTA-per-tile kernel (job.slot / branch[] as in TcRankPlan).
+  TcRankPlan rank_memo[kTcRanks];
+  TcRankPlan solo_memo;
 };
 
 __constant__ TcConst c_tc[kTcSlots];
@@ -106,7 +113,18 @@ struct TcArgs {
   long long *timeline;  // debug: clock64 stamps [4][128] (producer issue, data arrival, mma committed, epilogue) of one CTA or NULL
   int32_t timeline_cta; // blockIdx.x of the CTA that writes the timeline
   float4 *scratch;      // cluster kernel: [tile][dst rank 4][src rank 4][column half 2][float4 column 8][row 128] partial exchange (L2)
+  const float *memo;    // [video * n_chunks + chunk][256] or NULL (all branches through the tensor pipe)
+  const EnvState *memo_state;   // row i of the observations is the current observation of environment i of this array
+  int32_t memo_n_chunks;
 };
+
+// Row of the memo table for environment `e`: the chunk its current observation describes (emit_obs: min(next_chunk,
+// end_chunk), mansy_env.py:208-230) of its episode's video.
+__device__ __forceinline__ int memo_row_of(const EnvState *st, int e, int n_chunks) {
+  // (L2 loads: inside the fused rollout kernel the records change from step to step)
+  const int video = __ldcg(&st[e].video), nc = __ldcg(&st[e].next_chunk), ec = __ldcg(&st[e].end_chunk);
+  return video * n_chunks + min(nc, ec);
+}
 
 struct TcState {
   int slot = -1;
@@ -183,7 +201,9 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int n_jobs = K.n_jobs;
+  const bool memo = A.memo != nullptr;
+  const TcJob *const jobs = memo ? K.solo_memo.jobs : K.jobs;
+  const int n_jobs = memo ? K.solo_memo.n_jobs : K.n_jobs;
   if (A.timeline && blockIdx.x == 0 && threadIdx.x == 0) A.timeline[511] = clock64();
   griddep_launch();
 
@@ -201,7 +221,7 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
       for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
         for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
           if ((int)s != (warp >> 1)) continue;
-          const TcJob job = K.jobs[j];
+          const TcJob job = jobs[j];
           mbar_wait(bar_empty + 8 * s, ph ^ 1u);
           const uint32_t dst = stage0 + s * kStageBytes, full = bar_full + 16 * s + 8 * half;
           if (elect_one()) {
@@ -216,7 +236,8 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
             } else {                      // stage: [Wfc chunk c][Wfc chunk c + 1], 256 rows x 128 B each
               if (half < job.s_hi) {
                 mbar_expect_tx(full, 2 * kBoxBytes);
-                tma_load_2d(dst + half * 2 * kBoxBytes, &map_wfc, job.slot * kHidden + (job.chunk + half) * 32, 0, full);
+                tma_load_2d(dst + half * 2 * kBoxBytes, &map_wfc,
+                            (memo ? (int)K.solo_memo.branch[job.slot] : (int)job.slot) * kHidden + (job.chunk + half) * 32, 0, full);
               } else {
                 mbar_arrive(full);
               }
@@ -235,9 +256,9 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
       for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_i) {
         // the head epilogue of the previous tile reads D2 (hid), D1[1] (residual) and D3 (= D1[0] columns 0..15)
         if (tile_i > 0) mbar_wait(bar_d2_empty, (tile_i - 1) & 1u);
-        TcJob job = K.jobs[0];
+        TcJob job = jobs[0];
         for (int j = 0; j < n_jobs; ++j, ++it, s = (s + 1 == kTcStages ? 0 : s + 1), ph ^= (s == 0 ? 1u : 0u)) {
-          const TcJob next_job = K.jobs[j + 1 < n_jobs ? j + 1 : 0];      // fetched before the waits below
+          const TcJob next_job = jobs[j + 1 < n_jobs ? j + 1 : 0];      // fetched before the waits below
           const uint32_t buf = job.slot & 1u;
           const uint32_t st_addr = stage0 + s * kStageBytes;
           if (job.type == kJobL1) {
@@ -318,14 +339,17 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
     const int half = (warp - kTcEpiWarp0) >> 2;
     const int r = q * 32 + lane;            // row (environment) inside the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int nb = K.n_branches;
+    const int nb = memo ? K.solo_memo.n_branches : K.n_branches;
     uint32_t d1_use[2] = {0, 0}, tile_i = 0;
     griddep_wait();
     for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tile_i) {
       const int env = tile * 128 + r;
       const bool live = env < A.n;
+      const float4 *memo_row = memo ? reinterpret_cast<const float4 *>(A.memo + (size_t)memo_row_of(A.memo_state, live ? env : 0, A.memo_n_chunks) * 256)
+                                    : nullptr;
       for (int i = 0; i < nb; ++i) {
         const uint32_t buf = i & 1u;
+        const int bi = memo ? (int)K.solo_memo.branch[i] : i;      // processing-order index: bias row, feat_dbg block
         mbar_wait(bar_d1_full + 8 * buf, d1_use[buf] & 1u);
         ++d1_use[buf];
         tc_fence_after();
@@ -336,10 +360,10 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
           const uint32_t ta = tmem_base + lane_addr + buf * 128u + c * 32u;
           tmem_ld32(ta, v);
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = leaky(v[jj] + K.bias1[i][c * 32 + jj]);
+          for (int jj = 0; jj < 32; ++jj) v[jj] = leaky(v[jj] + K.bias1[bi][c * 32 + jj]);
           tmem_st32(ta, v);        // features replace the accumulator in place: A operand of layer 2
           if (A.feat_dbg && live) {
-            float *dst = A.feat_dbg + (size_t)env * (nb * kHidden) + i * kHidden + c * 32;
+            float *dst = A.feat_dbg + (size_t)env * (K.n_branches * kHidden) + bi * kHidden + c * 32;
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) dst[jj] = v[jj];
           }
@@ -354,10 +378,15 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
       mbar_wait(bar_d2_full, tile_i & 1u);
       tc_fence_after();
       if (A.timeline && blockIdx.x == 0 && threadIdx.x == 32 * kTcEpiWarp0 && tile_i == 0) A.timeline[384 + 2 * nb] = clock64();
-      const int rs = K.residual_slot;
+      const int rs = memo ? K.solo_memo.resid_local : K.residual_slot;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float va[32], rr[32];
+        float4 mm[8];
+        if (memo) {
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) mm[c4] = __ldg(memo_row + half * 32 + c * 8 + c4);
+        }
         if (rs >= 0) {           // residual: the features of the last branch are still in D1[rs & 1]
           tmem_ld32(tmem_base + lane_addr + (uint32_t)(rs & 1) * 128u + c * 32u, rr);
         } else {
@@ -367,6 +396,12 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
         {                                          // half 0: actor.fc columns, half 1: critic.fc columns
           const uint32_t ta = tmem_base + lane_addr + 256u + half * 128u + c * 32u;
           tmem_ld32(ta, va);
+          if (memo) {
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              va[4 * c4] += mm[c4].x; va[4 * c4 + 1] += mm[c4].y; va[4 * c4 + 2] += mm[c4].z; va[4 * c4 + 3] += mm[c4].w;
+            }
+          }
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj)          // mansy.py:65,79: fc(features) + qoe_features
             va[jj] = leaky(va[jj] + K.bias2[half * kHidden + c * 32 + jj]) + rr[jj];
@@ -501,7 +536,8 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const TcConst &K = c_tc[SLOT];
   const uint32_t rank = cluster_ctarank();
-  const TcRankPlan &P = K.rank[rank];
+  const bool memo = A.memo != nullptr;
+  const TcRankPlan &P = memo ? K.rank_memo[rank] : K.rank[rank];
   const int tile = blockIdx.x / kTcRanks;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage0 = base;
@@ -731,6 +767,14 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     // ================= phase B: reduce-scatter the partials through L2 =================
     float4 *const xch = A.scratch + (size_t)tile * kScratchF4PerTile;
     if (warp >= kTcEpiWarp0) {
+      float4 mm[8];          // memoised table branches: this thread's 32 hidden columns of its row's (video, chunk) entry
+      if (memo) {
+        const float4 *mrow = reinterpret_cast<const float4 *>(
+            A.memo + (size_t)memo_row_of(kFused ? F.S.state : A.memo_state, live ? env : 0, kFused ? F.S.n_chunks : A.memo_n_chunks) * 256 +
+            rank * 64u + (uint32_t)half * 32u);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) mm[c4] = __ldg(mrow + c4);
+      }
 #pragma unroll 1
       for (uint32_t d = 0; d < (uint32_t)kTcRanks; ++d) {
         float v[32];
@@ -742,6 +786,12 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           float4 *dst = xch + (((d * 4u + rank) * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) __stcg(dst + c4 * 128, make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
+        }
+      }
+      if (memo) {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          own[4 * c4] += mm[c4].x; own[4 * c4 + 1] += mm[c4].y; own[4 * c4 + 2] += mm[c4].z; own[4 * c4 + 3] += mm[c4].w;
         }
       }
       tc_fence_before();
@@ -855,7 +905,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     if (kFused && sim_live) {
       load_state(F.S, sim_i, sim_st);
       load_slot(F.S, sim_i, sim_et & 7, sim_slot);
-      sim_in = step_prefetch(F.S, sim_st, sim_et & 7);
+      sim_in = step_prefetch(F.S, sim_st, sim_et & 7, true);
     }
 
     // ================= phase D: each rank finishes its 32 rows (warp q == rank) =================
@@ -1181,6 +1231,57 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
       }
       rp.n_jobs = cnt;
     }
+    // the same plans without the memoised 320-input branches (k == 320: next chunk sizes / qualities)
+    auto build_plan = [&](TcRankPlan &rp) {      // rp.branch[0 .. n_branches) filled; emits its job list
+      const int nl = rp.n_branches;
+      int cnt = 0;
+      auto emit_l1 = [&](int li) {
+        const int before = nj;
+        push_l1(rp.branch[li]);
+        for (int j = before; j < nj; ++j) { rp.jobs[cnt] = hc->jobs[j]; rp.jobs[cnt].slot = (uint8_t)li; ++cnt; }
+        nj = before;
+      };
+      auto emit_l2 = [&](int li) {
+        const int before = nj;
+        push_l2(rp.branch[li]);
+        for (int j = before; j < nj; ++j) {
+          TcJob t = hc->jobs[j];
+          t.slot = (uint8_t)li;
+          t.flags = (uint8_t)(t.flags & ~(kFlagTileFirstL2 | kFlagTileLastL2));
+          if (li == 0 && t.chunk == 0) t.flags |= kFlagTileFirstL2;
+          if (li == nl - 1 && (t.flags & kFlagLast)) t.flags |= kFlagTileLastL2;
+          rp.jobs[cnt++] = t;
+        }
+        nj = before;
+      };
+      if (nl > 0) {
+        emit_l1(0);
+        for (int li = 1; li < nl; ++li) { emit_l1(li); emit_l2(li - 1); }
+        emit_l2(nl - 1);
+      }
+      rp.n_jobs = cnt;
+    };
+    {
+      int mload[kTcRanks] = {0, 0, 0, 0};
+      for (int r = 0; r < kTcRanks; ++r) { hc->rank_memo[r].n_branches = 0; hc->rank_memo[r].resid_local = -1; }
+      hc->solo_memo.n_branches = 0; hc->solo_memo.resid_local = -1;
+      for (int i = 0; i < nb; ++i) {
+        const BranchPlan &b = plan[i];
+        if (b.k == 320) continue;
+        const int lo = b.off / 8, hi = (b.off + b.k + 7) / 8;
+        const int boxes = (hi - 1) / 4 - lo / 4 + 1;
+        int best = 0;
+        for (int r = 1; r < kTcRanks; ++r) if (mload[r] < mload[best]) best = r;
+        mload[best] += boxes * 32 + 128;
+        TcRankPlan &rp = hc->rank_memo[best];
+        if (i == hc->residual_slot) rp.resid_local = rp.n_branches;
+        rp.branch[rp.n_branches++] = (uint8_t)i;
+        if (i == hc->residual_slot) hc->solo_memo.resid_local = hc->solo_memo.n_branches;
+        hc->solo_memo.branch[hc->solo_memo.n_branches++] = (uint8_t)i;
+      }
+      for (int r = 0; r < kTcRanks; ++r) build_plan(hc->rank_memo[r]);
+      build_plan(hc->solo_memo);
+    }
     memset(&hc->jobs[nj], 0, sizeof(TcJob) * (kTcMaxJobs - nj));     // scratch entries used above
   }
 
@@ -1268,7 +1369,7 @@ namespace mansy {
 int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
                              float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
                              int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
-                             int32_t timeline_cta, bool pdl, void *stream) {
+                             int32_t timeline_cta, bool pdl, void *stream, const SimDev *memo_sim) {
   if (!p || !obs_dev) return set_error(MANSY_E_INVALID, "NULL argument");
   if (!p->tc) return set_error(MANSY_E_STATE, std::string("tensor-core state unavailable: ") + mansy_last_error());
   if (n < 0) return set_error(MANSY_E_INVALID, "n < 0");
@@ -1289,6 +1390,12 @@ int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs
   a.seed = seed; a.step = step; a.env_offset = env_offset;
   a.timeline = reinterpret_cast<long long *>(timeline_dev);
   a.timeline_cta = timeline_cta;
+  if (memo_sim && !feat_dbg_dev && !hid_dbg_dev) {
+    if (n > memo_sim->n_envs) return set_error(MANSY_E_INVALID, "more observation rows than environments in the memo simulator");
+    if ((rc = policy_memo_for(p, *memo_sim, stream, &a.memo))) return rc;
+    a.memo_state = memo_sim->state;
+    a.memo_n_chunks = memo_sim->n_chunks;
+  }
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
@@ -1386,6 +1493,11 @@ int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t
   a.timeline = g_fused_timeline; a.timeline_cta = g_fused_timeline_cta;
   if ((rc = ensure_scratch(p, n_tiles))) return rc;
   a.scratch = p->tc->scratch;
+  if (!getenv("MANSY_NO_POLICY_MEMO")) {
+    if ((rc = policy_memo_for(p, S, stream, &a.memo))) return rc;
+    a.memo_state = S.state;
+    a.memo_n_chunks = S.n_chunks;
+  }
   FusedArgs f;
   memset(&f, 0, sizeof(f));
   f.S = S;
@@ -1439,6 +1551,14 @@ int mansy_policy_forward_tc(mansy_policy_t p, const float *obs_dev, int64_t obs_
                             int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, void *stream) {
   return policy_forward_tc_launch(p, obs_dev, obs_stride, n, logits_dev, value_dev, actions_dev, logp_dev, seed, step,
                                   env_offset, feat_dbg_dev, hid_dbg_dev, nullptr, 0, false, stream);
+}
+
+int mansy_policy_forward_tc_sim(mansy_policy_t p, mansy_handle_t h, const float *obs_dev, int64_t obs_stride, float *logits_dev,
+                                float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step, void *stream) {
+  if (!h) return set_error(MANSY_E_INVALID, "NULL argument");
+  const SimDev *S = sim_dev_of(h);
+  return policy_forward_tc_launch(p, obs_dev, obs_stride, S->n_envs, logits_dev, value_dev, actions_dev, logp_dev, seed, step,
+                                  S->env_offset, nullptr, nullptr, nullptr, 0, false, stream, getenv("MANSY_NO_POLICY_MEMO") ? nullptr : S);
 }
 
 int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,

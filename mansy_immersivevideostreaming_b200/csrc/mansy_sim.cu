@@ -280,6 +280,31 @@ __global__ void __launch_bounds__(kExpertThreads, 2) expert_mpc_kernel(const Sim
   }
 }
 
+// Fills the (viewport pair, chunk, action) outcome table with the gather form of step_env (chunk_parts_gather), one
+// 8-lane group per entry: what a step then reads back is bit-identical to what it would have computed.
+__global__ void __launch_bounds__(kThreadsPerBlock) outcome_build_kernel(const SimDev S, ChunkOutcome *__restrict__ out, long long total) {
+  const long long g = (long long)blockIdx.x * kEnvsPerBlock + (threadIdx.x >> 3);
+  if (g >= total) return;
+  const int sub = threadIdx.x & 7;
+  const unsigned gmask = group_mask();
+  const int a = (int)(g % kOutcomeActions);
+  const long long vi = g / kOutcomeActions;
+  const int j = (int)(vi % S.n_vp_chunks), pair = (int)(vi / S.n_vp_chunks);
+  const int video = pair / S.n_users;
+  const int c = __ldg(S.vp_start + pair) + j;
+  const int end = min(__ldg(S.vp_end + pair), __ldg(S.video_time + video) - 1);
+  ChunkOutcome o;
+  o.q1 = 0.0; o.intra = 0.0; o.size = 0; o.pad0 = 0; o.pad1 = 0;
+  if (c >= 0 && c <= end && c < S.n_chunks) {           // chunks an episode of this pair can download (simulator.py:41-45)
+    int rin, rout;
+    action_to_rates(a, rin, rout);                       // a == 15: out of the table -> (0, 0)
+    const ChunkParts cp = chunk_parts_gather(S, video, c, __ldg(S.vp_gt + vi), __ldg(S.vp_scale + vi * 8 + sub), rin, rout, sub,
+                                             gmask, nullptr);
+    o.q1 = cp.q1; o.intra = cp.intra; o.size = cp.sz;
+  }
+  if (sub == 0) out[g] = o;
+}
+
 __global__ void copy_i32_kernel(int32_t *__restrict__ dst, const int32_t *__restrict__ src, int32_t n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
@@ -375,7 +400,7 @@ namespace mansy {
 int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
                              float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
                              int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
-                             int32_t timeline_cta, bool pdl, void *stream);
+                             int32_t timeline_cta, bool pdl, void *stream, const SimDev *memo_sim);
 int rollout_fused_launch(mansy_policy_t p, const SimDev &S, const mansy_rollout_t *b, int32_t n_steps, int64_t t0,
                          uint64_t seed, void *stream, int *launched);
 }  // namespace mansy
@@ -383,6 +408,7 @@ int rollout_fused_launch(mansy_policy_t p, const SimDev &S, const mansy_rollout_
 struct mansy_sim {
   SimDev dev;
   int device = 0;
+  ChunkOutcome *outcome = nullptr;    // the table dev.outcome points at when enabled (mansy_set_outcome_table)
   std::vector<void *> allocs;
   // lazily allocated device staging for the host-buffer entry points
   int32_t *stage_actions = nullptr;
@@ -527,6 +553,8 @@ int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, ma
   h->device = device;
   SimDev &d = h->dev;
   memset(&d, 0, sizeof(d));
+  static std::atomic<uint64_t> next_uid{1};
+  d.uid = next_uid.fetch_add(1);
   const size_t n_tab = (size_t)t->n_videos * t->n_chunks * kTableRow;
   const size_t n_vp = (size_t)t->n_videos * t->n_users * t->n_vp_chunks;
   const size_t n_pairs = (size_t)t->n_videos * t->n_users;
@@ -607,6 +635,8 @@ int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, ma
     }
     MANSY_TRY(upload(h, padded.data(), padded.size(), &d.trace));
     d.trace_stride = stride_dev;
+    for (double &x : padded) x = 1.0 / x;               // correctly rounded reciprocals for ddiv_rcp (1 / 0 = inf is never used)
+    MANSY_TRY(upload(h, padded.data(), padded.size(), &d.trace_rcp));
   }
   MANSY_TRY(upload(h, t->trace_len, (size_t)t->n_traces, &d.trace_len));
   MANSY_TRY(upload(h, t->qoe_w, (size_t)t->n_qoe * 3, &d.qoe_w));
@@ -627,6 +657,10 @@ int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, ma
   d.max_throughput = (double)cfg->max_throughput;
   d.startup_d = (double)cfg->startup_download;
   d.startup_f = (float)cfg->startup_download;
+  d.rcp_max_quality = 1.0 / d.max_quality;
+  d.rcp_max_throughput = 1.0 / d.max_throughput;
+  d.rcp_startup_d = 1.0 / d.startup_d;
+  for (int k = 0; k <= kTiles; ++k) d.rcp_count[k] = 1.0 / (double)k;
   for (int i = 0; i < kRates; ++i) {
     d.rate_norm_hist[i] = (float)((double)cfg->video_rates[i] / (double)cfg->video_rates[4]);
     d.rate_norm_f32[i] = fdiv((float)cfg->video_rates[i], (float)cfg->video_rates[4]);
@@ -637,6 +671,20 @@ int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, ma
     cudaError_t e2 = cudaMemset(d.stats, 0, n * MANSY_STATS_DOUBLES * sizeof(double));
     cudaError_t e3 = cudaMemset(d.error_flag, 0, 16);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { mansy_destroy(h); return set_error(MANSY_E_CUDA, "cudaMemset failed"); }
+  }
+  {
+    // (viewport pair, chunk, action) outcome table: 32 B x 16 actions per (pair, chunk) -- 40 MB at 1 440 pairs x 54
+    // chunks; skipped above 1 GiB (steps then gather) or with MANSY_NO_OUTCOME_TABLE=1
+    const long long total = (long long)n_vp * kOutcomeActions;
+    const char *off = getenv("MANSY_NO_OUTCOME_TABLE");
+    if (!(off && off[0] == '1') && total * (long long)sizeof(ChunkOutcome) <= (1LL << 30)) {
+      MANSY_TRY(dev_alloc(h, (size_t)total, &h->outcome));
+      const long long grid = (total + kEnvsPerBlock - 1) / kEnvsPerBlock;
+      outcome_build_kernel<<<(unsigned)grid, kThreadsPerBlock>>>(d, h->outcome, total);
+      count_launch();
+      if (cudaGetLastError() != cudaSuccess) { mansy_destroy(h); return set_error(MANSY_E_CUDA, "outcome_build_kernel launch failed"); }
+      d.outcome = h->outcome;
+    }
   }
 #undef MANSY_TRY
   rc = launch_seed(h, cfg->seed, 1, nullptr);
@@ -822,7 +870,8 @@ int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout
                                         b->logp + cur * n, stream);
     } else {
       rc = policy_forward_tc_launch(p, obs, b->obs_stride, h->dev.n_envs, b->logits, b->value + cur * n, b->actions + cur * n,
-                                    b->logp + cur * n, seed, t, h->dev.env_offset, nullptr, nullptr, nullptr, 0, pdl, stream);
+                                    b->logp + cur * n, seed, t, h->dev.env_offset, nullptr, nullptr, nullptr, 0, pdl, stream,
+                                    getenv("MANSY_NO_POLICY_MEMO") ? nullptr : &h->dev);
     }
     if (rc) return rc;
     if (timed) MANSY_CUDA(cudaEventRecord(h->events[3 * k + 1], s));
@@ -876,8 +925,9 @@ int mansy_rollout_policy_host(mansy_handle_t h, mansy_policy_t p, const mansy_ro
       if (!rc) rc = mansy_policy_sample(b->logits, h->dev.n_envs, is_probs, seed, t, h->dev.env_offset, b->actions + cur * n,
                                         b->logp + cur * n, stream);
     } else {
-      rc = mansy_policy_forward_tc(p, obs, b->obs_stride, h->dev.n_envs, b->logits, b->value + cur * n, b->actions + cur * n,
-                                   b->logp + cur * n, seed, t, h->dev.env_offset, nullptr, nullptr, stream);
+      rc = policy_forward_tc_launch(p, obs, b->obs_stride, h->dev.n_envs, b->logits, b->value + cur * n, b->actions + cur * n,
+                                    b->logp + cur * n, seed, t, h->dev.env_offset, nullptr, nullptr, nullptr, 0, false, stream,
+                                    getenv("MANSY_NO_POLICY_MEMO") ? nullptr : &h->dev);
     }
     if (rc) return rc;
     // act_t -> host.  The device-to-host copy engine is busy with the previous step's 12.9 MB observation slab (copy
@@ -937,6 +987,13 @@ int mansy_episode_stats(mansy_handle_t h, double *stats_dev, void *stream) {
   MANSY_CUDA(use_device(h->device));
   MANSY_CUDA(cudaMemcpyAsync(stats_dev, h->dev.stats, (size_t)h->dev.n_envs * MANSY_STATS_DOUBLES * sizeof(double),
                              cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return MANSY_OK;
+}
+
+int mansy_set_outcome_table(mansy_handle_t h, int32_t enable) {
+  if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
+  if (enable && !h->outcome) return set_error(MANSY_E_STATE, "this handle has no outcome table (too large, or MANSY_NO_OUTCOME_TABLE=1)");
+  h->dev.outcome = enable ? h->outcome : nullptr;
   return MANSY_OK;
 }
 
@@ -1046,6 +1103,11 @@ int mansy_selftest_download(const double *thr, int32_t trace_len, int64_t size, 
   *download_time = dl;
   *rebuffer = buffer_push(*buf, 1.0, dl);
   return ok ? MANSY_OK : MANSY_E_STATE;
+}
+
+int mansy_selftest_ddiv_rcp(const double *a, const double *b, int64_t n, double *out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = ddiv_rcp(a[i], b[i], 1.0 / b[i]);
+  return MANSY_OK;
 }
 
 int mansy_selftest_hashed_action(uint64_t seed, uint64_t env, uint64_t step) { return hashed_action(seed, env, step, kActions); }

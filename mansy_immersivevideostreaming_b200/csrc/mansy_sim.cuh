@@ -53,6 +53,20 @@ constexpr int kFlagFinished = 1;
 // quality variance (qoe3), rebuffer/startup (qoe2/5), raw rebuffer (qoe2; SimpleRL observation).
 constexpr int kHistFloatsPerEnv = 64;
 
+// What the download / QoE part of a step needs from (viewport pair, chunk, action): a pure function of the read-only
+// tables (utils/common.py:101-193 allocation, simulator.py:94-101 gather + sums, qoe.py:23-28), tabulated once per
+// handle by the same device code a step runs (outcome_build_kernel) -- the reference's own ExpertEnv caches the same
+// per-(chunk, action) statistics (expert_env.py:121-160).  16 actions: 0..14 and the out-of-table action (rates 0, 0).
+struct __align__(16) ChunkOutcome {
+  double q1;       // viewport quality / max_quality                     (qoe.py:23,26)
+  double intra;    // sum |q - vq| over the actual viewport / count / max_quality   (qoe.py:24-25)
+  int32_t size;    // chunk bytes: exact integer sum of the 64 selected tiles       (simulator.py:100)
+  int32_t pad0;
+  int64_t pad1;
+};
+static_assert(sizeof(ChunkOutcome) == 32, "ChunkOutcome is two 16-byte quads");
+constexpr int kOutcomeActions = 16;
+
 struct SimDev {
   // read-only tables
   const int32_t *size;
@@ -67,6 +81,8 @@ struct SimDev {
   const int32_t *vp_start;
   const int32_t *vp_end;
   const double *trace;
+  const double *trace_rcp;   // RN(1 / trace[i]) for ddiv_rcp (same layout as trace)
+  const ChunkOutcome *outcome;  // [pairs][n_vp_chunks][16] or NULL (table disabled / too large): step_env then gathers
   const int32_t *trace_len;
   const float *qoe_w;
   const int32_t *samples;
@@ -76,10 +92,13 @@ struct SimDev {
   float *hist;
   double *stats;            // [n_envs][MANSY_STATS_DOUBLES]
   int32_t *error_flag;      // set by kernels on data errors (trace that can never finish a download)
+  uint64_t uid;             // unique per handle in this process (keys caches derived from the tables, e.g. the policy memo)
   // configuration
   int32_t n_envs, env_offset, worker_num, obs_mode, reward_mode;
   int32_t startup_download;
   double chunk_length, max_quality, max_throughput, startup_d;
+  double rcp_max_quality, rcp_max_throughput, rcp_startup_d;   // correctly rounded reciprocals (ddiv_rcp)
+  double rcp_count[kTiles + 1];                                // RN(1 / k), k = popcount of the actual viewport
   float startup_f;
   float rate_norm_hist[kRates];  // float(rates[r] / rates[-1]) with a float64 division (mansy_env.py:197,199)
   float rate_norm_f32[kRates];   // float(rates[r]) / float(rates[-1])          (simple_rl_env.py:137-138)

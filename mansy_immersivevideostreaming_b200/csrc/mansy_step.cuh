@@ -107,22 +107,26 @@ __device__ __forceinline__ void reset_episode(const SimDev &S, EnvState &st) {
 }
 
 // network.py:22-35 with the trace window held by the environment's 8 lanes: lane j of the group owns entry
-// cur_idx + j of the wrap-padded row (one load per lane, issued by the caller before the dependent work), the
-// sequential walk reads entry `pos` with a shuffle and only reloads every 8 seconds of simulated download.
-// Arithmetic and operation order are those of trace_download (mansy_core.cuh): results are bit-identical.
-__device__ __forceinline__ double trace_download_window(double size, double win, const double *__restrict__ tr, int trace_len,
-                                                        int &cur_idx, double &cur_time, int sub, unsigned gmask, bool &ok) {
+// cur_idx + j of the wrap-padded row and its reciprocal (one load each per lane, issued by the caller before the
+// dependent work), the sequential walk reads entry `pos` with a shuffle and only reloads every 8 seconds of simulated
+// download.  Arithmetic and operation order are those of trace_download (mansy_core.cuh) -- the one division of a
+// download, size / thr in the last, partial second, is ddiv_rcp on the tabulated reciprocal (bit-identical to an
+// IEEE division) -- so results are bit-identical to the scalar loop.
+__device__ __forceinline__ double trace_download_window(double size, double win, double rwin, const double *__restrict__ tr,
+                                                        const double *__restrict__ trr, int trace_len, int &cur_idx,
+                                                        double &cur_time, int sub, unsigned gmask, bool &ok) {
   const double start = cur_time;
   const int base = (threadIdx.x & 31) & ~7;
   int pos = 0, it = 0;
   if (gmask == 0xFFFFFFFFu) {
     // whole warp converged (the mask is a compile-time constant here): one warp-uniform loop over the longest of
     // the four downloads, plain full-mask shuffles instead of the partial-mask collective sequence
+    bool more = size > 0.0;
     while (true) {
-      const bool more = size > 0.0 && ok;
       if (!__any_sync(0xFFFFFFFFu, more)) break;
       if (pos == kTraceWindow) {
         win = __ldg(tr + cur_idx + sub);
+        rwin = __ldg(trr + cur_idx + sub);
         pos = 0;
       }
       const double thr = __shfl_sync(0xFFFFFFFFu, win, base + pos);
@@ -134,18 +138,22 @@ __device__ __forceinline__ double trace_download_window(double size, double win,
           cur_time = next_tick;
           size = dsub(size, remain);
           ++pos;
+          if (++it > (1 << 22)) { ok = false; more = false; }
+          else more = size > 0.0;
         } else {
-          cur_time = dadd(cur_time, ddiv(size, thr));
-          size = 0.0;
+          more = false;          // the last, partial second: one division, after the loop (`pos` stays on its entry)
         }
-        if (++it > (1 << 22)) ok = false;
       }
     }
+    const double thr = __shfl_sync(0xFFFFFFFFu, win, base + pos);
+    const double rthr = __shfl_sync(0xFFFFFFFFu, rwin, base + pos);
+    if (size > 0.0 && ok) cur_time = dadd(cur_time, ddiv_rcp(size, thr, rthr));
     return dsub(cur_time, start);
   }
   while (size > 0.0) {
     if (pos == kTraceWindow) {
       win = __ldg(tr + cur_idx + sub);
+      rwin = __ldg(trr + cur_idx + sub);
       pos = 0;
     }
     const double thr = __shfl_sync(gmask, win, base + pos);
@@ -157,7 +165,8 @@ __device__ __forceinline__ double trace_download_window(double size, double win,
       size = dsub(size, remain);
       ++pos;
     } else {
-      cur_time = dadd(cur_time, ddiv(size, thr));
+      const double rthr = __shfl_sync(gmask, rwin, base + pos);
+      cur_time = dadd(cur_time, ddiv_rcp(size, thr, rthr));
       size = 0.0;
     }
     if (++it > (1 << 22)) { ok = false; break; }
@@ -274,13 +283,20 @@ struct StepInputs {
   uint64_t gt;
   uint32_t scales;
   int tlen;
-  double acc, win;
-  const double *tr;
+  double acc, win, rwin;
+  const double *tr, *trr;
+  size_t vi;
+  // outcome-table path of the fused kernel: lane `sub` holds the entries of actions 2 * sub and 2 * sub + 1 of this
+  // (viewport pair, chunk), loaded before the action is known
+  double oq0, oi0, oq1, oi1;   // q1 / intra of the two actions
+  int os0, os1;                // their chunk sizes
+  bool outcomes;
 };
 
-__device__ __forceinline__ StepInputs step_prefetch(const SimDev &S, const EnvState &st, int sub) {
+__device__ __forceinline__ StepInputs step_prefetch(const SimDev &S, const EnvState &st, int sub, bool outcomes = false) {
   StepInputs in;
   const size_t vi = (size_t)st.pair * S.n_vp_chunks + (st.next_chunk - st.start_chunk);   // hmdtrace.py:16-19
+  in.vi = vi;
   in.gt = __ldg(S.vp_gt + vi);
   // pyramid scales (toroidal Chebyshev distance to the predicted viewport, utils/common.py:142-168) of this lane's
   // 8 tiles, 4 bits each: a table derived from vp_pred when the handle is created (same tile_scale_masks code)
@@ -288,33 +304,34 @@ __device__ __forceinline__ StepInputs step_prefetch(const SimDev &S, const EnvSt
   in.acc = __ldg(S.vp_acc + vi);
   // bandwidth-trace window and length: issued before the dependent gather / reduction work
   in.tr = S.trace + (size_t)st.trace * S.trace_stride;
+  in.trr = S.trace_rcp + (size_t)st.trace * S.trace_stride;
   in.win = __ldg(in.tr + st.cur_idx + sub);
+  in.rwin = __ldg(in.trr + st.cur_idx + sub);
   in.tlen = __ldg(S.trace_len + st.trace);
+  in.outcomes = outcomes && S.outcome != nullptr;
+  if (in.outcomes) {
+    const double2 *o = reinterpret_cast<const double2 *>(S.outcome + vi * kOutcomeActions + 2 * sub);
+    const double2 a0 = __ldg(o), a1 = __ldg(o + 2);
+    in.oq0 = a0.x; in.oi0 = a0.y; in.oq1 = a1.x; in.oi1 = a1.y;
+    in.os0 = __ldg(reinterpret_cast<const int *>(o + 1));
+    in.os1 = __ldg(reinterpret_cast<const int *>(o + 3));
+  }
   return in;
 }
 
-// One chunk-step of one environment (8 lanes).  Returns the reward; `over` tells whether the
-// episode ended.  aux_row / ver_row may be NULL.
-__device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float (&slot)[8], int sub, unsigned gmask,
-                                           int action, bool &over, double *__restrict__ aux_row,
-                                           uint8_t *__restrict__ ver_row, const StepInputs &in) {
-  MANSY_STEP_STAMP(0, action);
-  const int c = st.next_chunk;
-  const uint64_t gt = in.gt;
-  const uint32_t scales = in.scales;
-  const double acc = in.acc;
-  const double *tr = in.tr;
-  const double win = in.win;
-  const int tlen = in.tlen;
+struct ChunkParts {
+  int sz;              // chunk bytes (simulator.py:100)
+  double q1, intra;    // qoe.py:23-28
+};
 
-  int rin, rout;
-  action_to_rates(action, rin, rout);
+// The gather form of (chunk, action) -> parts (utils/common.py:101-193, simulator.py:94-101, qoe.py:23-28), 8 lanes
+// per chunk: lane `sub` owns tiles 8*sub .. 8*sub+7.  Steps use it when no outcome table exists (or tile versions are
+// asked for) and outcome_build_kernel uses it to fill the table, so both paths produce the same bits.
+__device__ __forceinline__ ChunkParts chunk_parts_gather(const SimDev &S, int video, int c, uint64_t gt, uint32_t scales, int rin,
+                                                         int rout, int sub, unsigned gmask, uint8_t *__restrict__ ver_row) {
   const uint32_t vtab = (S.lut[rout] & ~7u) | (uint32_t)rin;   // 3-bit entries: scale 0 -> rate_in, s >= 1 -> lut[rate_out][s]
   const uint32_t gbyte = (uint32_t)(gt >> (8 * sub)) & 0xFFu;  // actual-viewport bits of this lane's tiles
-  const size_t tab = ((size_t)st.video * S.n_chunks + c) * kTableRow;
-
-  // simulator.py:94-101: gather size / quality of the chosen version of each tile; this lane owns
-  // tiles 8*sub .. 8*sub+7.
+  const size_t tab = ((size_t)video * S.n_chunks + c) * kTableRow;
   int sz = 0;
   double mq = 0.0;
   float q[8];
@@ -330,29 +347,68 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
     if (i < 4) vpack_lo |= (uint32_t)ver << (8 * i); else vpack_hi |= (uint32_t)ver << (8 * (i - 4));
   }
   if (ver_row) reinterpret_cast<uint2 *>(ver_row)[sub] = make_uint2(vpack_lo, vpack_hi);
-  MANSY_STEP_STAMP(1, sz);
-  sz = group_sum(sz, gmask);
+  ChunkParts cp;
+  cp.sz = group_sum(sz, gmask);
   mq = group_sum(mq, gmask);
-  const double sm = (double)__popcll(gt);
-
-  // network.py:22-35 / buffer.py:8-15
-  bool ok = true;
-  const double dl = trace_download_window((double)sz, win, tr, tlen, st.cur_idx, st.cur_time, sub, gmask, ok);
-  if (!ok && sub == 0) atomicExch(S.error_flag, 1);
-  MANSY_STEP_STAMP(2, sz + (int)mq);
-  MANSY_STEP_STAMP(3, dl > 0.0);
-  const double rebuf = buffer_push(st.buf, S.chunk_length, dl);
-
-  // qoe.py:22-34 (float64 chain; |q - vq| is evaluated in float32 like the reference's array op)
-  const double vq = ddiv(mq, sm);
+  const int cnt = __popcll(gt);
+  const double sm = (double)cnt, rsm = S.rcp_count[cnt];
+  // qoe.py:22-28 (float64 chain; |q - vq| is evaluated in float32 like the reference's array op)
+  const double vq = ddiv_rcp(mq, sm, rsm);
   const float vq32 = (float)vq;
   double dev = 0.0;
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     if ((gbyte >> i) & 1u) dev = dadd(dev, (double)fabsf(fsub(q[i], vq32)));
   dev = group_sum(dev, gmask);
-  const QoE r = qoe_from_sums(vq, dev, sm, rebuf, st.ep_step == 0, st.prev_vq, (double)st.w0, (double)st.w1,
-                              (double)st.w2, S.max_quality);
+  cp.intra = ddiv_rcp(ddiv_rcp(dev, sm, rsm), S.max_quality, S.rcp_max_quality);
+  cp.q1 = ddiv_rcp(vq, S.max_quality, S.rcp_max_quality);
+  return cp;
+}
+
+// One chunk-step of one environment (8 lanes).  Returns the reward; `over` tells whether the
+// episode ended.  aux_row / ver_row may be NULL.
+__device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float (&slot)[8], int sub, unsigned gmask,
+                                           int action, bool &over, double *__restrict__ aux_row,
+                                           uint8_t *__restrict__ ver_row, const StepInputs &in) {
+  MANSY_STEP_STAMP(0, action);
+  const int c = st.next_chunk;
+  const uint64_t gt = in.gt;
+  const double acc = in.acc;
+
+  int rin, rout;
+  action_to_rates(action, rin, rout);
+  // (chunk, action) -> chunk bytes, viewport quality, intra-chunk variance: from the outcome table when the handle
+  // has one (and the caller does not want the per-tile versions), else gathered here
+  ChunkParts cp;
+  if (S.outcome != nullptr && ver_row == nullptr) {
+    const int a16 = (action >= 0 && action < kActions) ? action : kActions;      // 15 = out-of-table action, rates (0, 0)
+    if (in.outcomes) {
+      const int src = ((threadIdx.x & 31) & ~7) + (a16 >> 1);
+      const bool hi = a16 & 1;
+      cp.q1 = __shfl_sync(gmask, hi ? in.oq1 : in.oq0, src);
+      cp.intra = __shfl_sync(gmask, hi ? in.oi1 : in.oi0, src);
+      cp.sz = __shfl_sync(gmask, hi ? in.os1 : in.os0, src);
+    } else {
+      const double2 *o = reinterpret_cast<const double2 *>(S.outcome + in.vi * kOutcomeActions + a16);
+      const double2 qa = __ldg(o);
+      cp.q1 = qa.x; cp.intra = qa.y;
+      cp.sz = __ldg(reinterpret_cast<const int *>(o + 1));
+    }
+  } else {
+    cp = chunk_parts_gather(S, st.video, c, gt, in.scales, rin, rout, sub, gmask, ver_row);
+  }
+  const int sz = cp.sz;
+  MANSY_STEP_STAMP(1, sz);
+
+  // network.py:22-35 / buffer.py:8-15
+  bool ok = true;
+  const double dl = trace_download_window((double)sz, in.win, in.rwin, in.tr, in.trr, in.tlen, st.cur_idx, st.cur_time, sub, gmask, ok);
+  if (!ok && sub == 0) atomicExch(S.error_flag, 1);
+  MANSY_STEP_STAMP(2, sz);
+  MANSY_STEP_STAMP(3, dl > 0.0);
+  const double rebuf = buffer_push(st.buf, S.chunk_length, dl);
+
+  const QoE r = qoe_from_parts(cp.q1, cp.intra, rebuf, st.ep_step == 0, st.prev_vq, (double)st.w0, (double)st.w1, (double)st.w2);
   MANSY_STEP_STAMP(4, r.qoe > 0.0);
   double reward = r.qoe;
   if (S.reward_mode == MANSY_REWARD_QOE_NORM)
@@ -365,13 +421,13 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
 
   // mansy_env.py:192-206: push the newest history values (ring slot = episode step & 7)
   if (sub == (st.ep_step & 7)) {
-    slot[0] = (float)ddiv(ddiv((double)sz, dl), S.max_throughput);
+    slot[0] = (float)ddiv_rcp(ddiv((double)sz, dl), S.max_throughput, S.rcp_max_throughput);
     slot[1] = S.rate_norm_hist[rin];
     slot[2] = S.rate_norm_hist[rout];
     slot[3] = (float)acc;
     slot[4] = (float)r.q1;
     slot[5] = (float)r.q3;
-    slot[6] = (float)ddiv(r.q2, S.startup_d);
+    slot[6] = (float)ddiv_rcp(r.q2, S.startup_d, S.rcp_startup_d);
     slot[7] = (float)r.q2;
   }
   MANSY_STEP_STAMP(5, slot[0] > 0.f);

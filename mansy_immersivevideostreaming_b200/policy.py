@@ -144,6 +144,17 @@ class PolicyNet:
                                                torch.cuda.current_stream(self.device).cuda_stream))
         return logits, value, actions, logp
 
+    def forward_tc_sim(self, sim, obs: torch.Tensor, logits: torch.Tensor, value: torch.Tensor, actions: torch.Tensor,
+                       logp: torch.Tensor, seed: int = 0, step: int = 0):
+        """``forward_tc`` on the CURRENT observations of ``sim`` (row i = env i): the 320-input table branches come from the
+        (video, chunk) memo (``mansy_policy_forward_tc_sim``) -- the path every rollout entry point takes."""
+        if obs.device != self.device or obs.dtype != torch.float32 or obs.stride(-1) != 1 or obs.shape[0] != sim.n_envs:
+            raise ValueError("obs must hold one float32 row per environment of the simulator, on the policy's device")
+        check(self.lib.mansy_policy_forward_tc_sim(self._h, sim._h, obs.data_ptr(), obs.stride(0), logits.data_ptr(), value.data_ptr(),
+                                                   actions.data_ptr(), logp.data_ptr(), int(seed), int(step),
+                                                   torch.cuda.current_stream(self.device).cuda_stream))
+        return logits, value, actions, logp
+
     def sample(self, logits: torch.Tensor, seed: int, step: int, env_offset: int = 0,
                actions: Optional[torch.Tensor] = None, logp: Optional[torch.Tensor] = None):
         """Categorical(logits).sample() (run_mansy.py:228-229) with a counter-based generator."""

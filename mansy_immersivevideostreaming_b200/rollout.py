@@ -73,8 +73,7 @@ class PolicyRollout:
         b, s = self.buf, self.t % self.buf.slabs
         nxt = (self.t + 1) % b.slabs
         if self.tensor_cores:
-            self.policy.forward_tc(b.obs[s], b.logits, b.value[s], b.actions[s], b.logp[s], seed=self.seed, step=self.t,
-                                   env_offset=self.sim.env_offset)
+            self.policy.forward_tc_sim(self.sim, b.obs[s], b.logits, b.value[s], b.actions[s], b.logp[s], seed=self.seed, step=self.t)
         else:
             self.policy.forward(b.obs[s], b.logits, b.value[s])
             self.policy.sample(b.logits, self.seed, self.t, self.sim.env_offset, b.actions[s], b.logp[s])

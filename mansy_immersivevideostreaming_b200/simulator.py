@@ -200,6 +200,11 @@ class BatchSimulator:
         check(self.lib.mansy_episode_totals(self._h, out.data_ptr(), self._stream()))
         return out
 
+    def set_outcome_table(self, enable: bool) -> None:
+        """Steps read chunk bytes / viewport quality / intra-chunk variance of (pair, chunk, action) from the table built
+        at create (default) or gather them from the size / quality tables again (``mansy_set_outcome_table``)."""
+        check(self.lib.mansy_set_outcome_table(self._h, 1 if enable else 0))
+
     def stats_clear(self) -> None:
         check(self.lib.mansy_stats_clear(self._h, self._stream()))
 

@@ -155,3 +155,33 @@ def test_new_entry_points_validate_arguments_without_a_device(lib):
                         "bn_var", "pred_w", "pred_b"):
                 setattr(w, name, keep[0].ctypes.data)
         assert lib.mansy_mtio_create(C.byref(w), 0, 16, C.byref(h)) == -2       # MANSY_E_CUDA: no device
+
+
+def test_reciprocal_division_is_an_ieee_division(lib):
+    """csrc/mansy_core.cuh ddiv_rcp (what the kernels use for x / throughput, x / tile count, x / 35, x / 5e6, x / 5): bit-identical
+    to a / b on the divisors the simulator meets -- random numerators, and numerators built to land next to a rounding
+    midpoint of the quotient (the hard cases of a division)."""
+    rng = np.random.default_rng(20260102)
+    n = 2_000_000
+    cases = []
+    # (1) throughput entries: integers up to 1.4e7 B/s and rescaled (fractional) traces; numerators: remaining bytes
+    b = np.concatenate([np.floor(rng.uniform(1, 1.4e7, n)), rng.uniform(1e-3, 1.4e7, n)])
+    a = np.concatenate([np.floor(rng.uniform(0, 1e7, n)), rng.uniform(0, 1e7, n)])
+    cases.append((a, b))
+    # (2) the constant divisors with wide numerators
+    consts = np.array([35.0, 5e6, 5.0] + list(range(1, 65)), dtype=np.float64)
+    b = rng.choice(consts, 2 * n)
+    a = np.ldexp(rng.uniform(0.5, 1.0, 2 * n), rng.integers(-30, 30, 2 * n))
+    cases.append((a, b))
+    # (3) near-midpoint quotients: a = b * (q + ulp(q) / 2) nudged by -1 / 0 / +1 ulp
+    b = np.concatenate([rng.choice(consts, n), np.floor(rng.uniform(1, 1.4e7, n))])
+    q = np.ldexp(rng.uniform(1.0, 2.0, 2 * n), rng.integers(-15, 15, 2 * n))
+    a = q * b + (np.nextafter(q, np.inf) - q) * 0.5 * b
+    nudge = rng.integers(0, 3, 2 * n)
+    a = np.where(nudge == 1, np.nextafter(a, 0.0), np.where(nudge == 2, np.nextafter(a, np.inf), a))
+    cases.append((a, b))
+    for a, b in cases:
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        out = np.empty_like(a)
+        assert lib.mansy_selftest_ddiv_rcp(a.ctypes.data, b.ctypes.data, a.size, out.ctypes.data) == 0
+        assert np.array_equal(out, a / b)

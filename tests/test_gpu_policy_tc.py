@@ -101,3 +101,51 @@ def test_tc_policy_strided_rows_and_repeat_calls():
     for _ in range(3):
         logits, _, _, _ = net.forward_tc(dev[:, :784], sample=False)
         np.testing.assert_allclose(logits.cpu().numpy()[:, :15], ref_logits, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("split", [1, 4])
+@pytest.mark.parametrize("kind,n", [(OBS_MODE_MANSY, 700), (OBS_MODE_SIMPLE, 333), (OBS_MODE_MANSY, 4096)])
+def test_memoised_table_branches_equal_the_full_forward(kind, n, split):
+    """``forward_tc_sim`` (what every rollout runs): the 320-input branches come from the (video, chunk) memo computed in
+    exact fp32.  On the simulator's own observations -- mid-episode, after auto-resets, different videos / chunks per env --
+    it must agree with the torch fp32 restatement (same 5e-3 bound, in practice tighter than the all-TF32 forward) and with
+    the full tensor-core forward of the same rows."""
+    from mansy_immersivevideostreaming_b200 import synth
+    from mansy_immersivevideostreaming_b200.config import REWARD_QOE, SimConfig
+    from mansy_immersivevideostreaming_b200.simulator import BatchSimulator, ViewportTiler
+    shapes = mansy_state_dict_shapes() if kind == OBS_MODE_MANSY else simple_state_dict_shapes()
+    actor, critic = seeded_state_dict(shapes[0], 17), seeded_state_dict(shapes[1], 18)
+    net = PolicyNet(actor, critic, kind)
+    net.set_tc_split(split)
+    t = synth.make_synthetic_tables(ViewportTiler(SimConfig()).chunk_masks, n_videos=5, n_users=6, n_traces=7, seed=33,
+                                    trace_len_range=(40, 90))
+    t = t.with_samples(synth.per_env_samples(t, n))
+    sim = BatchSimulator(t, n, kind, REWARD_QOE, seed=4)
+    obs = sim.new_obs()
+    sim.reset(None, obs)
+    for steps in (0, 9, 61):                          # reset rows, mid-episode, after every env wrapped into a new episode
+        if steps:
+            sim.rollout_random(steps, seed=steps, obs=obs)
+        rows = obs.cpu().numpy()
+        ref_logits, ref_value = torch_reference(rows, actor, critic, kind)
+        lg = torch.empty((n, 16), device="cuda"); va = torch.empty(n, device="cuda")
+        ac = torch.empty(n, dtype=torch.int32, device="cuda"); lp = torch.empty(n, device="cuda")
+        net.forward_tc_sim(sim, obs, lg, va, ac, lp, seed=3, step=steps)
+        np.testing.assert_allclose(lg.cpu().numpy()[:, :15], ref_logits, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(va.cpu().numpy(), ref_value, rtol=RTOL, atol=ATOL)
+        full_l, full_v, _, _ = net.forward_tc(obs, sample=False)
+        np.testing.assert_allclose(lg.cpu().numpy()[:, :15], full_l.cpu().numpy()[:, :15], rtol=RTOL, atol=ATOL)
+        a2, _ = net.sample(lg, seed=3, step=steps)
+        assert torch.equal(ac, a2)
+    # a second simulator with other tables: the memo follows the simulator it is asked about
+    t2 = synth.make_synthetic_tables(ViewportTiler(SimConfig()).chunk_masks, n_videos=3, n_users=4, n_traces=5, seed=99,
+                                     trace_len_range=(40, 90))
+    sim2 = BatchSimulator(t2.with_samples(synth.per_env_samples(t2, n)), n, kind, REWARD_QOE, seed=1)
+    obs2 = sim2.new_obs()
+    sim2.reset(None, obs2)
+    sim2.rollout_random(5, seed=2, obs=obs2)
+    ref_logits, _ = torch_reference(obs2.cpu().numpy(), actor, critic, kind)
+    net.forward_tc_sim(sim2, obs2, lg, va, ac, lp)
+    np.testing.assert_allclose(lg.cpu().numpy()[:, :15], ref_logits, rtol=RTOL, atol=ATOL)
+    net.forward_tc_sim(sim, obs, lg, va, ac, lp)
+    np.testing.assert_allclose(lg.cpu().numpy()[:, :15], torch_reference(obs.cpu().numpy(), actor, critic, kind)[0], rtol=RTOL, atol=ATOL)
