@@ -36,8 +36,31 @@ __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeaky * 
 
 // Categorical(logits).sample() (bitrate_selection/run_mansy.py:228-229): inverse CDF on the
 // softmax with a uniform from a counter-based hash keyed by (seed, global env, step).
-// `p` holds logits (is_probs == 0) or probabilities; on return it holds unnormalised weights and
-// `s` their sum.
+__device__ __forceinline__ float categorical_uniform(uint64_t seed, uint64_t env, uint64_t step) {   // in [0, 1)
+  uint64_t z = seed * 0x9E3779B97F4A7C15ULL + env * 0xBF58476D1CE4E5B9ULL + step * 0x94D049BB133111EBULL +
+               0x2545F4914F6CDD1DULL;
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+  z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+// Second half of the sample: `p` holds unnormalised weights, `s` their sum (added in index order), `u01` the uniform.
+__device__ __forceinline__ void categorical_pick(const float (&p)[kActions], float s, float u01, int &act, float &logp) {
+  const float u = u01 * s;                                         // uniform in [0, s)
+  act = kActions - 1;
+  float cum = 0.f;
+  bool found = false;
+#pragma unroll
+  for (int o = 0; o < kActions; ++o) {
+    cum += p[o];
+    if (!found && u < cum) { act = o; found = true; }
+  }
+  float pa = p[0];
+#pragma unroll
+  for (int o = 1; o < kActions; ++o) if (o == act) pa = p[o];
+  logp = logf(pa / s);
+}
+// `p` holds logits (is_probs == 0) or probabilities; on return it holds unnormalised weights.
 __device__ __forceinline__ void categorical_sample(float (&p)[kActions], int is_probs, uint64_t seed, uint64_t env,
                                                    uint64_t step, int &act, float &logp) {
   float s = 0.f;
@@ -51,24 +74,7 @@ __device__ __forceinline__ void categorical_sample(float (&p)[kActions], int is_
 #pragma unroll
     for (int o = 0; o < kActions; ++o) s += p[o];
   }
-  uint64_t z = seed * 0x9E3779B97F4A7C15ULL + env * 0xBF58476D1CE4E5B9ULL + step * 0x94D049BB133111EBULL +
-               0x2545F4914F6CDD1DULL;
-  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
-  z ^= z >> 27; z *= 0x94D049BB133111EBULL;
-  z ^= z >> 31;
-  const float u = (float)(z >> 40) * (1.0f / 16777216.0f) * s;    // uniform in [0, s)
-  act = kActions - 1;
-  float cum = 0.f;
-  bool found = false;
-#pragma unroll
-  for (int o = 0; o < kActions; ++o) {
-    cum += p[o];
-    if (!found && u < cum) { act = o; found = true; }
-  }
-  float pa = p[0];
-#pragma unroll
-  for (int o = 1; o < kActions; ++o) if (o == act) pa = p[o];
-  logp = logf(pa / s);
+  categorical_pick(p, s, categorical_uniform(seed, env, step), act, logp);
 }
 
 struct TcState;   // tensor-core path state (mansy_policy_tc.cu)

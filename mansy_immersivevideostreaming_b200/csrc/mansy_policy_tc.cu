@@ -538,7 +538,9 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   const uint32_t rank = cluster_ctarank();
   const bool memo = A.memo != nullptr;
   const TcRankPlan &P = memo ? K.rank_memo[rank] : K.rank[rank];
-  const int tile = blockIdx.x / kTcRanks;
+  // A cluster walks the tiles cluster, cluster + n_clusters, ... (one tile per cluster when every tile's cluster is
+  // resident -- up to 33 tiles = 4 224 environments on B200 -- several per step beyond that, e.g. two at 8 192)
+  const int tile0 = blockIdx.x / kTcRanks, tile_stride = gridDim.x / kTcRanks;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage0 = base;
   const uint32_t wout_s = base + kTcStages * kStageBytes;   // this rank's K-slice of the head matrix: 2 boxes [16 x 32 floats]
@@ -554,10 +556,11 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   const uint32_t bar_d3_full = bars + 184;           //               MMA (commit) -> epilogue: head partial ready
   const uint32_t bar_wout = bars + 192;              //               TMA -> MMA: head matrices resident
   const uint32_t tmem_slot = bars + 200;
+  const uint32_t bar_tab = bars + 208;               // [4]           bulk table-row loads of 8 environments each (fused)
   const uint32_t d3recv = bars + 256;                // [src rank 4][float4 column 4][lane 32] x 16 B
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool tl = A.timeline != nullptr && (int)blockIdx.x == A.timeline_cta;
+  const bool tl = A.timeline != nullptr && (int)blockIdx.x == A.timeline_cta;     // (stamps of the cluster's last tile of the step win)
   const int tlk = kFused ? 1 : 0;          // the rollout step the timeline records (fused: the second, a steady-state one)
   const int n_jobs = P.n_jobs, nloc = P.n_branches, resid = P.resid_local;
   // D3 (head partial, 16 columns) lives in the D1 buffer the residual features do NOT occupy
@@ -577,6 +580,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     mbar_init(bar_hid_full, 256);
     mbar_init(bar_d3_full, 1);
     mbar_init(bar_wout, 1);
+    for (int g = 0; g < 4; ++g) mbar_init(bar_tab + 8 * g, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_obs) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
@@ -600,8 +604,6 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   const int half = (warp - kTcEpiWarp0) >> 2;
   const int r = q * 32 + lane;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-  const int env = tile * 128 + r;
-  const bool live = env < A.n;
   float own[32];      // this rank's own partial of the 32 hidden columns the thread finishes
 
   if (warp == 0 && elect_one()) {            // weights do not depend on the previous kernel in the stream
@@ -617,14 +619,26 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   uint32_t it = 0, s = 0, ph = 0;          // TMA producers and MMA issuer walk the same job sequence
   uint32_t feat_use[2] = {0, 0}, d1_use[2] = {0, 0};
   const int n_steps = kFused ? F.n_steps : 1;
+  uint32_t ts = 0;                          // tile-steps done by this cluster (parity of the once-per-tile-step barriers)
 
 #pragma unroll 1
   for (int k = 0; k < n_steps; ++k) {
-    const uint32_t par = (uint32_t)k & 1u;
-    const int64_t t = kFused ? F.t0 + k : A.step;
-    const int cur = kFused ? (int)(t % F.slabs) : 0;
+   const int64_t t = kFused ? F.t0 + k : A.step;
+   const int cur = kFused ? (int)(t % F.slabs) : 0;
+#pragma unroll 1
+   for (int tile = tile0; tile < A.n_tiles; tile += tile_stride, ++ts) {
+    const uint32_t par = ts & 1u;
+    const int env = tile * 128 + r;
+    const bool live = env < A.n;
     const int row0 = cur * A.n + tile * 128;          // first row of the tile in the (slab-stacked) observation tensor
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[489] = clock64();
+    // memoised table branches: which (video, chunk) entry this thread's row reads in phase B -- the state record is
+    // fetched now, while the epilogue warps wait for the first accumulator anyway
+    const float4 *memo_ptr = nullptr;
+    if (memo && warp >= kTcEpiWarp0)
+      memo_ptr = reinterpret_cast<const float4 *>(
+          A.memo + (size_t)memo_row_of(kFused ? F.S.state : A.memo_state, live ? env : 0, kFused ? F.S.n_chunks : A.memo_n_chunks) * 256 +
+          rank * 64u + (uint32_t)half * 32u);
 
     // ================= phase A: the rank's branches -> partial D2 =================
     if (warp < kTcProducers) {
@@ -720,7 +734,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       if (resid >= 0) {
         // residual through the heads: D3 = feat_qoe[128 x 128] * [actor.out ; critic.out]^T.  The qoe features sit in
         // D1[resid & 1] (their layer-2 MMAs above waited for them); the head MMAs of phase C accumulate on top.
-        if (k == 0) mbar_wait(bar_wout, 0);
+        if (ts == 0) mbar_wait(bar_wout, 0);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t w_lo = smem_desc_lo(wres_s);
@@ -769,11 +783,8 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     if (warp >= kTcEpiWarp0) {
       float4 mm[8];          // memoised table branches: this thread's 32 hidden columns of its row's (video, chunk) entry
       if (memo) {
-        const float4 *mrow = reinterpret_cast<const float4 *>(
-            A.memo + (size_t)memo_row_of(kFused ? F.S.state : A.memo_state, live ? env : 0, kFused ? F.S.n_chunks : A.memo_n_chunks) * 256 +
-            rank * 64u + (uint32_t)half * 32u);
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) mm[c4] = __ldg(mrow + c4);
+        for (int c4 = 0; c4 < 8; ++c4) mm[c4] = __ldg(memo_ptr + c4);
       }
 #pragma unroll 1
       for (uint32_t d = 0; d < (uint32_t)kTcRanks; ++d) {
@@ -849,7 +860,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       tc_fence_before();
     } else if (warp == kTcMmaWarp) {
       constexpr uint32_t kIdesc16 = idesc_tf32(16);
-      if (resid < 0 && k == 0) mbar_wait(bar_wout, 0);
+      if (resid < 0 && ts == 0) mbar_wait(bar_wout, 0);
       mbar_wait(bar_hid_full, par);
       tc_fence_after();
       if (elect_one()) {
@@ -867,49 +878,129 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     cluster_sync_all();              // (2) head partials delivered
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[485] = clock64();
 
-    if (kFused && warp < kTcEpiWarp0 && warp != kTcMmaWarp) {
+    if (kFused && warp == 0) {
       // Which chunk the NEXT observation describes does not depend on the action about to be sampled
-      // (simulator.py:105-106: next_chunk += 1; mansy_env.py:100-101: the sample after a finished episode), so
-      // its table rows (next chunk sizes / qualities, predicted viewport: 704 of 784 floats) are written by the
-      // seven warps that have nothing else to do (TMA producers, spare warp) while the epilogue warps sample the
-      // actions and run the simulator phase, which then only adds the dynamic columns.  (After cluster barrier 2:
-      // barrier.cluster counts every thread, so work placed earlier holds the other CTAs up; arriving early and
-      // waiting late was tried too -- it moves the table traffic onto the partial exchange and gains nothing.)
-      const int w7 = warp < kTcMmaWarp ? warp : kTcMmaWarp;     // 0..6
+      // (simulator.py:105-106: next_chunk += 1; mansy_env.py:100-101: the sample after a finished episode), so its
+      // table columns (next chunk sizes / qualities: floats 8..647 of a MANSY row, 8..327 of a SimpleRL row = one row of
+      // obs_tab / size_norm) are copied by ONE warp as bulk copies -- lane = environment: table row -> the idle TMA
+      // stages -> observation row -- while the epilogue warps sample and step.  No register staging and nothing in the
+      // L1 load/store queue the simulator phase waits on.  (After cluster barrier 2: every MMA that read the stages
+      // has completed -- the epilogue warps waited for bar_d2_full before they arrived there.)
+      const int ei = tile * 128 + (int)rank * 32 + lane;
       const int nxt = (int)((t + 1) % F.slabs);
-#pragma unroll 1
-      for (int el = w7 * 4 + (lane >> 3); el < 32; el += 28) {
-        const int ei = tile * 128 + (int)rank * 32 + el;
-        if (ei < A.n) {
-          EnvState nx;
-          load_state(F.S, ei, nx);
-          if (!(nx.flags & kFlagFinished)) {
-            if (nx.next_chunk + 1 > nx.end_chunk) reset_episode(F.S, nx);
-            else nx.next_chunk += 1;
-          }
-          emit_obs_tables<MODE>(F.S, nx.video, nx.pair, nx.start_chunk, min(nx.next_chunk, nx.end_chunk), lane & 7,
-                                F.obs + ((size_t)nxt * A.n + ei) * F.obs_stride);
+      const bool ok = ei < A.n;
+      size_t trow = 0;
+      if (ok) {
+        EnvState nx;
+        load_state(F.S, ei, nx);
+        if (!(nx.flags & kFlagFinished)) {
+          if (nx.next_chunk + 1 > nx.end_chunk) reset_episode(F.S, nx);
+          else nx.next_chunk += 1;
         }
+        trow = (size_t)nx.video * F.S.n_chunks + min(nx.next_chunk, nx.end_chunk);
       }
-      asm volatile("bar.arrive 2, 480;" ::: "memory");     // state(t) has been read: the simulator phase may overwrite it
-      asm volatile("fence.proxy.async;" ::: "memory");      // rows are read by the next step's TMA (async proxy)
+      asm volatile("bar.arrive 2, 288;" ::: "memory");     // state(t) has been read: the simulator phase may overwrite it
+      constexpr uint32_t kRowBytes = MODE == MANSY_OBS_MANSY ? 2560u : 1280u;
+      const uint32_t grp = (uint32_t)lane >> 3;            // one mbarrier per 8 environments (<= 20 KB of transactions each)
+      const uint32_t n_grp = __popc(__ballot_sync(0xFFFFFFFFu, ok) & (0xFFu << (8 * grp)));
+      const uint32_t tb = bar_tab + 8 * grp;
+      if ((lane & 7) == 0 && n_grp) mbar_expect_tx(tb, n_grp * kRowBytes);
+      __syncwarp();
+      const uint32_t sdst = stage0 + (uint32_t)lane * kRowBytes;
+      if (ok) bulk_load(sdst, MODE == MANSY_OBS_MANSY ? F.S.obs_tab + trow * (2 * kTableRow) : F.S.size_norm + trow * kTableRow, kRowBytes, tb);
+      if (n_grp) mbar_wait(tb, par);
+      if (ok) {
+        bulk_store(F.obs + ((size_t)nxt * A.n + ei) * F.obs_stride + 8, sdst, kRowBytes);
+        bulk_commit();
+      }
+      bulk_wait_all();       // rows written (a non-memo policy reads them next step) and the stages free for the next TMA loads
     }
-    // fused: the simulator phase's action-independent loads (state, history slot, viewport / trace entries) are
-    // issued now, so they land while warp q == rank samples the actions
+    // fused: the simulator phase's action-independent loads (state, history slot, viewport / trace entries, the
+    // outcomes of all 16 actions) are issued now, so they land while the actions are sampled
     EnvState sim_st;
     float sim_slot[8];
     StepInputs sim_in;
     const int sim_et = (int)threadIdx.x - 32 * kTcEpiWarp0;
     const int sim_i = tile * 128 + (int)rank * 32 + (sim_et >> 3);
     const bool sim_live = kFused && warp >= kTcEpiWarp0 && sim_i < A.n;
+    uint64_t sim_pred = 0;                       // predicted viewport of the next observation (when the episode goes on)
     if (kFused && sim_live) {
       load_state(F.S, sim_i, sim_st);
       load_slot(F.S, sim_i, sim_et & 7, sim_slot);
       sim_in = step_prefetch(F.S, sim_st, sim_et & 7, true);
+      sim_pred = __ldg(F.S.vp_pred + (size_t)sim_st.pair * F.S.n_vp_chunks + (min(sim_st.next_chunk + 1, sim_st.end_chunk) - sim_st.start_chunk));
     }
 
-    // ================= phase D: each rank finishes its 32 rows (warp q == rank) =================
-    if (warp >= kTcEpiWarp0 && half == 0 && (uint32_t)q == rank) {
+    // ================= phase D: each rank finishes its 32 rows =================
+    int sim_action = 0;
+    if (kFused) {
+      // The 8 lanes that step an environment also sample its action: lane `sub` owns logits 2 sub and 2 sub + 1 (the
+      // value is column 15).  Same arithmetic as categorical_sample -- partials added own rank first, then the other
+      // ranks ascending; exp per element; weights summed in index order -- spread over 8 lanes instead of one
+      // thread per row, so the result is bit-identical to the stand-alone kernel's.
+      if (warp >= kTcEpiWarp0) {
+        if (half == 0 && (uint32_t)q == rank) {      // this rank's own head partial joins the other three in shared memory
+          const uint32_t dst = d3recv + (rank * 4u) * 512u + (uint32_t)lane * 16u;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c4 * 512), "f"(own[4 * c4]), "f"(own[4 * c4 + 1]),
+                         "f"(own[4 * c4 + 2]), "f"(own[4 * c4 + 3]) : "memory");
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps: all four partials are in d3recv
+        const int sub = sim_et & 7, l = sim_et >> 3;
+        float l0, l1;
+        {
+          const uint32_t col = (uint32_t)(sub >> 1) * 512u + (uint32_t)l * 16u + (uint32_t)(sub & 1) * 8u;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(l0), "=f"(l1) : "r"(d3recv + (rank * 4u) * 512u + col) : "memory");
+#pragma unroll
+          for (uint32_t j3 = 0; j3 < 3; ++j3) {      // fixed order: own + the other ranks ascending
+            const uint32_t sr = j3 + (j3 >= rank ? 1u : 0u);
+            float x0, x1;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(d3recv + (sr * 4u) * 512u + col) : "memory");
+            l0 += x0; l1 += x1;
+          }
+          l0 += K.bout[2 * sub]; l1 += K.bout[2 * sub + 1];
+        }
+        const unsigned gm = group_mask();
+        const size_t orow = (size_t)cur * A.n + sim_i;      // outputs of step t live in slab t % slabs
+        if (sim_live && sub == 7 && A.value) A.value[orow] = l1;
+        float w0, w1;                                       // this lane's two weights
+        float m = sub == 7 ? l0 : fmaxf(l0, l1);
+        m = fmaxf(m, __shfl_xor_sync(gm, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(gm, m, 2));
+        m = fmaxf(m, __shfl_xor_sync(gm, m, 4));
+        w0 = expf(l0 - m);
+        w1 = sub == 7 ? 0.f : expf(l1 - m);
+        // all-gather of the 16 weights of the row through shared memory (the action hand-off buffer)
+        const uint32_t wrow = act_s + (uint32_t)l * 64u;
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(wrow + (uint32_t)sub * 8u), "f"(w0), "f"(w1) : "memory");
+        __syncwarp(gm);
+        float p[kActions + 1];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 v = ld_shared_v4(wrow + c4 * 16);
+          p[4 * c4] = v.x; p[4 * c4 + 1] = v.y; p[4 * c4 + 2] = v.z; p[4 * c4 + 3] = v.w;
+        }
+        float pp[kActions];
+        float ssum = 0.f;
+#pragma unroll
+        for (int o = 0; o < kActions; ++o) { pp[o] = p[o]; ssum += pp[o]; }
+        if (K.softmax == 1) {          // simple_rl.py:48: the actor returns probabilities; Categorical(probs) re-sums them
+#pragma unroll
+          for (int o = 0; o < kActions; ++o) pp[o] = pp[o] / ssum;
+          ssum = 0.f;
+#pragma unroll
+          for (int o = 0; o < kActions; ++o) ssum += pp[o];
+        }
+        float lp;
+        categorical_pick(pp, ssum, categorical_uniform(A.seed, (uint64_t)(A.env_offset + sim_i), (uint64_t)t), sim_action, lp);
+        if (sim_live && sub == 0) {
+          if (A.actions) A.actions[orow] = sim_action;
+          if (A.logp) A.logp[orow] = lp;
+        }
+        __syncwarp(gm);                // the weights row is rewritten next tile-step
+      }
+    } else if (warp >= kTcEpiWarp0 && half == 0 && (uint32_t)q == rank) {
       float acc[16];
 #pragma unroll
       for (int o = 0; o < 16; ++o) acc[o] = own[o];
@@ -925,9 +1016,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       }
 #pragma unroll
       for (int o = 0; o < 16; ++o) acc[o] += K.bout[o];
-      int act = 0;
       if (live) {
-        const size_t orow = kFused ? (size_t)cur * A.n + env : (size_t)env;   // fused: outputs of step t live in slab t % slabs
         float p[kActions];
 #pragma unroll
         for (int o = 0; o < kActions; ++o) p[o] = acc[o];
@@ -944,7 +1033,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
 #pragma unroll
           for (int o = 0; o < kActions; ++o) p[o] = p[o] / sum;
         }
-        if (A.value) A.value[orow] = acc[15];
+        if (A.value) A.value[env] = acc[15];
         if (A.logits) {
           float4 *dst = reinterpret_cast<float4 *>(A.logits + (size_t)env * 16);
           dst[0] = make_float4(p[0], p[1], p[2], p[3]);
@@ -953,35 +1042,33 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           dst[3] = make_float4(p[12], p[13], p[14], 0.f);
         }
         if (A.actions) {
+          int act;
           float lp;
           categorical_sample(p, K.softmax == 1, A.seed, (uint64_t)(A.env_offset + env), (uint64_t)t, act, lp);
-          A.actions[orow] = act;
-          if (A.logp) A.logp[orow] = lp;
+          A.actions[env] = act;
+          if (A.logp) A.logp[env] = lp;
         }
       }
-      if (kFused) asm volatile("st.shared.s32 [%0], %1;" ::"r"(act_s + (uint32_t)lane * 4u), "r"(act) : "memory");
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[486] = clock64();
 
     if (kFused) {
       // ================= phase E: simulator chunk-step of this CTA's 32 environments =================
       if (warp >= kTcEpiWarp0) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps: actions are in act_s
-        const int et = (int)threadIdx.x - 32 * kTcEpiWarp0;
-        const int i = tile * 128 + (int)rank * 32 + (et >> 3);
-        const int sub = et & 7;
+        const int i = sim_i;
+        const int sub = sim_et & 7;
         const SimDev &S = F.S;
         EnvState &st = sim_st;
         float (&slot)[8] = sim_slot;
         const bool live_e = sim_live;
         if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[490] = clock64() + (st.flags & 0);
-        int action;
-        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(action) : "r"(act_s + (uint32_t)(et >> 3) * 4u) : "memory");
+        const int action = sim_action;
         const int nxt = (int)((t + 1) % F.slabs);
         // full-mask collectives when all four environments of the warp step together (always, except in a tail tile)
         auto sim_step = [&](unsigned mask) {
           float reward_f = 0.f;
           bool over = true;
+          uint64_t pred = sim_pred;
           if (!(st.flags & kFlagFinished)) {
             const int slot_before = st.ep_step & 7;
             const double reward = step_env(S, st, slot, sub, mask, action, over, nullptr, nullptr, sim_in);
@@ -991,17 +1078,22 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
             if (over) {
               if (sub == 0) finish_episode(S, i, st);
               reset_episode(S, st);
+              pred = __ldg(S.vp_pred + (size_t)st.pair * S.n_vp_chunks + (min(st.next_chunk, st.end_chunk) - st.start_chunk));
             }
+          } else {
+            pred = __ldg(S.vp_pred + (size_t)st.pair * S.n_vp_chunks + (min(st.next_chunk, st.end_chunk) - st.start_chunk));
           }
           if (sub == 0) {
             F.reward[(size_t)cur * A.n + i] = reward_f;
             F.done[(size_t)cur * A.n + i] = over ? 1 : 0;
           }
-          emit_obs_dynamic<MODE>(S, st, slot, sub, mask, F.obs + ((size_t)nxt * A.n + i) * F.obs_stride);
+          float *row = F.obs + ((size_t)nxt * A.n + i) * F.obs_stride;
+          emit_obs_pred<MODE>(pred, sub, row);
+          emit_obs_dynamic<MODE>(S, st, slot, sub, mask, row);
         };
         if (__all_sync(0xFFFFFFFFu, live_e && !(st.flags & kFlagFinished))) sim_step(0xFFFFFFFFu);
         else if (live_e) sim_step(group_mask());
-        asm volatile("bar.sync 2, 480;" ::: "memory");       // the table-row warps have read state(t)
+        asm volatile("bar.sync 2, 288;" ::: "memory");       // the table-row warp has read state(t)
         if (i < A.n) store_state(S, i, st, sub);
         if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[492] = clock64();
         // the next step's TMA (async proxy) reads the rows just written through the generic proxy
@@ -1012,6 +1104,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       if (warp < kTcProducers) asm volatile("fence.proxy.async;" ::: "memory");
       if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[488] = clock64();
     }
+   }
   }
 
   tc_fence_before();
@@ -1513,7 +1606,11 @@ int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&mc, policy_tc4_kernel<SLOT, MODE>, &cfg);           \
       if (e == cudaSuccess) max_clusters = mc;                                                                      \
     }                                                                                                               \
-    if (e == cudaSuccess && n_tiles <= max_clusters) {                                                              \
+    if (e == cudaSuccess && max_clusters >= 1) {                                                                    \
+      /* every cluster of the grid must be resident (the rollout steps synchronise only inside a cluster, but a     \
+         cluster that is not scheduled until another one finishes would run its tiles late, not wrongly); more      \
+         tiles than resident clusters are walked in a loop */                                                       \
+      cfg.gridDim = dim3((unsigned)(kTcRanks * (n_tiles < max_clusters ? n_tiles : max_clusters)), 1, 1);           \
       e = cudaLaunchKernelEx(&cfg, policy_tc4_kernel<SLOT, MODE>, map_obs, p->tc->map_w1, p->tc->map_wfc, p->tc->map_wout, \
                              p->tc->map_wres, a, f);                                                                \
       if (e == cudaSuccess) *launched = 1;                                                                          \

@@ -600,6 +600,14 @@ int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, ma
   MANSY_TRY(upload(h, t->quality, n_tab, &d.quality));
   MANSY_TRY(upload(h, size_norm.data(), n_tab, &d.size_norm));
   MANSY_TRY(upload(h, qual_norm.data(), n_tab, &d.qual_norm));
+  {
+    std::vector<float> merged(2 * n_tab);
+    for (size_t r = 0; r < n_tab / kTableRow; ++r) {
+      memcpy(&merged[r * 2 * kTableRow], &size_norm[r * kTableRow], kTableRow * sizeof(float));
+      memcpy(&merged[r * 2 * kTableRow + kTableRow], &qual_norm[r * kTableRow], kTableRow * sizeof(float));
+    }
+    MANSY_TRY(upload(h, merged.data(), merged.size(), &d.obs_tab));
+  }
   MANSY_TRY(upload(h, t->video_time, (size_t)t->n_videos, &d.video_time));
   MANSY_TRY(upload(h, t->vp_gt, n_vp, &d.vp_gt));
   MANSY_TRY(upload(h, t->vp_pred, n_vp, &d.vp_pred));

@@ -73,6 +73,7 @@ struct SimDev {
   const float *quality;
   const float *size_norm;   // float(size) / float(max_size)           (utils/common.py:45-47)
   const float *qual_norm;   // quality / float(video_rates[-1])        (utils/common.py:40-42)
+  const float *obs_tab;     // [videos][chunks][640]: size_norm row | qual_norm row -- columns 8..647 of a MANSY observation, one bulk copy
   const int32_t *video_time;
   const uint64_t *vp_gt;
   const uint64_t *vp_pred;

@@ -179,16 +179,24 @@ __device__ __forceinline__ double trace_download_window(double size, double win,
 // comes next, and the dynamic part (history columns, last action, buffer, qoe weights).  The fused rollout
 // kernel writes the table part early (the next chunk is known before the action is), everything else calls
 // emit_obs.
+// Predicted-viewport columns of the row (mansy_env.py:229,236 / simple_rl_env.py:156): bit t of the mask -> float t.
 template <int MODE>
-__device__ __forceinline__ void emit_obs_tables(const SimDev &S, int video, int pair, int start_chunk, int obs_chunk, int sub,
-                                                float *__restrict__ row) {
-  const uint64_t pred = __ldg(S.vp_pred + (size_t)pair * S.n_vp_chunks + (obs_chunk - start_chunk));
-  const size_t tab = ((size_t)video * S.n_chunks + obs_chunk) * kTableRow;
+__device__ __forceinline__ void emit_obs_pred(uint64_t pred, int sub, float *__restrict__ row) {
   const uint32_t pbyte = (uint32_t)(pred >> (8 * sub)) & 0xFFu;
   const float4 p0 = make_float4((float)(pbyte & 1u), (float)((pbyte >> 1) & 1u), (float)((pbyte >> 2) & 1u),
                                 (float)((pbyte >> 3) & 1u));
   const float4 p1 = make_float4((float)((pbyte >> 4) & 1u), (float)((pbyte >> 5) & 1u),
                                 (float)((pbyte >> 6) & 1u), (float)((pbyte >> 7) & 1u));
+  float4 *dp = reinterpret_cast<float4 *>(row + (MODE == MANSY_OBS_MANSY ? 648 : 328));
+  dp[2 * sub] = p0;
+  dp[2 * sub + 1] = p1;
+}
+
+template <int MODE>
+__device__ __forceinline__ void emit_obs_tables(const SimDev &S, int video, int pair, int start_chunk, int obs_chunk, int sub,
+                                                float *__restrict__ row) {
+  const uint64_t pred = __ldg(S.vp_pred + (size_t)pair * S.n_vp_chunks + (obs_chunk - start_chunk));
+  const size_t tab = ((size_t)video * S.n_chunks + obs_chunk) * kTableRow;
   const float4 *s4 = reinterpret_cast<const float4 *>(S.size_norm + tab);
   float4 *ds = reinterpret_cast<float4 *>(row + 8);
   float4 tv[10];
@@ -204,16 +212,11 @@ __device__ __forceinline__ void emit_obs_tables(const SimDev &S, int video, int 
     for (int i = 0; i < 10; ++i) ds[sub + 8 * i] = tv[i];
 #pragma unroll
     for (int i = 0; i < 10; ++i) dq[sub + 8 * i] = tq[i];
-    float4 *dp = reinterpret_cast<float4 *>(row + 648);
-    dp[2 * sub] = p0;
-    dp[2 * sub + 1] = p1;
   } else {  // MANSY_OBS_SIMPLE
 #pragma unroll
     for (int i = 0; i < 10; ++i) ds[sub + 8 * i] = tv[i];
-    float4 *dp = reinterpret_cast<float4 *>(row + 328);
-    dp[2 * sub] = p0;
-    dp[2 * sub + 1] = p1;
   }
+  emit_obs_pred<MODE>(pred, sub, row);
 }
 
 template <int MODE>
