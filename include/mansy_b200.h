@@ -325,6 +325,8 @@ int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int
  * [480, 482..486] are the phase stamps (partial done, partials stored, cluster sync 1, heads issued, cluster sync 2,
  * rows written) of the CTA selected with the environment variable MANSY_TC_TIMELINE_CTA. */
 int mansy_policy_tc_set_split(mansy_policy_t p, int32_t split);
+/* debugging builds (-DMANSY_MBAR_WATCHDOG) only: host-mapped int32[grid * 16] that every warp of the fused rollout kernel stamps with (step << 16 | phase code) */
+int mansy_debug_progress(int32_t *progress_dev);
 /* Profiling hook of the fused rollout kernel (mansy_rollout_policy's one-launch path): CTA `cta` stamps the SM clock
  * of its SECOND rollout step into timeline_dev (int64[512], layout as above plus [489] step begin, [487] simulator
  * phase done, [488] cluster sync 3, [490..492] state loaded / step_env done / observation written); NULL turns it off. */

@@ -167,6 +167,7 @@ SIGNATURES = {
     "mansy_policy_forward_tc_timeline": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, C.c_uint64, C.c_int64,
                                                    C.c_int32, _vp, _vp, _vp, _vp]),
     "mansy_policy_tc_set_split": (C.c_int, [_vp, C.c_int32]),
+    "mansy_debug_progress": (C.c_int, [_vp]),
     "mansy_identifier_reward": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_double, C.c_int32, _vp, _vp, _vp]),
     "mansy_gae": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_double, C.c_double, _vp, _vp, _vp]),
     "mansy_debug_fused_timeline": (C.c_int, [_vp, C.c_int32]),

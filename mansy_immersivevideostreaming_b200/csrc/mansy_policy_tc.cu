@@ -527,6 +527,13 @@ struct FusedArgs {
   uint8_t *done;
 };
 
+#ifdef MANSY_MBAR_WATCHDOG     // debugging builds: every warp leaves (step << 16 | code) in a host-mapped buffer as it moves along
+static __device__ volatile int *d_dbg_progress = nullptr;
+#define MANSY_DBG(code) do { if (d_dbg_progress && (threadIdx.x & 31) == 0) d_dbg_progress[blockIdx.x * 16 + (threadIdx.x >> 5)] = ((int)k << 16) | (code); } while (0)
+#else
+#define MANSY_DBG(code) do { } while (0)
+#endif
+
 template <int SLOT, int MODE>
 __global__ void __cluster_dims__(kTcRanks, 1, 1) __launch_bounds__(kTcThreads, 1)
 policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_constant__ CUtensorMap map_w1,
@@ -620,6 +627,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   uint32_t feat_use[2] = {0, 0}, d1_use[2] = {0, 0};
   const int n_steps = kFused ? F.n_steps : 1;
   uint32_t ts = 0;                          // tile-steps done by this cluster (parity of the once-per-tile-step barriers)
+  uint32_t tab_use = 0;                     // phases this lane's bar_tab barrier has been through (a tail tile may skip one)
 
 #pragma unroll 1
   for (int k = 0; k < n_steps; ++k) {
@@ -778,6 +786,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[480] = clock64();
 
+    MANSY_DBG(5);
     // ================= phase B: reduce-scatter the partials through L2 =================
     float4 *const xch = A.scratch + (size_t)tile * kScratchF4PerTile;
     if (warp >= kTcEpiWarp0) {
@@ -809,6 +818,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[482] = clock64();
     cluster_sync_all();              // (1) partials of all four ranks are in L2 (release / acquire at cluster scope)
+    MANSY_DBG(10);
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[483] = clock64();
 
     // ================= phase C: hidden slice, this rank's K-slice of the heads =================
@@ -876,6 +886,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[484] = clock64();
     cluster_sync_all();              // (2) head partials delivered
+    MANSY_DBG(20);
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[485] = clock64();
 
     if (kFused && warp == 0) {
@@ -893,13 +904,12 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       if (ok) {
         EnvState nx;
         load_state(F.S, ei, nx);
-        if (!(nx.flags & kFlagFinished)) {
-          if (nx.next_chunk + 1 > nx.end_chunk) reset_episode(F.S, nx);
-          else nx.next_chunk += 1;
-        }
-        trow = (size_t)nx.video * F.S.n_chunks + min(nx.next_chunk, nx.end_chunk);
+        int video, pair, start, chunk;
+        next_obs_chunk(F.S, nx, 1, video, pair, start, chunk);
+        trow = (size_t)video * F.S.n_chunks + chunk;
       }
       asm volatile("bar.arrive 2, 288;" ::: "memory");     // state(t) has been read: the simulator phase may overwrite it
+    MANSY_DBG(21);
       constexpr uint32_t kRowBytes = MODE == MANSY_OBS_MANSY ? 2560u : 1280u;
       const uint32_t grp = (uint32_t)lane >> 3;            // one mbarrier per 8 environments (<= 20 KB of transactions each)
       const uint32_t n_grp = __popc(__ballot_sync(0xFFFFFFFFu, ok) & (0xFFu << (8 * grp)));
@@ -908,11 +918,14 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       __syncwarp();
       const uint32_t sdst = stage0 + (uint32_t)lane * kRowBytes;
       if (ok) bulk_load(sdst, MODE == MANSY_OBS_MANSY ? F.S.obs_tab + trow * (2 * kTableRow) : F.S.size_norm + trow * kTableRow, kRowBytes, tb);
-      if (n_grp) mbar_wait(tb, par);
+      MANSY_DBG(22);
+      if (n_grp) { mbar_wait(tb, tab_use & 1u, 77); ++tab_use; }
+      MANSY_DBG(23);
       if (ok) {
         bulk_store(F.obs + ((size_t)nxt * A.n + ei) * F.obs_stride + 8, sdst, kRowBytes);
         bulk_commit();
       }
+      MANSY_DBG(24);
       bulk_wait_all();       // rows written (a non-memo policy reads them next step) and the stages free for the next TMA loads
     }
     // fused: the simulator phase's action-independent loads (state, history slot, viewport / trace entries, the
@@ -947,6 +960,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
                          "f"(own[4 * c4 + 2]), "f"(own[4 * c4 + 3]) : "memory");
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps: all four partials are in d3recv
+    MANSY_DBG(30);
         const int sub = sim_et & 7, l = sim_et >> 3;
         float l0, l1;
         {
@@ -999,6 +1013,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           if (A.logp) A.logp[orow] = lp;
         }
         __syncwarp(gm);                // the weights row is rewritten next tile-step
+        MANSY_DBG(31);
       }
     } else if (warp >= kTcEpiWarp0 && half == 0 && (uint32_t)q == rank) {
       float acc[16];
@@ -1093,14 +1108,18 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         };
         if (__all_sync(0xFFFFFFFFu, live_e && !(st.flags & kFlagFinished))) sim_step(0xFFFFFFFFu);
         else if (live_e) sim_step(group_mask());
+        MANSY_DBG(32);
         asm volatile("bar.sync 2, 288;" ::: "memory");       // the table-row warp has read state(t)
+        MANSY_DBG(33);
         if (i < A.n) store_state(S, i, st, sub);
         if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[492] = clock64();
         // the next step's TMA (async proxy) reads the rows just written through the generic proxy
         asm volatile("fence.proxy.async;" ::: "memory");
       }
       if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[487] = clock64();
+      MANSY_DBG(39);
       cluster_sync_all();            // (3) the next observation rows of the tile are complete
+      MANSY_DBG(40);
       if (warp < kTcProducers) asm volatile("fence.proxy.async;" ::: "memory");
       if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[488] = clock64();
     }
@@ -1675,6 +1694,17 @@ int mansy_debug_fused_timeline(int64_t *timeline_dev, int32_t cta) {
   cudaMemcpyToSymbol(d_step_prof, &sp, sizeof(sp));
 #endif
   return MANSY_OK;
+}
+
+int mansy_debug_progress(int32_t *progress_dev) {
+#ifdef MANSY_MBAR_WATCHDOG
+  volatile int *ptr = progress_dev;
+  if (cudaMemcpyToSymbol(d_dbg_progress, &ptr, sizeof(ptr)) != cudaSuccess) return set_error(MANSY_E_CUDA, "cudaMemcpyToSymbol failed");
+  return MANSY_OK;
+#else
+  (void)progress_dev;
+  return set_error(MANSY_E_STATE, "library was built without MANSY_MBAR_WATCHDOG");
+#endif
 }
 
 int mansy_policy_tc_set_split(mansy_policy_t p, int32_t split) {

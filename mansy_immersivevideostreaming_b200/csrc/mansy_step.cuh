@@ -272,6 +272,24 @@ __device__ __forceinline__ void emit_obs(const SimDev &S, const EnvState &st, co
   emit_obs_dynamic<MODE>(S, st, slot, sub, gmask, row);
 }
 
+// Which table rows the observation AFTER this step shows: known before the step runs -- next_chunk + 1 while the episode
+// goes on (simulator.py:105-106), the first chunk of the next sample when it ends and the env resets itself
+// (mansy_env.py:100-101, simulator.py:45), the last chunk again for a terminal observation (mansy_env.py:208-223).
+__device__ __forceinline__ void next_obs_chunk(const SimDev &S, const EnvState &st, int auto_reset, int &video, int &pair,
+                                               int &start_chunk, int &chunk) {
+  video = st.video; pair = st.pair; start_chunk = st.start_chunk;
+  if (st.flags & kFlagFinished) { chunk = min(st.next_chunk, st.end_chunk); return; }
+  if (st.next_chunk + 1 > st.end_chunk && auto_reset) {
+    const int4 smp = __ldg(reinterpret_cast<const int4 *>(S.samples) + st.cursor % S.n_samples);
+    video = smp.x;
+    pair = smp.x * S.n_users + smp.y;
+    start_chunk = __ldg(S.vp_start + pair);
+    chunk = min(S.startup_download + 1, min(__ldg(S.vp_end + pair), __ldg(S.video_time + video) - 1));
+    return;
+  }
+  chunk = min(st.next_chunk + 1, st.end_chunk);
+}
+
 // What a step reads before it knows the action: the actual-viewport mask, the pyramid scales of this lane's tile
 // row, the prediction accuracy, this lane's entry of the bandwidth-trace window and the trace length.  The fused
 // rollout kernel issues these loads while the policy is still sampling.
