@@ -67,7 +67,9 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 cmd += ["-Xptxas", "-v"]
             jobs.append(cmd)
-    if not jobs and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(o) for o in objs):
+    tag_file = os.path.join(OBJ_DIR, "linked.tag")      # which flag set the library on disk was linked from
+    linked = open(tag_file).read().strip() if os.path.exists(tag_file) else ""
+    if not jobs and linked == tag and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(o) for o in objs):
         return LIB
 
     def run(cmd):
@@ -84,6 +86,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    with open(tag_file, "w") as fh:
+        fh.write(tag)
     return LIB
 
 

@@ -74,4 +74,7 @@ for kind in (OBS_MODE_MANSY, OBS_MODE_SIMPLE):
                     d = (x != y)
                     idx = d.nonzero()[:5].tolist()
                     print(f"      {k}: {int(d.sum())} differing elements, first at {idx}", flush=True)
+        for r in rolls:
+            r.sim.close()
+            r.policy.close()
 print("fused_smoke done")
