@@ -509,7 +509,9 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t saddr) {
 // Exchange buffer of the partial D2 tiles in global memory (it stays in L2): distributed shared memory moves
 // only ~20 B/clk per SM (measured: 96 KB of st.shared::cluster took 4 600 - 7 800 cycles), the L2 path several
 // times that.  Index in float4: ((((tile * 4 + dst) * 4 + src) * 2 + half) * 8 + c4) * 128 + row.
-constexpr size_t kScratchF4PerTile = 4 * 4 * 2 * 8 * 128;
+constexpr size_t kScratchPartialF4 = 4 * 4 * 2 * 8 * 128;
+// + the memoised table branches of the tile's rows in the same transposed layout: [dst rank 4][half 2][float4 column 8][row 128]
+constexpr size_t kScratchF4PerTile = kScratchPartialF4 + 4 * 2 * 8 * 128;
 
 // Fused rollout (MODE != MANSY_OBS_NONE): the same cluster also runs the simulator step of its 128 environments
 // (32 per CTA, 8 lanes each, on the eight epilogue warps) with the action it has just sampled, writes the next
@@ -620,7 +622,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       for (int b = 0; b < 4; ++b) tma_load_2d(wres_s + b * 2048, &map_wres, b * 32, 0, bar_wout);
   }
   __syncwarp();
-  if (warp < kTcProducers || warp >= kTcEpiWarp0) griddep_wait();   // rows come from / results go to stream-ordered memory
+  if (warp != kTcMmaWarp) griddep_wait();   // rows / state records come from, results go to stream-ordered memory
 
   // pipeline state carried across the rollout steps of the fused kernel
   uint32_t it = 0, s = 0, ph = 0;          // TMA producers and MMA issuer walk the same job sequence
@@ -640,14 +642,6 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     const bool live = env < A.n;
     const int row0 = cur * A.n + tile * 128;          // first row of the tile in the (slab-stacked) observation tensor
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[489] = clock64();
-    // memoised table branches: which (video, chunk) entry this thread's row reads in phase B -- the state record is
-    // fetched now, while the epilogue warps wait for the first accumulator anyway
-    const float4 *memo_ptr = nullptr;
-    if (memo && warp >= kTcEpiWarp0)
-      memo_ptr = reinterpret_cast<const float4 *>(
-          A.memo + (size_t)memo_row_of(kFused ? F.S.state : A.memo_state, live ? env : 0, kFused ? F.S.n_chunks : A.memo_n_chunks) * 256 +
-          rank * 64u + (uint32_t)half * 32u);
-
     // ================= phase A: the rank's branches -> partial D2 =================
     if (warp < kTcProducers) {
       const int hf = warp & 1;
@@ -754,6 +748,25 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         }
         __syncwarp();
       }
+    } else if (warp == kTcMmaWarp + 1) {
+      // The spare warp brings the memoised table branches of the tile's 128 rows into the exchange layout while phase A
+      // runs: row r's (video, chunk) entry, this rank's 64 hidden columns, written [half][float4 column][row] next to
+      // the partials the other ranks will deliver -- so that phase C reads it as one more coalesced source.  (A thread
+      // reading its own row's 128 bytes straight from the table in phase B is 32 cache lines per warp instruction.)
+      if (memo) {
+        float4 *const xm = A.scratch + (size_t)tile * kScratchF4PerTile + kScratchPartialF4 + (size_t)(rank * 2u) * 8u * 128u;
+#pragma unroll 1
+        for (int pass = 0; pass < 4; ++pass) {
+          const int rr = pass * 32 + lane, e = tile * 128 + rr;
+          const float4 *src = reinterpret_cast<const float4 *>(
+              A.memo + (size_t)memo_row_of(kFused ? F.S.state : A.memo_state, e < A.n ? e : 0, kFused ? F.S.n_chunks : A.memo_n_chunks) * 256 + rank * 64u);
+          float4 v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __ldg(src + j);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) __stcg(xm + (size_t)j * 128 + rr, v[j]);     // j = half * 8 + float4 column
+        }
+      }
     } else if (warp >= kTcEpiWarp0) {
       for (int i = 0; i < nloc; ++i) {
         const uint32_t buf = i & 1u;
@@ -790,11 +803,6 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     // ================= phase B: reduce-scatter the partials through L2 =================
     float4 *const xch = A.scratch + (size_t)tile * kScratchF4PerTile;
     if (warp >= kTcEpiWarp0) {
-      float4 mm[8];          // memoised table branches: this thread's 32 hidden columns of its row's (video, chunk) entry
-      if (memo) {
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) mm[c4] = __ldg(memo_ptr + c4);
-      }
 #pragma unroll 1
       for (uint32_t d = 0; d < (uint32_t)kTcRanks; ++d) {
         float v[32];
@@ -806,12 +814,6 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           float4 *dst = xch + (((d * 4u + rank) * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) __stcg(dst + c4 * 128, make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
-        }
-      }
-      if (memo) {
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          own[4 * c4] += mm[c4].x; own[4 * c4 + 1] += mm[c4].y; own[4 * c4 + 2] += mm[c4].z; own[4 * c4 + 3] += mm[c4].w;
         }
       }
       tc_fence_before();
@@ -839,6 +841,15 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
             own[4 * c4] += tt[j3 * 8 + c4].x; own[4 * c4 + 1] += tt[j3 * 8 + c4].y;
             own[4 * c4 + 2] += tt[j3 * 8 + c4].z; own[4 * c4 + 3] += tt[j3 * 8 + c4].w;
           }
+        if (memo) {                         // ... + the memoised table branches (gathered by the spare warp in phase A)
+          const float4 *src = xch + kScratchPartialF4 + ((rank * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) tt[c4] = __ldcg(src + c4 * 128);
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            own[4 * c4] += tt[c4].x; own[4 * c4 + 1] += tt[c4].y; own[4 * c4 + 2] += tt[c4].z; own[4 * c4 + 3] += tt[c4].w;
+          }
+        }
       }
       const int col0 = (int)rank * 64 + half * 32;      // hidden column (0..127 actor.fc, 128..255 critic.fc)
 #pragma unroll

@@ -73,7 +73,7 @@ def test_host_rollout_equals_device_rollout():
 @pytest.mark.parametrize("kind,n,steps,slabs", [(OBS_MODE_MANSY, 160, 60, 61), (OBS_MODE_MANSY, 4096, 12, 3),
                                                 (OBS_MODE_SIMPLE, 333, 60, 7), (OBS_MODE_MANSY, 1, 55, 4),
                                                 (OBS_MODE_MANSY, 8192 + 77, 7, 3),      # > 33 tiles: clusters walk several tiles per step
-                                                (OBS_MODE_SIMPLE, 13000, 5, 3)])
+                                                (OBS_MODE_SIMPLE, 13000, 7, 3)])
 def test_fused_rollout_equals_two_kernel_rollout(kind, n, steps, slabs):
     """ONE launch of the fused policy+step cluster kernel for all steps == two launches per step (with and without
     programmatic dependent launch), bit for bit, including the ring wrap of the slabs and a continued rollout."""
