@@ -642,6 +642,15 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     const bool live = env < A.n;
     const int row0 = cur * A.n + tile * 128;          // first row of the tile in the (slab-stacked) observation tensor
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[489] = clock64();
+    // fused: what the simulator phase of this CTA's 32 environments needs (8 lanes per environment on the epilogue warps)
+    EnvState sim_st;
+    float sim_slot[8];
+    StepInputs sim_in;
+    const int sim_et = (int)threadIdx.x - 32 * kTcEpiWarp0;
+    const int sim_i = tile * 128 + (int)rank * 32 + (sim_et >> 3);
+    const bool sim_live = kFused && warp >= kTcEpiWarp0 && sim_i < A.n;
+    uint64_t sim_pred = 0;                       // predicted viewport of the next observation (when the episode goes on)
+    float sim_wn[3] = {0.f, 0.f, 0.f};           // normalised QoE weights of the observation (utils/common.py:55-57)
     // ================= phase A: the rank's branches -> partial D2 =================
     if (warp < kTcProducers) {
       const int hf = warp & 1;
@@ -826,28 +835,36 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     // ================= phase C: hidden slice, this rank's K-slice of the heads =================
     if (warp >= kTcEpiWarp0) {
       {
-        float4 tt[24];
-#pragma unroll
-        for (uint32_t j3 = 0; j3 < 3; ++j3) {
-          const uint32_t sr = j3 + (j3 >= rank ? 1u : 0u);      // the three other ranks
-          const float4 *src = xch + (((rank * 4u + sr) * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) tt[j3 * 8 + c4] = __ldcg(src + c4 * 128);
-        }
-#pragma unroll
-        for (int j3 = 0; j3 < 3; ++j3)      // fixed summation order: own + the other ranks in ascending order
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            own[4 * c4] += tt[j3 * 8 + c4].x; own[4 * c4 + 1] += tt[j3 * 8 + c4].y;
-            own[4 * c4 + 2] += tt[j3 * 8 + c4].z; own[4 * c4 + 3] += tt[j3 * 8 + c4].w;
+        // the three other ranks' partials, then the memoised table branches (gathered by the spare warp in phase A): read one
+        // source ahead of the one being added (fixed summation order: own + ranks ascending + memo)
+        float4 tt[8], tn[8];
+        auto src_of = [&](uint32_t j3) -> const float4 * {
+          if (j3 < 3) {
+            const uint32_t sr = j3 + (j3 >= rank ? 1u : 0u);
+            return xch + (((rank * 4u + sr) * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
           }
-        if (memo) {                         // ... + the memoised table branches (gathered by the spare warp in phase A)
-          const float4 *src = xch + kScratchPartialF4 + ((rank * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
+          return xch + kScratchPartialF4 + ((rank * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
+        };
+        const uint32_t n_src = memo ? 4u : 3u;
+        {
+          const float4 *src = src_of(0);
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) tt[c4] = __ldcg(src + c4 * 128);
+        }
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) {
-            own[4 * c4] += tt[c4].x; own[4 * c4 + 1] += tt[c4].y; own[4 * c4 + 2] += tt[c4].z; own[4 * c4 + 3] += tt[c4].w;
+        for (uint32_t j3 = 0; j3 < 4; ++j3) {
+          if (j3 < n_src) {
+            if (j3 + 1 < n_src) {
+              const float4 *src = src_of(j3 + 1);
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4) tn[c4] = __ldcg(src + c4 * 128);
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              own[4 * c4] += tt[c4].x; own[4 * c4 + 1] += tt[c4].y; own[4 * c4 + 2] += tt[c4].z; own[4 * c4 + 3] += tt[c4].w;
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) tt[c4] = tn[c4];
           }
         }
       }
@@ -863,6 +880,17 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_hid_full);
+      if (kFused && sim_live) {
+        // The simulator phase's action-independent loads -- state record, history slot, viewport / trace entries, the
+        // outcomes of all 16 actions: two dependent round trips to L2 -- are issued here, under the heads MMA, the
+        // head-partial exchange and cluster barrier 2, instead of in front of the sampling.
+        load_state(F.S, sim_i, sim_st);
+        load_slot(F.S, sim_i, sim_et & 7, sim_slot);
+        sim_in = step_prefetch(F.S, sim_st, sim_et & 7, true);
+        sim_pred = __ldg(F.S.vp_pred + (size_t)sim_st.pair * F.S.n_vp_chunks + (min(sim_st.next_chunk + 1, sim_st.end_chunk) - sim_st.start_chunk));
+        const float ws = (float)dadd(dadd((double)sim_st.w0, (double)sim_st.w1), (double)sim_st.w2);
+        sim_wn[0] = fdiv(sim_st.w0, ws); sim_wn[1] = fdiv(sim_st.w1, ws); sim_wn[2] = fdiv(sim_st.w2, ws);
+      }
       if (half == 0) {
         // head partials: rows 32q .. 32q+31 are finished by rank q -> this warp's 32 rows all go to the same CTA
         mbar_wait(bar_d3_full, par);
@@ -939,21 +967,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       MANSY_DBG(24);
       bulk_wait_all();       // rows written (a non-memo policy reads them next step) and the stages free for the next TMA loads
     }
-    // fused: the simulator phase's action-independent loads (state, history slot, viewport / trace entries, the
-    // outcomes of all 16 actions) are issued now, so they land while the actions are sampled
-    EnvState sim_st;
-    float sim_slot[8];
-    StepInputs sim_in;
-    const int sim_et = (int)threadIdx.x - 32 * kTcEpiWarp0;
-    const int sim_i = tile * 128 + (int)rank * 32 + (sim_et >> 3);
-    const bool sim_live = kFused && warp >= kTcEpiWarp0 && sim_i < A.n;
-    uint64_t sim_pred = 0;                       // predicted viewport of the next observation (when the episode goes on)
-    if (kFused && sim_live) {
-      load_state(F.S, sim_i, sim_st);
-      load_slot(F.S, sim_i, sim_et & 7, sim_slot);
-      sim_in = step_prefetch(F.S, sim_st, sim_et & 7, true);
-      sim_pred = __ldg(F.S.vp_pred + (size_t)sim_st.pair * F.S.n_vp_chunks + (min(sim_st.next_chunk + 1, sim_st.end_chunk) - sim_st.start_chunk));
-    }
+    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[493] = clock64() + (sim_pred & 0);
 
     // ================= phase D: each rank finishes its 32 rows =================
     int sim_action = 0;
@@ -972,6 +986,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps: all four partials are in d3recv
     MANSY_DBG(30);
+        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[494] = clock64();
         const int sub = sim_et & 7, l = sim_et >> 3;
         float l0, l1;
         {
@@ -986,6 +1001,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           }
           l0 += K.bout[2 * sub]; l1 += K.bout[2 * sub + 1];
         }
+        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[495] = clock64() + (l0 > 1e30f);
         const unsigned gm = group_mask();
         const size_t orow = (size_t)cur * A.n + sim_i;      // outputs of step t live in slab t % slabs
         if (sim_live && sub == 7 && A.value) A.value[orow] = l1;
@@ -1017,6 +1033,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
 #pragma unroll
           for (int o = 0; o < kActions; ++o) ssum += pp[o];
         }
+        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[502] = clock64() + (ssum > 1e30f);
         float lp;
         categorical_pick(pp, ssum, categorical_uniform(A.seed, (uint64_t)(A.env_offset + sim_i), (uint64_t)t), sim_action, lp);
         if (sim_live && sub == 0) {
@@ -1105,6 +1122,8 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
               if (sub == 0) finish_episode(S, i, st);
               reset_episode(S, st);
               pred = __ldg(S.vp_pred + (size_t)st.pair * S.n_vp_chunks + (min(st.next_chunk, st.end_chunk) - st.start_chunk));
+              const float ws = (float)dadd(dadd((double)st.w0, (double)st.w1), (double)st.w2);      // the next sample's weights
+              sim_wn[0] = fdiv(st.w0, ws); sim_wn[1] = fdiv(st.w1, ws); sim_wn[2] = fdiv(st.w2, ws);
             }
           } else {
             pred = __ldg(S.vp_pred + (size_t)st.pair * S.n_vp_chunks + (min(st.next_chunk, st.end_chunk) - st.start_chunk));
@@ -1115,7 +1134,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           }
           float *row = F.obs + ((size_t)nxt * A.n + i) * F.obs_stride;
           emit_obs_pred<MODE>(pred, sub, row);
-          emit_obs_dynamic<MODE>(S, st, slot, sub, mask, row);
+          emit_obs_dynamic<MODE>(S, st, slot, sub, mask, row, sim_wn);
         };
         if (__all_sync(0xFFFFFFFFu, live_e && !(st.flags & kFlagFinished))) sim_step(0xFFFFFFFFu);
         else if (live_e) sim_step(group_mask());

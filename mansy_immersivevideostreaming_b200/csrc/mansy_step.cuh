@@ -219,9 +219,10 @@ __device__ __forceinline__ void emit_obs_tables(const SimDev &S, int video, int 
   emit_obs_pred<MODE>(pred, sub, row);
 }
 
+// `wn`: the normalised QoE weights w / (w0 + w1 + w2) when the caller has them already (they only change with the sample).
 template <int MODE>
 __device__ __forceinline__ void emit_obs_dynamic(const SimDev &S, const EnvState &st, const float (&slot)[8], int sub,
-                                                 unsigned gmask, float *__restrict__ row) {
+                                                 unsigned gmask, float *__restrict__ row, const float *wn = nullptr) {
   const int pushes = st.ep_step;
   const int newest = (pushes - 1) & 7;
   const int k = (newest - sub) & 7;         // observation index of this lane's slot (0 = newest)
@@ -241,9 +242,13 @@ __device__ __forceinline__ void emit_obs_dynamic(const SimDev &S, const EnvState
           make_float4(la == b ? 1.f : 0.f, la == b + 1 ? 1.f : 0.f, la == b + 2 ? 1.f : 0.f,
                       (la == b + 3 && b + 3 < kActions) ? 1.f : 0.f);
     } else if (sub == 4) {    // qoe_weight (utils/common.py:55-57) and buffer / startup_download
-      const float ws = (float)dadd(dadd((double)st.w0, (double)st.w1), (double)st.w2);
-      reinterpret_cast<float4 *>(row + 776)[0] =
-          make_float4(fdiv(st.w0, ws), fdiv(st.w1, ws), fdiv(st.w2, ws), fdiv((float)st.buf, S.startup_f));
+      if (wn) {
+        reinterpret_cast<float4 *>(row + 776)[0] = make_float4(wn[0], wn[1], wn[2], fdiv((float)st.buf, S.startup_f));
+      } else {
+        const float ws = (float)dadd(dadd((double)st.w0, (double)st.w1), (double)st.w2);
+        reinterpret_cast<float4 *>(row + 776)[0] =
+            make_float4(fdiv(st.w0, ws), fdiv(st.w1, ws), fdiv(st.w2, ws), fdiv((float)st.buf, S.startup_f));
+      }
     } else if (sub == 5) {
       reinterpret_cast<float4 *>(row + 780)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
     }

@@ -23,7 +23,9 @@ roll = PolicyRollout(sim, policy, 27, seed=1234)
 roll.run(20)
 torch.cuda.synchronize()
 tl = torch.zeros(512, dtype=torch.int64, device="cuda")
-names = {489: "step begin", 480: "partial D2 done", 482: "partials stored (L2 exchange)", 483: "cluster sync 1",
+names = {493: "sim loads issued (state, slot, prefetch)", 494: "bar.sync 1 (partials published)", 495: "logits summed",
+         502: "weights gathered + summed",
+         489: "step begin", 480: "partial D2 done", 482: "partials stored (L2 exchange)", 483: "cluster sync 1",
          484: "hidden slice + heads, D3 pushed", 485: "cluster sync 2", 486: "own 32 rows finished (sample)", 490: "state loaded",
          491: "step_env done", 492: "observation row + state stored", 487: "simulator phase done (fences)", 488: "cluster sync 3"}
 for cta in ctas:
@@ -38,7 +40,7 @@ for cta in ctas:
         if t[j] == 0:
             break
         print(f"  job {j:2d}: TMA issue {t[j]-t0:6d}  operands {t[128+j]-t0:6d}  MMAs issued {t[256+j]-t0:6d}")
-    for key in (480, 482, 483, 484, 485, 486, 490, 491, 492, 487, 488):
+    for key in (480, 482, 483, 484, 485, 493, 494, 495, 502, 486, 490, 491, 492, 487, 488):
         print(f"  {names[key]:34s} {t[key]-t0:7d}")
     if t[496]:      # -DMANSY_STEP_PROFILE build: inside step_env (thread 256 of CTA 0, last stamped step)
         for j, nm in enumerate(["entry", "gathers issued+summed (own)", "group sums done", "trace walk done", "qoe done", "history slot done"]):
