@@ -554,7 +554,9 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   const uint32_t stage0 = base;
   const uint32_t wout_s = base + kTcStages * kStageBytes;   // this rank's K-slice of the head matrix: 2 boxes [16 x 32 floats]
   const uint32_t wres_s = wout_s + 4096;                    // [actor.out ; critic.out] for the residual: 4 boxes
-  const uint32_t act_s = wout_s + 12288;                    // fused: sampled actions of this CTA's 32 environments
+  const uint32_t act_s = wout_s + 12288;                    // fused: the 16 sampling weights of each of this CTA's 32 environments
+  const uint32_t sim_s = stage0 + 2 * kStageBytes;          // fused: the third TMA stage, idle between phase A and the next one, stages
+                                                            // the simulator phase's loads: [32 records x 128 B][32 x 8 slots x 32 B][32 x 8 lanes x 128 B]
   const uint32_t bars = wout_s + kWoutBytes;
   const uint32_t bar_full = bars;                    // [kTcStages][2] TMA -> MMA
   const uint32_t bar_empty = bars + 64;              // [kTcStages]    MMA (commit) -> TMA
@@ -881,15 +883,16 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       tc_fence_before();
       mbar_arrive(bar_hid_full);
       if (kFused && sim_live) {
-        // The simulator phase's action-independent loads -- state record, history slot, viewport / trace entries, the
-        // outcomes of all 16 actions: two dependent round trips to L2 -- are issued here, under the heads MMA, the
-        // head-partial exchange and cluster barrier 2, instead of in front of the sampling.
-        load_state(F.S, sim_i, sim_st);
-        load_slot(F.S, sim_i, sim_et & 7, sim_slot);
-        sim_in = step_prefetch(F.S, sim_st, sim_et & 7, true);
-        sim_pred = __ldg(F.S.vp_pred + (size_t)sim_st.pair * F.S.n_vp_chunks + (min(sim_st.next_chunk + 1, sim_st.end_chunk) - sim_st.start_chunk));
-        const float ws = (float)dadd(dadd((double)sim_st.w0, (double)sim_st.w1), (double)sim_st.w2);
-        sim_wn[0] = fdiv(sim_st.w0, ws); sim_wn[1] = fdiv(sim_st.w1, ws); sim_wn[2] = fdiv(sim_st.w2, ws);
+        // The simulator phase's action-independent loads are two dependent round trips to L2.  Both go through cp.async
+        // into the idle third TMA stage, not through registers (a register load blocks the in-order warp at its first
+        // use, and this kernel sits at its 128-register cap): the state record and the history slot are requested here,
+        // under the heads MMA, the head-partial exchange and cluster barrier 2; what the record points at (viewport /
+        // trace entries, the outcomes of all 16 actions) right after that barrier, under the sampling.
+        const uint32_t el = (uint32_t)sim_et >> 3, sb = (uint32_t)sim_et & 7u;
+        cp_async16(sim_s + el * 128u + sb * 16u, reinterpret_cast<const uint4 *>(F.S.state + sim_i) + sb);
+        const float *hs = F.S.hist + (size_t)sim_i * kHistFloatsPerEnv + sb * 8;
+        cp_async16(sim_s + 4096u + (el * 8u + sb) * 32u, hs);
+        cp_async16(sim_s + 4096u + (el * 8u + sb) * 32u + 16u, hs + 4);
       }
       if (half == 0) {
         // head partials: rows 32q .. 32q+31 are finished by rank q -> this warp's 32 rows all go to the same CTA
@@ -967,7 +970,43 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       MANSY_DBG(24);
       bulk_wait_all();       // rows written (a non-memo policy reads them next step) and the stages free for the next TMA loads
     }
-    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[493] = clock64() + (sim_pred & 0);
+    if (kFused && warp >= kTcEpiWarp0) {
+      cp_async_wait_all();                       // this lane's quad of the state record and its history slot have landed ...
+      __syncwarp(group_mask());                  // ... and so have the other seven quads of the record
+      if (sim_live) {
+        const uint32_t el = (uint32_t)sim_et >> 3, sb = (uint32_t)sim_et & 7u;
+        StateQuads u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = ld_shared_v4(sim_s + el * 128u + (uint32_t)i * 16u);
+          u.q[i] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+        }
+        sim_st = u.s;
+        {
+          const float4 a = ld_shared_v4(sim_s + 4096u + (el * 8u + sb) * 32u), b = ld_shared_v4(sim_s + 4096u + (el * 8u + sb) * 32u + 16u);
+          sim_slot[0] = a.x; sim_slot[1] = a.y; sim_slot[2] = a.z; sim_slot[3] = a.w;
+          sim_slot[4] = b.x; sim_slot[5] = b.y; sim_slot[6] = b.z; sim_slot[7] = b.w;
+        }
+        // second round trip: what the record points at, 112 bytes per lane
+        const SimDev &S = F.S;
+        const uint32_t pf = sim_s + 12288u + (el * 8u + sb) * 128u;
+        const size_t vi = (size_t)sim_st.pair * S.n_vp_chunks + (sim_st.next_chunk - sim_st.start_chunk);
+        const double *tr = S.trace + (size_t)sim_st.trace * S.trace_stride, *trr = S.trace_rcp + (size_t)sim_st.trace * S.trace_stride;
+        cp_async8(pf + 0u, S.vp_gt + vi);
+        cp_async8(pf + 8u, S.vp_acc + vi);
+        cp_async8(pf + 16u, tr + sim_st.cur_idx + sb);
+        cp_async8(pf + 24u, trr + sim_st.cur_idx + sb);
+        if (S.outcome != nullptr) {
+          const uint4 *o = reinterpret_cast<const uint4 *>(S.outcome + vi * kOutcomeActions + 2 * sb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cp_async16(pf + 32u + 16u * j, o + j);
+        }
+        cp_async8(pf + 96u, S.vp_pred + (size_t)sim_st.pair * S.n_vp_chunks + (min(sim_st.next_chunk + 1, sim_st.end_chunk) - sim_st.start_chunk));
+        cp_async4(pf + 104u, S.vp_scale + vi * 8 + sb);
+        cp_async4(pf + 108u, S.trace_len + sim_st.trace);
+      }
+    }
+    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[493] = clock64();
 
     // ================= phase D: each rank finishes its 32 rows =================
     int sim_action = 0;
@@ -1039,6 +1078,31 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         if (sim_live && sub == 0) {
           if (A.actions) A.actions[orow] = sim_action;
           if (A.logp) A.logp[orow] = lp;
+        }
+        if (sim_live) {
+          const float ws = (float)dadd(dadd((double)sim_st.w0, (double)sim_st.w1), (double)sim_st.w2);
+          sim_wn[0] = fdiv(sim_st.w0, ws); sim_wn[1] = fdiv(sim_st.w1, ws); sim_wn[2] = fdiv(sim_st.w2, ws);
+        }
+        cp_async_wait_all();                     // the second round trip (each lane reads back only what it requested)
+        if (sim_live) {
+          const SimDev &S = F.S;
+          const uint32_t pf = sim_s + 12288u + (((uint32_t)sim_et >> 3) * 8u + ((uint32_t)sim_et & 7u)) * 128u;
+          const float4 a = ld_shared_v4(pf), b = ld_shared_v4(pf + 16u), o0 = ld_shared_v4(pf + 32u), s0 = ld_shared_v4(pf + 48u),
+                       o1 = ld_shared_v4(pf + 64u), s1 = ld_shared_v4(pf + 80u), c = ld_shared_v4(pf + 96u);
+          auto f2d = [](float lo, float hi) { return __hiloint2double((int)__float_as_uint(hi), (int)__float_as_uint(lo)); };
+          sim_in.vi = (size_t)sim_st.pair * S.n_vp_chunks + (sim_st.next_chunk - sim_st.start_chunk);
+          sim_in.gt = ((uint64_t)__float_as_uint(a.y) << 32) | __float_as_uint(a.x);
+          sim_in.acc = f2d(a.z, a.w);
+          sim_in.win = f2d(b.x, b.y);
+          sim_in.rwin = f2d(b.z, b.w);
+          sim_in.oq0 = f2d(o0.x, o0.y); sim_in.oi0 = f2d(o0.z, o0.w); sim_in.os0 = (int)__float_as_uint(s0.x);
+          sim_in.oq1 = f2d(o1.x, o1.y); sim_in.oi1 = f2d(o1.z, o1.w); sim_in.os1 = (int)__float_as_uint(s1.x);
+          sim_pred = ((uint64_t)__float_as_uint(c.y) << 32) | __float_as_uint(c.x);
+          sim_in.scales = __float_as_uint(c.z);
+          sim_in.tlen = (int)__float_as_uint(c.w);
+          sim_in.tr = S.trace + (size_t)sim_st.trace * S.trace_stride;
+          sim_in.trr = S.trace_rcp + (size_t)sim_st.trace * S.trace_stride;
+          sim_in.outcomes = S.outcome != nullptr;
         }
         __syncwarp(gm);                // the weights row is rewritten next tile-step
         MANSY_DBG(31);

@@ -57,7 +57,6 @@ cudaError_t use_device(int device) {
 }  // namespace mansy
 
 #include "mansy_step.cuh"  // StepArgs, step_env, emit_obs, reset_episode, finish_episode (device code)
-#include "mansy_tc.cuh"    // mbarrier / bulk-copy wrappers
 
 namespace mansy {
 
@@ -66,11 +65,10 @@ namespace mansy {
 // ------------------------------------------------------------------------------------------
 // One step of one environment group inside step_kernel.  `mask` is the shuffle mask of the group's collectives:
 // the constant 0xFFFFFFFF when the whole warp is known to execute this together (plain SHFL), else the 8-lane
-// group mask (partial-mask collectives cost ~10x the instructions).  `pred` is the predicted-viewport mask of the
-// observation after the step (next_obs_chunk); the table columns of that row travel as a bulk copy (step_kernel).
+// group mask (partial-mask collectives cost ~10x the instructions).
 template <int MODE>
 __device__ __forceinline__ void step_once(const SimDev &S, const StepArgs &A, EnvState &st, float (&slot)[8], int e, int i,
-                                          int sub, unsigned mask, int t, uint64_t pred) {
+                                          int sub, unsigned mask, int t) {
   const size_t r = (size_t)t * A.rows_per_step + i;
   float reward_f = 0.f;
   bool over = true;
@@ -94,24 +92,15 @@ __device__ __forceinline__ void step_once(const SimDev &S, const StepArgs &A, En
     if (A.out.reward) A.out.reward[r] = reward_f;
     if (A.out.done) A.out.done[r] = over ? 1 : 0;
   }
-  if (MODE != MANSY_OBS_NONE && A.out.obs) {
-    float *row = A.out.obs + r * A.out.obs_stride;
-    emit_obs_pred<MODE>(pred, sub, row);
-    emit_obs_dynamic<MODE>(S, st, slot, sub, mask, row);
-  }
+  if (MODE != MANSY_OBS_NONE && A.out.obs) emit_obs<MODE>(S, st, slot, sub, mask, A.out.obs + r * A.out.obs_stride);
 }
 
-// The observation row is 3.1 KB (MANSY) / 1.6 KB (SimpleRL), of which 2 560 / 1 280 bytes -- next chunk sizes and
-// qualities, floats 8..647 / 8..327 -- are a verbatim row of a read-only table whose index is known before the step
-// runs.  That part never touches registers: lane 0 of each environment issues a bulk copy (TMA) table row -> shared
-// memory at the top of the step and shared memory -> observation row at its end; the lanes only write the 64
-// predicted-viewport floats and the dynamic columns.  40 KB of staging per 16-environment CTA.
+// (Measured and rejected, profiles/r02e_step_sweep.txt: the 2 560 / 1 280 table bytes of the row as bulk copies table ->
+// shared memory -> row, 40 KB of staging per CTA: 79.4 % / 54.7 % of the HBM peak at 1 Mi envs against 82.7 % / 58.8 % for
+// the cooperative 128-bit loads and stores below.)
 template <int MODE>
 __global__ void __launch_bounds__(kThreadsPerBlock, MANSY_STEP_MIN_BLOCKS)
 step_kernel(const __grid_constant__ SimDev S, const __grid_constant__ StepArgs A) {
-  constexpr uint32_t kRowBytes = MODE == MANSY_OBS_MANSY ? 2 * kTableRow * 4u : (MODE == MANSY_OBS_SIMPLE ? kTableRow * 4u : 0u);
-  __shared__ __align__(128) uint8_t tab_s[kRowBytes ? kEnvsPerBlock * kRowBytes : 16];
-  __shared__ __align__(8) uint64_t tab_bar_s;
   // Programmatic dependent launch (no-ops without the launch attribute): the next kernel of the stream may be
   // scheduled right away -- it orders itself behind our completion -- and everything we read below (actions,
   // state, history) may have been written by the kernels before us.
@@ -120,12 +109,6 @@ step_kernel(const __grid_constant__ SimDev S, const __grid_constant__ StepArgs A
   bool live = i < A.n;                                             // lanes past the end stay for the warp votes below
   const int sub = threadIdx.x & 7;
   const unsigned gmask = group_mask();
-  const bool copy = MODE != MANSY_OBS_NONE && A.out.obs != nullptr;
-  const uint32_t bar = smem_u32(&tab_bar_s), srow = smem_u32(tab_s) + (uint32_t)(threadIdx.x >> 3) * kRowBytes;
-  if (copy && threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   int e = live ? (A.env_ids ? __ldg(A.env_ids + i) : i) : 0;
   if (e < 0 || e >= S.n_envs) {            // the host wrappers validate ids (the reference raises IndexError); never index out of range
@@ -133,7 +116,6 @@ step_kernel(const __grid_constant__ SimDev S, const __grid_constant__ StepArgs A
     live = false;
     e = 0;
   }
-  const int n_copy = __syncthreads_count(copy && live && sub == 0);   // rows this CTA copies per step (also orders the barrier init)
 
   EnvState st;
   float slot[8];
@@ -142,36 +124,14 @@ step_kernel(const __grid_constant__ SimDev S, const __grid_constant__ StepArgs A
     load_slot(S, e, sub, slot);
   }
   for (int t = 0; t < A.n_steps; ++t) {
-    uint64_t pred = 0;
-    if (copy) {
-      if (threadIdx.x == 0 && n_copy) mbar_expect_tx(bar, (uint32_t)n_copy * kRowBytes);
-      if (live) {
-        int video, pair, start, chunk;
-        next_obs_chunk(S, st, A.auto_reset, video, pair, start, chunk);
-        if (sub == 0) {
-          bulk_wait_read_all();          // the previous step's copy out of this staging row has been read
-          const size_t trow = (size_t)video * S.n_chunks + chunk;
-          bulk_load(srow, MODE == MANSY_OBS_MANSY ? S.obs_tab + trow * (2 * kTableRow) : S.size_norm + trow * kTableRow, kRowBytes, bar);
-        }
-        pred = __ldg(S.vp_pred + (size_t)pair * S.n_vp_chunks + (chunk - start));
-      }
-    }
     const bool run = live && !(st.flags & kFlagFinished);
-    if (__all_sync(0xFFFFFFFFu, run)) step_once<MODE>(S, A, st, slot, e, i, sub, 0xFFFFFFFFu, t, pred);   // the common case
-    else if (live) step_once<MODE>(S, A, st, slot, e, i, sub, gmask, t, pred);
-    if (copy && n_copy && ((live && sub == 0) || threadIdx.x == 0)) {
-      mbar_wait(bar, (uint32_t)t & 1u, 78);   // every table row of the CTA has landed (one barrier per CTA and step)
-      if (live && sub == 0) {
-        bulk_store(A.out.obs + ((size_t)t * A.rows_per_step + i) * A.out.obs_stride + 8, srow, kRowBytes);
-        bulk_commit();
-      }
-    }
+    if (__all_sync(0xFFFFFFFFu, run)) step_once<MODE>(S, A, st, slot, e, i, sub, 0xFFFFFFFFu, t);   // the common case
+    else if (live) step_once<MODE>(S, A, st, slot, e, i, sub, gmask, t);
   }
   if (live) {
     if (A.n_steps != 1) store_slot(S, e, sub, slot);
     store_state(S, e, st, sub);
   }
-  if (copy) bulk_wait_read_all();          // shared memory must outlive the reads of the last copies
 }
 
 template <int MODE>
@@ -537,12 +497,6 @@ int launch_step(mansy_sim *h, const StepArgs &a, cudaStream_t s, bool pdl = fals
   cfg.stream = s;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  static bool carveout_done = false;       // 5 resident CTAs x 40 KB of table-row staging need the large shared-memory carve-out
-  if (!carveout_done) {
-    cudaFuncSetAttribute(step_kernel<MANSY_OBS_MANSY>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(step_kernel<MANSY_OBS_SIMPLE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    carveout_done = true;
-  }
   switch (h->dev.obs_mode) {
     case MANSY_OBS_MANSY: MANSY_CUDA(cudaLaunchKernelEx(&cfg, step_kernel<MANSY_OBS_MANSY>, h->dev, a)); break;
     case MANSY_OBS_SIMPLE: MANSY_CUDA(cudaLaunchKernelEx(&cfg, step_kernel<MANSY_OBS_SIMPLE>, h->dev, a)); break;
