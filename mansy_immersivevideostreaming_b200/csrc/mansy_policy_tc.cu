@@ -523,6 +523,7 @@ struct FusedArgs {
   float *obs;          // [slabs][n][obs_stride]   (the TMA map `map_obs` views it as [slabs * n] rows)
   int64_t obs_stride;
   int32_t slabs, n_steps;
+  int32_t outcome_prefetch;   // 1: fetch the outcomes of all 16 actions before the action is known; 0: one entry afterwards
   int64_t t0;
   int32_t *actions;    // [slabs][n]
   float *logp, *value, *reward;
@@ -652,7 +653,6 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     const int sim_i = tile * 128 + (int)rank * 32 + (sim_et >> 3);
     const bool sim_live = kFused && warp >= kTcEpiWarp0 && sim_i < A.n;
     uint64_t sim_pred = 0;                       // predicted viewport of the next observation (when the episode goes on)
-    float sim_wn[3] = {0.f, 0.f, 0.f};           // normalised QoE weights of the observation (utils/common.py:55-57)
     // ================= phase A: the rank's branches -> partial D2 =================
     if (warp < kTcProducers) {
       const int hf = warp & 1;
@@ -882,18 +882,6 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_hid_full);
-      if (kFused && sim_live) {
-        // The simulator phase's action-independent loads are two dependent round trips to L2.  Both go through cp.async
-        // into the idle third TMA stage, not through registers (a register load blocks the in-order warp at its first
-        // use, and this kernel sits at its 128-register cap): the state record and the history slot are requested here,
-        // under the heads MMA, the head-partial exchange and cluster barrier 2; what the record points at (viewport /
-        // trace entries, the outcomes of all 16 actions) right after that barrier, under the sampling.
-        const uint32_t el = (uint32_t)sim_et >> 3, sb = (uint32_t)sim_et & 7u;
-        cp_async16(sim_s + el * 128u + sb * 16u, reinterpret_cast<const uint4 *>(F.S.state + sim_i) + sb);
-        const float *hs = F.S.hist + (size_t)sim_i * kHistFloatsPerEnv + sb * 8;
-        cp_async16(sim_s + 4096u + (el * 8u + sb) * 32u, hs);
-        cp_async16(sim_s + 4096u + (el * 8u + sb) * 32u + 16u, hs + 4);
-      }
       if (half == 0) {
         // head partials: rows 32q .. 32q+31 are finished by rank q -> this warp's 32 rows all go to the same CTA
         mbar_wait(bar_d3_full, par);
@@ -970,144 +958,22 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       MANSY_DBG(24);
       bulk_wait_all();       // rows written (a non-memo policy reads them next step) and the stages free for the next TMA loads
     }
-    if (kFused && warp >= kTcEpiWarp0) {
-      cp_async_wait_all();                       // this lane's quad of the state record and its history slot have landed ...
-      __syncwarp(group_mask());                  // ... and so have the other seven quads of the record
-      if (sim_live) {
-        const uint32_t el = (uint32_t)sim_et >> 3, sb = (uint32_t)sim_et & 7u;
-        StateQuads u;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 v = ld_shared_v4(sim_s + el * 128u + (uint32_t)i * 16u);
-          u.q[i] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
-        }
-        sim_st = u.s;
-        {
-          const float4 a = ld_shared_v4(sim_s + 4096u + (el * 8u + sb) * 32u), b = ld_shared_v4(sim_s + 4096u + (el * 8u + sb) * 32u + 16u);
-          sim_slot[0] = a.x; sim_slot[1] = a.y; sim_slot[2] = a.z; sim_slot[3] = a.w;
-          sim_slot[4] = b.x; sim_slot[5] = b.y; sim_slot[6] = b.z; sim_slot[7] = b.w;
-        }
-        // second round trip: what the record points at, 112 bytes per lane
-        const SimDev &S = F.S;
-        const uint32_t pf = sim_s + 12288u + (el * 8u + sb) * 128u;
-        const size_t vi = (size_t)sim_st.pair * S.n_vp_chunks + (sim_st.next_chunk - sim_st.start_chunk);
-        const double *tr = S.trace + (size_t)sim_st.trace * S.trace_stride, *trr = S.trace_rcp + (size_t)sim_st.trace * S.trace_stride;
-        cp_async8(pf + 0u, S.vp_gt + vi);
-        cp_async8(pf + 8u, S.vp_acc + vi);
-        cp_async8(pf + 16u, tr + sim_st.cur_idx + sb);
-        cp_async8(pf + 24u, trr + sim_st.cur_idx + sb);
-        if (S.outcome != nullptr) {
-          const uint4 *o = reinterpret_cast<const uint4 *>(S.outcome + vi * kOutcomeActions + 2 * sb);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) cp_async16(pf + 32u + 16u * j, o + j);
-        }
-        cp_async8(pf + 96u, S.vp_pred + (size_t)sim_st.pair * S.n_vp_chunks + (min(sim_st.next_chunk + 1, sim_st.end_chunk) - sim_st.start_chunk));
-        cp_async4(pf + 104u, S.vp_scale + vi * 8 + sb);
-        cp_async4(pf + 108u, S.trace_len + sim_st.trace);
-      }
+    // fused: the simulator phase's action-independent loads (state record, history slot, viewport / trace entries) are issued
+    // by all eight epilogue warps now, so they land while warp q == rank samples the actions.  (Measured alternatives that
+    // did not pay, profiles/r02*_fused_timeline.txt: sampling spread over the 8 lanes of each environment, the loads staged
+    // through cp.async into an idle TMA stage, the outcomes of all 16 actions fetched ahead -- every one of them lengthens
+    // this phase by as much as it shortens the next: eight warps each walking the whole dependent chain are slower than one
+    // warp sampling while seven only wait for their loads.)
+    if (kFused && sim_live) {
+      load_state(F.S, sim_i, sim_st);
+      load_slot(F.S, sim_i, sim_et & 7, sim_slot);
+      sim_in = step_prefetch(F.S, sim_st, sim_et & 7);
+      sim_pred = __ldg(F.S.vp_pred + (size_t)sim_st.pair * F.S.n_vp_chunks + (min(sim_st.next_chunk + 1, sim_st.end_chunk) - sim_st.start_chunk));
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[493] = clock64();
 
-    // ================= phase D: each rank finishes its 32 rows =================
-    int sim_action = 0;
-    if (kFused) {
-      // The 8 lanes that step an environment also sample its action: lane `sub` owns logits 2 sub and 2 sub + 1 (the
-      // value is column 15).  Same arithmetic as categorical_sample -- partials added own rank first, then the other
-      // ranks ascending; exp per element; weights summed in index order -- spread over 8 lanes instead of one
-      // thread per row, so the result is bit-identical to the stand-alone kernel's.
-      if (warp >= kTcEpiWarp0) {
-        if (half == 0 && (uint32_t)q == rank) {      // this rank's own head partial joins the other three in shared memory
-          const uint32_t dst = d3recv + (rank * 4u) * 512u + (uint32_t)lane * 16u;
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4)
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c4 * 512), "f"(own[4 * c4]), "f"(own[4 * c4 + 1]),
-                         "f"(own[4 * c4 + 2]), "f"(own[4 * c4 + 3]) : "memory");
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps: all four partials are in d3recv
-    MANSY_DBG(30);
-        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[494] = clock64();
-        const int sub = sim_et & 7, l = sim_et >> 3;
-        float l0, l1;
-        {
-          const uint32_t col = (uint32_t)(sub >> 1) * 512u + (uint32_t)l * 16u + (uint32_t)(sub & 1) * 8u;
-          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(l0), "=f"(l1) : "r"(d3recv + (rank * 4u) * 512u + col) : "memory");
-#pragma unroll
-          for (uint32_t j3 = 0; j3 < 3; ++j3) {      // fixed order: own + the other ranks ascending
-            const uint32_t sr = j3 + (j3 >= rank ? 1u : 0u);
-            float x0, x1;
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(d3recv + (sr * 4u) * 512u + col) : "memory");
-            l0 += x0; l1 += x1;
-          }
-          l0 += K.bout[2 * sub]; l1 += K.bout[2 * sub + 1];
-        }
-        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[495] = clock64() + (l0 > 1e30f);
-        const unsigned gm = group_mask();
-        const size_t orow = (size_t)cur * A.n + sim_i;      // outputs of step t live in slab t % slabs
-        if (sim_live && sub == 7 && A.value) A.value[orow] = l1;
-        float w0, w1;                                       // this lane's two weights
-        float m = sub == 7 ? l0 : fmaxf(l0, l1);
-        m = fmaxf(m, __shfl_xor_sync(gm, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(gm, m, 2));
-        m = fmaxf(m, __shfl_xor_sync(gm, m, 4));
-        w0 = expf(l0 - m);
-        w1 = sub == 7 ? 0.f : expf(l1 - m);
-        // all-gather of the 16 weights of the row through shared memory (the action hand-off buffer)
-        const uint32_t wrow = act_s + (uint32_t)l * 64u;
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(wrow + (uint32_t)sub * 8u), "f"(w0), "f"(w1) : "memory");
-        __syncwarp(gm);
-        float p[kActions + 1];
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 v = ld_shared_v4(wrow + c4 * 16);
-          p[4 * c4] = v.x; p[4 * c4 + 1] = v.y; p[4 * c4 + 2] = v.z; p[4 * c4 + 3] = v.w;
-        }
-        float pp[kActions];
-        float ssum = 0.f;
-#pragma unroll
-        for (int o = 0; o < kActions; ++o) { pp[o] = p[o]; ssum += pp[o]; }
-        if (K.softmax == 1) {          // simple_rl.py:48: the actor returns probabilities; Categorical(probs) re-sums them
-#pragma unroll
-          for (int o = 0; o < kActions; ++o) pp[o] = pp[o] / ssum;
-          ssum = 0.f;
-#pragma unroll
-          for (int o = 0; o < kActions; ++o) ssum += pp[o];
-        }
-        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[502] = clock64() + (ssum > 1e30f);
-        float lp;
-        categorical_pick(pp, ssum, categorical_uniform(A.seed, (uint64_t)(A.env_offset + sim_i), (uint64_t)t), sim_action, lp);
-        if (sim_live && sub == 0) {
-          if (A.actions) A.actions[orow] = sim_action;
-          if (A.logp) A.logp[orow] = lp;
-        }
-        if (sim_live) {
-          const float ws = (float)dadd(dadd((double)sim_st.w0, (double)sim_st.w1), (double)sim_st.w2);
-          sim_wn[0] = fdiv(sim_st.w0, ws); sim_wn[1] = fdiv(sim_st.w1, ws); sim_wn[2] = fdiv(sim_st.w2, ws);
-        }
-        cp_async_wait_all();                     // the second round trip (each lane reads back only what it requested)
-        if (sim_live) {
-          const SimDev &S = F.S;
-          const uint32_t pf = sim_s + 12288u + (((uint32_t)sim_et >> 3) * 8u + ((uint32_t)sim_et & 7u)) * 128u;
-          const float4 a = ld_shared_v4(pf), b = ld_shared_v4(pf + 16u), o0 = ld_shared_v4(pf + 32u), s0 = ld_shared_v4(pf + 48u),
-                       o1 = ld_shared_v4(pf + 64u), s1 = ld_shared_v4(pf + 80u), c = ld_shared_v4(pf + 96u);
-          auto f2d = [](float lo, float hi) { return __hiloint2double((int)__float_as_uint(hi), (int)__float_as_uint(lo)); };
-          sim_in.vi = (size_t)sim_st.pair * S.n_vp_chunks + (sim_st.next_chunk - sim_st.start_chunk);
-          sim_in.gt = ((uint64_t)__float_as_uint(a.y) << 32) | __float_as_uint(a.x);
-          sim_in.acc = f2d(a.z, a.w);
-          sim_in.win = f2d(b.x, b.y);
-          sim_in.rwin = f2d(b.z, b.w);
-          sim_in.oq0 = f2d(o0.x, o0.y); sim_in.oi0 = f2d(o0.z, o0.w); sim_in.os0 = (int)__float_as_uint(s0.x);
-          sim_in.oq1 = f2d(o1.x, o1.y); sim_in.oi1 = f2d(o1.z, o1.w); sim_in.os1 = (int)__float_as_uint(s1.x);
-          sim_pred = ((uint64_t)__float_as_uint(c.y) << 32) | __float_as_uint(c.x);
-          sim_in.scales = __float_as_uint(c.z);
-          sim_in.tlen = (int)__float_as_uint(c.w);
-          sim_in.tr = S.trace + (size_t)sim_st.trace * S.trace_stride;
-          sim_in.trr = S.trace_rcp + (size_t)sim_st.trace * S.trace_stride;
-          sim_in.outcomes = S.outcome != nullptr;
-        }
-        __syncwarp(gm);                // the weights row is rewritten next tile-step
-        MANSY_DBG(31);
-      }
-    } else if (warp >= kTcEpiWarp0 && half == 0 && (uint32_t)q == rank) {
+    // ================= phase D: each rank finishes its 32 rows (warp q == rank) =================
+    if (warp >= kTcEpiWarp0 && half == 0 && (uint32_t)q == rank) {
       float acc[16];
 #pragma unroll
       for (int o = 0; o < 16; ++o) acc[o] = own[o];
@@ -1123,7 +989,9 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       }
 #pragma unroll
       for (int o = 0; o < 16; ++o) acc[o] += K.bout[o];
+      int act = 0;
       if (live) {
+        const size_t orow = kFused ? (size_t)cur * A.n + env : (size_t)env;   // fused: outputs of step t live in slab t % slabs
         float p[kActions];
 #pragma unroll
         for (int o = 0; o < kActions; ++o) p[o] = acc[o];
@@ -1140,8 +1008,8 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
 #pragma unroll
           for (int o = 0; o < kActions; ++o) p[o] = p[o] / sum;
         }
-        if (A.value) A.value[env] = acc[15];
-        if (A.logits) {
+        if (A.value) A.value[orow] = acc[15];
+        if (!kFused && A.logits) {
           float4 *dst = reinterpret_cast<float4 *>(A.logits + (size_t)env * 16);
           dst[0] = make_float4(p[0], p[1], p[2], p[3]);
           dst[1] = make_float4(p[4], p[5], p[6], p[7]);
@@ -1149,13 +1017,13 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           dst[3] = make_float4(p[12], p[13], p[14], 0.f);
         }
         if (A.actions) {
-          int act;
           float lp;
           categorical_sample(p, K.softmax == 1, A.seed, (uint64_t)(A.env_offset + env), (uint64_t)t, act, lp);
-          A.actions[env] = act;
-          if (A.logp) A.logp[env] = lp;
+          A.actions[orow] = act;
+          if (A.logp) A.logp[orow] = lp;
         }
       }
+      if (kFused) asm volatile("st.shared.s32 [%0], %1;" ::"r"(act_s + (uint32_t)lane * 4u), "r"(act) : "memory");
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[486] = clock64();
 
@@ -1168,8 +1036,10 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         EnvState &st = sim_st;
         float (&slot)[8] = sim_slot;
         const bool live_e = sim_live;
-        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[490] = clock64() + (st.flags & 0);
-        const int action = sim_action;
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps: actions are in act_s
+        if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[490] = clock64();
+        int action;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(action) : "r"(act_s + (uint32_t)(sim_et >> 3) * 4u) : "memory");
         const int nxt = (int)((t + 1) % F.slabs);
         // full-mask collectives when all four environments of the warp step together (always, except in a tail tile)
         auto sim_step = [&](unsigned mask) {
@@ -1186,8 +1056,6 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
               if (sub == 0) finish_episode(S, i, st);
               reset_episode(S, st);
               pred = __ldg(S.vp_pred + (size_t)st.pair * S.n_vp_chunks + (min(st.next_chunk, st.end_chunk) - st.start_chunk));
-              const float ws = (float)dadd(dadd((double)st.w0, (double)st.w1), (double)st.w2);      // the next sample's weights
-              sim_wn[0] = fdiv(st.w0, ws); sim_wn[1] = fdiv(st.w1, ws); sim_wn[2] = fdiv(st.w2, ws);
             }
           } else {
             pred = __ldg(S.vp_pred + (size_t)st.pair * S.n_vp_chunks + (min(st.next_chunk, st.end_chunk) - st.start_chunk));
@@ -1198,7 +1066,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           }
           float *row = F.obs + ((size_t)nxt * A.n + i) * F.obs_stride;
           emit_obs_pred<MODE>(pred, sub, row);
-          emit_obs_dynamic<MODE>(S, st, slot, sub, mask, row, sim_wn);
+          emit_obs_dynamic<MODE>(S, st, slot, sub, mask, row);
         };
         if (__all_sync(0xFFFFFFFFu, live_e && !(st.flags & kFlagFinished))) sim_step(0xFFFFFFFFu);
         else if (live_e) sim_step(group_mask());
@@ -1708,6 +1576,10 @@ int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t
   memset(&f, 0, sizeof(f));
   f.S = S;
   f.obs = b->obs; f.obs_stride = b->obs_stride; f.slabs = b->slabs; f.n_steps = n_steps; f.t0 = t0;
+  {
+    const char *op = getenv("MANSY_FUSED_OUTCOME_PREFETCH");
+    f.outcome_prefetch = (op && op[0] == '0') ? 0 : 1;
+  }
   f.actions = b->actions; f.logp = b->logp; f.value = b->value; f.reward = b->reward; f.done = b->done;
   cudaError_t e = cudaSuccess;
 #define MANSY_FUSED_LAUNCH(SLOT, MODE)                                                                              \

@@ -40,7 +40,7 @@ for cta in ctas:
         if t[j] == 0:
             break
         print(f"  job {j:2d}: TMA issue {t[j]-t0:6d}  operands {t[128+j]-t0:6d}  MMAs issued {t[256+j]-t0:6d}")
-    for key in (480, 482, 483, 484, 485, 493, 494, 495, 502, 486, 490, 491, 492, 487, 488):
+    for key in (480, 482, 483, 484, 485, 493, 486, 490, 491, 492, 487, 488):
         print(f"  {names[key]:34s} {t[key]-t0:7d}")
     if t[496]:      # -DMANSY_STEP_PROFILE build: inside step_env (thread 256 of CTA 0, last stamped step)
         for j, nm in enumerate(["entry", "gathers issued+summed (own)", "group sums done", "trace walk done", "qoe done", "history slot done"]):
