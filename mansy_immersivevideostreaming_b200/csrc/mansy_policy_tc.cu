@@ -969,6 +969,19 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       load_slot(F.S, sim_i, sim_et & 7, sim_slot);
       sim_in = step_prefetch(F.S, sim_st, sim_et & 7);
       sim_pred = __ldg(F.S.vp_pred + (size_t)sim_st.pair * F.S.n_vp_chunks + (min(sim_st.next_chunk + 1, sim_st.end_chunk) - sim_st.start_chunk));
+      // What depends on the action about to be sampled -- which of the 16 (pair, chunk, action) outcomes -- and what an
+      // episode end needs -- the next sample's record -- go to the idle third TMA stage through cp.async: no destination
+      // registers, nothing waits for them before the step itself.
+      const uint32_t el = (uint32_t)sim_et >> 3, sb = (uint32_t)sim_et & 7u;
+      if (F.S.outcome != nullptr && F.outcome_prefetch) {
+        const uint4 *o = reinterpret_cast<const uint4 *>(F.S.outcome + sim_in.vi * kOutcomeActions + 2 * sb);
+        const uint32_t dst = sim_s + (el * 8u + sb) * 64u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cp_async16(dst + 16u * j, o + j);
+        sim_in.outcomes_smem = sim_s + el * 512u;
+      }
+      if (sb < 3 && sim_st.next_chunk + 1 > sim_st.end_chunk)
+        cp_async16(sim_s + 16384u + el * 64u + sb * 16u, reinterpret_cast<const uint4 *>(F.S.ep_init + sim_st.cursor % F.S.n_samples) + sb);
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[493] = clock64();
 
@@ -1036,7 +1049,8 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         EnvState &st = sim_st;
         float (&slot)[8] = sim_slot;
         const bool live_e = sim_live;
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps: actions are in act_s
+        cp_async_wait_all();                                // this lane's share of the staged outcomes / next-sample record ...
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // ... and everyone's; the actions are in act_s
         if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[490] = clock64();
         int action;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(action) : "r"(act_s + (uint32_t)(sim_et >> 3) * 4u) : "memory");
@@ -1053,9 +1067,12 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
             if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[491] = clock64() + (reward_f > 1e30f);
             if (sub == slot_before) store_slot(S, i, sub, slot);
             if (over) {
-              if (sub == 0) finish_episode(S, i, st);
-              reset_episode(S, st);
-              pred = __ldg(S.vp_pred + (size_t)st.pair * S.n_vp_chunks + (min(st.next_chunk, st.end_chunk) - st.start_chunk));
+              finish_episode(S, i, st, sub);
+              union { EpisodeInit e; float4 q[3]; } u;      // staged before the action was known (the episode end was not in doubt)
+              const uint32_t src = sim_s + 16384u + ((uint32_t)sim_et >> 3) * 64u;
+              u.q[0] = lds128(src); u.q[1] = lds128(src + 16u); u.q[2] = lds128(src + 32u);
+              reset_episode(S, st, u.e);
+              pred = u.e.first_pred;
             }
           } else {
             pred = __ldg(S.vp_pred + (size_t)st.pair * S.n_vp_chunks + (min(st.next_chunk, st.end_chunk) - st.start_chunk));

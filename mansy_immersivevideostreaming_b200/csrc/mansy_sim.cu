@@ -83,7 +83,7 @@ __device__ __forceinline__ void step_once(const SimDev &S, const StepArgs &A, En
     reward_f = (float)reward;
     if (A.n_steps == 1 && sub == slot_before) store_slot(S, e, sub, slot);
     if (over) {
-      if (sub == 0) finish_episode(S, e, st);
+      finish_episode(S, e, st, sub);
       if (A.auto_reset) reset_episode(S, st);
       else st.flags |= kFlagFinished;
     }
@@ -652,6 +652,24 @@ int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, ma
   MANSY_TRY(upload(h, t->trace_len, (size_t)t->n_traces, &d.trace_len));
   MANSY_TRY(upload(h, t->qoe_w, (size_t)t->n_qoe * 3, &d.qoe_w));
   MANSY_TRY(upload(h, t->samples, (size_t)t->n_samples * 4, &d.samples));
+  {
+    std::vector<EpisodeInit> init((size_t)t->n_samples);
+    for (int s = 0; s < t->n_samples; ++s) {
+      const int32_t *q = t->samples + 4 * (size_t)s;
+      EpisodeInit &e = init[(size_t)s];
+      memset(&e, 0, sizeof(e));
+      e.video = q[0];
+      e.pair = q[0] * t->n_users + q[1];
+      e.trace = q[2];
+      e.w0 = t->qoe_w[q[3] * 3 + 0]; e.w1 = t->qoe_w[q[3] * 3 + 1]; e.w2 = t->qoe_w[q[3] * 3 + 2];
+      e.start_chunk = t->vp_start[e.pair];
+      const int vend = t->vp_end[e.pair], tend = t->video_time[e.video] - 1;
+      e.end_chunk = vend < tend ? vend : tend;
+      const int first = cfg->startup_download + 1 < e.end_chunk ? cfg->startup_download + 1 : e.end_chunk;
+      e.first_pred = t->vp_pred[(size_t)e.pair * t->n_vp_chunks + (first - e.start_chunk)];
+    }
+    MANSY_TRY(upload(h, init.data(), init.size(), &d.ep_init));
+  }
   d.n_videos = t->n_videos; d.n_chunks = t->n_chunks; d.n_users = t->n_users; d.n_vp_chunks = t->n_vp_chunks;
   d.n_traces = t->n_traces; d.n_qoe = t->n_qoe; d.n_samples = t->n_samples;
 

@@ -67,6 +67,17 @@ struct __align__(16) ChunkOutcome {
 static_assert(sizeof(ChunkOutcome) == 32, "ChunkOutcome is two 16-byte quads");
 constexpr int kOutcomeActions = 16;
 
+// Everything reset_episode needs about a sample (mansy_env.py:99-134, simulator.py:15-46), resolved once per handle from
+// the sample list and the tables: one 48-byte record instead of a chain of dependent lookups at every episode end.
+struct __align__(16) EpisodeInit {
+  int32_t video, pair, trace, end_chunk;      // end_chunk = min(last viewport chunk, Video_Time - 1)   (simulator.py:41-42)
+  float w0, w1, w2;                           // QoE weights of the sample
+  int32_t start_chunk;                        // first chunk of the viewport list (hmdtrace.py:10)
+  uint64_t first_pred;                        // predicted viewport of the first observation's chunk (mansy_env.py:119-121)
+  uint64_t pad;
+};
+static_assert(sizeof(EpisodeInit) == 48, "EpisodeInit is three 16-byte quads");
+
 struct SimDev {
   // read-only tables
   const int32_t *size;
@@ -87,6 +98,7 @@ struct SimDev {
   const int32_t *trace_len;
   const float *qoe_w;
   const int32_t *samples;
+  const EpisodeInit *ep_init;   // [n_samples]
   int32_t n_videos, n_chunks, n_users, n_vp_chunks, n_traces, trace_stride, n_qoe, n_samples;
   // per-env state
   EnvState *state;

@@ -81,29 +81,41 @@ __device__ __forceinline__ void store_slot(const SimDev &S, int e, int sub, cons
 }
 
 // envs/mansy_env.py:99-134 + simulators/simulator.py:15-46: pick the next sample and rebuild the
-// episode state.  Executed identically by the 8 lanes of the group.
-__device__ __forceinline__ void reset_episode(const SimDev &S, EnvState &st) {
-  const int sid = st.cursor % S.n_samples;
-  st.sample_id = sid;
+// episode state.  Executed identically by the 8 lanes of the group.  `ei` = S.ep_init[st.cursor % S.n_samples].
+__device__ __forceinline__ void reset_episode(const SimDev &S, EnvState &st, const EpisodeInit &ei) {
+  st.sample_id = st.cursor % S.n_samples;
   st.cursor = (st.cursor + S.worker_num) % S.n_samples;          // mansy_env.py:100-101
-  const int4 smp = __ldg(reinterpret_cast<const int4 *>(S.samples) + sid);
-  st.video = smp.x;
-  st.pair = smp.x * S.n_users + smp.y;
-  st.trace = smp.z;
-  st.w0 = __ldg(S.qoe_w + smp.w * 3 + 0);
-  st.w1 = __ldg(S.qoe_w + smp.w * 3 + 1);
-  st.w2 = __ldg(S.qoe_w + smp.w * 3 + 2);
+  st.video = ei.video;
+  st.pair = ei.pair;
+  st.trace = ei.trace;
+  st.w0 = ei.w0; st.w1 = ei.w1; st.w2 = ei.w2;
   st.buf = S.chunk_length * 3.0;                                  // buffer.py:6
   st.cur_time = 0.0;                                              // network.py:19-20
   st.cur_idx = 0;
   st.next_chunk = S.startup_download + 1;                         // simulator.py:45
-  st.start_chunk = __ldg(S.vp_start + st.pair);
-  st.end_chunk = min(__ldg(S.vp_end + st.pair), __ldg(S.video_time + st.video) - 1);  // simulator.py:41-42
+  st.start_chunk = ei.start_chunk;
+  st.end_chunk = ei.end_chunk;                                    // simulator.py:41-42
   st.prev_vq = 0.0;
   st.ep_step = 0;
   st.flags = kNoAction << 8;
   st.sum_qoe = st.sum_q1 = st.sum_q2 = st.sum_q3 = 0.0;
   st.ep_return = 0.0;
+}
+__device__ __forceinline__ EpisodeInit load_episode_init(const SimDev &S, int cursor) {
+  const uint4 *p = reinterpret_cast<const uint4 *>(S.ep_init + cursor % S.n_samples);
+  union { EpisodeInit e; uint4 q[3]; } u;
+  u.q[0] = __ldg(p); u.q[1] = __ldg(p + 1); u.q[2] = __ldg(p + 2);
+  return u.e;
+}
+__device__ __forceinline__ void reset_episode(const SimDev &S, EnvState &st) { reset_episode(S, st, load_episode_init(S, st.cursor)); }
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ double f2_as_double(float lo, float hi) {
+  return __hiloint2double((int)__float_as_uint(hi), (int)__float_as_uint(lo));
 }
 
 // network.py:22-35 with the trace window held by the environment's 8 lanes: lane j of the group owns entry
@@ -285,11 +297,11 @@ __device__ __forceinline__ void next_obs_chunk(const SimDev &S, const EnvState &
   video = st.video; pair = st.pair; start_chunk = st.start_chunk;
   if (st.flags & kFlagFinished) { chunk = min(st.next_chunk, st.end_chunk); return; }
   if (st.next_chunk + 1 > st.end_chunk && auto_reset) {
-    const int4 smp = __ldg(reinterpret_cast<const int4 *>(S.samples) + st.cursor % S.n_samples);
-    video = smp.x;
-    pair = smp.x * S.n_users + smp.y;
-    start_chunk = __ldg(S.vp_start + pair);
-    chunk = min(S.startup_download + 1, min(__ldg(S.vp_end + pair), __ldg(S.video_time + video) - 1));
+    const int4 q0 = __ldg(reinterpret_cast<const int4 *>(S.ep_init + st.cursor % S.n_samples));     // video, pair, trace, end_chunk
+    video = q0.x;
+    pair = q0.y;
+    start_chunk = __ldg(&S.ep_init[st.cursor % S.n_samples].start_chunk);
+    chunk = min(S.startup_download + 1, q0.w);
     return;
   }
   chunk = min(st.next_chunk + 1, st.end_chunk);
@@ -312,14 +324,12 @@ struct StepInputs {
   double acc, win, rwin;
   const double *tr, *trr;
   size_t vi;
-  // outcome-table path of the fused kernel: lane `sub` holds the entries of actions 2 * sub and 2 * sub + 1 of this
-  // (viewport pair, chunk), loaded before the action is known
-  double oq0, oi0, oq1, oi1;   // q1 / intra of the two actions
-  int os0, os1;                // their chunk sizes
-  bool outcomes;
+  // outcome-table path of the fused kernel: shared-memory address of this (viewport pair, chunk)'s 16 entries, copied there
+  // (cp.async) before the action is known; 0 = read the one entry from the table once it is
+  uint32_t outcomes_smem;
 };
 
-__device__ __forceinline__ StepInputs step_prefetch(const SimDev &S, const EnvState &st, int sub, bool outcomes = false) {
+__device__ __forceinline__ StepInputs step_prefetch(const SimDev &S, const EnvState &st, int sub) {
   StepInputs in;
   const size_t vi = (size_t)st.pair * S.n_vp_chunks + (st.next_chunk - st.start_chunk);   // hmdtrace.py:16-19
   in.vi = vi;
@@ -334,14 +344,7 @@ __device__ __forceinline__ StepInputs step_prefetch(const SimDev &S, const EnvSt
   in.win = __ldg(in.tr + st.cur_idx + sub);
   in.rwin = __ldg(in.trr + st.cur_idx + sub);
   in.tlen = __ldg(S.trace_len + st.trace);
-  in.outcomes = outcomes && S.outcome != nullptr;
-  if (in.outcomes) {
-    const double2 *o = reinterpret_cast<const double2 *>(S.outcome + vi * kOutcomeActions + 2 * sub);
-    const double2 a0 = __ldg(o), a1 = __ldg(o + 2);
-    in.oq0 = a0.x; in.oi0 = a0.y; in.oq1 = a1.x; in.oi1 = a1.y;
-    in.os0 = __ldg(reinterpret_cast<const int *>(o + 1));
-    in.os1 = __ldg(reinterpret_cast<const int *>(o + 3));
-  }
+  in.outcomes_smem = 0;
   return in;
 }
 
@@ -408,12 +411,11 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
   ChunkParts cp;
   if (S.outcome != nullptr && ver_row == nullptr) {
     const int a16 = (action >= 0 && action < kActions) ? action : kActions;      // 15 = out-of-table action, rates (0, 0)
-    if (in.outcomes) {
-      const int src = ((threadIdx.x & 31) & ~7) + (a16 >> 1);
-      const bool hi = a16 & 1;
-      cp.q1 = __shfl_sync(gmask, hi ? in.oq1 : in.oq0, src);
-      cp.intra = __shfl_sync(gmask, hi ? in.oi1 : in.oi0, src);
-      cp.sz = __shfl_sync(gmask, hi ? in.os1 : in.os0, src);
+    if (in.outcomes_smem) {
+      const float4 x = lds128(in.outcomes_smem + (uint32_t)a16 * 32u), y = lds128(in.outcomes_smem + (uint32_t)a16 * 32u + 16u);
+      cp.q1 = f2_as_double(x.x, x.y);
+      cp.intra = f2_as_double(x.z, x.w);
+      cp.sz = (int)__float_as_uint(y.x);
     } else {
       const double2 *o = reinterpret_cast<const double2 *>(S.outcome + in.vi * kOutcomeActions + a16);
       const double2 qa = __ldg(o);
@@ -480,23 +482,27 @@ __device__ __forceinline__ double step_env(const SimDev &S, EnvState &st, float 
   return reward;
 }
 
-// envs/mansy_env.py:271-290: what `_log` records when an episode ends, plus running totals.
-__device__ __forceinline__ void finish_episode(const SimDev &S, int e, const EnvState &st) {
+// envs/mansy_env.py:271-290: what `_log` records when an episode ends, plus running totals.  Lane `sub` of the
+// environment's 8 lanes writes one "last episode" column and updates one "totals" column (same additions as a single
+// thread walking the row, spread over the lanes so that an episode end costs one load round trip, not seven).
+__device__ __forceinline__ void finish_episode(const SimDev &S, int e, const EnvState &st, int sub) {
   double *row = S.stats + (size_t)e * MANSY_STATS_DOUBLES;
-  row[MANSY_STAT_LAST_SUM_QOE] = st.sum_qoe;
-  row[MANSY_STAT_LAST_SUM_QOE1] = st.sum_q1;
-  row[MANSY_STAT_LAST_SUM_QOE2] = st.sum_q2;
-  row[MANSY_STAT_LAST_SUM_QOE3] = st.sum_q3;
-  row[MANSY_STAT_LAST_STEPS] = (double)st.ep_step;
-  row[MANSY_STAT_LAST_SAMPLE] = (double)st.sample_id;
-  row[MANSY_STAT_LAST_RETURN] = st.ep_return;
-  row[MANSY_STAT_TOT_SUM_QOE] += st.sum_qoe;
-  row[MANSY_STAT_TOT_SUM_QOE1] += st.sum_q1;
-  row[MANSY_STAT_TOT_SUM_QOE2] += st.sum_q2;
-  row[MANSY_STAT_TOT_SUM_QOE3] += st.sum_q3;
-  row[MANSY_STAT_TOT_STEPS] += (double)st.ep_step;
-  row[MANSY_STAT_TOT_EPISODES] += 1.0;
-  row[MANSY_STAT_TOT_RETURN] += st.ep_return;
+  double last = 0.0, add = 0.0;
+  int lc = -1, tc = -1;
+  switch (sub) {
+    case 0: last = add = st.sum_qoe; lc = MANSY_STAT_LAST_SUM_QOE; tc = MANSY_STAT_TOT_SUM_QOE; break;
+    case 1: last = add = st.sum_q1; lc = MANSY_STAT_LAST_SUM_QOE1; tc = MANSY_STAT_TOT_SUM_QOE1; break;
+    case 2: last = add = st.sum_q2; lc = MANSY_STAT_LAST_SUM_QOE2; tc = MANSY_STAT_TOT_SUM_QOE2; break;
+    case 3: last = add = st.sum_q3; lc = MANSY_STAT_LAST_SUM_QOE3; tc = MANSY_STAT_TOT_SUM_QOE3; break;
+    case 4: last = add = (double)st.ep_step; lc = MANSY_STAT_LAST_STEPS; tc = MANSY_STAT_TOT_STEPS; break;
+    case 5: last = (double)st.sample_id; add = 1.0; lc = MANSY_STAT_LAST_SAMPLE; tc = MANSY_STAT_TOT_EPISODES; break;
+    case 6: last = add = st.ep_return; lc = MANSY_STAT_LAST_RETURN; tc = MANSY_STAT_TOT_RETURN; break;
+    default: break;
+  }
+  if (lc >= 0) {
+    row[lc] = last;
+    row[tc] += add;
+  }
 }
 
 
