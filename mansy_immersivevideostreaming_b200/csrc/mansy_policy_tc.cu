@@ -1493,9 +1493,10 @@ int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm < 1) n_sm = 148;
   }
-  // split-K clusters pay off while the tiles alone cannot fill the SMs (a cluster finishes a tile ~3-4x sooner
-  // but occupies four SMs); beyond ~3/4 of the SM count the persistent one-CTA-per-tile kernel is as fast.
-  const bool split4 = p->tc->split == 4 || (p->tc->split == 0 && 4 * a.n_tiles <= 3 * n_sm);
+  // split-K clusters pay off while every tile's 4-CTA cluster is resident at once (a cluster finishes a tile ~3x sooner
+  // but occupies four SMs): up to 37 tiles on 148 SMs.  Beyond that a second wave of clusters costs more than one CTA per
+  // tile (measured, tools/rollout_sweep.py: 8 192 envs 38.5 vs 37.1 us per rollout step, 12 288 envs 56.0 vs 40.8 us).
+  const bool split4 = p->tc->split == 4 || (p->tc->split == 0 && 4 * a.n_tiles <= n_sm);
   if (split4) {
     if ((rc = ensure_scratch(p, a.n_tiles))) return rc;
     a.scratch = p->tc->scratch;
@@ -1608,10 +1609,11 @@ int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&mc, policy_tc4_kernel<SLOT, MODE>, &cfg);           \
       if (e == cudaSuccess) max_clusters = mc;                                                                      \
     }                                                                                                               \
-    if (e == cudaSuccess && max_clusters >= 1) {                                                                    \
-      /* every cluster of the grid must be resident (the rollout steps synchronise only inside a cluster, but a     \
-         cluster that is not scheduled until another one finishes would run its tiles late, not wrongly); more      \
-         tiles than resident clusters are walked in a loop */                                                       \
+    /* One tile per resident cluster is the fast configuration (<= 33 tiles = 4 224 environments on B200).  The kernel   \
+       walks more tiles per cluster when asked to (MANSY_FUSED_MULTI_TILE=1: correct, bit-identical, tested), but a     \
+       cluster then runs its tiles' policy and simulator phases back to back, and from ~6 000 environments on the two   \
+       kernels of the PDL loop, each filling the machine, are faster (tools/rollout_sweep.py) */                         \
+    if (e == cudaSuccess && max_clusters >= 1 && (n_tiles <= max_clusters || getenv("MANSY_FUSED_MULTI_TILE"))) {     \
       cfg.gridDim = dim3((unsigned)(kTcRanks * (n_tiles < max_clusters ? n_tiles : max_clusters)), 1, 1);           \
       e = cudaLaunchKernelEx(&cfg, policy_tc4_kernel<SLOT, MODE>, map_obs, p->tc->map_w1, p->tc->map_wfc, p->tc->map_wout, \
                              p->tc->map_wres, a, f);                                                                \

@@ -74,9 +74,11 @@ def test_host_rollout_equals_device_rollout():
                                                 (OBS_MODE_SIMPLE, 333, 60, 7), (OBS_MODE_MANSY, 1, 55, 4),
                                                 (OBS_MODE_MANSY, 8192 + 77, 7, 3),      # > 33 tiles: clusters walk several tiles per step
                                                 (OBS_MODE_SIMPLE, 13000, 7, 3)])
-def test_fused_rollout_equals_two_kernel_rollout(kind, n, steps, slabs):
+def test_fused_rollout_equals_two_kernel_rollout(kind, n, steps, slabs, monkeypatch):
     """ONE launch of the fused policy+step cluster kernel for all steps == two launches per step (with and without
-    programmatic dependent launch), bit for bit, including the ring wrap of the slabs and a continued rollout."""
+    programmatic dependent launch), bit for bit, including the ring wrap of the slabs and a continued rollout.  (More
+    tiles than resident clusters: the kernel walks several tiles per cluster -- not the default above 4 224 envs.)"""
+    monkeypatch.setenv("MANSY_FUSED_MULTI_TILE", "1")
     _, _, a = _setup(kind, n, True, slabs=slabs)
     _, _, b = _setup(kind, n, True, slabs=slabs)
     _, _, c = _setup(kind, n, True, slabs=slabs)
