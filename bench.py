@@ -27,9 +27,12 @@ METRIC = "simulated chunk-steps/sec"
 UNIT = "chunk-steps/s"
 ENVS_PER_GPU = 4096
 # algorithmic HBM bytes per MANSY chunk-step with materialised observation
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE 2000-step launch of the fused kernel at 4096 envs, per rollout
-# step (ncu --set full, profiles/r01r_fused_kernel_2000steps_ncu.txt: 1.05 GB read + 26.59 GB written / 2000)
-FUSED_DRAM_BYTES_PER_STEP_4096 = 13_819_256
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE 200-step launch of the fused kernel at 4096 envs, per rollout
+# step (ncu --set full, profiles/r02p_fused_kernel_200steps_ncu.txt: 213.6 MB read + 2 672.6 MB written / 200)
+FUSED_DRAM_BYTES_PER_STEP_4096 = 14_431_325
+# the same for one launch of step_kernel<MANSY> at 1 048 576 envs (profiles/r02p_step_kernel_1048576_ncu.txt: 413.6 MB read
+# + 3 433.1 MB written; algorithmic 3 513 B x 1 048 576 = 3 683.6 MB)
+STEP_DRAM_BYTES_MANSY_1M = 3_846_669_864
 BYTES_PER_STEP_MANSY = 3513
 FLOP_PER_STEP_POLICY = 2 * 425_472        # 0.851 MFLOP, shared FeatureNet evaluated once
 
@@ -377,6 +380,7 @@ def run_ours(args):
     elapsed_ms, stats, launches = timed_rollout(roll, sim, peers, K, W, world)
     # per-kernel durations for the rooflines: the same K steps again with CUDA events around every launch on the
     # launching stream (events between the launches serialise them, so this pass is not the one `value` is from)
+    roll.run(3, timed=True)       # first launches of the stand-alone kernels in this process (module load) stay out of the averages
     roll.run(K, timed=True)
     torch.cuda.synchronize()
     policy_sum, step_sum, timed_steps = roll.kernel_ms()
@@ -450,7 +454,7 @@ def run_ours(args):
                                     "around every launch on the launching stream (serialised launches)"},
         "roofline": ({"bound": "hbm", "achieved": fused_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": fused_gbs / hbm_gbs,
                       "traffic": FUSED_DRAM_BYTES_PER_STEP_4096 * K if n_local == 4096 else None,
-                      "traffic_source": "ncu --set full of one 2000-step launch, scaled by K (profiles/r01r_fused_kernel_2000steps_ncu.txt)",
+                      "traffic_source": "ncu --set full of one 200-step launch, scaled by K (profiles/r02p_fused_kernel_200steps_ncu.txt)",
                       "kernel": "policy_tc4_kernel<fused> (policy + sample + simulator step, K steps per launch)",
                       "bytes_per_launch": fused_bytes * K, "avg_launch_ms": elapsed_ms, "peak_source": peak_src,
                       "note": "4096 envs move 14.7 MB per step (2.2 us of HBM time): the step is latency-bound, see "
@@ -756,7 +760,9 @@ def simulator_sweep(tables, device_index, world=1, sizes=(65536, 1048576)):
             gbs = n * bytes_per_step / (ms * 1e-3) / 1e9              # this GPU's kernel against this GPU's HBM peak
             ms_all = _max_over_ranks(ms, world)
             out.append({"env": name, "envs_per_gpu": n, "ms_per_step": ms_all, "chunk_steps_per_s": world * n / (ms_all * 1e-3),
-                        "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_gbs, "bytes_per_chunk_step": bytes_per_step})
+                        "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_gbs, "bytes_per_chunk_step": bytes_per_step,
+                        "kernel": "step_kernel<%s>" % ("MANSY" if mode == OBS_MODE_MANSY else "SIMPLE"),
+                        "traffic": STEP_DRAM_BYTES_MANSY_1M if (mode == OBS_MODE_MANSY and n == 1048576) else None})
             sim.close()
             del obs
             torch.cuda.empty_cache()
