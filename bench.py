@@ -403,6 +403,22 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = _max_over_ranks(time.perf_counter() - t0, world)
     h2d, d2h = e2e_roll.host_bytes_per_step()
+    # the ceiling of that path: plain device -> pinned-host copies of the same 12.9 MB slabs into the same ring, all ranks
+    # at once (the box's host link is shared by its GPUs)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_slab = e2e_roll.buf.obs[0]
+    for i in range(3):
+        host["obs"][i % host["obs"].shape[0]].copy_(dev_slab, non_blocking=True)
+    torch.cuda.synchronize()
+    c0.record()
+    for i in range(20):
+        host["obs"][i % host["obs"].shape[0]].copy_(dev_slab, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    d2h_ceiling_gbs = 20 * dev_slab.numel() * 4 / (_max_over_ranks(c0.elapsed_time(c1), world) * 1e-3) / 1e9    # per rank
     e2e_sim.close()
     del e2e_roll, host
 
@@ -473,6 +489,11 @@ def run_ours(args):
                             "peak_source": "1/2 x measured bf16 cuBLAS burst (MEASURED_PEAKS.json); TF32 runs at half the bf16 rate"},
         "e2e": {"value": n_global * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps,
+                "d2h_achieved_GBps_per_gpu": d2h * e2e_steps / e2e_s / 1e9,
+                "d2h_ceiling_GBps_per_gpu": d2h_ceiling_gbs,
+                "frac_of_d2h_ceiling": (d2h * e2e_steps / e2e_s / 1e9) / d2h_ceiling_gbs,
+                "d2h_ceiling_how": "20 back-to-back cudaMemcpyAsync of one 12.9 MB observation slab into the same pinned ring, every rank at "
+                                   "the same time, slowest rank",
                 "path": "mansy_rollout_policy_host: per step policy launch, actions to the host (store kernel into the mapped "
                         "pinned buffer) + sync, H2D actions, step launch, D2H obs+reward+done+logp+value into pinned host slabs "
                         "on a copy stream (overlaps the next step); all copies complete inside the timed region"},

@@ -4,7 +4,8 @@
 
 TEST INFRASTRUCTURE.  Writes a small synthetic dataset in the reference's on-disk formats, runs the reference's MPC
 expert (bitrate_selection/envs/expert_env.py: ``reset`` / ``choose_action`` / ``step``) over whole episodes with
-horizons 1..3, and asserts that the restatement (``oracle.sim_oracle.expert_choose_action`` on ``OracleEnv``)
+horizons 1..4 (4 = the reference's default, expert_env.py / run_expert.py: a handful of decisions, 50 625 Python roll-outs
+each), and asserts that the restatement (``oracle.sim_oracle.expert_choose_action`` on ``OracleEnv``)
 chooses the same action at every decision in the numeric chain the reference runs in under this container's numpy
 (float32).  The fixture stores the float64-chain decisions (what the CUDA kernel follows, like the
 step kernel) together with the float32-chain ones the reference produced, plus the tables.
@@ -37,7 +38,7 @@ def main() -> None:
     samples = [tuple(int(x) for x in s) for s in tables.samples[::5][:4]]
     tb = tables.with_samples(np.asarray(samples, dtype=np.int32))
     out = {}
-    for horizon in (1, 2, 3):
+    for horizon in (1, 2, 3, 4):
         ref.expert_env.ExpertEnv.init = False            # class-level cache flag (expert_env.py:18)
         with silence_prints():
             env = ref.expert_env.ExpertEnv(config, "Synth", "SynthNet", qoe_weights, samples, root,
@@ -46,13 +47,14 @@ def main() -> None:
         o32 = so.OracleEnv(tb, OBS_MODE_MANSY, REWARD_QOE, "f32", worker_id=0, worker_num=1)
         o64 = so.OracleEnv(tb, OBS_MODE_MANSY, REWARD_QOE, "f64", worker_id=0, worker_num=1)
         acts32, acts64, vals64, eps = [], [], [], []
-        n_ep = 4 if horizon < 3 else 2
+        n_ep = 4 if horizon < 3 else (2 if horizon == 3 else 1)
+        max_decisions = 10 if horizon == 4 else 10 ** 9
         for ep in range(n_ep):
             with silence_prints():
                 env.reset()
             o32.reset(); o64.reset()
             done = False
-            while not done:
+            while not done and len(acts32) < max_decisions:
                 a_ref = int(env.choose_action())
                 a32 = so.expert_choose_action(o32, horizon)
                 a64, v64 = so.expert_choose_action(o64, horizon, return_value=True)

@@ -24,11 +24,18 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from mansy_immersivevideostreaming_b200.config import (ACTION_TABLE, OBS_MODE_MANSY, OBS_MODE_SIMPLE,
-                                                       REWARD_QOE, REWARD_QOE_NORM, SimConfig)
+# Shared with the product package: only the plain containers the tests hand to both sides (constants of config.yml and the
+# dense table arrays) and the mode enums.  Nothing computed: the action table below is the oracle's own restatement.
+from mansy_immersivevideostreaming_b200.config import OBS_MODE_MANSY, OBS_MODE_SIMPLE, REWARD_QOE, REWARD_QOE_NORM, SimConfig
 from mansy_immersivevideostreaming_b200.tables import SimTables
 
 F32 = np.float32
+
+# bitrate_selection/utils/common.py:101-119: action -> (rate_in, rate_out) version indices, the if-chain written out.
+# (The kernels carry their own packed copy, csrc/mansy_core.cuh action_to_rates, and the host package another,
+# config.ACTION_TABLE; tests/test_oracle_golden.py checks all of them against the reference-generated allocate_kat.npz.)
+ACTION_TABLE: Tuple[Tuple[int, int], ...] = ((1, 0), (2, 0), (3, 0), (4, 0), (2, 1), (3, 1), (4, 1), (3, 2), (4, 2), (4, 3),
+                                             (0, 0), (1, 1), (2, 2), (3, 3), (4, 4))
 
 
 # ---------------------------------------------------------------------------

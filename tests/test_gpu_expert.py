@@ -13,7 +13,7 @@ from oracle import sim_oracle as so
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("horizon", [1, 2, 3])
+@pytest.mark.parametrize("horizon", [1, 2, 3, 4])      # 4 = the reference's default horizon (10 decisions, 50 625 sequences each)
 def test_reference_golden_decisions(horizon):
     """Teacher-forced with the reference's own actions; the kernel's decisions equal the float64-chain oracle's at every
     step (the chain step_env follows; the reference under numpy 2 runs float32, whose decisions the fixture also holds)."""
