@@ -301,6 +301,21 @@ def _max_over_ranks(x: float, world: int) -> float:
     return float(t.item())
 
 
+def make_peers(args, n_local, device):
+    """The NVLink peer-memory group for the per-rollout exchange, or None (-> torch.distributed all-gather over NCCL) when
+    asked for with --nccl-gather or when some rank cannot map a peer's mailbox: PeerGroup raises on EVERY rank in that
+    case, so the whole job takes the same path."""
+    from mansy_immersivevideostreaming_b200.rollout import PeerGroup
+    if args.nccl_gather:
+        return None
+    try:
+        return PeerGroup(n_local, device)
+    except RuntimeError as exc:
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(f"bench: peer-memory gather unavailable ({exc}); using the NCCL all-gather", file=sys.stderr)
+        return None
+
+
 def timed_rollout(roll, sim, peers, K, W, world):
     """W warm-up steps, then EXACTLY K rollout steps + the per-rollout gather between CUDA events on the launching
     stream, bracketed by barrier + synchronize on both sides; the device-side peer barrier right before the start
@@ -370,9 +385,7 @@ def run_ours(args):
     slab_bytes = n_local * sim.obs_stride * 4
     slabs = max(4, -(-(320 << 20) // slab_bytes))                # rollout buffer > 2.5 x L2 (126 MB)
     roll = PolicyRollout(sim, policy, slabs, seed=1234)
-    peers = None
-    if not args.nccl_gather:
-        peers = PeerGroup(n_local, local)        # world 1: a plain pack kernel; world > 1: one NVLink push kernel
+    peers = make_peers(args, n_local, local)     # world 1: a plain pack kernel; world > 1: one NVLink push kernel
 
     W = max(args.warmup, 3)
     K = args.steps
@@ -495,7 +508,7 @@ def run_ours(args):
                 "d2h_ceiling_how": "20 back-to-back cudaMemcpyAsync of one 12.9 MB observation slab into the same pinned ring, every rank at "
                                    "the same time, slowest rank",
                 "path": "mansy_rollout_policy_host: per step policy launch, actions to the host (store kernel into the mapped "
-                        "pinned buffer) + sync, H2D actions, step launch, D2H obs+reward+done+logp+value into pinned host slabs "
+                        "pinned buffer) + sync, H2D actions, step launch, reward+done+logp+value stored by one kernel into the mapped pinned buffers, D2H copy of the observation slab into the pinned host ring "
                         "on a copy stream (overlaps the next step); all copies complete inside the timed region"},
         "gpu_launches": int(launches),
         "clocks": clk,
@@ -526,7 +539,7 @@ def config3_section(args, tiler, policy, rank, world, local):
                          env_offset=rank * n_local, device=local)
     slabs = max(4, -(-(320 << 20) // (n_local * sim.obs_stride * 4)))
     roll = PolicyRollout(sim, policy, slabs, seed=1234)
-    peers = None if args.nccl_gather else PeerGroup(n_local, local)
+    peers = make_peers(args, n_local, local)
     K = max(20, min(args.steps, 200))
     ms, _, launches = timed_rollout(roll, sim, peers, K, 5, world)
     out = {"workload": "mansy_ppo_rollout_8192_envs_per_gpu_diverse_qoe", "envs": n_global, "envs_per_gpu": n_local, "steps": K,

@@ -314,6 +314,22 @@ __global__ void copy_i32_kernel(int32_t *__restrict__ dst, const int32_t *__rest
   __threadfence_system();
 }
 
+// reward / done / log-prob / value of one step, stored straight into the caller's mapped pinned buffers: four 4-16 KB
+// cudaMemcpyAsync calls cost the device-to-host copy engine more idle time between the 12.9 MB observation slabs than
+// the bytes they move
+__global__ void store_step_scalars_kernel(float *__restrict__ reward_h, uint8_t *__restrict__ done_h, float *__restrict__ logp_h,
+                                          float *__restrict__ value_h, const float *__restrict__ reward, const uint8_t *__restrict__ done,
+                                          const float *__restrict__ logp, const float *__restrict__ value, int32_t n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    reward_h[i] = reward[i];
+    done_h[i] = done[i];
+    logp_h[i] = logp[i];
+    value_h[i] = value[i];
+  }
+  __threadfence_system();
+}
+
 __global__ void seed_kernel(const SimDev S, int32_t seed, int full) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= S.n_envs) return;
@@ -986,11 +1002,27 @@ int mansy_rollout_policy_host(mansy_handle_t h, mansy_policy_t p, const mansy_ro
     if ((rc = launch_step(h, a, s))) return rc;
     MANSY_CUDA(cudaEventRecord(h->step_done[k % kCopyRing], s));
     MANSY_CUDA(cudaStreamWaitEvent(cs, h->step_done[k % kCopyRing], 0));
+    float *reward_m = nullptr, *logp_m = nullptr, *value_m = nullptr;
+    uint8_t *done_m = nullptr;
+    const bool scalars_mapped = !(flags & MANSY_ROLLOUT_NO_ZERO_COPY) &&
+        cudaHostGetDevicePointer(reinterpret_cast<void **>(&reward_m), host->reward + hs * n, 0) == cudaSuccess &&
+        cudaHostGetDevicePointer(reinterpret_cast<void **>(&done_m), host->done + hs * n, 0) == cudaSuccess &&
+        cudaHostGetDevicePointer(reinterpret_cast<void **>(&logp_m), host->logp + hs * n, 0) == cudaSuccess &&
+        cudaHostGetDevicePointer(reinterpret_cast<void **>(&value_m), host->value + hs * n, 0) == cudaSuccess;
+    if (scalars_mapped) {                                        // after the event: the slab copy does not wait for it
+      store_step_scalars_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reward_m, done_m, logp_m, value_m, a.out.reward, a.out.done,
+                                                                            b->logp + cur * n, b->value + cur * n, (int32_t)n);
+      count_launch();
+    } else {
+      cudaGetLastError();
+    }
     MANSY_CUDA(cudaMemcpyAsync(host->obs + hs * n * (size_t)b->obs_stride, a.out.obs, n * row_bytes, cudaMemcpyDeviceToHost, cs));
-    MANSY_CUDA(cudaMemcpyAsync(host->reward + hs * n, a.out.reward, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
-    MANSY_CUDA(cudaMemcpyAsync(host->done + hs * n, a.out.done, n, cudaMemcpyDeviceToHost, cs));
-    MANSY_CUDA(cudaMemcpyAsync(host->logp + hs * n, b->logp + cur * n, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
-    MANSY_CUDA(cudaMemcpyAsync(host->value + hs * n, b->value + cur * n, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    if (!scalars_mapped) {
+      MANSY_CUDA(cudaMemcpyAsync(host->reward + hs * n, a.out.reward, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
+      MANSY_CUDA(cudaMemcpyAsync(host->done + hs * n, a.out.done, n, cudaMemcpyDeviceToHost, cs));
+      MANSY_CUDA(cudaMemcpyAsync(host->logp + hs * n, b->logp + cur * n, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
+      MANSY_CUDA(cudaMemcpyAsync(host->value + hs * n, b->value + cur * n, n * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    }
     MANSY_CUDA(cudaEventRecord(h->copy_done[k % kCopyRing], cs));
   }
   MANSY_CUDA(cudaStreamSynchronize(cs));                        // every result of the n_steps is in host memory

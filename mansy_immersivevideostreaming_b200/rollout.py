@@ -190,8 +190,16 @@ class PeerGroup:
             every = [None] * self.world
             dist.all_gather_object(every, bytes(mine), group=group)
             blob = (C.c_uint8 * (_capi.PEER_HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(every))
-            check(self.lib.mansy_peer_connect(self._h, blob))
-            dist.barrier(group)          # every rank has mapped every mailbox before the first store
+            # every rank has mapped every mailbox before the first store -- or every rank raises: a rank that cannot
+            # open a peer's handle (no P2P route) must not leave the others waiting on its epoch flags
+            rc = self.lib.mansy_peer_connect(self._h, blob)
+            why = self.lib.mansy_last_error().decode() if rc else ""
+            failed = [None] * self.world
+            dist.all_gather_object(failed, (self.rank, why) if rc else None, group=group)
+            failed = [f for f in failed if f is not None]
+            if failed:
+                self.close()
+                raise RuntimeError(f"peer-memory mailboxes unavailable on rank(s) {[f[0] for f in failed]}: {failed[0][1]}")
 
     def barrier(self, stream: Optional[int] = None) -> None:
         """Device-side barrier over the group's GPUs on ``stream`` (no host synchronisation)."""
