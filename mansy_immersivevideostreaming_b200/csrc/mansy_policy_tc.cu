@@ -892,9 +892,12 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           const uint32_t dst = map_to_rank(d3recv + (rank * 4u) * 512u + (uint32_t)lane * 16u, (uint32_t)q);
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) st_cluster_v4(dst + c4 * 512, acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
-        } else {
+        } else {           // the rows this CTA finishes itself: same mailbox, local store (phase D runs on another warp)
+          const uint32_t dst = d3recv + (rank * 4u) * 512u + (uint32_t)lane * 16u;
 #pragma unroll
-          for (int o = 0; o < 16; ++o) own[o] = acc[o];
+          for (int c4 = 0; c4 < 4; ++c4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c4 * 512), "f"(acc[4 * c4]), "f"(acc[4 * c4 + 1]),
+                         "f"(acc[4 * c4 + 2]), "f"(acc[4 * c4 + 3]) : "memory");
         }
       }
       tc_fence_before();
@@ -961,9 +964,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     // fused: the simulator phase's action-independent loads (state record, history slot, viewport / trace entries) are issued
     // by all eight epilogue warps now, so they land while warp q == rank samples the actions.  (Measured alternatives that
     // did not pay, profiles/r02*_fused_timeline.txt: sampling spread over the 8 lanes of each environment, the loads staged
-    // through cp.async into an idle TMA stage, the outcomes of all 16 actions fetched ahead -- every one of them lengthens
-    // this phase by as much as it shortens the next: eight warps each walking the whole dependent chain are slower than one
-    // warp sampling while seven only wait for their loads.)
+    // through cp.async into an idle TMA stage -- each lengthens this phase by as much as it shortens the next.)
     if (kFused && sim_live) {
       load_state(F.S, sim_i, sim_st);
       load_slot(F.S, sim_i, sim_et & 7, sim_slot);
@@ -985,11 +986,22 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[493] = clock64();
 
-    // ================= phase D: each rank finishes its 32 rows (warp q == rank) =================
-    if (warp >= kTcEpiWarp0 && half == 0 && (uint32_t)q == rank) {
+    // ================= phase D: each rank finishes its 32 rows =================
+    // On the spare warp (lane = row 32 * rank + lane of the tile): in the fused kernel the eight epilogue warps are walking
+    // the dependent load chain of the simulator phase meanwhile, so the action is in shared memory by the time they need it
+    // instead of ~2 200 cycles after their loads were issued.
+    if (warp == kTcMmaWarp + 1) {
+      const int env = tile * 128 + (int)rank * 32 + lane;
+      const bool live = env < A.n;
       float acc[16];
+      {
+        const uint32_t src = d3recv + (rank * 4u) * 512u + (uint32_t)lane * 16u;
 #pragma unroll
-      for (int o = 0; o < 16; ++o) acc[o] = own[o];
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 tt = ld_shared_v4(src + c4 * 512);
+          acc[4 * c4] = tt.x; acc[4 * c4 + 1] = tt.y; acc[4 * c4 + 2] = tt.z; acc[4 * c4 + 3] = tt.w;
+        }
+      }
 #pragma unroll
       for (uint32_t j3 = 0; j3 < 3; ++j3) {     // fixed order: own + the other ranks ascending
         const uint32_t sr = j3 + (j3 >= rank ? 1u : 0u);
@@ -1036,9 +1048,12 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           if (A.logp) A.logp[orow] = lp;
         }
       }
-      if (kFused) asm volatile("st.shared.s32 [%0], %1;" ::"r"(act_s + (uint32_t)lane * 4u), "r"(act) : "memory");
+      if (kFused) {
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(act_s + (uint32_t)lane * 4u), "r"(act) : "memory");
+        asm volatile("bar.arrive 1, 288;" ::: "memory");     // the simulator phase picks the actions up from act_s
+      }
+      if (tl && k == tlk && lane == 0) A.timeline[486] = clock64();
     }
-    if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[486] = clock64();
 
     if (kFused) {
       // ================= phase E: simulator chunk-step of this CTA's 32 environments =================
@@ -1050,7 +1065,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         float (&slot)[8] = sim_slot;
         const bool live_e = sim_live;
         cp_async_wait_all();                                // this lane's share of the staged outcomes / next-sample record ...
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // ... and everyone's; the actions are in act_s
+        asm volatile("bar.sync 1, 288;" ::: "memory");      // ... and everyone's; the spare warp has put the actions in act_s
         if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[490] = clock64();
         int action;
         asm volatile("ld.shared.s32 %0, [%1];" : "=r"(action) : "r"(act_s + (uint32_t)(sim_et >> 3) * 4u) : "memory");
