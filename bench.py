@@ -407,7 +407,7 @@ def run_ours(args):
     e2e_roll = PolicyRollout(e2e_sim, policy, 4, seed=1234)
     host = e2e_roll.make_host_buffers(host_slabs=8)              # 8 x 12.9 MB pinned ring
     e2e_steps = max(20, min(K, 100))
-    e2e_roll.run_host(5, host)
+    e2e_roll.run_host(max(5, host["obs"].shape[0]), host)        # warm-up: every slab of the pinned ring has been written once
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

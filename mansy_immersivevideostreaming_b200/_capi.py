@@ -12,7 +12,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmansy_b200.so")
+# MANSY_LIB_PATH: another build of the same library (A/B timing of two builds on one box); never a different implementation
+LIB_PATH = os.environ.get("MANSY_LIB_PATH") or os.path.join(_HERE, "csrc", "libmansy_b200.so")
 
 AUX_DOUBLES = 16
 STATS_DOUBLES = 16

@@ -50,7 +50,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     extra = os.environ.get("MANSY_NVCC_EXTRA", "").split()          # tuning experiments, e.g. -DMANSY_STEP_MIN_BLOCKS=6
     tag = _flags_tag(extra)
     srcs = [os.path.join(CSRC, f) for f in SOURCES] + _deps()
-    if not force and not extra and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in srcs):
+    tag_file = os.path.join(OBJ_DIR, "linked.tag")      # which flag set the library on disk was linked from
+    linked = open(tag_file).read().strip() if os.path.exists(tag_file) else ""
+    if (not force and not extra and linked in ("", tag) and os.path.exists(LIB)
+            and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in srcs)):
         return LIB            # e.g. on the GPU box: the library travels with the snapshot, the objects do not
     os.makedirs(OBJ_DIR, exist_ok=True)
     hdr_m = max(os.path.getmtime(d) for d in _deps())
@@ -67,8 +70,6 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 cmd += ["-Xptxas", "-v"]
             jobs.append(cmd)
-    tag_file = os.path.join(OBJ_DIR, "linked.tag")      # which flag set the library on disk was linked from
-    linked = open(tag_file).read().strip() if os.path.exists(tag_file) else ""
     if not jobs and linked == tag and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(o) for o in objs):
         return LIB
 

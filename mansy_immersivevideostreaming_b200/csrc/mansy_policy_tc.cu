@@ -62,8 +62,8 @@ enum : uint8_t { kFlagFirst = 1, kFlagLast = 2, kFlagTileFirstL2 = 4, kFlagTileL
 
 struct TcJob {
   uint8_t type;     // kJobL1 / kJobL2
-  uint8_t a_box;    // L1: first observation box (32 floats)       L2: -
-  uint8_t w_box;    // L1: first box of the layer-1 weight image   L2: -
+  uint8_t a_box;    // L1: first float of the first observation box (32 floats wide), in units of 4 floats   L2: -
+  uint8_t w_box;    // L1: first column of the first box of the layer-1 weight image, same units               L2: -
   uint8_t s_lo;     // L1: first K-step inside the job (0..7)      L2: -
   uint8_t s_hi;     // L1: one past the last K-step (<= 8)         L2: -
   uint8_t slot;     // branch in processing order (D1 / feature buffer = slot & 1)
@@ -228,8 +228,8 @@ policy_tc_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_const
             if (job.type == kJobL1) {     // stage: [A box 0][A box 1][W1 box 0][W1 box 1]
               if (half < job.chunk) {
                 mbar_expect_tx(full, 2 * kBoxBytes);
-                tma_load_2d(dst + half * kBoxBytes, &map_obs, (job.a_box + half) * 32, tile * 128, full);
-                tma_load_2d(dst + (2 + half) * kBoxBytes, &map_w1, (job.w_box + half) * 32, 0, full);
+                tma_load_2d(dst + half * kBoxBytes, &map_obs, job.a_box * 4 + half * 32, tile * 128, full);
+                tma_load_2d(dst + (2 + half) * kBoxBytes, &map_w1, job.w_box * 4 + half * 32, 0, full);
               } else {
                 mbar_arrive(full);        // nothing to load: keep both halves' phases in step
               }
@@ -665,8 +665,8 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           if (job.type == kJobL1) {
             if (hf < job.chunk) {
               mbar_expect_tx(full, 2 * kBoxBytes);
-              tma_load_2d(dst + hf * kBoxBytes, &map_obs, (job.a_box + hf) * 32, row0, full);
-              tma_load_2d(dst + (2 + hf) * kBoxBytes, &map_w1, (job.w_box + hf) * 32, 0, full);
+              tma_load_2d(dst + hf * kBoxBytes, &map_obs, job.a_box * 4 + hf * 32, row0, full);
+              tma_load_2d(dst + (2 + hf) * kBoxBytes, &map_w1, job.w_box * 4 + hf * 32, 0, full);
             } else {
               mbar_arrive(full);
             }
@@ -1114,7 +1114,9 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       MANSY_DBG(39);
       cluster_sync_all();            // (3) the next observation rows of the tile are complete
       MANSY_DBG(40);
-      if (warp < kTcProducers) asm volatile("fence.proxy.async;" ::: "memory");
+      // (No proxy fence on the consumer side: every writer of the rows ran fence.proxy.async before it arrived at the
+      // barrier, which is what orders its generic-proxy stores before the TMA loads issued after the barrier.  A second
+      // fence in the producer warps delayed the first load of every step by ~700 cycles.)
       if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[488] = clock64();
     }
    }
@@ -1263,14 +1265,20 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
   int nj = 0;
   const int pair1 = getenv("MANSY_TC_PAIR1") ? atoi(getenv("MANSY_TC_PAIR1")) : 2;   // debugging knobs: boxes / chunks per job
   const int pair2 = getenv("MANSY_TC_PAIR2") ? atoi(getenv("MANSY_TC_PAIR2")) : 2;
+  // A TMA box may start at any 16-byte aligned column: a branch's boxes start at the branch's first float (all offsets are
+  // multiples of 8 floats = one K-step), not at the multiple of 32 floats below it -- the 64 floats at 648 are 2 boxes = one
+  // job instead of 3 boxes = two jobs, a 320-float branch 10 boxes instead of 11.  The K-steps and their order are the same
+  // either way (bit-identical sums).  The `extra` branch keeps the 32-aligned box its weight box mirrors.
+  const bool aligned = !(getenv("MANSY_TC_BRANCH_BOXES") && getenv("MANSY_TC_BRANCH_BOXES")[0] == '0');
   auto push_l1 = [&](int i) {
     const BranchPlan &b = plan[i];
-    const int lo = b.off / 8, hi = (b.off + b.k + 7) / 8;      // K-steps of 8 floats
+    const int origin = (aligned && !b.extra && b.off % 8 == 0) ? b.off / 8 : (b.off / 32) * 4;   // K-step the first box starts at
+    const int lo = b.off / 8 - origin, hi = (b.off + b.k + 7) / 8 - origin;      // K-steps of 8 floats, relative to it
     const int box_lo = lo / 4, box_hi = (hi - 1) / 4;          // boxes of 4 K-steps; a job takes up to two
     for (int box = box_lo; box <= box_hi; box += pair1) {
       const int nbox = (pair1 == 2 && box + 1 <= box_hi) ? 2 : 1;
       TcJob &j = hc->jobs[nj++];
-      j.type = kJobL1; j.a_box = (uint8_t)box; j.w_box = (uint8_t)(b.extra ? main_boxes : box);
+      j.type = kJobL1; j.a_box = (uint8_t)(origin * 2 + box * 8); j.w_box = (uint8_t)(b.extra ? main_boxes * 8 : origin * 2 + box * 8);
       j.s_lo = (uint8_t)((lo > box * 4 ? lo : box * 4) - box * 4);
       j.s_hi = (uint8_t)((hi < (box + nbox) * 4 ? hi : (box + nbox) * 4) - box * 4);
       j.slot = (uint8_t)i; j.chunk = (uint8_t)nbox;
@@ -1285,6 +1293,10 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
                           (i == nb - 1 && c + pair2 == 4 ? kFlagTileLastL2 : 0));
     }
   };
+  auto branch_boxes = [&](const BranchPlan &b) {
+    const int origin = (aligned && !b.extra && b.off % 8 == 0) ? b.off / 8 : (b.off / 32) * 4;
+    return ((b.off + b.k + 7) / 8 - origin - 1) / 4 + 1;
+  };
   push_l1(0);
   for (int i = 1; i < nb; ++i) { push_l1(i); push_l2(i - 1); }
   push_l2(nb - 1);
@@ -1298,8 +1310,7 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
     for (int r = 0; r < kTcRanks; ++r) { hc->rank[r].n_branches = 0; hc->rank[r].resid_local = -1; }
     for (int i = 0; i < nb; ++i) {
       const BranchPlan &b = plan[i];
-      const int lo = b.off / 8, hi = (b.off + b.k + 7) / 8;
-      const int boxes = (hi - 1) / 4 - lo / 4 + 1;
+      const int boxes = branch_boxes(b);
       int best = 0;
       for (int r = 1; r < kTcRanks; ++r) if (load[r] < load[best]) best = r;
       load[best] += boxes * 32 + 128;
@@ -1374,8 +1385,7 @@ int tc_create(mansy_policy *p, const mansy_policy_weights_t *w) {
       for (int i = 0; i < nb; ++i) {
         const BranchPlan &b = plan[i];
         if (b.k == 320) continue;
-        const int lo = b.off / 8, hi = (b.off + b.k + 7) / 8;
-        const int boxes = (hi - 1) / 4 - lo / 4 + 1;
+        const int boxes = branch_boxes(b);
         int best = 0;
         for (int r = 1; r < kTcRanks; ++r) if (mload[r] < mload[best]) best = r;
         mload[best] += boxes * 32 + 128;
