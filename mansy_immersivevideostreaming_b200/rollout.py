@@ -99,11 +99,15 @@ class PolicyRollout:
         return pm.value, sm.value, n.value
 
     def make_host_buffers(self, host_slabs: int = 2) -> Dict[str, torch.Tensor]:
+        """Pinned host ring for ``run_host``, allocated on the memory node of this simulator's GPU when the machine has
+        more than one and says which (``numa.memory_on_node``; a no-op otherwise)."""
+        from . import numa
         n, st = self.sim.n_envs, self.sim.obs_stride
         pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()   # noqa: E731
-        return {"obs": pin(host_slabs, n, st, dtype=torch.float32), "actions": pin(host_slabs, n, dtype=torch.int32),
-                "logp": pin(host_slabs, n, dtype=torch.float32), "value": pin(host_slabs, n, dtype=torch.float32),
-                "reward": pin(host_slabs, n, dtype=torch.float32), "done": pin(host_slabs, n, dtype=torch.uint8)}
+        with numa.memory_on_node(numa.gpu_numa_node(self.sim.device_index)):
+            return {"obs": pin(host_slabs, n, st, dtype=torch.float32), "actions": pin(host_slabs, n, dtype=torch.int32),
+                    "logp": pin(host_slabs, n, dtype=torch.float32), "value": pin(host_slabs, n, dtype=torch.float32),
+                    "reward": pin(host_slabs, n, dtype=torch.float32), "done": pin(host_slabs, n, dtype=torch.uint8)}
 
     def run_host(self, n_steps: int, host: Dict[str, torch.Tensor], zero_copy: bool = True) -> None:
         """Rollout with host storage: per step actions to the host + sync, H2D actions, step, D2H results + sync.

@@ -166,3 +166,18 @@ def test_all_gather_stats_world_size_2_gloo():
     for r in range(2):
         assert torch.equal(torch.load(os.path.join(out_dir, f"r{r}.pt")), expect)   # sharded == unsharded order
         assert bool(torch.load(os.path.join(out_dir, f"b{r}.pt")))                  # broadcast weights == rank 0's
+
+
+def test_numa_helpers_degrade_to_no_ops():
+    """numa.py is best-effort host plumbing: list parsing, and no policy change where there is nothing to choose from."""
+    from mansy_immersivevideostreaming_b200 import numa
+    assert numa._parse_list("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and numa._parse_list("") == set()
+    nodes = numa.online_nodes()
+    assert nodes and nodes[0] == 0
+    with numa.memory_on_node(None) as applied:
+        assert applied is False
+    with numa.memory_on_node(max(nodes) + 7) as applied:          # a node that does not exist
+        assert applied is False
+    buf = np.ones(1 << 16, dtype=np.float32)
+    where = numa.pages_node(buf.ctypes.data, buf.nbytes)
+    assert where == {} or set(where) <= set(nodes) | {-2, -14}     # (negative = errno of an unmapped / foreign page)
