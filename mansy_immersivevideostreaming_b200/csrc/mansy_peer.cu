@@ -65,6 +65,7 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p) {
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ uint32_t *timeout_flag(uint8_t *box) { return reinterpret_cast<uint32_t *>(box + 16 * 8 * 3 + 8); }
 // Wait until *f >= epoch; gives up after ~4 s (a peer that died must not hang this GPU) and records it.
 __device__ __forceinline__ void wait_flag(const uint64_t *f, uint64_t epoch, uint8_t *mine) {
@@ -98,6 +99,8 @@ __global__ void stats_totals_kernel(const double *__restrict__ stats, int n, dou
 // All-gather of the totals: pack + push to every mailbox + flags + wait (see the file header).
 __global__ void __launch_bounds__(256) peer_allgather_stats_kernel(const PeerDev P, const double *__restrict__ stats, int n,
                                                                   uint64_t epoch) {
+  // (launched with programmatic stream serialisation: scheduled while the rollout kernel before it drains, ordered here)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int parity = (int)(epoch & 1);
   const size_t region = (size_t)P.world * P.slot_bytes;
   const size_t my_off = kHeaderBytes + (size_t)parity * region + (size_t)P.rank * P.slot_bytes;
@@ -110,16 +113,23 @@ __global__ void __launch_bounds__(256) peer_allgather_stats_kernel(const PeerDev
       *reinterpret_cast<double2 *>(P.box[dst] + my_off + ((size_t)e * kTotCols + c) * sizeof(double)) = v;
     }
   }
-  __threadfence_system();
+  if (P.world == 1) return;                                  // one GPU: a local pack, ordered by the stream
+  // Release pattern with ONE system-scope fence per block (a fence in each of the 256 threads was most of this kernel's
+  // 13 us): the block's stores happen before the barrier, thread 0's fence orders them -- cumulatively -- before its
+  // counter increment; the last block to increment has every block's stores ordered before the flags it publishes.
   __syncthreads();
   __shared__ bool last;
   uint8_t *mine = P.box[P.rank];
-  if (threadIdx.x == 0) last = atomicAdd(done_blocks(mine), 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    fence_acq_rel_sys();
+    last = atomicAdd(done_blocks(mine), 1u) == gridDim.x - 1;
+    if (last) fence_acq_rel_sys();                           // acquire side: the other blocks' increments were observed
+  }
   __syncthreads();
   if (!last) return;
-  __threadfence_system();                                    // every block's stores precede the flags below
   const int t = threadIdx.x;
   if (t < P.world) {
+    fence_acq_rel_sys();
     st_release_sys(flag_gather(P.box[t], parity, P.rank), epoch);
     wait_flag(flag_gather(mine, parity, t), epoch, mine);
   }
@@ -220,7 +230,17 @@ int mansy_peer_allgather_stats(mansy_peer_t p, mansy_handle_t h, void *stream, c
   const int items = S->n_envs * 3;
   int grid = (items + 255) / 256;
   if (grid > 64) grid = 64;
-  peer_allgather_stats_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, S->stats, S->n_envs, epoch);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;    // its launch overlaps the tail of the rollout kernel before it
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MANSY_CUDA(cudaLaunchKernelEx(&cfg, peer_allgather_stats_kernel, p->dev, static_cast<const double *>(S->stats), (int)S->n_envs, epoch));
   count_launch();
   MANSY_CUDA(cudaGetLastError());
   if (gathered_dev)

@@ -139,6 +139,8 @@ class BatchSimulator:
         n = self.n_envs if ids is None else int(ids.numel())
         if obs is None and self.obs_mode != OBS_MODE_NONE:
             obs = self.new_obs(n)
+        if n == 0:                 # an empty id list touches nothing (and has no device pointer to pass)
+            return obs
         check(self.lib.mansy_reset(self._h, self._ptr(ids), n, self._ptr(obs),
                                    obs.stride(0) if obs is not None else 0, self._stream()))
         return obs
@@ -159,6 +161,8 @@ class BatchSimulator:
             reward = torch.empty(n, dtype=torch.float32, device=self.device)
         if done is None:
             done = torch.empty(n, dtype=torch.uint8, device=self.device)
+        if n == 0:                 # an empty id list touches nothing (and has no device pointer to pass)
+            return obs, reward, done
         o = Out()
         o.obs, o.obs_stride = self._ptr(obs), (obs.stride(0) if obs is not None else 0)
         o.reward, o.done = self._ptr(reward), self._ptr(done)

@@ -79,6 +79,14 @@ def test_env_ids_are_validated_on_the_host():
     obs, rew, done, info = venv.step([4, 5], id=[7, 2])
     assert rew.dtype == np.float64 and [i["env_id"] for i in info] == [7, 2]
     assert sim.error_flag() == 0
+    # an empty id list is a call that touches nothing (tianshou passes one when no environment is ready)
+    before = sim.episode_state_host().copy()
+    rows, r0, d0 = sim.step(acts[:0], env_ids=[])
+    assert rows.shape[0] == 0 and r0.numel() == 0 and d0.numel() == 0
+    assert sim.reset([]).shape[0] == 0
+    obs0, rew0, done0, info0 = venv.step([], id=[])
+    assert len(rew0) == 0 and len(done0) == 0 and len(info0) == 0
+    assert before.tobytes() == sim.episode_state_host().tobytes() and sim.error_flag() == 0
 
 
 def test_seed_moves_the_cursor_without_touching_a_running_episode():
