@@ -813,20 +813,27 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     MANSY_DBG(5);
     // ================= phase B: reduce-scatter the partials through L2 =================
     float4 *const xch = A.scratch + (size_t)tile * kScratchF4PerTile;
-    if (warp >= kTcEpiWarp0) {
+    // Twelve warps move the partials: per TMEM lane quarter q the two epilogue warps (q, half) and producer warp q (idle
+    // since its last load) each take ONE destination rank, both 32-column halves -- 16 stores per thread instead of 24.
+    auto push = [&](uint32_t j3, uint32_t laddr, uint32_t row) {     // j3-th other rank (ascending)
+      const uint32_t d = j3 + (j3 >= rank ? 1u : 0u);
 #pragma unroll 1
-      for (uint32_t d = 0; d < (uint32_t)kTcRanks; ++d) {
+      for (uint32_t hh = 0; hh < 2; ++hh) {
         float v[32];
-        tmem_ld32(tmem_base + lane_addr + 256u + d * 64u + (uint32_t)half * 32u, v);
-        if (d == rank) {
+        tmem_ld32(tmem_base + laddr + 256u + d * 64u + hh * 32u, v);
+        float4 *dst = xch + (((d * 4u + rank) * 2u + hh) * 8u) * 128u + row;
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) own[jj] = v[jj];
-        } else {
-          float4 *dst = xch + (((d * 4u + rank) * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
-#pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) __stcg(dst + c4 * 128, make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
-        }
+        for (int c4 = 0; c4 < 8; ++c4) __stcg(dst + c4 * 128, make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
       }
+    };
+    if (warp >= kTcEpiWarp0) {
+      tmem_ld32(tmem_base + lane_addr + 256u + rank * 64u + (uint32_t)half * 32u, own);
+      push(1u + (uint32_t)half, lane_addr, (uint32_t)r);
+      tc_fence_before();
+    } else if (warp < 4) {
+      mbar_wait(bar_d2_full, par);      // every MMA of this CTA has completed (the epilogue warps waited for the same phase)
+      tc_fence_after();
+      push(0u, (uint32_t)(warp * 32) << 16, (uint32_t)(warp * 32 + lane));
       tc_fence_before();
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[482] = clock64();
