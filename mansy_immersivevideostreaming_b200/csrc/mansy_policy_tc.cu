@@ -55,7 +55,11 @@ constexpr uint32_t kStageBytes = 65536;   // L1 job: up to 2 A boxes + 2 W1 boxe
 constexpr uint32_t kBoxBytes = 16384;     // 128 rows x 128 B
 constexpr uint32_t kWoutBytes = 16384;     // head matrix [16 rows x 256 K] fp32 = 8 boxes of [16 x 32 floats]
 constexpr uint32_t kD3RecvBytes = 8192;    // cluster kernel: head partials of this CTA's 32 rows from the 4 ranks
-constexpr uint32_t kTcSmemBytes = kTcStages * kStageBytes + kWoutBytes + 256 /*barriers*/ + kD3RecvBytes + 1024 /*alignment*/;
+// cluster kernel: the WHOLE head matrix (8 boxes [16 x 32 floats]) + the residual head matrix (4 boxes) + the sampled actions
+constexpr uint32_t kClWoutBytes = 16384 + 8192 + 256;
+constexpr uint32_t kTcSmemBytesSolo = kTcStages * kStageBytes + kWoutBytes + 256 /*barriers*/ + kD3RecvBytes + 1024 /*alignment*/;
+constexpr uint32_t kTcSmemBytesCluster = kTcStages * kStageBytes + kClWoutBytes + 256 /*barriers*/ + 1024 /*alignment*/;
+constexpr uint32_t kTcSmemBytes = kTcSmemBytesSolo > kTcSmemBytesCluster ? kTcSmemBytesSolo : kTcSmemBytesCluster;
 
 enum : uint8_t { kJobL1 = 0, kJobL2 = 1 };
 enum : uint8_t { kFlagFirst = 1, kFlagLast = 2, kFlagTileFirstL2 = 4, kFlagTileLastL2 = 8 };
@@ -509,9 +513,15 @@ __device__ __forceinline__ float4 ld_shared_v4(uint32_t saddr) {
 // Exchange buffer of the partial D2 tiles in global memory (it stays in L2): distributed shared memory moves
 // only ~20 B/clk per SM (measured: 96 KB of st.shared::cluster took 4 600 - 7 800 cycles), the L2 path several
 // times that.  Index in float4: ((((tile * 4 + dst) * 4 + src) * 2 + half) * 8 + c4) * 128 + row.
-constexpr size_t kScratchPartialF4 = 4 * 4 * 2 * 8 * 128;
-// + the memoised table branches of the tile's rows in the same transposed layout: [dst rank 4][half 2][float4 column 8][row 128]
-constexpr size_t kScratchF4PerTile = kScratchPartialF4 + 4 * 2 * 8 * 128;
+// (Row split: rank d finishes rows 32d .. 32d+31 of the tile for all 256 hidden columns.)  Index in float4:
+// ((tile * 4 + dst) * 4 + src) * 2048 + c4 * 32 + row  with c4 = float4 column 0..63, row = 0..31 of the destination's rows.
+constexpr size_t kScratchBlockF4 = 64 * 32;
+constexpr size_t kScratchPartialF4 = 4 * 4 * kScratchBlockF4;
+// + the memoised table branches of the destination's rows in the same layout: [dst rank 4][c4 64][row 32]
+constexpr size_t kScratchMemoF4 = 4 * kScratchBlockF4;
+// + the residual's head contribution (feat_qoe * [actor.out ; critic.out]^T, 16 columns) for the destination's rows: [dst 4][c4 4][row 32]
+constexpr size_t kScratchResF4 = 4 * 4 * 32;
+constexpr size_t kScratchF4PerTile = kScratchPartialF4 + kScratchMemoF4 + kScratchResF4;
 
 // Fused rollout (MODE != MANSY_OBS_NONE): the same cluster also runs the simulator step of its 128 environments
 // (32 per CTA, 8 lanes each, on the eight epilogue warps) with the action it has just sampled, writes the next
@@ -553,23 +563,26 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   const int tile0 = blockIdx.x / kTcRanks, tile_stride = gridDim.x / kTcRanks;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stage0 = base;
-  const uint32_t wout_s = base + kTcStages * kStageBytes;   // this rank's K-slice of the head matrix: 2 boxes [16 x 32 floats]
-  const uint32_t wres_s = wout_s + 4096;                    // [actor.out ; critic.out] for the residual: 4 boxes
-  const uint32_t act_s = wout_s + 12288;                    // fused: the 16 sampling weights of each of this CTA's 32 environments
+  const uint32_t wout_s = base + kTcStages * kStageBytes;   // the head matrix [16 x 256]: 8 boxes [16 x 32 floats]
+  const uint32_t wres_s = wout_s + 16384;                   // [actor.out ; critic.out] for the residual: 4 boxes
+  const uint32_t act_s = wout_s + 24576;                    // fused: the action sampled for each of this CTA's 32 environments
+  const uint32_t hid_s = stage0;                            // phase C: the finished hidden rows as the A operand of the heads -- 8 boxes
+                                                            // [128 rows x 32 floats] (stages 0 and 1), rows 96..127 of each
+  const uint32_t own_s = stage0 + 2 * kStageBytes + 32768;  // phase B -> C: this rank's own partial of its rows, [c4 64][row 32] float4
   const uint32_t sim_s = stage0 + 2 * kStageBytes;          // fused: the third TMA stage, idle between phase A and the next one, stages
                                                             // the simulator phase's loads: [32 records x 128 B][32 x 8 slots x 32 B][32 x 8 lanes x 128 B]
-  const uint32_t bars = wout_s + kWoutBytes;
+  const uint32_t bars = wout_s + kClWoutBytes;
   const uint32_t bar_full = bars;                    // [kTcStages][2] TMA -> MMA
   const uint32_t bar_empty = bars + 64;              // [kTcStages]    MMA (commit) -> TMA
   const uint32_t bar_d1_full = bars + 128;           // [2]           MMA (commit) -> epilogue
   const uint32_t bar_feat_full = bars + 144;         // [2]           epilogue (256 arrivals) -> MMA
-  const uint32_t bar_d2_full = bars + 160;           //               MMA (commit) -> epilogue: partial D2 complete
-  const uint32_t bar_hid_full = bars + 176;          //               epilogue (256 arrivals) -> MMA: hidden slice stored
-  const uint32_t bar_d3_full = bars + 184;           //               MMA (commit) -> epilogue: head partial ready
+  const uint32_t bar_d2_full = bars + 160;           //               MMA (commit) -> everyone: partial D2 complete
+  const uint32_t bar_hid_full = bars + 176;          //               384 arrivals -> MMA: hidden rows stored (shared memory)
+  const uint32_t bar_d3_full = bars + 184;           //               MMA (commit) -> spare warp / table-row warp: heads done
+  const uint32_t bar_res_full = bars + 240;          //               MMA (commit) -> residual head contribution in tensor memory
   const uint32_t bar_wout = bars + 192;              //               TMA -> MMA: head matrices resident
   const uint32_t tmem_slot = bars + 200;
   const uint32_t bar_tab = bars + 208;               // [4]           bulk table-row loads of 8 environments each (fused)
-  const uint32_t d3recv = bars + 256;                // [src rank 4][float4 column 4][lane 32] x 16 B
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool tl = A.timeline != nullptr && (int)blockIdx.x == A.timeline_cta;     // (stamps of the cluster's last tile of the step win)
@@ -589,8 +602,9 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       mbar_init(bar_feat_full + 8 * b, 256);
     }
     mbar_init(bar_d2_full, 1);
-    mbar_init(bar_hid_full, 256);
+    mbar_init(bar_hid_full, 384);
     mbar_init(bar_d3_full, 1);
+    mbar_init(bar_res_full, 1);
     mbar_init(bar_wout, 1);
     for (int g = 0; g < 4; ++g) mbar_init(bar_tab + 8 * g, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -616,11 +630,10 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   const int half = (warp - kTcEpiWarp0) >> 2;
   const int r = q * 32 + lane;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-  float own[32];      // this rank's own partial of the 32 hidden columns the thread finishes
 
   if (warp == 0 && elect_one()) {            // weights do not depend on the previous kernel in the stream
-    mbar_expect_tx(bar_wout, 4096u + (resid >= 0 ? 8192u : 0u));
-    for (int b = 0; b < 2; ++b) tma_load_2d(wout_s + b * 2048, &map_wout, (int)(2 * rank + b) * 32, 0, bar_wout);
+    mbar_expect_tx(bar_wout, 16384u + (resid >= 0 ? 8192u : 0u));
+    for (int b = 0; b < 8; ++b) tma_load_2d(wout_s + b * 2048, &map_wout, b * 32, 0, bar_wout);
     if (resid >= 0)
       for (int b = 0; b < 4; ++b) tma_load_2d(wres_s + b * 2048, &map_wres, b * 32, 0, bar_wout);
   }
@@ -745,8 +758,8 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
         job = next_job;
       }
       if (resid >= 0) {
-        // residual through the heads: D3 = feat_qoe[128 x 128] * [actor.out ; critic.out]^T.  The qoe features sit in
-        // D1[resid & 1] (their layer-2 MMAs above waited for them); the head MMAs of phase C accumulate on top.
+        // residual through the heads: feat_qoe[128 x 128] * [actor.out ; critic.out]^T for all 128 rows.  The qoe features sit
+        // in D1[resid & 1] (their layer-2 MMAs above waited for them); phase B ships the 16 columns to the ranks that finish the rows.
         if (ts == 0) mbar_wait(bar_wout, 0);
         tc_fence_after();
         if (elect_one()) {
@@ -756,26 +769,26 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
           for (int ks = 0; ks < 16; ++ks)
             umma_tf32_ts(tmem_base + d3_col, fa + ks * 8, make_desc(w_lo + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2), kIdesc16,
                          ks > 0 ? 1u : 0u);
+          umma_commit(bar_res_full);
         }
         __syncwarp();
       }
     } else if (warp == kTcMmaWarp + 1) {
-      // The spare warp brings the memoised table branches of the tile's 128 rows into the exchange layout while phase A
-      // runs: row r's (video, chunk) entry, this rank's 64 hidden columns, written [half][float4 column][row] next to
-      // the partials the other ranks will deliver -- so that phase C reads it as one more coalesced source.  (A thread
-      // reading its own row's 128 bytes straight from the table in phase B is 32 cache lines per warp instruction.)
+      // The spare warp brings the memoised table branches of the rows this rank finishes (lane = row 32 * rank + lane, all 256
+      // hidden columns) into the exchange layout [c4][row] while phase A runs, so that phase C reads them as one more
+      // coalesced source.  (Threads reading the table rows directly in phase C would touch 32 cache lines per instruction.)
       if (memo) {
-        float4 *const xm = A.scratch + (size_t)tile * kScratchF4PerTile + kScratchPartialF4 + (size_t)(rank * 2u) * 8u * 128u;
+        float4 *const xm = A.scratch + (size_t)tile * kScratchF4PerTile + kScratchPartialF4 + (size_t)rank * kScratchBlockF4 + lane;
+        const int e = tile * 128 + (int)rank * 32 + lane;
+        const float4 *src = reinterpret_cast<const float4 *>(
+            A.memo + (size_t)memo_row_of(kFused ? F.S.state : A.memo_state, e < A.n ? e : 0, kFused ? F.S.n_chunks : A.memo_n_chunks) * 256);
 #pragma unroll 1
         for (int pass = 0; pass < 4; ++pass) {
-          const int rr = pass * 32 + lane, e = tile * 128 + rr;
-          const float4 *src = reinterpret_cast<const float4 *>(
-              A.memo + (size_t)memo_row_of(kFused ? F.S.state : A.memo_state, e < A.n ? e : 0, kFused ? F.S.n_chunks : A.memo_n_chunks) * 256 + rank * 64u);
           float4 v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __ldg(src + j);
+          for (int j = 0; j < 16; ++j) v[j] = __ldg(src + pass * 16 + j);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) __stcg(xm + (size_t)j * 128 + rr, v[j]);     // j = half * 8 + float4 column
+          for (int j = 0; j < 16; ++j) __stcg(xm + (size_t)(pass * 16 + j) * 32, v[j]);
         }
       }
     } else if (warp >= kTcEpiWarp0) {
@@ -811,29 +824,46 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[480] = clock64();
 
     MANSY_DBG(5);
-    // ================= phase B: reduce-scatter the partials through L2 =================
+    // ================= phase B: reduce-scatter the partials through L2, split by ROWS =================
+    // Rank d finishes rows 32d .. 32d+31 of the tile for all 256 hidden columns (and then their heads: no second exchange).
+    // Rows 32q .. 32q+31 are TMEM lane quarter q, which warps q, q+4, q+8, q+12 can read: all sixteen warps take part, warp w
+    // moves columns 64 (w >> 2) .. +63 of quarter w & 3 -- to rank q's block of the exchange buffer, or, for this rank's own
+    // quarter, to shared memory.  Layout of a block: [c4 = float4 column 0..63][row 0..31] (lanes = rows: coalesced both ways).
     float4 *const xch = A.scratch + (size_t)tile * kScratchF4PerTile;
-    // Twelve warps move the partials: per TMEM lane quarter q the two epilogue warps (q, half) and producer warp q (idle
-    // since its last load) each take ONE destination rank, both 32-column halves -- 16 stores per thread instead of 24.
-    auto push = [&](uint32_t j3, uint32_t laddr, uint32_t row) {     // j3-th other rank (ascending)
-      const uint32_t d = j3 + (j3 >= rank ? 1u : 0u);
+    {
+      if (warp < kTcEpiWarp0) {          // (the epilogue warps waited for this phase at the end of phase A)
+        mbar_wait(bar_d2_full, par);     // every MMA of this CTA has completed: partial D2 final, TMA stages idle
+        tc_fence_after();
+      }
+      const uint32_t bq = (uint32_t)warp & 3u, cpair = (uint32_t)warp >> 2;
+      const uint32_t laddr = (bq * 32u) << 16;
 #pragma unroll 1
       for (uint32_t hh = 0; hh < 2; ++hh) {
+        const uint32_t chunk = 2u * cpair + hh;      // 32 columns
         float v[32];
-        tmem_ld32(tmem_base + laddr + 256u + d * 64u + hh * 32u, v);
-        float4 *dst = xch + (((d * 4u + rank) * 2u + hh) * 8u) * 128u + row;
+        tmem_ld32(tmem_base + laddr + 256u + chunk * 32u, v);
+        if (bq == rank) {
+          const uint32_t dst = own_s + ((chunk * 8u) * 32u + (uint32_t)lane) * 16u;
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) __stcg(dst + c4 * 128, make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
+          for (int c4 = 0; c4 < 8; ++c4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c4 * 512), "f"(v[4 * c4]), "f"(v[4 * c4 + 1]),
+                         "f"(v[4 * c4 + 2]), "f"(v[4 * c4 + 3]) : "memory");
+        } else {
+          float4 *dst = xch + (size_t)(bq * 4u + rank) * kScratchBlockF4 + (chunk * 8u) * 32u + (uint32_t)lane;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) __stcg(dst + c4 * 32, make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
+        }
       }
-    };
-    if (warp >= kTcEpiWarp0) {
-      tmem_ld32(tmem_base + lane_addr + 256u + rank * 64u + (uint32_t)half * 32u, own);
-      push(1u + (uint32_t)half, lane_addr, (uint32_t)r);
-      tc_fence_before();
-    } else if (warp < 4) {
-      mbar_wait(bar_d2_full, par);      // every MMA of this CTA has completed (the epilogue warps waited for the same phase)
-      tc_fence_after();
-      push(0u, (uint32_t)(warp * 32) << 16, (uint32_t)(warp * 32 + lane));
+      if (resid >= 0 && cpair == 0) {
+        // the residual's 16 head columns of quarter bq's rows -> the rank that finishes them (through L2 for this rank too)
+        mbar_wait(bar_res_full, par);
+        tc_fence_after();
+        float a16[16];
+        tmem_ld16(tmem_base + laddr + d3_col, a16);
+        float4 *dst = xch + kScratchPartialF4 + kScratchMemoF4 + (size_t)bq * 128 + (uint32_t)lane;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) __stcg(dst + c4 * 32, make_float4(a16[4 * c4], a16[4 * c4 + 1], a16[4 * c4 + 2], a16[4 * c4 + 3]));
+      }
       tc_fence_before();
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[482] = clock64();
@@ -841,91 +871,74 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     MANSY_DBG(10);
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[483] = clock64();
 
-    // ================= phase C: hidden slice, this rank's K-slice of the heads =================
-    if (warp >= kTcEpiWarp0) {
-      {
-        // the three other ranks' partials, then the memoised table branches (gathered by the spare warp in phase A): read one
-        // source ahead of the one being added (fixed summation order: own + ranks ascending + memo)
-        float4 tt[8], tn[8];
-        auto src_of = [&](uint32_t j3) -> const float4 * {
-          if (j3 < 3) {
-            const uint32_t sr = j3 + (j3 >= rank ? 1u : 0u);
-            return xch + (((rank * 4u + sr) * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
-          }
-          return xch + kScratchPartialF4 + ((rank * 2u + (uint32_t)half) * 8u) * 128u + (uint32_t)r;
-        };
-        const uint32_t n_src = memo ? 4u : 3u;
-        {
-          const float4 *src = src_of(0);
+    // ================= phase C: this rank's 32 rows -- hidden layer, then the heads from shared memory =================
+    if (warp >= kTcEpiWarp0 || warp < 4) {
+      // 384 threads, item f = c4 * 32 + row (2 048 float4 per source): own partial (shared memory) + the three other ranks'
+      // (ascending) + the memoised table branches, bias, LeakyReLU -> the heads' A operand: box c4 >> 3 of [128 rows x 32 floats]
+      // in the 128-byte-swizzled K-major layout the TMA boxes have, rows 96 .. 127 (so that the heads land in TMEM lane quarter
+      // 3, the spare warp's).
+      const uint32_t t12 = (uint32_t)(warp < 4 ? warp : warp - 4) * 32u + (uint32_t)lane;
+      const float4 *const xin = xch + (size_t)(rank * 4u) * kScratchBlockF4;
+      const float4 *const xmemo = xch + kScratchPartialF4 + (size_t)rank * kScratchBlockF4;
+      const uint32_t row_s = 96u + (uint32_t)lane;
+#pragma unroll 1
+      for (uint32_t base_f = 0; base_f < 2048u; base_f += 3u * 384u) {
+        float4 acc[3], sv[4][3];
+        uint32_t f[3];
 #pragma unroll
-          for (int c4 = 0; c4 < 8; ++c4) tt[c4] = __ldcg(src + c4 * 128);
-        }
+        for (int u = 0; u < 3; ++u) f[u] = base_f + (uint32_t)u * 384u + t12;
+        // all twelve loads of the pass are in flight together (one L2 round trip per pass, not one per source) ...
 #pragma unroll
         for (uint32_t j3 = 0; j3 < 4; ++j3) {
-          if (j3 < n_src) {
-            if (j3 + 1 < n_src) {
-              const float4 *src = src_of(j3 + 1);
+          const float4 *from = j3 < 3 ? xin + (size_t)(j3 + (j3 >= rank ? 1u : 0u)) * kScratchBlockF4 : xmemo;
 #pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4) tn[c4] = __ldcg(src + c4 * 128);
+          for (int u = 0; u < 3; ++u)
+            sv[j3][u] = (f[u] < 2048u && (j3 < 3 || memo)) ? __ldcg(from + f[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) acc[u] = f[u] < 2048u ? lds128(own_s + f[u] * 16u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // ... and added in a fixed order: own + the other ranks ascending + memo
+#pragma unroll
+        for (uint32_t j3 = 0; j3 < 4; ++j3) {
+          if (j3 == 3 && !memo) break;
+#pragma unroll
+          for (int u = 0; u < 3; ++u) { acc[u].x += sv[j3][u].x; acc[u].y += sv[j3][u].y; acc[u].z += sv[j3][u].z; acc[u].w += sv[j3][u].w; }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          if (f[u] < 2048u) {
+            const uint32_t c4 = f[u] >> 5;               // (f & 31 == lane: the row)
+            float4 h;
+            h.x = leaky(acc[u].x + K.bias2[c4 * 4u]); h.y = leaky(acc[u].y + K.bias2[c4 * 4u + 1]);
+            h.z = leaky(acc[u].z + K.bias2[c4 * 4u + 2]); h.w = leaky(acc[u].w + K.bias2[c4 * 4u + 3]);
+            const uint32_t dst = hid_s + (c4 >> 3) * kBoxBytes + row_s * 128u + (((c4 & 7u) ^ (row_s & 7u)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+            if (!kFused && A.hid_dbg) {      // NOTE: without the residual (it enters through the heads in this kernel)
+              const int e = tile * 128 + (int)rank * 32 + lane;
+              if (e < A.n) *reinterpret_cast<float4 *>(A.hid_dbg + (size_t)e * 256 + c4 * 4u) = h;
             }
-#pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              own[4 * c4] += tt[c4].x; own[4 * c4 + 1] += tt[c4].y; own[4 * c4 + 2] += tt[c4].z; own[4 * c4 + 3] += tt[c4].w;
-            }
-#pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) tt[c4] = tn[c4];
           }
         }
       }
-      const int col0 = (int)rank * 64 + half * 32;      // hidden column (0..127 actor.fc, 128..255 critic.fc)
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) own[jj] = leaky(own[jj] + K.bias2[col0 + jj]);
-      tmem_st32(tmem_base + lane_addr + 256u + (uint32_t)col0, own);
-      if (!kFused && A.hid_dbg && live) {      // NOTE: without the residual (it enters through the heads in this kernel)
-        float *dst = A.hid_dbg + (size_t)env * 256 + col0;
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) dst[jj] = own[jj];
-      }
-      tmem_st_wait();
-      tc_fence_before();
+      fence_async_smem();              // the tensor pipe (async proxy) reads what the generic proxy has just stored
       mbar_arrive(bar_hid_full);
-      if (half == 0) {
-        // head partials: rows 32q .. 32q+31 are finished by rank q -> this warp's 32 rows all go to the same CTA
-        mbar_wait(bar_d3_full, par);
-        tc_fence_after();
-        float acc[16];
-        tmem_ld16(tmem_base + lane_addr + d3_col, acc);
-        if ((uint32_t)q != rank) {
-          const uint32_t dst = map_to_rank(d3recv + (rank * 4u) * 512u + (uint32_t)lane * 16u, (uint32_t)q);
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) st_cluster_v4(dst + c4 * 512, acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
-        } else {           // the rows this CTA finishes itself: same mailbox, local store (phase D runs on another warp)
-          const uint32_t dst = d3recv + (rank * 4u) * 512u + (uint32_t)lane * 16u;
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4)
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c4 * 512), "f"(acc[4 * c4]), "f"(acc[4 * c4 + 1]),
-                         "f"(acc[4 * c4 + 2]), "f"(acc[4 * c4 + 3]) : "memory");
-        }
-      }
-      tc_fence_before();
     } else if (warp == kTcMmaWarp) {
       constexpr uint32_t kIdesc16 = idesc_tf32(16);
       if (resid < 0 && ts == 0) mbar_wait(bar_wout, 0);
       mbar_wait(bar_hid_full, par);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t w_lo = smem_desc_lo(wout_s);
-        const uint32_t ha = tmem_base + 256u + rank * 64u;
+        const uint32_t a_lo = smem_desc_lo(hid_s), w_lo = smem_desc_lo(wout_s);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_tf32_ts(tmem_base + d3_col, ha + ks * 8, make_desc(w_lo + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2), kIdesc16,
-                       (ks > 0 || resid >= 0) ? 1u : 0u);
+        for (int ks = 0; ks < 32; ++ks)      // K = 256 hidden units: 8 boxes of 4 K-steps
+          umma_tf32(tmem_base + 256u, make_desc(a_lo + (ks >> 2) * (kBoxBytes >> 4) + (ks & 3) * 2),
+                    make_desc(w_lo + (ks >> 2) * (2048 >> 4) + (ks & 3) * 2), kIdesc16, ks > 0 ? 1u : 0u);
         umma_commit(bar_d3_full);
       }
       __syncwarp();
     }
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[484] = clock64();
-    cluster_sync_all();              // (2) head partials delivered
+    // (No second cluster barrier: the heads of a rank's rows are computed where the rows are finished.)
     MANSY_DBG(20);
     if (tl && k == tlk && threadIdx.x == 32 * kTcEpiWarp0) A.timeline[485] = clock64();
 
@@ -937,6 +950,7 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
       // stages -> observation row -- while the epilogue warps sample and step.  No register staging and nothing in the
       // L1 load/store queue the simulator phase waits on.  (After cluster barrier 2: every MMA that read the stages
       // has completed -- the epilogue warps waited for bar_d2_full before they arrived there.)
+      mbar_wait(bar_d3_full, par);       // stages 0 and 1 hold the heads' A operand until the head MMAs have completed
       const int ei = tile * 128 + (int)rank * 32 + lane;
       const int nxt = (int)((t + 1) % F.slabs);
       const bool ok = ei < A.n;
@@ -1000,23 +1014,21 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
     if (warp == kTcMmaWarp + 1) {
       const int env = tile * 128 + (int)rank * 32 + lane;
       const bool live = env < A.n;
-      float acc[16];
-      {
-        const uint32_t src = d3recv + (rank * 4u) * 512u + (uint32_t)lane * 16u;
+      float4 res[4];
+      if (K.residual_slot >= 0) {          // requested before the wait below: it hides their latency
+        const float4 *xr = xch + kScratchPartialF4 + kScratchMemoF4 + (size_t)rank * 128 + lane;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 tt = ld_shared_v4(src + c4 * 512);
-          acc[4 * c4] = tt.x; acc[4 * c4 + 1] = tt.y; acc[4 * c4 + 2] = tt.z; acc[4 * c4 + 3] = tt.w;
-        }
+        for (int c4 = 0; c4 < 4; ++c4) res[c4] = __ldcg(xr + c4 * 32);
       }
-#pragma unroll
-      for (uint32_t j3 = 0; j3 < 3; ++j3) {     // fixed order: own + the other ranks ascending
-        const uint32_t sr = j3 + (j3 >= rank ? 1u : 0u);
-        const uint32_t src = d3recv + (sr * 4u) * 512u + (uint32_t)lane * 16u;
+      mbar_wait(bar_d3_full, par);         // heads of rows 32 * rank .. + 31 in TMEM lanes 96 .. 127 (this warp's quarter)
+      tc_fence_after();
+      float acc[16];
+      tmem_ld16(tmem_base + (96u << 16) + 256u, acc);
+      tc_fence_before();
+      if (K.residual_slot >= 0) {
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 tt = ld_shared_v4(src + c4 * 512);
-          acc[4 * c4] += tt.x; acc[4 * c4 + 1] += tt.y; acc[4 * c4 + 2] += tt.z; acc[4 * c4 + 3] += tt.w;
+          acc[4 * c4] += res[c4].x; acc[4 * c4 + 1] += res[c4].y; acc[4 * c4 + 2] += res[c4].z; acc[4 * c4 + 3] += res[c4].w;
         }
       }
 #pragma unroll
