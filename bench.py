@@ -28,8 +28,8 @@ UNIT = "chunk-steps/s"
 ENVS_PER_GPU = 4096
 # algorithmic HBM bytes per MANSY chunk-step with materialised observation
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE 40-step launch of the fused kernel at 4096 envs, per rollout
-# step (ncu --set full, profiles/r02y_fused_kernel_40steps_ncu.txt: 48.1 MB read + 502.4 MB written / 40; r02p: 14.43 MB)
-FUSED_DRAM_BYTES_PER_STEP_4096 = 13_763_194
+# step (ncu --set full, profiles/r02zz_fused_kernel_40steps_ncu.txt: 47.9 MB read + 486.5 MB written / 40; r02p: 14.43 MB)
+FUSED_DRAM_BYTES_PER_STEP_4096 = 13_358_572
 # the same for one launch of step_kernel<MANSY> at 1 048 576 envs (profiles/r02p_step_kernel_1048576_ncu.txt: 413.6 MB read
 # + 3 433.1 MB written; algorithmic 3 513 B x 1 048 576 = 3 683.6 MB)
 STEP_DRAM_BYTES_MANSY_1M = 3_846_669_864
@@ -483,7 +483,7 @@ def run_ours(args):
                                     "around every launch on the launching stream (serialised launches)"},
         "roofline": ({"bound": "hbm", "achieved": fused_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": fused_gbs / hbm_gbs,
                       "traffic": FUSED_DRAM_BYTES_PER_STEP_4096 * K if n_local == 4096 else None,
-                      "traffic_source": "ncu --set full of one 40-step launch, scaled by K (profiles/r02y_fused_kernel_40steps_ncu.txt)",
+                      "traffic_source": "ncu --set full of one 40-step launch, scaled by K (profiles/r02zz_fused_kernel_40steps_ncu.txt)",
                       "kernel": "policy_tc4_kernel<fused> (policy + sample + simulator step, K steps per launch)",
                       "bytes_per_launch": fused_bytes * K, "avg_launch_ms": elapsed_ms, "peak_source": peak_src,
                       "note": "4096 envs move 14.7 MB per step (2.2 us of HBM time): the step is latency-bound, see "

@@ -1653,11 +1653,15 @@ int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&mc, policy_tc4_kernel<SLOT, MODE>, &cfg);           \
       if (e == cudaSuccess) max_clusters = mc;                                                                      \
     }                                                                                                               \
-    /* One tile per resident cluster is the fast configuration (<= 33 tiles = 4 224 environments on B200).  The kernel   \
-       walks more tiles per cluster when asked to (MANSY_FUSED_MULTI_TILE=1: correct, bit-identical, tested), but a     \
-       cluster then runs its tiles' policy and simulator phases back to back, and from ~6 000 environments on the two   \
-       kernels of the PDL loop, each filling the machine, are faster (tools/rollout_sweep.py) */                         \
-    if (e == cudaSuccess && max_clusters >= 1 && (n_tiles <= max_clusters || getenv("MANSY_FUSED_MULTI_TILE"))) {     \
+    /* One tile per resident cluster is the fast configuration (<= 33 tiles = 4 224 environments on B200: 17.5 us per    \
+       step).  Up to TWO tiles per cluster (<= 8 448 environments) the cluster walking its tiles back to back still      \
+       beats the two-kernel PDL loop (8 192 envs: 34.8 vs 36.8 us per step, tools/rollout_sweep.py); from three on       \
+       the two kernels, each filling the machine, win (12 288 envs: 53.6 vs 40.6 us).  MANSY_FUSED_MULTI_TILE=1 / =0     \
+       forces / forbids more than one tile per cluster (tests, A/B runs). */                                              \
+    const char *mt = getenv("MANSY_FUSED_MULTI_TILE");                                                               \
+    const int tiles_per_cluster = max_clusters >= 1 ? (n_tiles + max_clusters - 1) / max_clusters : 0;               \
+    const bool take = tiles_per_cluster == 1 || (mt ? mt[0] != '0' : tiles_per_cluster == 2);                        \
+    if (e == cudaSuccess && max_clusters >= 1 && take) {                                                             \
       cfg.gridDim = dim3((unsigned)(kTcRanks * (n_tiles < max_clusters ? n_tiles : max_clusters)), 1, 1);           \
       e = cudaLaunchKernelEx(&cfg, policy_tc4_kernel<SLOT, MODE>, map_obs, p->tc->map_w1, p->tc->map_wfc, p->tc->map_wout, \
                              p->tc->map_wres, a, f);                                                                \
