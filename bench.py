@@ -301,6 +301,21 @@ def _max_over_ranks(x: float, world: int) -> float:
     return float(t.item())
 
 
+LAST_RANK_MS = None      # per rank [ms to the end of the rollout launches, ms to the end of the exchange] of the last timed_rollout
+
+
+def _all_ranks(values, world):
+    """[world][len(values)] floats, every rank's `values` (torch.distributed all_gather; world 1: just this rank's)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return [[float(v) for v in values]]
+    t = torch.tensor(values, dtype=torch.float64, device="cuda")
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [[float(x) for x in o.cpu()] for o in out]
+
+
 def make_peers(args, n_local, device):
     """The NVLink peer-memory group for the per-rollout exchange, or None (-> torch.distributed all-gather over NCCL) when
     asked for with --nccl-gather or when some rank cannot map a peer's mailbox: PeerGroup raises on EVERY rank in that
@@ -339,13 +354,17 @@ def timed_rollout(roll, sim, peers, K, W, world):
     barrier()
     if peers is not None:
         peers.barrier()                          # device-side: all GPUs pass this point within microseconds
+    mid = torch.cuda.Event(enable_timing=True)
     launches0 = lib.mansy_kernel_launches()
     start.record()
     roll.run(K)
+    mid.record()                                 # (diagnostic only: when this rank's rollout launches were done, before the exchange)
     stats = gather_episode_stats(sim, peers=peers)
     stop.record()
     launches = lib.mansy_kernel_launches() - launches0
     barrier()
+    global LAST_RANK_MS
+    LAST_RANK_MS = _all_ranks([start.elapsed_time(mid), start.elapsed_time(stop)], world)
     return _max_over_ranks(start.elapsed_time(stop), world), stats, int(launches)
 
 
@@ -391,6 +410,7 @@ def run_ours(args):
     K = args.steps
     roll.reserve_timing(K)
     elapsed_ms, stats, launches = timed_rollout(roll, sim, peers, K, W, world)
+    rank_ms = LAST_RANK_MS
     # per-kernel durations for the rooflines: the same K steps again with CUDA events around every launch on the
     # launching stream (events between the launches serialise them, so this pass is not the one `value` is from)
     roll.run(3, timed=True)       # first launches of the stand-alone kernels in this process (module load) stay out of the averages
@@ -511,6 +531,8 @@ def run_ours(args):
                         "pinned buffer) + sync, H2D actions, step launch, reward+done+logp+value stored by one kernel into the mapped pinned buffers, D2H copy of the observation slab into the pinned host ring "
                         "on a copy stream (overlaps the next step); all copies complete inside the timed region"},
         "gpu_launches": int(launches),
+        "per_rank_ms": {"rollout_launches_done": [round(r[0], 4) for r in rank_ms], "exchange_done": [round(r[1], 4) for r in rank_ms],
+                        "what": "device time from the start event on each rank: ms_per_step uses the maximum of the second list"},
         "clocks": clk,
         "rollout_summary": summary,
     }

@@ -16,6 +16,7 @@
 //                             [4096, ...) data: [2 parities][world][slot_bytes]
 // Two data parities: a rank can only push epoch e + 2 after every peer has pushed e + 1, which each peer does
 // after (in stream order) it consumed epoch e.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -239,7 +240,8 @@ int mansy_peer_allgather_stats(mansy_peer_t p, mansy_handle_t h, void *stream, c
   cfg.blockDim = dim3(256, 1, 1);
   cfg.stream = static_cast<cudaStream_t>(stream);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static const bool pdl = !(getenv("MANSY_PEER_GATHER_PDL") && getenv("MANSY_PEER_GATHER_PDL")[0] == '0');
+  cfg.numAttrs = pdl ? 1 : 0;
   MANSY_CUDA(cudaLaunchKernelEx(&cfg, peer_allgather_stats_kernel, p->dev, static_cast<const double *>(S->stats), (int)S->n_envs, epoch));
   count_launch();
   MANSY_CUDA(cudaGetLastError());
