@@ -54,6 +54,8 @@ def parse_args():
                         "sweep at 65,536 / 1,048,576 envs) and configs[4] (MTIO masks feeding the environments)")
     p.add_argument("--nccl-gather", action="store_true",
                    help="exchange the episode totals with torch.distributed (NCCL) instead of the NVLink peer-memory kernel")
+    p.add_argument("--rank-times", action="store_true",
+                   help="diagnostic: also record when each rank's rollout kernel ended (an extra event inside the timed region)")
     p.add_argument("--workload", default="rollout", choices=["rollout", "mtio"],
                    help="rollout = BASELINE configs[1] (the bench line the driver records); mtio = BASELINE configs[4], the "
                         "MTIO viewport-prediction inference feeding predicted tile masks to the environments")
@@ -301,6 +303,7 @@ def _max_over_ranks(x: float, world: int) -> float:
     return float(t.item())
 
 
+RANK_TIMES = False       # --rank-times
 LAST_RANK_MS = None      # per rank [ms to the end of the rollout launches, ms to the end of the exchange] of the last timed_rollout
 
 
@@ -354,17 +357,19 @@ def timed_rollout(roll, sim, peers, K, W, world):
     barrier()
     if peers is not None:
         peers.barrier()                          # device-side: all GPUs pass this point within microseconds
-    mid = torch.cuda.Event(enable_timing=True)
+    mid = torch.cuda.Event(enable_timing=True) if RANK_TIMES else None
     launches0 = lib.mansy_kernel_launches()
     start.record()
     roll.run(K)
-    mid.record()                                 # (diagnostic only: when this rank's rollout launches were done, before the exchange)
+    if mid is not None:
+        mid.record()         # --rank-times: when this rank's rollout launches were done (an event between the rollout kernel and
+                             # the exchange kernel costs ~2 us and their overlap, so it is not in the default line)
     stats = gather_episode_stats(sim, peers=peers)
     stop.record()
     launches = lib.mansy_kernel_launches() - launches0
     barrier()
     global LAST_RANK_MS
-    LAST_RANK_MS = _all_ranks([start.elapsed_time(mid), start.elapsed_time(stop)], world)
+    LAST_RANK_MS = _all_ranks([start.elapsed_time(mid) if mid is not None else float("nan"), start.elapsed_time(stop)], world)
     return _max_over_ranks(start.elapsed_time(stop), world), stats, int(launches)
 
 
@@ -531,7 +536,8 @@ def run_ours(args):
                         "pinned buffer) + sync, H2D actions, step launch, reward+done+logp+value stored by one kernel into the mapped pinned buffers, D2H copy of the observation slab into the pinned host ring "
                         "on a copy stream (overlaps the next step); all copies complete inside the timed region"},
         "gpu_launches": int(launches),
-        "per_rank_ms": {"rollout_launches_done": [round(r[0], 4) for r in rank_ms], "exchange_done": [round(r[1], 4) for r in rank_ms],
+        "per_rank_ms": {"rollout_launches_done": [round(r[0], 4) for r in rank_ms] if RANK_TIMES else None,
+                        "exchange_done": [round(r[1], 4) for r in rank_ms],
                         "what": "device time from the start event on each rank: ms_per_step uses the maximum of the second list"},
         "clocks": clk,
         "rollout_summary": summary,
@@ -845,6 +851,8 @@ def profile_sim(n):
 
 def main():
     args = parse_args()
+    global RANK_TIMES
+    RANK_TIMES = bool(args.rank_times)
     if args.profile_sim:
         profile_sim(args.profile_sim)
         return

@@ -16,6 +16,7 @@
 //                             [4096, ...) data: [2 parities][world][slot_bytes]
 // Two data parities: a rank can only push epoch e + 2 after every peer has pushed e + 1, which each peer does
 // after (in stream order) it consumed epoch e.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -50,6 +51,7 @@ struct PeerDev {
   uint8_t *box[kMaxPeers];       // mapped mailbox of every rank (box[rank] = the local one)
   int32_t world, rank;
   uint64_t slot_bytes;
+  int32_t debug;                 // MANSY_PEER_TIMELINE=1: the gather kernel prints its own phase times (globaltimer, ns)
 };
 
 __device__ __forceinline__ uint64_t *flag_barrier(uint8_t *box, int src) { return reinterpret_cast<uint64_t *>(box) + src; }
@@ -102,6 +104,8 @@ __global__ void __launch_bounds__(256) peer_allgather_stats_kernel(const PeerDev
                                                                   uint64_t epoch) {
   // (launched with programmatic stream serialisation: scheduled while the rollout kernel before it drains, ordered here)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  uint64_t ts0 = 0, ts1 = 0, ts2 = 0, ts3 = 0, ts4 = 0;
+  if (P.debug) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts0));
   const int parity = (int)(epoch & 1);
   const size_t region = (size_t)P.world * P.slot_bytes;
   const size_t my_off = kHeaderBytes + (size_t)parity * region + (size_t)P.rank * P.slot_bytes;
@@ -115,26 +119,39 @@ __global__ void __launch_bounds__(256) peer_allgather_stats_kernel(const PeerDev
     }
   }
   if (P.world == 1) return;                                  // one GPU: a local pack, ordered by the stream
-  // Release pattern with ONE system-scope fence per block (a fence in each of the 256 threads was most of this kernel's
-  // 13 us): the block's stores happen before the barrier, thread 0's fence orders them -- cumulatively -- before its
-  // counter increment; the last block to increment has every block's stores ordered before the flags it publishes.
+  // Release pattern with ONE system-scope fence per block (a fence in each of the 256 threads was most of the first
+  // version's 13 us; each one waits for the acknowledgements of the remote stores, ~3 us over NVLink): the block's stores
+  // happen before the barrier, thread 0's fence orders them -- cumulatively -- before its counter increment.  The last block
+  // to increment has every block's stores performed at their destinations; its thread 0 fences once more (the acquire side
+  // of the counter, the release side of the flags) and posts the flags itself as relaxed system-scope stores -- fence and
+  // stores in one thread.  (The first cut ran fence, fence, fence + st.release in a row there: 10 of the kernel's 12 us.)
   __syncthreads();
+  if (P.debug) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts1));
   __shared__ bool last;
   uint8_t *mine = P.box[P.rank];
   if (threadIdx.x == 0) {
     fence_acq_rel_sys();
     last = atomicAdd(done_blocks(mine), 1u) == gridDim.x - 1;
-    if (last) fence_acq_rel_sys();                           // acquire side: the other blocks' increments were observed
+    if (last) {
+      if (P.debug) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts2));
+      fence_acq_rel_sys();
+      for (int d = 0; d < P.world; ++d)
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(flag_gather(P.box[d], parity, P.rank)), "l"(epoch) : "memory");
+      if (P.debug) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts3));
+      *done_blocks(mine) = 0u;
+    }
   }
   __syncthreads();
   if (!last) return;
   const int t = threadIdx.x;
   if (t < P.world) {
-    fence_acq_rel_sys();
-    st_release_sys(flag_gather(P.box[t], parity, P.rank), epoch);
     wait_flag(flag_gather(mine, parity, t), epoch, mine);
+    if (P.debug) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts4));
   }
-  if (t == 0) *done_blocks(mine) = 0u;
+  if (P.debug && t == 0)
+    printf("gather rank %d epoch %llu: start->pushed %llu ns, ->last block %llu, ->flags posted %llu, ->peer 0's flag seen %llu\n", P.rank,
+           (unsigned long long)epoch, (unsigned long long)(ts1 - ts0), (unsigned long long)(ts2 - ts1), (unsigned long long)(ts3 - ts2),
+           (unsigned long long)(ts4 - ts3));
 }
 
 }  // namespace
@@ -160,6 +177,7 @@ int mansy_peer_create(int32_t world, int32_t rank, int64_t slot_bytes, int devic
   p->device = device;
   memset(&p->dev, 0, sizeof(p->dev));
   p->dev.world = world; p->dev.rank = rank; p->dev.slot_bytes = (uint64_t)slot_bytes;
+  p->dev.debug = (getenv("MANSY_PEER_TIMELINE") && getenv("MANSY_PEER_TIMELINE")[0] == '1') ? 1 : 0;
   const size_t bytes = kHeaderBytes + 2 * (size_t)world * (size_t)slot_bytes;
   void *d = nullptr;
   if (cudaMalloc(&d, bytes) != cudaSuccess) { delete p; return set_error(MANSY_E_NOMEM, "cudaMalloc failed (peer mailbox)"); }
