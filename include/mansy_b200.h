@@ -354,10 +354,10 @@ typedef struct {
 #define MANSY_ROLLOUT_FP32_POLICY 1 /* use the exact-fp32 CUDA-core policy kernels instead of tcgen05 */
 #define MANSY_ROLLOUT_TIME_KERNELS 2 /* record CUDA events around every policy / step launch */
 #define MANSY_ROLLOUT_NO_PDL 4       /* launch without programmatic dependent launch (kernels strictly one after another) */
-#define MANSY_ROLLOUT_NO_ZERO_COPY 16 /* mansy_rollout_policy_host: hand the actions to the host with cudaMemcpyAsync even when
-                                         the host buffer is device-mapped (default: a kernel stores them into it directly) */
+#define MANSY_ROLLOUT_NO_ZERO_COPY 16 /* mansy_rollout_policy_host: hand actions and per-step scalars to the host with cudaMemcpyAsync even
+                                         when the host buffers are device-mapped (default: kernels store them into the buffers directly) */
 #define MANSY_ROLLOUT_TWO_KERNELS 8  /* never use the fused policy+step cluster kernel (one launch for all n_steps), which
-                                        mansy_rollout_policy picks when every 128-env tile's 4-CTA cluster is resident at once */
+                                        mansy_rollout_policy picks up to two 128-env tiles per resident 4-CTA cluster (<= 8 448 envs on B200) */
 int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout_t *buffers, int32_t n_steps, int64_t t0,
                          uint64_t seed, int32_t flags, void *stream);
 /*
