@@ -585,8 +585,10 @@ policy_tc4_kernel(const __grid_constant__ CUtensorMap map_obs, const __grid_cons
   const uint32_t bar_tab = bars + 208;               // [4]           bulk table-row loads of 8 environments each (fused)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool tl = A.timeline != nullptr && (int)blockIdx.x == A.timeline_cta;     // (stamps of the cluster's last tile of the step win)
-  const int tlk = kFused ? 1 : 0;          // the rollout step the timeline records (fused: the second, a steady-state one)
+  const bool tl = A.timeline != nullptr && (int)blockIdx.x == (A.timeline_cta & 0xFFFF);     // (stamps of the cluster's last tile of the step win)
+  // the rollout step the timeline records: bits 16.. of timeline_cta, default (0) = the second step of a fused launch, a
+  // steady-state one; 1 + s = step s (MANSY_TC_TIMELINE_STEP, tools/fused_timeline.py: step 0 is the cold one)
+  const int tlk = (A.timeline_cta >> 16) ? (A.timeline_cta >> 16) - 1 : (kFused ? 1 : 0);
   const int n_jobs = P.n_jobs, nloc = P.n_branches, resid = P.resid_local;
   // D3 (head partial, 16 columns) lives in the D1 buffer the residual features do NOT occupy
   const uint32_t d3_col = resid >= 0 ? (uint32_t)((resid & 1) ^ 1) * 128u : 0u;
@@ -1722,6 +1724,7 @@ int mansy_policy_forward_tc_timeline(mansy_policy_t p, const float *obs_dev, int
 int mansy_debug_fused_timeline(int64_t *timeline_dev, int32_t cta) {
   g_fused_timeline = reinterpret_cast<long long *>(timeline_dev);
   g_fused_timeline_cta = cta;
+  if (const char *st = getenv("MANSY_TC_TIMELINE_STEP")) g_fused_timeline_cta |= (atoi(st) + 1) << 16;
 #ifdef MANSY_STEP_PROFILE
   long long *sp = timeline_dev ? reinterpret_cast<long long *>(timeline_dev) + 496 : nullptr;   // stamps [496..501]
   cudaMemcpyToSymbol(d_step_prof, &sp, sizeof(sp));

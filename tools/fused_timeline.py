@@ -2,6 +2,7 @@
 bench workload -- a profiling aid, run on a GPU box:  python tools/fused_timeline.py [n_envs] [cta ...]"""
 import os
 import sys
+import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -31,11 +32,15 @@ names = {493: "sim loads issued (state, slot, prefetch)", 494: "bar.sync 1 (part
 for cta in ctas:
     tl.zero_()
     check(sim.lib.mansy_debug_fused_timeline(tl.data_ptr(), cta))
+    torch.cuda.synchronize()
+    time.sleep(0.02)          # an idle GPU before the launch, as in bench.py's timed region
     roll.run(4)
     torch.cuda.synchronize()
     t = tl.cpu().numpy()
     t0 = t[489]
-    print(f"--- CTA {cta} (cluster rank {cta % 4}), second rollout step of the launch, cycles since step begin")
+    which = os.environ.get("MANSY_TC_TIMELINE_STEP")
+    print(f"--- CTA {cta} (cluster rank {cta % 4}), {'step ' + which if which else 'second rollout step'} of the launch, cycles since step begin"
+          f" (kernel prologue ended {t0 - t[511]} cycles before it)")
     for j in range(40):
         if t[j] == 0:
             break
