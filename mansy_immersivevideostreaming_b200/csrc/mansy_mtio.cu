@@ -1177,7 +1177,7 @@ extern "C" {
 
 int mansy_mtio_destroy(mansy_mtio_t m) {
   if (!m) return MANSY_OK;
-  cudaSetDevice(m->device);
+  DeviceScope dscope(m->device);
   for (void *p : m->allocs) cudaFree(p);
   for (cudaEvent_t e : m->events) cudaEventDestroy(e);
   if (m->s2) cudaStreamDestroy(m->s2);
@@ -1204,7 +1204,8 @@ int mansy_mtio_create(const mansy_mtio_weights_t *w, int device, int32_t max_bat
     cudaGetLastError();
     return set_error(MANSY_E_CUDA, "no such CUDA device (this library has no CPU fallback)");
   }
-  MTIO_CUDA(cudaSetDevice(device));
+  DeviceScope dscope(device);
+  MTIO_CUDA(dscope.err);
   mansy_mtio *m = new (std::nothrow) mansy_mtio();
   if (!m) return set_error(MANSY_E_NOMEM, "out of host memory");
   m->device = device;
@@ -1332,6 +1333,8 @@ int mansy_mtio_sample(mansy_mtio_t m, const float *history_dev, const float *cur
   if (n < 0) return set_error(MANSY_E_INVALID, "n must be >= 0");
   if (n_steps < 0 || n_steps > m->F) return set_error(MANSY_E_INVALID, "n_steps must be 0 (= fut_window) .. fut_window");
   if (n_steps == 0) n_steps = m->F;
+  DeviceScope dscope(m->device);               // the handle's device whatever the caller's current one is
+  MTIO_CUDA(dscope.err);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   m->timed = (flags & MANSY_MTIO_TIME_KERNELS) != 0;
   m->ev_used = 0;
@@ -1364,6 +1367,8 @@ int mansy_mtio_sample_host(mansy_mtio_t m, const float *history_host, const floa
   if (n < 0) return set_error(MANSY_E_INVALID, "n must be >= 0");
   if (n_steps < 0 || n_steps > m->F) return set_error(MANSY_E_INVALID, "n_steps must be 0 (= fut_window) .. fut_window");
   if (n_steps == 0) n_steps = m->F;
+  DeviceScope dscope(m->device);
+  MTIO_CUDA(dscope.err);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!m->io_hist) {
     const size_t B = (size_t)m->max_batch;
@@ -1392,6 +1397,7 @@ int mansy_linreg_sample(const float *history_dev, const float *current_dev, int6
   if (!history_dev || !current_dev || !pred_dev) return set_error(MANSY_E_INVALID, "NULL argument");
   if (n < 0 || his_window < 1 || fut_window < 1) return set_error(MANSY_E_INVALID, "n >= 0, his_window >= 1, fut_window >= 1");
   if (n == 0) return MANSY_OK;
+  DeviceScope dscope(device_of_pointer(history_dev));
   linreg_kernel<<<(unsigned)((2 * n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(history_dev, current_dev, n, his_window,
                                                                                               fut_window, pred_dev);
   count_launch();

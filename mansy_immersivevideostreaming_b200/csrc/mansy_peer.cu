@@ -30,6 +30,7 @@ namespace mansy {
 int set_error(int code, const std::string &msg);
 void count_launch();
 const SimDev *sim_dev_of(mansy_handle_t h);     // mansy_sim.cu
+int sim_device_of(mansy_handle_t h);            // mansy_sim.cu
 }  // namespace mansy
 
 using namespace mansy;
@@ -171,7 +172,8 @@ int mansy_peer_create(int32_t world, int32_t rank, int64_t slot_bytes, int devic
   *out = nullptr;
   if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return set_error(MANSY_E_INVALID, "bad world / rank (world <= 16)");
   if (slot_bytes < 16 || (slot_bytes & 15)) return set_error(MANSY_E_INVALID, "slot_bytes must be a positive multiple of 16");
-  MANSY_CUDA(cudaSetDevice(device));
+  DeviceScope dscope(device);
+  MANSY_CUDA(dscope.err);
   mansy_peer *p = new (std::nothrow) mansy_peer();
   if (!p) return set_error(MANSY_E_NOMEM, "out of host memory");
   p->device = device;
@@ -195,7 +197,8 @@ int mansy_peer_export(mansy_peer_t p, void *handle_out) {
   if (!p || !handle_out) return set_error(MANSY_E_INVALID, "NULL argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == MANSY_PEER_HANDLE_BYTES, "IPC handle size");
   cudaIpcMemHandle_t h;
-  MANSY_CUDA(cudaSetDevice(p->device));
+  DeviceScope dscope(p->device);
+  MANSY_CUDA(dscope.err);
   MANSY_CUDA(cudaIpcGetMemHandle(&h, p->dev.box[p->dev.rank]));
   memcpy(handle_out, &h, sizeof(h));
   return MANSY_OK;
@@ -204,7 +207,8 @@ int mansy_peer_export(mansy_peer_t p, void *handle_out) {
 int mansy_peer_connect(mansy_peer_t p, const void *all_handles) {
   if (!p || !all_handles) return set_error(MANSY_E_INVALID, "NULL argument");
   if (p->connected) return MANSY_OK;
-  MANSY_CUDA(cudaSetDevice(p->device));
+  DeviceScope dscope(p->device);
+  MANSY_CUDA(dscope.err);
   for (int r = 0; r < p->dev.world; ++r) {
     if (r == p->dev.rank) continue;
     cudaIpcMemHandle_t h;
@@ -220,7 +224,7 @@ int mansy_peer_connect(mansy_peer_t p, const void *all_handles) {
 
 int mansy_peer_destroy(mansy_peer_t p) {
   if (!p) return MANSY_OK;
-  cudaSetDevice(p->device);
+  DeviceScope dscope(p->device);
   cudaDeviceSynchronize();
   for (int r = 0; r < kMaxPeers; ++r)
     if (p->opened[r]) cudaIpcCloseMemHandle(p->opened[r]);
@@ -233,6 +237,8 @@ int mansy_peer_barrier(mansy_peer_t p, void *stream) {
   if (!p) return set_error(MANSY_E_INVALID, "NULL argument");
   if (!p->connected) return set_error(MANSY_E_STATE, "peer group is not connected");
   if (p->dev.world == 1) return MANSY_OK;
+  DeviceScope dscope(p->device);
+  MANSY_CUDA(dscope.err);
   peer_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(p->dev, ++p->barrier_epoch);
   count_launch();
   MANSY_CUDA(cudaGetLastError());
@@ -242,6 +248,8 @@ int mansy_peer_barrier(mansy_peer_t p, void *stream) {
 int mansy_peer_allgather_stats(mansy_peer_t p, mansy_handle_t h, void *stream, const double **gathered_dev) {
   if (!p || !h) return set_error(MANSY_E_INVALID, "NULL argument");
   if (!p->connected) return set_error(MANSY_E_STATE, "peer group is not connected");
+  DeviceScope dscope(p->device);
+  MANSY_CUDA(dscope.err);
   const SimDev *S = sim_dev_of(h);
   const size_t need = (size_t)S->n_envs * kTotCols * sizeof(double);
   if (need > p->dev.slot_bytes) return set_error(MANSY_E_INVALID, "mailbox slot smaller than n_envs x 6 doubles");
@@ -280,6 +288,8 @@ int mansy_peer_timed_out(mansy_peer_t p, int32_t *flag_host) {
 int mansy_episode_totals(mansy_handle_t h, double *totals_dev, void *stream) {
   if (!h || !totals_dev) return set_error(MANSY_E_INVALID, "NULL argument");
   if (reinterpret_cast<uintptr_t>(totals_dev) & 15) return set_error(MANSY_E_INVALID, "totals must be 16-byte aligned");
+  DeviceScope dscope(sim_device_of(h));
+  MANSY_CUDA(dscope.err);
   const SimDev *S = sim_dev_of(h);
   const int items = S->n_envs * 3;
   stats_totals_kernel<<<(items + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(S->stats, S->n_envs, totals_dev);

@@ -273,6 +273,10 @@ __global__ void gae_kernel(const float *__restrict__ reward, const float *__rest
   }
 }
 
+namespace mansy {
+int policy_device_of(mansy_policy_t p) { return p->device; }
+}  // namespace mansy
+
 extern "C" {
 
 int mansy_policy_create(const mansy_policy_weights_t *w, int device, mansy_policy_t *out) {
@@ -285,7 +289,8 @@ int mansy_policy_create(const mansy_policy_weights_t *w, int device, mansy_polic
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
     return set_error(MANSY_E_CUDA, "no CUDA device available: this library has no CPU fallback");
   if (device < 0 || device >= ndev) return set_error(MANSY_E_INVALID, "bad device index");
-  if (cudaSetDevice(device) != cudaSuccess) return set_error(MANSY_E_CUDA, "cudaSetDevice failed");
+  DeviceScope dscope(device);
+  if (dscope.err != cudaSuccess) return set_error(MANSY_E_CUDA, "cudaSetDevice failed");
 
   // branch -> (observation offset, K) in FeatureNet order (config.py row layouts)
   static const int mansy_off[10] = {0, 8, 328, 648, 728, 736, 744, 752, 779, 776};
@@ -364,7 +369,7 @@ int mansy_policy_create(const mansy_policy_weights_t *w, int device, mansy_polic
 
 int mansy_policy_destroy(mansy_policy_t p) {
   if (!p) return MANSY_OK;
-  cudaSetDevice(p->device);
+  DeviceScope dscope(p->device);
   tc_destroy(p);
   if (p->memo) cudaFree(p->memo);
   for (void *q : p->allocs) cudaFree(q);
@@ -376,6 +381,8 @@ int mansy_policy_forward(mansy_policy_t p, const float *obs_dev, int64_t obs_str
                          float *value_dev, void *stream) {
   if (!p || !obs_dev) return set_error(MANSY_E_INVALID, "NULL argument");
   if (n < 0) return set_error(MANSY_E_INVALID, "n < 0");
+  DeviceScope dscope(p->device);
+  if (dscope.err != cudaSuccess) return set_error(MANSY_E_CUDA, "cudaSetDevice failed");
   const int need = p->dev.kind == MANSY_OBS_SIMPLE ? MANSY_OBS_SIMPLE_STRIDE : MANSY_OBS_MANSY_STRIDE;
   if (obs_stride < need - 4) return set_error(MANSY_E_INVALID, "obs_stride smaller than the observation row");
   if (logits_dev && (reinterpret_cast<uintptr_t>(logits_dev) & 15)) return set_error(MANSY_E_INVALID, "logits must be 16-byte aligned");
@@ -393,6 +400,7 @@ int mansy_policy_sample(const float *logits_dev, int32_t n, int32_t is_probs, ui
   if (!logits_dev || !actions_dev) return set_error(MANSY_E_INVALID, "NULL argument");
   if (n < 0) return set_error(MANSY_E_INVALID, "n < 0");
   if (n == 0) return MANSY_OK;
+  DeviceScope dscope(device_of_pointer(logits_dev));
   policy_sample_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       logits_dev, n, is_probs, seed, step, env_offset, actions_dev, logp_dev);
   count_launch();
@@ -406,6 +414,7 @@ int mansy_identifier_reward(const float *pred_dev, const float *obs_dev, int64_t
   if (mixed_dev && !qoe_reward_dev) return set_error(MANSY_E_INVALID, "the blended reward needs qoe_reward");
   if (n < 0 || obs_stride < MANSY_OBS_MANSY_STRIDE) return set_error(MANSY_E_INVALID, "bad n / obs_stride");
   if (n == 0) return MANSY_OK;
+  DeviceScope dscope(device_of_pointer(pred_dev));
   identifier_reward_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred_dev, obs_dev, obs_stride,
                                                                                           qoe_reward_dev, lamb, n, ident_dev,
                                                                                           mixed_dev);
@@ -420,6 +429,7 @@ int mansy_gae(const float *reward_dev, const float *value_dev, const uint8_t *do
   if (!reward_dev || !value_dev || !done_dev || !last_value_dev) return set_error(MANSY_E_INVALID, "NULL argument");
   if (n_steps < 0 || n < 0) return set_error(MANSY_E_INVALID, "bad n_steps / n");
   if (n_steps == 0 || n == 0) return MANSY_OK;
+  DeviceScope dscope(device_of_pointer(reward_dev));
   gae_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(reward_dev, value_dev, done_dev, last_value_dev,
                                                                             n_steps, n, gamma, lam, adv_dev, ret_dev);
   count_launch();

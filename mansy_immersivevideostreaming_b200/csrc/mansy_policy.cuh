@@ -10,6 +10,7 @@ namespace mansy {
 
 int set_error(int code, const std::string &msg);
 void count_launch();
+int sim_device_of(mansy_handle_t h);     // mansy_sim.cu
 
 constexpr int kHidden = 128;
 constexpr int kMaxBranches = 10;

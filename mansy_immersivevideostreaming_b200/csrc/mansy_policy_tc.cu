@@ -1510,6 +1510,8 @@ int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs
   if (!p || !obs_dev) return set_error(MANSY_E_INVALID, "NULL argument");
   if (!p->tc) return set_error(MANSY_E_STATE, std::string("tensor-core state unavailable: ") + mansy_last_error());
   if (n < 0) return set_error(MANSY_E_INVALID, "n < 0");
+  DeviceScope dscope(p->device);
+  if (dscope.err != cudaSuccess) return set_error(MANSY_E_CUDA, "cudaSetDevice failed");
   if (obs_stride < p->tc->obs_floats || (obs_stride & 3))
     return set_error(MANSY_E_INVALID, "obs_stride must be >= the padded row length and a multiple of 4 floats");
   if (reinterpret_cast<uintptr_t>(obs_dev) & 15) return set_error(MANSY_E_INVALID, "obs must be 16-byte aligned");
@@ -1562,7 +1564,8 @@ int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs
   cfg.numAttrs = pdl ? 1 : 0;
 #define MANSY_TC_LAUNCH(SLOT)                                                                                       \
   do {                                                                                                              \
-    static bool attr_done = false;                                                                                  \
+    static bool attr_done_dev[64] = {false};      /* function attributes are per device */                           \
+    bool &attr_done = attr_done_dev[p->device & 63];                                                                \
     if (!attr_done) {                                                                                               \
       e = cudaFuncSetAttribute(policy_tc_kernel<SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes); \
       if (e == cudaSuccess)                                                                                         \
@@ -1648,7 +1651,10 @@ int rollout_fused_launch(mansy_policy *p, const SimDev &S, const mansy_rollout_t
   cudaError_t e = cudaSuccess;
 #define MANSY_FUSED_LAUNCH(SLOT, MODE)                                                                              \
   do {                                                                                                              \
-    static int max_clusters = -1;                                                                                   \
+    static int max_clusters_dev[64];              /* function attributes / occupancy are per device */               \
+    static bool max_clusters_init = false;                                                                          \
+    if (!max_clusters_init) { for (int i = 0; i < 64; ++i) max_clusters_dev[i] = -1; max_clusters_init = true; }     \
+    int &max_clusters = max_clusters_dev[p->device & 63];                                                           \
     if (max_clusters < 0) {                                                                                         \
       e = cudaFuncSetAttribute(policy_tc4_kernel<SLOT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes); \
       int mc = 0;                                                                                                   \

@@ -46,14 +46,6 @@ int set_error(int code, const std::string &msg) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-// Entry points run on the handle's device whatever the caller's current device is (a process driving several GPUs).
-cudaError_t use_device(int device) {
-  int cur = -1;
-  cudaError_t e = cudaGetDevice(&cur);
-  if (e != cudaSuccess) return e;
-  return cur == device ? cudaSuccess : cudaSetDevice(device);
-}
-
 }  // namespace mansy
 
 #include "mansy_step.cuh"  // StepArgs, step_env, emit_obs, reset_episode, finish_episode (device code)
@@ -416,6 +408,7 @@ using namespace mansy;
 
 namespace mansy {
 // tensor-core policy launch (mansy_policy_tc.cu); mansy_policy_t is opaque here
+int policy_device_of(mansy_policy_t p);     // mansy_policy.cu
 int policy_forward_tc_launch(mansy_policy_t p, const float *obs_dev, int64_t obs_stride, int32_t n, float *logits_dev,
                              float *value_dev, int32_t *actions_dev, float *logp_dev, uint64_t seed, int64_t step,
                              int32_t env_offset, float *feat_dbg_dev, float *hid_dbg_dev, int64_t *timeline_dev,
@@ -446,6 +439,7 @@ constexpr int kCopyRing = 64;
 
 namespace mansy {
 const SimDev *sim_dev_of(mansy_handle_t h) { return &h->dev; }    // mansy_peer.cu packs the statistics rows
+int sim_device_of(mansy_handle_t h) { return h->device; }
 }
 
 namespace {
@@ -565,7 +559,8 @@ int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, ma
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
     return set_error(MANSY_E_CUDA, "no CUDA device available: this library has no CPU fallback");
   if (device < 0 || device >= ndev) return set_error(MANSY_E_INVALID, "bad device index");
-  MANSY_CUDA(cudaSetDevice(device));
+  DeviceScope dscope(device);
+  MANSY_CUDA(dscope.err);
 
   mansy_sim *h = new (std::nothrow) mansy_sim();
   if (!h) return set_error(MANSY_E_NOMEM, "out of host memory");
@@ -742,7 +737,7 @@ int mansy_create(const mansy_tables_t *t, const mansy_cfg_t *cfg, int device, ma
 
 int mansy_destroy(mansy_handle_t h) {
   if (!h) return MANSY_OK;
-  cudaSetDevice(h->device);
+  DeviceScope dscope(h->device);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   for (cudaEvent_t e : h->step_done) cudaEventDestroy(e);
   for (cudaEvent_t e : h->copy_done) cudaEventDestroy(e);
@@ -766,14 +761,16 @@ extern "C" {
 
 int mansy_seed(mansy_handle_t h, int32_t seed, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   return launch_seed(h, seed, 0, stream);
 }
 
 int mansy_reset(mansy_handle_t h, const int32_t *env_ids_dev, int32_t n, float *obs_dev, int64_t obs_stride,
                 void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   if (n < 0 || (!env_ids_dev && n != h->dev.n_envs))
     return set_error(MANSY_E_INVALID, "n must equal n_envs when env_ids is NULL");
   if (n == 0) return MANSY_OK;
@@ -797,7 +794,8 @@ int mansy_reset(mansy_handle_t h, const int32_t *env_ids_dev, int32_t n, float *
 int mansy_step(mansy_handle_t h, const int32_t *actions_dev, const int32_t *env_ids_dev, int32_t n, int32_t auto_reset,
                const mansy_out_t *out, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   if (!actions_dev) return set_error(MANSY_E_INVALID, "actions is NULL");
   if (n < 0 || (!env_ids_dev && n != h->dev.n_envs))
     return set_error(MANSY_E_INVALID, "n must equal n_envs when env_ids is NULL");
@@ -813,7 +811,8 @@ int mansy_step(mansy_handle_t h, const int32_t *actions_dev, const int32_t *env_
 int mansy_rollout_random(mansy_handle_t h, int32_t n_steps, uint64_t seed, int64_t step0, int32_t per_step_outputs,
                          const mansy_out_t *out, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   if (n_steps < 1) return set_error(MANSY_E_INVALID, "n_steps must be >= 1");
   int rc = check_out(h, out);
   if (rc) return rc;
@@ -828,7 +827,8 @@ int mansy_rollout_random(mansy_handle_t h, int32_t n_steps, uint64_t seed, int64
 int mansy_step_host(mansy_handle_t h, const int32_t *actions_host, int32_t auto_reset, float *obs_host,
                     float *reward_host, uint8_t *done_host, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   if (!actions_host) return set_error(MANSY_E_INVALID, "actions is NULL");
   int rc = ensure_staging(h);
   if (rc) return rc;
@@ -852,7 +852,8 @@ int mansy_step_host(mansy_handle_t h, const int32_t *actions_host, int32_t auto_
 
 int mansy_reset_host(mansy_handle_t h, float *obs_host, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   int rc = ensure_staging(h);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -878,12 +879,14 @@ int mansy_rollout_reserve_timing(mansy_handle_t h, int32_t n_steps) {
 int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout_t *b, int32_t n_steps, int64_t t0,
                          uint64_t seed, int32_t flags, void *stream) {
   if (!h || !p || !b) return set_error(MANSY_E_INVALID, "NULL argument");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   if (n_steps < 0 || t0 < 0) return set_error(MANSY_E_INVALID, "n_steps / t0 must be >= 0");
   if (b->slabs < 2) return set_error(MANSY_E_INVALID, "a rollout needs at least 2 observation slabs");
   if (!b->obs || !b->actions || !b->logp || !b->value || !b->reward || !b->done || !b->logits)
     return set_error(MANSY_E_INVALID, "a rollout buffer pointer is NULL");
   if (h->dev.obs_mode == MANSY_OBS_NONE) return set_error(MANSY_E_INVALID, "the policy consumes observation rows");
+  if (policy_device_of(p) != h->device) return set_error(MANSY_E_INVALID, "policy and simulator live on different devices");
   const size_t n = (size_t)h->dev.n_envs;
   const bool timed = (flags & MANSY_ROLLOUT_TIME_KERNELS) != 0;
   // back-to-back launches overlap their scheduling / prologues (programmatic dependent launch) unless events
@@ -935,13 +938,15 @@ int mansy_rollout_policy(mansy_handle_t h, mansy_policy_t p, const mansy_rollout
 int mansy_rollout_policy_host(mansy_handle_t h, mansy_policy_t p, const mansy_rollout_t *b, const mansy_rollout_host_t *host,
                               int32_t n_steps, int64_t t0, uint64_t seed, int32_t flags, void *stream) {
   if (!h || !p || !b || !host) return set_error(MANSY_E_INVALID, "NULL argument");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   if (n_steps < 0 || t0 < 0) return set_error(MANSY_E_INVALID, "n_steps / t0 must be >= 0");
   if (b->slabs < 2 || host->host_slabs < 1) return set_error(MANSY_E_INVALID, "need >= 2 device slabs and >= 1 host slab");
   if (!b->obs || !b->actions || !b->logp || !b->value || !b->reward || !b->done || !b->logits || !host->obs ||
       !host->actions || !host->logp || !host->value || !host->reward || !host->done)
     return set_error(MANSY_E_INVALID, "a rollout buffer pointer is NULL");
   if (h->dev.obs_mode == MANSY_OBS_NONE) return set_error(MANSY_E_INVALID, "the policy consumes observation rows");
+  if (policy_device_of(p) != h->device) return set_error(MANSY_E_INVALID, "policy and simulator live on different devices");
   const size_t n = (size_t)h->dev.n_envs;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int is_probs = h->dev.obs_mode == MANSY_OBS_SIMPLE ? 1 : 0;
@@ -1045,7 +1050,8 @@ int mansy_rollout_kernel_ms(mansy_handle_t h, double *policy_ms, double *step_ms
 
 int mansy_episode_stats(mansy_handle_t h, double *stats_dev, void *stream) {
   if (!h || !stats_dev) return set_error(MANSY_E_INVALID, "NULL argument");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   MANSY_CUDA(cudaMemcpyAsync(stats_dev, h->dev.stats, (size_t)h->dev.n_envs * MANSY_STATS_DOUBLES * sizeof(double),
                              cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return MANSY_OK;
@@ -1060,7 +1066,8 @@ int mansy_set_outcome_table(mansy_handle_t h, int32_t enable) {
 
 int mansy_stats_clear(mansy_handle_t h, void *stream) {
   if (!h) return set_error(MANSY_E_INVALID, "handle is NULL");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   const size_t n = (size_t)h->dev.n_envs * MANSY_STATS_DOUBLES;
   stats_clear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(h->dev.stats, n);
   count_launch();
@@ -1070,7 +1077,8 @@ int mansy_stats_clear(mansy_handle_t h, void *stream) {
 
 int mansy_expert_actions(mansy_handle_t h, int32_t horizon, int32_t *actions_dev, double *best_value_dev, void *stream) {
   if (!h || !actions_dev) return set_error(MANSY_E_INVALID, "NULL argument");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   if (horizon < 1 || horizon > kExpertMaxHorizon) return set_error(MANSY_E_INVALID, "horizon must be 1..6");
   expert_mpc_kernel<<<(unsigned)h->dev.n_envs, kExpertThreads, 0, static_cast<cudaStream_t>(stream)>>>(h->dev, horizon, actions_dev,
                                                                                                        best_value_dev);
@@ -1081,7 +1089,8 @@ int mansy_expert_actions(mansy_handle_t h, int32_t horizon, int32_t *actions_dev
 
 int mansy_state_snapshot(mansy_handle_t h, void *state_dev, void *stream) {
   if (!h || !state_dev) return set_error(MANSY_E_INVALID, "NULL argument");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   MANSY_CUDA(cudaMemcpyAsync(state_dev, h->dev.state, (size_t)h->dev.n_envs * sizeof(EnvState),
                              cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return MANSY_OK;
@@ -1089,7 +1098,8 @@ int mansy_state_snapshot(mansy_handle_t h, void *state_dev, void *stream) {
 
 int mansy_error_flag(mansy_handle_t h, int32_t *flag_host) {
   if (!h || !flag_host) return set_error(MANSY_E_INVALID, "NULL argument");
-  MANSY_CUDA(use_device(h->device));
+  DeviceScope dscope(h->device);
+  MANSY_CUDA(dscope.err);
   MANSY_CUDA(cudaMemcpy(flag_host, h->dev.error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost));
   return MANSY_OK;
 }
@@ -1098,6 +1108,7 @@ int mansy_viewport_tiles(const float *gt_xy_dev, const float *pred_xy_dev, int64
                          int32_t video_width, int32_t video_height, int32_t fov_width, int32_t fov_height,
                          uint64_t *gt_mask_dev, uint64_t *pred_mask_dev, double *acc_dev, void *stream) {
   if (!gt_xy_dev || !gt_mask_dev) return set_error(MANSY_E_INVALID, "gt pointers are NULL");
+  DeviceScope dscope(device_of_pointer(gt_xy_dev));
   if ((pred_xy_dev != nullptr) != (pred_mask_dev != nullptr) || (pred_xy_dev != nullptr) != (acc_dev != nullptr))
     return set_error(MANSY_E_INVALID, "pred_xy, pred_mask and acc must be given together");
   if (n_chunks < 0 || points < 1) return set_error(MANSY_E_INVALID, "bad n_chunks / points");
@@ -1121,6 +1132,7 @@ int mansy_allocate_tile_versions(const uint64_t *masks_dev, const int32_t *actio
   if (!masks_dev || !actions_dev || !versions_dev || !video_rates) return set_error(MANSY_E_INVALID, "NULL argument");
   if (n < 0) return set_error(MANSY_E_INVALID, "n < 0");
   if (n == 0) return MANSY_OK;
+  DeviceScope dscope(device_of_pointer(masks_dev));
   uint32_t lut[5];
   build_rate_lut(video_rates, lut);
   const int threads = 128;

@@ -118,4 +118,34 @@ struct SimDev {
   uint32_t lut[kRates];
 };
 
+// Entry points without a handle run where their (device) buffers live.
+inline int device_of_pointer(const void *dev_ptr) {
+  cudaPointerAttributes a;
+  int cur = 0;
+  if (cudaPointerGetAttributes(&a, dev_ptr) == cudaSuccess && a.type == cudaMemoryTypeDevice) return a.device;
+  cudaGetLastError();
+  cudaGetDevice(&cur);
+  return cur;
+}
+
+// Entry points run on their handle's device whatever the caller's current device is (a process driving several GPUs) and
+// leave the caller's current device as they found it.
+struct DeviceScope {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceScope(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) {
+      err = cudaSetDevice(device);
+      switched = err == cudaSuccess;
+    }
+  }
+  ~DeviceScope() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope &) = delete;
+  DeviceScope &operator=(const DeviceScope &) = delete;
+};
+
 }  // namespace mansy

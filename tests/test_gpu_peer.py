@@ -124,3 +124,33 @@ def test_finished_env_stepped_again_is_logged_once(tmp_path):
         assert d.all() and (rew == 0).all()
     venv.close()
     assert len(open(log).read().strip().splitlines()) == 1 + n
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_handles_run_on_their_own_device_whatever_the_current_one_is():
+    """One process driving two GPUs: every entry point switches to its handle's device (the stream it is given belongs to
+    it).  The same rollout on device 1 -- with device 0 current throughout -- must equal the one on device 0 bit for bit."""
+    from mansy_immersivevideostreaming_b200.policy import PolicyNet, mansy_state_dict_shapes, seeded_state_dict
+    from mansy_immersivevideostreaming_b200.rollout import PolicyRollout
+    n, steps = 300, 60
+    a, c = mansy_state_dict_shapes()
+    out = []
+    torch.cuda.set_device(0)
+    for dev in (0, 1):
+        t = synth.make_synthetic_tables(ViewportTiler(CFG, device=dev).chunk_masks, n_videos=3, n_users=4, n_traces=5, seed=21,
+                                        trace_len_range=(40, 90))
+        t = t.with_samples(synth.per_env_samples(t, n))
+        sim = BatchSimulator(t, n, OBS_MODE_MANSY, REWARD_QOE, seed=3, device=dev)
+        pol = PolicyNet(seeded_state_dict(a, 1), seeded_state_dict(c, 2), OBS_MODE_MANSY, device=dev)
+        roll = PolicyRollout(sim, pol, 4, seed=77)
+        assert torch.cuda.current_device() == 0
+        roll.run(steps)
+        torch.cuda.synchronize(dev)
+        out.append((sim.episode_totals().cpu(), roll.buf.actions.cpu(), roll.buf.obs.cpu(), sim.error_flag()))
+        peers = PeerGroup(n, dev)
+        assert torch.equal(peers.gather_episode_stats(sim).cpu(), out[-1][0])
+        peers.close(); sim.close(); pol.close()
+    assert torch.cuda.current_device() == 0
+    assert out[0][3] == 0 and out[1][3] == 0
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    assert float(out[0][0][:, 5].sum()) > 0          # episodes finished: the comparison covers resets
