@@ -77,7 +77,8 @@ def test_host_rollout_equals_device_rollout():
 def test_fused_rollout_equals_two_kernel_rollout(kind, n, steps, slabs, monkeypatch):
     """ONE launch of the fused policy+step cluster kernel for all steps == two launches per step (with and without
     programmatic dependent launch), bit for bit, including the ring wrap of the slabs and a continued rollout.  (More
-    tiles than resident clusters: the kernel walks several tiles per cluster -- not the default above 4 224 envs.)"""
+    tiles than resident clusters: the kernel walks several tiles per cluster -- the default up to two tiles per cluster,
+    forced here beyond that.)"""
     monkeypatch.setenv("MANSY_FUSED_MULTI_TILE", "1")
     _, _, a = _setup(kind, n, True, slabs=slabs)
     _, _, b = _setup(kind, n, True, slabs=slabs)
